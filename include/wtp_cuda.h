@@ -1,0 +1,271 @@
+/*
+ * wtp_cuda.h — C ABI of libwtp_cuda.so, the B200 (sm_100a) replacement for the
+ * data-parallel hot path of WhatsThePoint.jl.
+ *
+ * The reference has no FFI; the boundary is created by overriding the three
+ * internal Julia functions that are the only call sites of the third-party
+ * KD-tree on this path (paths relative to the reference checkout):
+ *
+ *   _build_knn_neighbors(points, k)          src/topology.jl:79-84    -> wtp_knn_{f32,f64}
+ *   _build_radius_neighbors(points, radius)  src/topology.jl:91-97    -> wtp_radius_count/fill_{f32,f64}
+ *   _relax!(p, p_old, snap, spacing, ...)    src/repel.jl:202-339     -> wtp_repel_{f32,f64}
+ *
+ * plus the sibling consumers of the same k-NN primitive:
+ *
+ *   searchdists(cloud, KNearestSearch)       src/neighbors.jl:16-21   -> wtp_knn_self_{f32,f64}
+ *   spacing.(points)                         src/repel.jl:61,209,251  -> wtp_spacing_eval_{f32,f64}
+ *   metrics / spacing_metrics / ..._fidelity src/metrics.jl:19-129    -> wtp_metrics_{f32,f64}
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ types, no exceptions cross the ABI.
+ *   - every entry point returns a wtp_status (0 = OK); the message for the last
+ *     failure on a context is wtp_last_error(ctx).
+ *   - point sets are N x D row-major arrays of T (D = 2 or 3): exactly the bytes of
+ *     a Julia Vector{Point{𝔼{D},Cartesian{...,Quantity{T}}}} (units are type-level).
+ *   - indices crossing the ABI are int64, 1-based, in the caller's point order.
+ *   - neighbour order is canonical: ascending (d2, index), d2 = ((dx*dx + dy*dy) + dz*dz)
+ *     evaluated in T without fused multiply-add.
+ *   - host entry points take HOST pointers and do their own H2D/D2H; the *_dev entry
+ *     points take DEVICE pointers (same layouts) and enqueue on the context stream.
+ *   - the caller owns every buffer it passes; the library owns all device memory in
+ *     the context and keeps no host pointer after a call returns.
+ *   - one context is not re-entrant. There is no CPU fallback: without a usable
+ *     CUDA device wtp_create fails with WTP_ERR_CUDA.
+ */
+#ifndef WTP_CUDA_H
+#define WTP_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wtp_ctx wtp_ctx;
+
+typedef enum {
+    WTP_OK = 0,
+    WTP_ERR_BAD_ARG = 1,       /* null pointer, D not in {2,3}, negative size ...       -> ArgumentError */
+    WTP_ERR_K_TOO_LARGE = 2,   /* k+1 > N (upstream knn throws), or k above WTP_MAX_K   -> ArgumentError */
+    WTP_ERR_UNSUPPORTED = 3,   /* user force model / spacing callable / kick / deposit   -> ErrorException */
+    WTP_ERR_CUDA = 4,          /* CUDA runtime failure (message has the CUDA error)     */
+    WTP_ERR_NCCL = 5,
+    WTP_ERR_OOM = 6,
+    WTP_ERR_STATE = 7          /* e.g. wtp_radius_fill without a preceding count        */
+} wtp_status;
+
+/* Largest list length the warp-resident top-k holds (k+1 for topology, k for repel). */
+#define WTP_MAX_K 128
+
+/* ------------------------------------------------------------------ context */
+
+/* device: CUDA ordinal. Fails (no fallback) if the device is unusable. */
+int32_t wtp_create(wtp_ctx** out, int32_t device);
+void wtp_destroy(wtp_ctx* ctx);
+const char* wtp_last_error(const wtp_ctx* ctx);
+const char* wtp_status_string(int32_t status);
+int32_t wtp_version(void);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*) for all work of this
+ * context; NULL restores the context's own stream. */
+int32_t wtp_set_stream(wtp_ctx* ctx, void* cuda_stream);
+
+/* Pin / unpin a host range so H2D/D2H of the host entry points run at full PCIe rate. */
+int32_t wtp_host_register(wtp_ctx* ctx, void* ptr, int64_t bytes);
+int32_t wtp_host_unregister(wtp_ctx* ctx, void* ptr);
+
+/* Tuning knob: target number of points per grid cell (default 8 in 3-D, 6 in 2-D; <=0 restores). */
+int32_t wtp_set_cell_occupancy(wtp_ctx* ctx, double points_per_cell);
+
+/* Multi-GPU, one process per GPU. The NCCL unique id (128 bytes) is created on one
+ * rank with wtp_comm_unique_id and distributed by the host program. After wtp_comm_init
+ * the k-NN / radius entry points answer only this rank's contiguous query range
+ * [wtp_shard_begin, wtp_shard_end) of the caller's point order (no collective), and
+ * wtp_repel_* all-gathers the moved positions over NCCL every iteration. */
+int32_t wtp_comm_unique_id(void* out128);
+int32_t wtp_comm_init(wtp_ctx* ctx, int32_t rank, int32_t world, const void* unique_id128);
+int32_t wtp_comm_rank(const wtp_ctx* ctx);
+int32_t wtp_comm_world(const wtp_ctx* ctx);
+/* Contiguous block partition of n items: rank r owns [begin, end). */
+int64_t wtp_shard_begin(int64_t n, int32_t rank, int32_t world);
+int64_t wtp_shard_end(int64_t n, int32_t rank, int32_t world);
+
+/* ------------------------------------------------------------ instrumentation */
+
+typedef struct {
+    float ms_h2d;        /* host entry points only */
+    float ms_bbox;       /* bounding box + grid parameters */
+    float ms_cellkey;    /* cell-key kernel */
+    float ms_sort;       /* radix sort (all passes) */
+    float ms_reorder;    /* gather into sorted float4 tiles + cell starts */
+    float ms_query;      /* k-NN query / radius count+fill / repel sweep */
+    float ms_scan;       /* exclusive scan (radius CSR) */
+    float ms_reduce;     /* repel reductions + stop-test scalars */
+    float ms_comm;       /* NCCL all-gather (multi-GPU repel) */
+    float ms_d2h;        /* host entry points only */
+    float ms_total;
+    int32_t sort_passes; /* radix passes actually run (8-bit digits) */
+    int32_t query_launches;
+    int64_t n_cells;
+    int64_t n_ring_expanded; /* queries that needed more than the 3^D block */
+} wtp_timing;
+
+/* enable != 0: record CUDA events around each phase of subsequent calls. */
+int32_t wtp_set_timing(wtp_ctx* ctx, int32_t enable);
+/* Timing of the most recent call (synchronises the context stream). */
+int32_t wtp_get_timing(wtp_ctx* ctx, wtp_timing* out);
+/* Number of kernels this context has launched since creation. */
+int64_t wtp_launch_count(const wtp_ctx* ctx);
+
+/* ---------------------------------------------------------------- topology */
+
+/* _build_knn_neighbors (src/topology.jl:79-84): for every point the k nearest OTHER
+ * points. Queries k+1, orders by (d2, index), drops position 1 (the reference's
+ * n[2:end]). out_idx: N x k int64, 1-based. out_dist (nullable): N x k distances
+ * sqrt(d2) in T. Requires N >= k+1. In sharded mode only rows [begin,end) are written. */
+int32_t wtp_knn_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_t k,
+                    int64_t* out_idx, float* out_dist);
+int32_t wtp_knn_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k,
+                    int64_t* out_idx, double* out_dist);
+int32_t wtp_knn_dev_f32(wtp_ctx*, const float* d_pts, int64_t N, int32_t D, int32_t k,
+                        int64_t* d_out_idx, float* d_out_dist);
+int32_t wtp_knn_dev_f64(wtp_ctx*, const double* d_pts, int64_t N, int32_t D, int32_t k,
+                        int64_t* d_out_idx, double* d_out_dist);
+
+/* search / searchdists (src/neighbors.jl:9-21): the k nearest points INCLUDING the
+ * query's own entry (position 1 whenever the point is not duplicated). */
+int32_t wtp_knn_self_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_t k,
+                         int64_t* out_idx, float* out_dist);
+int32_t wtp_knn_self_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k,
+                         int64_t* out_idx, double* out_dist);
+
+/* _build_radius_neighbors (src/topology.jl:91-97): two calls so the caller allocates
+ * the exact CSR. count: offsets[N+1] (0-based exclusive prefix, offsets[N] = nnz).
+ * fill: indices[nnz], 1-based, each row ascending by index, self removed BY INDEX,
+ * inclusion test d2 <= r*r in T. fill must directly follow count on the same ctx. */
+int32_t wtp_radius_count_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, float r,
+                             int64_t* offsets);
+int32_t wtp_radius_count_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, double r,
+                             int64_t* offsets);
+int32_t wtp_radius_fill(wtp_ctx*, int64_t* indices);
+int32_t wtp_radius_count_dev_f32(wtp_ctx*, const float* d_pts, int64_t N, int32_t D, float r,
+                                 int64_t* d_offsets);
+int32_t wtp_radius_count_dev_f64(wtp_ctx*, const double* d_pts, int64_t N, int32_t D, double r,
+                                 int64_t* d_offsets);
+int32_t wtp_radius_fill_dev(wtp_ctx*, int64_t* d_indices);
+/* nnz of the pending count (host copy of offsets[N]); -1 if none. */
+int64_t wtp_radius_nnz(const wtp_ctx*);
+
+/* -------------------------------------------------------------------- repel */
+
+/* Force laws F(u), u = r/s (src/repel_forces.jl). */
+enum { WTP_FORCE_INVERSE = 0,      /* 1/(u^2+beta)^2                      :37      */
+       WTP_FORCE_EQUILIBRIUM = 1,  /* (1-u^2)/(u^2+beta)^2                :57-60   */
+       WTP_FORCE_CLIPPED = 2,      /* max((u0^2-u^2)/(u^2+beta)^2, 0)     :96-100  */
+       WTP_FORCE_STRONG = 3 };     /* (1-u^2)/(u^2+beta)^gamma            :124-127 */
+typedef struct {
+    int32_t kind;
+    double beta, u0, gamma;        /* converted to T at the boundary */
+} wtp_force;
+
+/* Spacing callables (src/discretization/spacings.jl). */
+enum { WTP_SPACING_CONSTANT = 0,        /* a = dx                                  :35-39   */
+       WTP_SPACING_LOGLIKE = 1,         /* a = base_size, b = growth_rate          :67-72   */
+       WTP_SPACING_BOUNDARY_LAYER = 2 };/* a = at_wall, b = bulk, c = thickness    :121-133 */
+typedef struct {
+    int32_t kind;
+    double a, b, c;
+    const void* bnd_pts;           /* the spacing's own boundary point set (T, D), HOST pointer */
+    int64_t n_bnd;                 /* (DEVICE pointer for the *_dev entry points)               */
+} wtp_spacing;
+
+enum { WTP_WALL_IDENTITY = 0,      /* repel(cloud, spacing): src/repel.jl:82         */
+       WTP_WALL_MESH = 1 };        /* repel(cloud, spacing, octree): :158-160,448-469 */
+
+/* Triangle mesh for the wall rule of the 3-argument repel (3-D only). The library
+ * builds its own device search structure; results equal the reference's octree
+ * queries (nearest triangle, pseudonormal-signed inside test). HOST pointers. */
+typedef struct {
+    const void* vertices;          /* n_tri x 3 x 3 of T: v1,v2,v3 per triangle        */
+    const void* face_normals;      /* n_tri x 3 of T (octree.index.face)               */
+    int64_t n_tri;
+    double offset_dist;            /* 1e-6 * |bbox_max - bbox_min|  (src/repel.jl:150) */
+    const uint8_t* is_bnd;         /* n_move flags (src/repel.jl:155)                  */
+    int64_t* tri_indices;          /* out, n_move, 1-based landing triangle (0 = none) */
+    uint8_t* escaped;              /* out, n_move                                       */
+} wtp_wall_mesh;
+
+typedef struct {
+    int32_t k;                     /* neighbourhood size INCLUDING self (default 21)      */
+    int32_t max_iters;
+    int32_t rebuild_every;         /* >= 1 (src/repel.jl:74)                              */
+    int32_t stall_after;
+    int32_t kick_after;            /* must be 0: the kick draws randn (src/repel.jl:430)  */
+    int32_t wall;                  /* WTP_WALL_*                                          */
+    int32_t want_trace;
+    int32_t reserved;
+    double alpha_lo, alpha_max;    /* ustrip(α_min), ustrip(α) (src/repel.jl:86)          */
+    double tol, cv_target;
+} wtp_repel_params;
+
+enum { WTP_STOP_MAX_ITERS = 0, WTP_STOP_TOL = 1, WTP_STOP_CV_TARGET = 2, WTP_STOP_STALL = 3 };
+typedef struct {
+    int32_t iters;                 /* length of conv                                      */
+    int32_t stop_reason;           /* WTP_STOP_*                                          */
+    double last_cv;                /* d_NN/s CV of the last monitored sweep (NaN if off)  */
+} wtp_repel_result;
+
+/* One closest-pair record per iteration (src/repel.jl:294-296, 396-403). */
+typedef struct {
+    double r, s, r_over_s;
+    int64_t idx_a, idx_b;          /* snapshot-global, 1-based, idx_a < idx_b */
+} wtp_trace_entry;
+
+/* _relax! (src/repel.jl:202-339). snap = (n_fixed + n_move) x D of T: static head,
+ * movable tail, the tail is updated in place with the final positions (pre-sweep
+ * positions on a cv_target stop). conv has max_iters slots, trace (nullable) too. */
+int32_t wtp_repel_f32(wtp_ctx*, float* snap, int64_t n_fixed, int64_t n_move, int32_t D,
+                      const wtp_spacing*, const wtp_force*, const wtp_repel_params*,
+                      const wtp_wall_mesh* wall /*nullable*/, float* conv,
+                      wtp_trace_entry* trace /*nullable*/, wtp_repel_result* result);
+int32_t wtp_repel_f64(wtp_ctx*, double* snap, int64_t n_fixed, int64_t n_move, int32_t D,
+                      const wtp_spacing*, const wtp_force*, const wtp_repel_params*,
+                      const wtp_wall_mesh* wall /*nullable*/, double* conv,
+                      wtp_trace_entry* trace /*nullable*/, wtp_repel_result* result);
+/* Device-resident variant: d_snap and spacing->bnd_pts are DEVICE pointers; conv, trace,
+ * result stay HOST pointers (a few scalars per iteration). Wall must be identity. */
+int32_t wtp_repel_dev_f32(wtp_ctx*, float* d_snap, int64_t n_fixed, int64_t n_move, int32_t D,
+                          const wtp_spacing*, const wtp_force*, const wtp_repel_params*,
+                          float* conv, wtp_trace_entry* trace, wtp_repel_result* result);
+int32_t wtp_repel_dev_f64(wtp_ctx*, double* d_snap, int64_t n_fixed, int64_t n_move, int32_t D,
+                          const wtp_spacing*, const wtp_force*, const wtp_repel_params*,
+                          double* conv, wtp_trace_entry* trace, wtp_repel_result* result);
+
+/* spacing.(points) for the three built-in spacings (used for the default
+ * α = minimum(spacing.(to(cloud)))/20, src/repel.jl:61, and by the metrics). */
+int32_t wtp_spacing_eval_f32(wtp_ctx*, const wtp_spacing*, const float* pts, int64_t N,
+                             int32_t D, float* out);
+int32_t wtp_spacing_eval_f64(wtp_ctx*, const wtp_spacing*, const double* pts, int64_t N,
+                             int32_t D, double* out);
+
+/* compute_force(model, u) elementwise on the device (src/repel_forces.jl:22). */
+int32_t wtp_force_eval_f32(wtp_ctx*, const wtp_force*, const float* u, int64_t n, float* out);
+int32_t wtp_force_eval_f64(wtp_ctx*, const wtp_force*, const double* u, int64_t n, double* out);
+
+/* ------------------------------------------------------------------ metrics */
+
+/* metrics(cloud; k) (src/metrics.jl:19-41): statistics of the distances to the k-1
+ * nearest other points (the reference queries k including self and drops it). */
+typedef struct {
+    double avg, std, max, min;         /* means over points of per-point mean/std/max/min */
+    double separation, fill, mesh_ratio;
+} wtp_cloud_metrics;
+int32_t wtp_metrics_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_t k,
+                        wtp_cloud_metrics* out);
+int32_t wtp_metrics_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k,
+                        wtp_cloud_metrics* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WTP_CUDA_H */

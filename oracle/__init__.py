@@ -1,0 +1,201 @@
+"""ctypes front end of the CPU oracle (oracle/wtp_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY — "parity unpinned" for neighbour identities and repel
+trajectories (see the header of wtp_oracle.cpp). May be imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by
+the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libwtp_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "wtp_oracle.cpp")
+    hdr = os.path.join(_HERE, "..", "include", "wtp_cuda.h")
+    stale = (not os.path.exists(_SO)) or any(
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _SO
+
+
+class Force(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("beta", C.c_double), ("u0", C.c_double), ("gamma", C.c_double)]
+
+
+class Spacing(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a", C.c_double), ("b", C.c_double), ("c", C.c_double),
+                ("bnd_pts", C.c_void_p), ("n_bnd", C.c_int64)]
+
+
+class RepelParams(C.Structure):
+    _fields_ = [("k", C.c_int32), ("max_iters", C.c_int32), ("rebuild_every", C.c_int32),
+                ("stall_after", C.c_int32), ("kick_after", C.c_int32), ("wall", C.c_int32),
+                ("want_trace", C.c_int32), ("reserved", C.c_int32),
+                ("alpha_lo", C.c_double), ("alpha_max", C.c_double),
+                ("tol", C.c_double), ("cv_target", C.c_double)]
+
+
+class RepelResult(C.Structure):
+    _fields_ = [("iters", C.c_int32), ("stop_reason", C.c_int32), ("last_cv", C.c_double)]
+
+
+class TraceEntry(C.Structure):
+    _fields_ = [("r", C.c_double), ("s", C.c_double), ("r_over_s", C.c_double),
+                ("idx_a", C.c_int64), ("idx_b", C.c_int64)]
+
+
+class CloudMetrics(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("avg", "std", "max", "min", "separation", "fill", "mesh_ratio")]
+
+
+FORCE_KINDS = {"inverse": 0, "equilibrium": 1, "clipped": 2, "strong": 3}
+SPACING_KINDS = {"constant": 0, "loglike": 1, "boundary_layer": 2}
+STOP_REASONS = {0: "max_iters", 1: "tol", 2: "cv_target", 3: "stall"}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _sfx(dtype) -> str:
+    dtype = np.dtype(dtype)
+    if dtype == np.float32:
+        return "f32"
+    if dtype == np.float64:
+        return "f64"
+    raise TypeError(f"oracle supports float32/float64, got {dtype}")
+
+
+def _pts(pts):
+    pts = np.ascontiguousarray(pts)
+    assert pts.ndim == 2 and pts.shape[1] in (2, 3), pts.shape
+    return pts
+
+
+def max_threads() -> int:
+    return int(lib().wtpo_max_threads())
+
+
+def knn(pts, k, *, drop_first=True, algo="kdtree", threads=0, dists=False):
+    """_build_knn_neighbors (drop_first) / search+searchdists (not drop_first)."""
+    pts = _pts(pts)
+    n, d = pts.shape
+    idx = np.empty((n, k), dtype=np.int64)
+    dist = np.empty((n, k), dtype=pts.dtype) if dists else None
+    fn = getattr(lib(), "wtpo_knn_" + _sfx(pts.dtype))
+    rc = fn(pts.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int32(d), C.c_int32(k),
+            C.c_int32(1 if drop_first else 0), C.c_int32(0 if algo == "brute" else 1),
+            C.c_int32(threads), idx.ctypes.data_as(C.c_void_p),
+            dist.ctypes.data_as(C.c_void_p) if dists else None)
+    if rc != 0:
+        raise ValueError(f"oracle knn failed with status {rc}")
+    return (idx, dist) if dists else idx
+
+
+def radius(pts, r, *, threads=0):
+    """_build_radius_neighbors as CSR (offsets 0-based, indices 1-based ascending)."""
+    pts = _pts(pts)
+    n, d = pts.shape
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    sfx = _sfx(pts.dtype)
+    fn = getattr(lib(), "wtpo_radius_" + sfx)
+    rr = C.c_float(r) if sfx == "f32" else C.c_double(r)
+    rc = fn(pts.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int32(d), rr, C.c_int32(threads),
+            offsets.ctypes.data_as(C.c_void_p), None)
+    assert rc == 0, rc
+    indices = np.empty(int(offsets[-1]), dtype=np.int64)
+    rc = fn(pts.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int32(d), rr, C.c_int32(threads),
+            offsets.ctypes.data_as(C.c_void_p), indices.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return offsets, indices
+
+
+def make_force(kind="clipped", beta=0.2, u0=1.0, gamma=3.0) -> Force:
+    return Force(FORCE_KINDS[kind], float(beta), float(u0), float(gamma))
+
+
+def make_spacing(kind="constant", a=0.0, b=0.0, c=0.0, bnd_pts=None):
+    """Returns (Spacing, keepalive)."""
+    if bnd_pts is not None:
+        bnd_pts = np.ascontiguousarray(bnd_pts)
+        return Spacing(SPACING_KINDS[kind], float(a), float(b), float(c),
+                       bnd_pts.ctypes.data, bnd_pts.shape[0]), bnd_pts
+    return Spacing(SPACING_KINDS[kind], float(a), float(b), float(c), None, 0), None
+
+
+def force(f: Force, u):
+    u = np.ascontiguousarray(u)
+    out = np.empty_like(u)
+    getattr(lib(), "wtpo_force_" + _sfx(u.dtype))(C.byref(f), u.ctypes.data_as(C.c_void_p),
+                                                  C.c_int64(u.size), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def spacing_eval(sp: Spacing, pts):
+    pts = _pts(pts)
+    out = np.empty(pts.shape[0], dtype=pts.dtype)
+    rc = getattr(lib(), "wtpo_spacing_" + _sfx(pts.dtype))(
+        C.byref(sp), pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]),
+        out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return out
+
+
+def repel(snap, n_fixed, sp: Spacing, f: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
+          stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, threads=0):
+    """_relax! on snap = [fixed head; movable tail]. Returns (new_snap, conv, result dict, trace)."""
+    snap = np.array(_pts(snap), copy=True)
+    n_all, d = snap.shape
+    n_move = n_all - n_fixed
+    prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 0, 1 if trace else 0, 0,
+                      float(alpha_lo), float(alpha_max), float(tol), float(cv_target))
+    conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
+    tr = (TraceEntry * max(max_iters, 1))() if trace else None
+    res = RepelResult()
+    rc = getattr(lib(), "wtpo_repel_" + _sfx(snap.dtype))(
+        snap.ctypes.data_as(C.c_void_p), C.c_int64(n_fixed), C.c_int64(n_move), C.c_int32(d),
+        C.byref(sp), C.byref(f), C.byref(prm), conv.ctypes.data_as(C.c_void_p),
+        tr, C.byref(res), C.c_int32(threads))
+    if rc != 0:
+        raise ValueError(f"oracle repel failed with status {rc}")
+    out_tr = None
+    if trace:
+        out_tr = [dict(iteration=i + 1, r=tr[i].r, s=tr[i].s, r_over_s=tr[i].r_over_s,
+                       idx_a=tr[i].idx_a, idx_b=tr[i].idx_b) for i in range(res.iters)]
+    return snap, conv[:res.iters].copy(), dict(iters=res.iters, stop_reason=STOP_REASONS[res.stop_reason],
+                                               last_cv=res.last_cv), out_tr
+
+
+def metrics(pts, k=20, *, threads=0):
+    pts = _pts(pts)
+    out = CloudMetrics()
+    rc = getattr(lib(), "wtpo_metrics_" + _sfx(pts.dtype))(
+        pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]), C.c_int32(k),
+        C.c_int32(threads), C.byref(out))
+    if rc != 0:
+        raise ValueError(f"oracle metrics failed with status {rc}")
+    return {n: getattr(out, n) for n, _ in CloudMetrics._fields_}
+
+
+def closest_point_on_triangle(p, a, b, c):
+    p, a, b, c = (np.ascontiguousarray(x) for x in (p, a, b, c))
+    out = np.empty(3, dtype=p.dtype)
+    getattr(lib(), "wtpo_closest_point_on_triangle_" + _sfx(p.dtype))(
+        *(x.ctypes.data_as(C.c_void_p) for x in (p, a, b, c)), out.ctypes.data_as(C.c_void_p))
+    return out

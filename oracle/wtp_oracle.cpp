@@ -1,0 +1,582 @@
+// wtp_oracle.cpp — CPU restatement of the WhatsThePoint.jl hot path.
+//
+// TEST INFRASTRUCTURE ONLY. Nothing in the product path (libwtp_cuda.so, the
+// whatsthepoint.jl_b200 package) may call, link or load this file. Allowed users:
+// tests/, __graft_entry__.smoke(), and bench.py's cpu_baseline / --impl reference legs.
+//
+// PARITY STATUS: "parity unpinned" for neighbour identities and repel trajectories.
+// The reference cannot run here (no Julia) and its k-NN arithmetic lives in the
+// un-vendored NearestNeighbors.jl (compat "0.4.8", Project.toml:42) reached through
+// Meshes.jl (compat "0.56, 0.57", Project.toml:41). The reference's own tests pin only
+// list shapes, self exclusion, sortedness, compute_force known answers and the cull
+// mask (test/topology.jl:28-65, test/neighbors.jl:55,104-106, test/repel.jl:117-183,
+// 301-325); those known answers are checked in tests/test_oracle_golden.py. Neighbour
+// sets are additionally cross-checked against scipy.spatial.cKDTree.
+//
+// What is restated, and from where (paths relative to the reference checkout):
+//   knn / knn_self      src/topology.jl:79-84, src/neighbors.jl:9-21  (+ published
+//                       NearestNeighbors.jl KDTree algorithm: widest-dimension split,
+//                       leaf size 25, bounded max-heap, sqrt applied to the k results)
+//   radius              src/topology.jl:91-100 (inrange d2 <= r2, self removed by index)
+//   compute_force x4    src/repel_forces.jl:37, 57-60, 96-100, 124-127
+//   spacings x3         src/discretization/spacings.jl:19-23, 35-39, 67-72, 121-133
+//   _relax!             src/repel.jl:202-339 (sweep :256-292, reductions :293, 374-403,
+//                       stop logic :305-337)
+//   metrics             src/metrics.jl:19-41
+//   closest point / wall rule   src/octree/geometric_utils.jl:68-136, src/repel.jl:448-469,522-537
+//
+// Canonical order: candidates are ordered by (d2, index) ascending with
+// d2 = ((dx*dx + dy*dy) + dz*dz) evaluated in T; compile with -ffp-contract=off.
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/wtp_cuda.h"
+
+namespace {
+
+// ---------------------------------------------------------------- distances
+template <class T, int D>
+inline T dist2(const T* a, const T* b) {
+    T s = T(0);
+    for (int d = 0; d < D; ++d) {
+        T t = a[d] - b[d];
+        s = s + t * t;  // -ffp-contract=off: no FMA
+    }
+    return s;
+}
+
+template <class T>
+struct Cand {
+    T d2;
+    int64_t idx;  // 0-based
+};
+template <class T>
+inline bool cand_less(const Cand<T>& a, const Cand<T>& b) {
+    return a.d2 < b.d2 || (a.d2 == b.d2 && a.idx < b.idx);
+}
+
+// Bounded max-heap on (d2, idx): top = current worst.
+template <class T>
+struct TopK {
+    Cand<T>* h;
+    int k, n;
+    TopK(Cand<T>* buf, int k_) : h(buf), k(k_), n(0) {}
+    inline bool full() const { return n == k; }
+    inline const Cand<T>& worst() const { return h[0]; }
+    inline void offer(T d2, int64_t idx) {
+        Cand<T> c{d2, idx};
+        if (n < k) {
+            int i = n++;
+            h[i] = c;
+            while (i > 0) {
+                int p = (i - 1) / 2;
+                if (cand_less(h[p], h[i])) { std::swap(h[p], h[i]); i = p; } else break;
+            }
+        } else if (cand_less(c, h[0])) {
+            h[0] = c;
+            int i = 0;
+            for (;;) {
+                int l = 2 * i + 1, r = l + 1, m = i;
+                if (l < n && cand_less(h[m], h[l])) m = l;
+                if (r < n && cand_less(h[m], h[r])) m = r;
+                if (m == i) break;
+                std::swap(h[m], h[i]);
+                i = m;
+            }
+        }
+    }
+    inline void sort_ascending() { std::sort(h, h + n, cand_less<T>); }
+};
+
+// ------------------------------------------------------------------ KD-tree
+// Widest-dimension median split, leaf size 25, points reordered into tree order
+// (the published NearestNeighbors.jl KDTree layout choices; see header).
+template <class T, int D>
+struct KDTree {
+    struct Node {
+        T lo[D], hi[D];
+        int32_t left, right;  // children (internal) or -1
+        int64_t begin, end;   // range in perm (leaf and internal)
+    };
+    static constexpr int LEAF = 25;
+    int64_t n = 0;
+    std::vector<T> data;        // reordered coordinates
+    std::vector<int64_t> perm;  // tree order -> original index
+    std::vector<Node> nodes;
+
+    void build(const T* pts, int64_t n_) {
+        n = n_;
+        perm.resize(n);
+        std::iota(perm.begin(), perm.end(), int64_t(0));
+        nodes.clear();
+        nodes.reserve(size_t(2 * (n / LEAF + 2)));
+        if (n > 0) build_rec(pts, 0, n);
+        data.resize(size_t(n) * D);
+        for (int64_t i = 0; i < n; ++i)
+            for (int d = 0; d < D; ++d) data[size_t(i) * D + d] = pts[size_t(perm[i]) * D + d];
+    }
+    int32_t build_rec(const T* pts, int64_t b, int64_t e) {
+        Node nd;
+        for (int d = 0; d < D; ++d) { nd.lo[d] = std::numeric_limits<T>::infinity(); nd.hi[d] = -nd.lo[d]; }
+        for (int64_t i = b; i < e; ++i)
+            for (int d = 0; d < D; ++d) {
+                T v = pts[size_t(perm[i]) * D + d];
+                nd.lo[d] = std::min(nd.lo[d], v);
+                nd.hi[d] = std::max(nd.hi[d], v);
+            }
+        nd.left = nd.right = -1;
+        nd.begin = b; nd.end = e;
+        int32_t id = int32_t(nodes.size());
+        nodes.push_back(nd);
+        if (e - b > LEAF) {
+            int sd = 0;
+            T best = nd.hi[0] - nd.lo[0];
+            for (int d = 1; d < D; ++d) { T w = nd.hi[d] - nd.lo[d]; if (w > best) { best = w; sd = d; } }
+            int64_t mid = b + (e - b) / 2;
+            std::nth_element(perm.begin() + b, perm.begin() + mid, perm.begin() + e,
+                             [&](int64_t x, int64_t y) {
+                                 T vx = pts[size_t(x) * D + sd], vy = pts[size_t(y) * D + sd];
+                                 return vx < vy || (vx == vy && x < y);
+                             });
+            int32_t l = build_rec(pts, b, mid);
+            int32_t r = build_rec(pts, mid, e);
+            nodes[id].left = l; nodes[id].right = r;
+        }
+        return id;
+    }
+    // Lower bound of d2 from q to any point of the node's tight box, evaluated with the
+    // same operation order as dist2 (monotone rounding => never above a member's d2).
+    inline T box_d2(const Node& nd, const T* q) const {
+        T s = T(0);
+        for (int d = 0; d < D; ++d) {
+            T g = T(0);
+            if (q[d] < nd.lo[d]) g = nd.lo[d] - q[d];
+            else if (q[d] > nd.hi[d]) g = q[d] - nd.hi[d];
+            s = s + g * g;
+        }
+        return s;
+    }
+    void knn_rec(int32_t id, const T* q, TopK<T>& tk) const {
+        const Node& nd = nodes[id];
+        if (nd.left < 0) {
+            for (int64_t i = nd.begin; i < nd.end; ++i) tk.offer(dist2<T, D>(q, &data[size_t(i) * D]), perm[i]);
+            return;
+        }
+        T dl = box_d2(nodes[nd.left], q), dr = box_d2(nodes[nd.right], q);
+        int32_t first = nd.left, second = nd.right;
+        if (dr < dl) { std::swap(first, second); std::swap(dl, dr); }
+        if (!tk.full() || dl <= tk.worst().d2) knn_rec(first, q, tk);
+        if (!tk.full() || dr <= tk.worst().d2) knn_rec(second, q, tk);
+    }
+    // k nearest (k <= n), ascending (d2, idx).
+    void knn(const T* q, int k, Cand<T>* buf) const {
+        TopK<T> tk(buf, k);
+        if (n > 0) knn_rec(0, q, tk);
+        tk.sort_ascending();
+    }
+    template <class F>
+    void inrange_rec(int32_t id, const T* q, T r2, F&& emit) const {
+        const Node& nd = nodes[id];
+        if (box_d2(nd, q) > r2) return;
+        if (nd.left < 0) {
+            for (int64_t i = nd.begin; i < nd.end; ++i)
+                if (dist2<T, D>(q, &data[size_t(i) * D]) <= r2) emit(perm[i]);
+            return;
+        }
+        inrange_rec(nd.left, q, r2, emit);
+        inrange_rec(nd.right, q, r2, emit);
+    }
+};
+
+// --------------------------------------------------------------- force laws
+// src/repel_forces.jl:37, 57-60, 96-100, 124-127. (x)^2 in Julia lowers to x*x.
+template <class T>
+inline T force_eval(int kind, T beta, T u0, T gamma, T u) {
+    T u2 = u * u;
+    switch (kind) {
+        case WTP_FORCE_INVERSE: { T t = u2 + beta; return T(1) / (t * t); }
+        case WTP_FORCE_EQUILIBRIUM: { T t = u2 + beta; return (T(1) - u2) / (t * t); }
+        case WTP_FORCE_CLIPPED: { T t = u2 + beta; T F = (u0 * u0 - u2) / (t * t); return F > T(0) ? F : T(0); }
+        case WTP_FORCE_STRONG: { return (T(1) - u2) / std::pow(u2 + beta, gamma); }
+    }
+    return std::numeric_limits<T>::quiet_NaN();
+}
+
+// ---------------------------------------------------------------- spacings
+// src/discretization/spacings.jl. _min_distance (:19-23) is a 1-NN KD-tree query on
+// the spacing's own boundary set, distance in the tree's float type.
+template <class T, int D>
+struct Spacing {
+    int kind;
+    T a, b, c;
+    KDTree<T, D> tree;
+    void init(const wtp_spacing* sp) {
+        kind = sp->kind; a = T(sp->a); b = T(sp->b); c = T(sp->c);
+        if (kind != WTP_SPACING_CONSTANT) tree.build(static_cast<const T*>(sp->bnd_pts), sp->n_bnd);
+    }
+    inline T operator()(const T* x) const {
+        if (kind == WTP_SPACING_CONSTANT) return a;                         // :35-39
+        Cand<T> nn;
+        tree.knn(x, 1, &nn);
+        T dmin = std::sqrt(nn.d2);
+        if (kind == WTP_SPACING_LOGLIKE) {                                  // :67-72
+            T inv_growth = T(1) - (b - T(1));
+            T aa = a * inv_growth;
+            return a * dmin / (aa + dmin);
+        }
+        T delta = c;                                                         // :121-133
+        T center = delta / T(2), width = delta / T(6);
+        T sigma = T(1) / (T(1) + std::exp(-(dmin - center) / width));
+        return a + (b - a) * sigma;
+    }
+};
+
+// ------------------------------------------------------ closest point (wall)
+// Ericson's closest point on triangle (src/octree/geometric_utils.jl:68-136).
+template <class T>
+inline void closest_point_on_triangle(const T* p, const T* a, const T* b, const T* c, T* out) {
+    T ab[3], ac[3], ap[3];
+    for (int i = 0; i < 3; ++i) { ab[i] = b[i] - a[i]; ac[i] = c[i] - a[i]; ap[i] = p[i] - a[i]; }
+    auto dot = [](const T* x, const T* y) { return (x[0] * y[0] + x[1] * y[1]) + x[2] * y[2]; };
+    T d1 = dot(ab, ap), d2 = dot(ac, ap);
+    if (d1 <= 0 && d2 <= 0) { for (int i = 0; i < 3; ++i) out[i] = a[i]; return; }
+    T bp[3]; for (int i = 0; i < 3; ++i) bp[i] = p[i] - b[i];
+    T d3 = dot(ab, bp), d4 = dot(ac, bp);
+    if (d3 >= 0 && d4 <= d3) { for (int i = 0; i < 3; ++i) out[i] = b[i]; return; }
+    T vc = d1 * d4 - d3 * d2;
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) { T v = d1 / (d1 - d3); for (int i = 0; i < 3; ++i) out[i] = a[i] + v * ab[i]; return; }
+    T cp[3]; for (int i = 0; i < 3; ++i) cp[i] = p[i] - c[i];
+    T d5 = dot(ab, cp), d6 = dot(ac, cp);
+    if (d6 >= 0 && d5 <= d6) { for (int i = 0; i < 3; ++i) out[i] = c[i]; return; }
+    T vb = d5 * d2 - d1 * d6;
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) { T w = d2 / (d2 - d6); for (int i = 0; i < 3; ++i) out[i] = a[i] + w * ac[i]; return; }
+    T va = d3 * d6 - d5 * d4;
+    if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
+        T w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        for (int i = 0; i < 3; ++i) out[i] = b[i] + w * (c[i] - b[i]);
+        return;
+    }
+    T denom = T(1) / (va + vb + vc);
+    T v = vb * denom, w = vc * denom;
+    for (int i = 0; i < 3; ++i) out[i] = a[i] + ab[i] * v + ac[i] * w;
+}
+
+// ------------------------------------------------------------------- relax
+template <class T, int D>
+int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in, const wtp_force* fm,
+              const wtp_repel_params* prm, T* conv, wtp_trace_entry* trace, wtp_repel_result* res,
+              int threads) {
+    const int64_t n_all = n_fixed + n_move;
+    if (prm->rebuild_every < 1) return WTP_ERR_BAD_ARG;                      // src/repel.jl:74
+    if (prm->kick_after > 0) return WTP_ERR_UNSUPPORTED;                     // randn, :430
+    if (prm->wall != WTP_WALL_IDENTITY) return WTP_ERR_UNSUPPORTED;
+    const int kk = int(std::min<int64_t>(prm->k, n_all));                   // :208
+    Spacing<T, D> spacing;
+    spacing.init(sp_in);
+    const T beta = T(fm->beta), u0 = T(fm->u0), gamma = T(fm->gamma);
+    std::vector<T> spacings(size_t(n_all) > 0 ? size_t(n_all) : 1);
+    for (int64_t i = 0; i < n_all; ++i) spacings[i] = spacing(&snap[size_t(i) * D]);   // :209
+    std::vector<T> p(snap + size_t(n_fixed) * D, snap + size_t(n_all) * D);  // movable, current
+    std::vector<T> p_old(p);
+    std::vector<T> coords(snap, snap + size_t(n_all) * D);                   // :216
+    KDTree<T, D> tree;
+    tree.build(coords.data(), n_all);                                         // :218
+    const T a_lo = T(prm->alpha_lo), a_max = T(prm->alpha_max);              // :226
+    std::vector<T> forces(size_t(n_move), T(0)), nn_dist(size_t(n_move), std::numeric_limits<T>::max());
+    std::vector<int64_t> nn_id(size_t(n_move), 0);
+    T best_cv = std::numeric_limits<T>::max();
+    int64_t last_impr = 0;
+    int it = 1, n_conv = 0;
+    int stop = WTP_STOP_MAX_ITERS;
+    double last_cv = std::numeric_limits<double>::quiet_NaN();
+    (void)threads;
+    while (it <= prm->max_iters) {                                            // :243
+        p_old = p;                                                            // :244
+        if ((it - 1) % prm->rebuild_every == 0) {                             // :245-253
+            std::copy(p.begin(), p.end(), coords.begin() + size_t(n_fixed) * D);
+            for (int64_t i = 0; i < n_move; ++i) spacings[size_t(n_fixed + i)] = spacing(&p[size_t(i) * D]);
+            tree.build(coords.data(), n_all);
+        }
+#pragma omp parallel num_threads(threads)
+        {
+            std::vector<Cand<T>> buf(size_t(kk) > 0 ? size_t(kk) : 1);
+#pragma omp for schedule(dynamic, 256)
+            for (int64_t id = 0; id < n_move; ++id) {                         // :256-292
+                const T* xi = &p_old[size_t(id) * D];
+                tree.knn(xi, kk, buf.data());                                 // :259
+                const T s = spacing(xi);                                      // :260
+                const int64_t self = id + n_fixed;                            // :266
+                int64_t nid = 0; T nd = std::numeric_limits<T>::max();
+                T F[D]; for (int d = 0; d < D; ++d) F[d] = T(0);
+                for (int j = 0; j < kk; ++j) {                                // :270-280
+                    if (buf[j].idx == self) continue;
+                    const T r = std::sqrt(buf[j].d2);
+                    if (nid == 0) { nid = buf[j].idx + 1; nd = r; }
+                    const T* xj = &coords[size_t(buf[j].idx) * D];
+                    const T f = force_eval<T>(fm->kind, beta, u0, gamma, r / s);
+                    // _safe_direction :358-364 (r == 0 draws randn: parity inputs avoid it;
+                    // here the term is dropped deterministically).
+                    if (r > T(0))
+                        for (int d = 0; d < D; ++d) F[d] = F[d] + f * ((xi[d] - xj[d]) / r);
+                }
+                T n2 = T(0); for (int d = 0; d < D; ++d) n2 = n2 + F[d] * F[d];
+                const T Fn = std::sqrt(n2);                                   // :282
+                forces[size_t(id)] = Fn * s;                                  // :283
+                T ai = T(1) / (Fn + T(1.0e-30));                              // :285
+                ai = ai > a_max ? a_max : (ai < a_lo ? a_lo : ai);
+                T disp[D]; const T sa = s * ai;
+                T dn2 = T(0);
+                for (int d = 0; d < D; ++d) { disp[d] = sa * F[d]; dn2 = dn2 + disp[d] * disp[d]; }
+                const T dn = std::sqrt(dn2);
+                if (dn > s) { const T sc = s / dn; for (int d = 0; d < D; ++d) disp[d] = disp[d] * sc; }  // :288-290
+                for (int d = 0; d < D; ++d) p[size_t(id) * D + d] = xi[d] + disp[d];  // :291 (identity wall)
+                nn_id[size_t(id)] = nid; nn_dist[size_t(id)] = nd;
+            }
+        }
+        T mx = T(0); for (int64_t i = 0; i < n_move; ++i) mx = std::max(mx, forces[size_t(i)]);
+        conv[n_conv++] = mx;                                                  // :293
+        if (n_move > 0 && trace) {                                            // :294-296, 396-403
+            int64_t i = 0; for (int64_t j = 1; j < n_move; ++j) if (nn_dist[size_t(j)] < nn_dist[size_t(i)]) i = j;
+            int64_t j = nn_id[size_t(i)], ig = i + n_fixed + 1;
+            T r = nn_dist[size_t(i)];
+            T s = j > 0 ? (spacings[size_t(ig - 1)] + spacings[size_t(j - 1)]) / T(2) : spacings[size_t(ig - 1)];
+            wtp_trace_entry& te = trace[n_conv - 1];
+            te.r = double(r); te.s = double(s); te.r_over_s = double(r / s);
+            te.idx_a = std::min(ig, j); te.idx_b = std::max(ig, j);
+        }
+        bool stopped = false;
+        if ((prm->stall_after > 0 || prm->cv_target > 0) && n_move > 0) {     // :305-327
+            T s1 = T(0), s2 = T(0);                                           // _dnn_cv :374-386 (serial, in T)
+            for (int64_t i = 0; i < n_move; ++i) {
+                T u = nn_dist[size_t(i)] / spacings[size_t(i + n_fixed)];
+                s1 = s1 + u; s2 = s2 + u * u;
+            }
+            T mu = s1 / T(n_move);
+            T var = s2 / T(n_move) - mu * mu;
+            T cv = std::sqrt(var > T(0) ? var : T(0)) / mu;
+            last_cv = double(cv);
+            if (prm->cv_target > 0 && double(cv) <= prm->cv_target) {
+                p = p_old; stop = WTP_STOP_CV_TARGET; stopped = true;         // :307-317
+            } else if (prm->stall_after > 0) {
+                // :319 — Julia evaluates best_cv * (1 - 1.0e-3) with a Float64 literal.
+                if (double(cv) < double(best_cv) * (1 - 1.0e-3)) { best_cv = cv; last_impr = it; }
+                else if (it - last_impr >= prm->stall_after) { stop = WTP_STOP_STALL; stopped = true; }
+            }
+        }
+        if (stopped) break;
+        if (double(conv[n_conv - 1]) < prm->tol) { stop = WTP_STOP_TOL; break; }   // :329-332
+        ++it;
+    }
+    std::copy(p.begin(), p.end(), snap + size_t(n_fixed) * D);
+    res->iters = n_conv; res->stop_reason = stop; res->last_cv = last_cv;
+    return WTP_OK;
+}
+
+template <class T, int D>
+int32_t knn_impl(const T* pts, int64_t N, int k, int drop_first, int algo, int threads, int64_t* out_idx, T* out_dist) {
+    const int K1 = k + (drop_first ? 1 : 0);
+    if (K1 > N) return WTP_ERR_K_TOO_LARGE;
+    if (algo == 0) {  // brute force: the independent check of the KD-tree
+#pragma omp parallel num_threads(threads)
+        {
+            std::vector<Cand<T>> all(static_cast<size_t>(N));
+#pragma omp for schedule(static)
+            for (int64_t i = 0; i < N; ++i) {
+                for (int64_t j = 0; j < N; ++j) all[size_t(j)] = Cand<T>{dist2<T, D>(&pts[size_t(i) * D], &pts[size_t(j) * D]), j};
+                std::partial_sort(all.begin(), all.begin() + K1, all.end(), cand_less<T>);
+                for (int j = 0; j < k; ++j) {
+                    const Cand<T>& c = all[size_t(j + (drop_first ? 1 : 0))];
+                    out_idx[size_t(i) * k + j] = c.idx + 1;
+                    if (out_dist) out_dist[size_t(i) * k + j] = std::sqrt(c.d2);
+                }
+            }
+        }
+        return WTP_OK;
+    }
+    KDTree<T, D> tree;
+    tree.build(pts, N);
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<Cand<T>> buf(static_cast<size_t>(K1));
+#pragma omp for schedule(dynamic, 1024)
+        for (int64_t i = 0; i < N; ++i) {
+            tree.knn(&pts[size_t(i) * D], K1, buf.data());
+            for (int j = 0; j < k; ++j) {
+                const Cand<T>& c = buf[size_t(j + (drop_first ? 1 : 0))];
+                out_idx[size_t(i) * k + j] = c.idx + 1;
+                if (out_dist) out_dist[size_t(i) * k + j] = std::sqrt(c.d2);
+            }
+        }
+    }
+    return WTP_OK;
+}
+
+template <class T, int D>
+int32_t radius_impl(const T* pts, int64_t N, T r, int threads, int64_t* offsets, int64_t* indices) {
+    KDTree<T, D> tree;
+    tree.build(pts, N);
+    const T r2 = r * r;
+    if (!indices) {
+        offsets[0] = 0;
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1024)
+        for (int64_t i = 0; i < N; ++i) {
+            int64_t c = 0;
+            tree.inrange_rec(0, &pts[size_t(i) * D], r2, [&](int64_t j) { if (j != i) ++c; });
+            offsets[i + 1] = c;
+        }
+        for (int64_t i = 0; i < N; ++i) offsets[i + 1] += offsets[i];
+        return WTP_OK;
+    }
+#pragma omp parallel for num_threads(threads) schedule(dynamic, 1024)
+    for (int64_t i = 0; i < N; ++i) {
+        int64_t* row = indices + offsets[i];
+        int64_t c = 0;
+        tree.inrange_rec(0, &pts[size_t(i) * D], r2, [&](int64_t j) { if (j != i) row[c++] = j + 1; });
+        std::sort(row, row + c);
+    }
+    return WTP_OK;
+}
+
+template <class T, int D>
+int32_t metrics_impl(const T* pts, int64_t N, int k, int threads, wtp_cloud_metrics* out) {
+    // src/metrics.jl:19-41: k nearest including self, drop the first, per-point
+    // mean/std/max/min of the remaining k-1 distances, then means over points.
+    if (k > N || k < 2) return WTP_ERR_K_TOO_LARGE;
+    KDTree<T, D> tree;
+    tree.build(pts, N);
+    const int m = k - 1;
+    const size_t NN = static_cast<size_t>(N);
+    std::vector<double> a(NN), sd(NN), mx(NN), mn(NN), nn(NN);
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<Cand<T>> buf(static_cast<size_t>(k));
+#pragma omp for schedule(dynamic, 1024)
+        for (int64_t i = 0; i < N; ++i) {
+            tree.knn(&pts[size_t(i) * D], k, buf.data());
+            T s = T(0);
+            for (int j = 1; j < k; ++j) s = s + std::sqrt(buf[size_t(j)].d2);
+            T mean = s / T(m);
+            T v = T(0);
+            for (int j = 1; j < k; ++j) { T e = std::sqrt(buf[size_t(j)].d2) - mean; v = v + e * e; }
+            a[size_t(i)] = double(mean);
+            sd[size_t(i)] = m > 1 ? double(std::sqrt(v / T(m - 1))) : std::numeric_limits<double>::quiet_NaN();
+            mx[size_t(i)] = double(std::sqrt(buf[size_t(k - 1)].d2));
+            mn[size_t(i)] = double(std::sqrt(buf[1].d2));
+            nn[size_t(i)] = mn[size_t(i)];
+        }
+    }
+    auto mean_of = [&](const std::vector<double>& v) { double s = 0; for (double x : v) s += x; return s / double(N); };
+    out->avg = mean_of(a); out->std = mean_of(sd); out->max = mean_of(mx); out->min = mean_of(mn);
+    out->separation = *std::min_element(nn.begin(), nn.end());
+    out->fill = *std::max_element(nn.begin(), nn.end());
+    out->mesh_ratio = out->fill / out->separation;
+    return WTP_OK;
+}
+
+int default_threads(int threads) {
+#ifdef _OPENMP
+    return threads > 0 ? threads : omp_get_max_threads();
+#else
+    (void)threads; return 1;
+#endif
+}
+
+}  // namespace
+
+#define DISPATCH_D(T, D, call2, call3) ((D) == 2 ? (call2) : (D) == 3 ? (call3) : int32_t(WTP_ERR_BAD_ARG))
+
+extern "C" {
+
+int32_t wtpo_max_threads(void) { return default_threads(0); }
+
+// algo: 0 brute force, 1 KD-tree. drop_first: 1 = _build_knn_neighbors, 0 = search/searchdists.
+int32_t wtpo_knn_f32(const float* pts, int64_t N, int32_t D, int32_t k, int32_t drop_first, int32_t algo,
+                     int32_t threads, int64_t* out_idx, float* out_dist) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (knn_impl<float, 2>(pts, N, k, drop_first, algo, threads, out_idx, out_dist)),
+                      (knn_impl<float, 3>(pts, N, k, drop_first, algo, threads, out_idx, out_dist)));
+}
+int32_t wtpo_knn_f64(const double* pts, int64_t N, int32_t D, int32_t k, int32_t drop_first, int32_t algo,
+                     int32_t threads, int64_t* out_idx, double* out_dist) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (knn_impl<double, 2>(pts, N, k, drop_first, algo, threads, out_idx, out_dist)),
+                      (knn_impl<double, 3>(pts, N, k, drop_first, algo, threads, out_idx, out_dist)));
+}
+
+// indices == NULL: fill offsets[N+1]; else fill indices using offsets.
+int32_t wtpo_radius_f32(const float* pts, int64_t N, int32_t D, float r, int32_t threads, int64_t* offsets, int64_t* indices) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (radius_impl<float, 2>(pts, N, r, threads, offsets, indices)),
+                      (radius_impl<float, 3>(pts, N, r, threads, offsets, indices)));
+}
+int32_t wtpo_radius_f64(const double* pts, int64_t N, int32_t D, double r, int32_t threads, int64_t* offsets, int64_t* indices) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (radius_impl<double, 2>(pts, N, r, threads, offsets, indices)),
+                      (radius_impl<double, 3>(pts, N, r, threads, offsets, indices)));
+}
+
+void wtpo_force_f32(const wtp_force* f, const float* u, int64_t n, float* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = force_eval<float>(f->kind, float(f->beta), float(f->u0), float(f->gamma), u[i]);
+}
+void wtpo_force_f64(const wtp_force* f, const double* u, int64_t n, double* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = force_eval<double>(f->kind, f->beta, f->u0, f->gamma, u[i]);
+}
+
+#define SPACING_EVAL(T, DD)                                                   \
+    {                                                                         \
+        Spacing<T, DD> s; s.init(sp);                                         \
+        for (int64_t i = 0; i < N; ++i) out[i] = s(&pts[size_t(i) * DD]);     \
+        return WTP_OK;                                                        \
+    }
+int32_t wtpo_spacing_f32(const wtp_spacing* sp, const float* pts, int64_t N, int32_t D, float* out) {
+    if (D == 2) SPACING_EVAL(float, 2) else if (D == 3) SPACING_EVAL(float, 3)
+    return WTP_ERR_BAD_ARG;
+}
+int32_t wtpo_spacing_f64(const wtp_spacing* sp, const double* pts, int64_t N, int32_t D, double* out) {
+    if (D == 2) SPACING_EVAL(double, 2) else if (D == 3) SPACING_EVAL(double, 3)
+    return WTP_ERR_BAD_ARG;
+}
+
+int32_t wtpo_repel_f32(float* snap, int64_t n_fixed, int64_t n_move, int32_t D, const wtp_spacing* sp,
+                       const wtp_force* fm, const wtp_repel_params* prm, float* conv, wtp_trace_entry* trace,
+                       wtp_repel_result* res, int32_t threads) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (relax<float, 2>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)),
+                      (relax<float, 3>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)));
+}
+int32_t wtpo_repel_f64(double* snap, int64_t n_fixed, int64_t n_move, int32_t D, const wtp_spacing* sp,
+                       const wtp_force* fm, const wtp_repel_params* prm, double* conv, wtp_trace_entry* trace,
+                       wtp_repel_result* res, int32_t threads) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (relax<double, 2>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)),
+                      (relax<double, 3>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)));
+}
+
+int32_t wtpo_metrics_f32(const float* pts, int64_t N, int32_t D, int32_t k, int32_t threads, wtp_cloud_metrics* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (metrics_impl<float, 2>(pts, N, k, threads, out)), (metrics_impl<float, 3>(pts, N, k, threads, out)));
+}
+int32_t wtpo_metrics_f64(const double* pts, int64_t N, int32_t D, int32_t k, int32_t threads, wtp_cloud_metrics* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (metrics_impl<double, 2>(pts, N, k, threads, out)), (metrics_impl<double, 3>(pts, N, k, threads, out)));
+}
+
+void wtpo_closest_point_on_triangle_f64(const double* p, const double* a, const double* b, const double* c, double* out) {
+    closest_point_on_triangle<double>(p, a, b, c, out);
+}
+void wtpo_closest_point_on_triangle_f32(const float* p, const float* a, const float* b, const float* c, float* out) {
+    closest_point_on_triangle<float>(p, a, b, c, out);
+}
+
+}  // extern "C"

@@ -1,0 +1,247 @@
+// api.cu — the C ABI of libwtp_cuda.so (include/wtp_cuda.h): context, instrumentation,
+// and the topology entry points. Repel lives in repel.cu, multi-GPU plumbing in comm.cu.
+#include <cmath>
+#include <new>
+
+#include "kernels.cuh"
+
+using namespace wtp;
+
+namespace wtp {
+int32_t fail(wtp_ctx* ctx, const Error& e) {
+    if (ctx) ctx->last_error = e.msg;
+    return e.status;
+}
+void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_cells, int64_t n_expanded);
+}  // namespace wtp
+
+#define API_BEGIN(ctx)                                                       \
+    if (!(ctx)) return WTP_ERR_BAD_ARG;                                      \
+    try {                                                                    \
+        WTP_CUDA_CHECK(cudaSetDevice((ctx)->device));
+#define API_END(ctx)                                                         \
+    }                                                                        \
+    catch (const Error& e) { return fail((ctx), e); }                        \
+    catch (const std::bad_alloc&) { return fail((ctx), Error{WTP_ERR_OOM, "host allocation failed"}); } \
+    catch (...) { return fail((ctx), Error{WTP_ERR_CUDA, "unknown failure"}); }  \
+    return WTP_OK;
+
+extern "C" {
+
+int32_t wtp_version(void) { return 100; }
+
+const char* wtp_status_string(int32_t s) {
+    switch (s) {
+        case WTP_OK: return "ok";
+        case WTP_ERR_BAD_ARG: return "bad argument";
+        case WTP_ERR_K_TOO_LARGE: return "k too large for the point set or above WTP_MAX_K";
+        case WTP_ERR_UNSUPPORTED: return "unsupported force model / spacing / option (no CPU fallback)";
+        case WTP_ERR_CUDA: return "CUDA error";
+        case WTP_ERR_NCCL: return "NCCL error";
+        case WTP_ERR_OOM: return "out of memory";
+        case WTP_ERR_STATE: return "call sequence error";
+    }
+    return "unknown status";
+}
+
+int32_t wtp_create(wtp_ctx** out, int32_t device) {
+    if (!out) return WTP_ERR_BAD_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || device < 0 || device >= count) { (void)cudaGetLastError(); return WTP_ERR_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return WTP_ERR_CUDA;
+    if (prop.major < 10) return WTP_ERR_CUDA;  // sm_100a code only
+    wtp_ctx* ctx = new (std::nothrow) wtp_ctx();
+    if (!ctx) return WTP_ERR_OOM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return WTP_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    ctx->h_pinned_bytes = 4096;
+    if (cudaMallocHost(&ctx->h_pinned, ctx->h_pinned_bytes) != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return WTP_ERR_CUDA; }
+    *out = ctx;
+    return WTP_OK;
+}
+
+void wtp_comm_destroy_internal(wtp_ctx* ctx);
+
+void wtp_destroy(wtp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    wtp_comm_destroy_internal(ctx);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* wtp_last_error(const wtp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int32_t wtp_set_stream(wtp_ctx* ctx, void* s) {
+    if (!ctx) return WTP_ERR_BAD_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return WTP_OK;
+}
+
+int32_t wtp_host_register(wtp_ctx* ctx, void* ptr, int64_t bytes) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(ptr && bytes > 0, WTP_ERR_BAD_ARG, "wtp_host_register: null range");
+    WTP_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    API_END(ctx)
+}
+int32_t wtp_host_unregister(wtp_ctx* ctx, void* ptr) {
+    API_BEGIN(ctx)
+    WTP_CUDA_CHECK(cudaHostUnregister(ptr));
+    API_END(ctx)
+}
+
+int32_t wtp_set_cell_occupancy(wtp_ctx* ctx, double m) {
+    if (!ctx) return WTP_ERR_BAD_ARG;
+    ctx->cell_occupancy = m;
+    return WTP_OK;
+}
+
+int32_t wtp_set_timing(wtp_ctx* ctx, int32_t enable) {
+    if (!ctx) return WTP_ERR_BAD_ARG;
+    ctx->timer.enabled = enable != 0;
+    return WTP_OK;
+}
+
+int32_t wtp_get_timing(wtp_ctx* ctx, wtp_timing* out) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(out, WTP_ERR_BAD_ARG, "null output");
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    wtp_timing t = ctx->last_timing;
+    float* slot[PH_COUNT] = {&t.ms_h2d, &t.ms_bbox, &t.ms_cellkey, &t.ms_sort, &t.ms_reorder, &t.ms_query,
+                             &t.ms_scan, &t.ms_reduce, &t.ms_comm, &t.ms_d2h};
+    for (int i = 0; i < PH_COUNT; ++i) *slot[i] = 0.f;
+    t.ms_total = 0.f;
+    for (auto& s : ctx->timer.spans) {
+        if (!s.b) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) *slot[s.phase] += ms;
+    }
+    if (ctx->timer.have_total) cudaEventElapsedTime(&t.ms_total, ctx->timer.total_a, ctx->timer.total_b);
+    *out = t;
+    API_END(ctx)
+}
+
+int64_t wtp_launch_count(const wtp_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+int64_t wtp_shard_begin(int64_t n, int32_t rank, int32_t world) {
+    if (world <= 1) return 0;
+    return (n * (int64_t)rank) / world;
+}
+int64_t wtp_shard_end(int64_t n, int32_t rank, int32_t world) {
+    if (world <= 1) return n;
+    return (n * (int64_t)(rank + 1)) / world;
+}
+
+}  // extern "C"
+
+namespace wtp {
+
+void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_cells, int64_t n_expanded) {
+    ctx->last_timing = wtp_timing{};
+    ctx->last_timing.sort_passes = sort_passes;
+    ctx->last_timing.query_launches = query_launches;
+    ctx->last_timing.n_cells = n_cells;
+    ctx->last_timing.n_ring_expanded = n_expanded;
+}
+
+// ------------------------------------------------------------------- k-NN
+template <class T>
+static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bool drop_first, int64_t* d_out_idx,
+                       T* d_out_dist, int64_t* rows_begin, int64_t* rows_end) {
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(k >= 1, WTP_ERR_BAD_ARG, "k must be >= 1");
+    const int K1 = k + (drop_first ? 1 : 0);
+    WTP_REQUIRE((int64_t)K1 <= N, WTP_ERR_K_TOO_LARGE, "k-nearest search needs at least k+1 points (k <= N for search)");
+    WTP_REQUIRE(K1 <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K");
+    IndexBuffers& ib = ctx->index[0];
+    double lo[3], hi[3];
+    compute_bbox<T>(ctx, ib, d_pts, N, D, lo, hi);
+    Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy, 0.0);
+    int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
+    const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
+    const uint32_t* qlist = nullptr;
+    if (ctx->world > 1) {
+        build_query_list(ctx, ib, N, qb, qe, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
+        qlist = ctx->d_qlist.get<uint32_t>();
+    }
+    unsigned long long* d_exp = ctx->d_reduce.as<unsigned long long>(1);
+    WTP_CUDA_CHECK(cudaMemsetAsync(d_exp, 0, sizeof(unsigned long long), ctx->stream));
+    knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, qlist, qe - qb, qb, d_out_idx, d_out_dist, d_exp);
+    unsigned long long* h_exp = static_cast<unsigned long long*>(ctx->h_pinned);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    finish_timing(ctx, passes, 1, g.ncells, (int64_t)*h_exp);
+    *rows_begin = qb; *rows_end = qe;
+}
+
+template <class T>
+void knn_device_self(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, int64_t* d_out_idx, T* d_out_dist) {
+    int64_t rb, re;
+    knn_device<T>(ctx, d_pts, N, D, k, false, d_out_idx, d_out_dist, &rb, &re);
+}
+template void knn_device_self<float>(wtp_ctx*, const float*, int64_t, int, int, int64_t*, float*);
+template void knn_device_self<double>(wtp_ctx*, const double*, int64_t, int, int, int64_t*, double*);
+
+template <class T>
+static int32_t knn_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_t k, bool drop_first, int64_t* out_idx, T* out_dist) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(pts && out_idx && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(k >= 1, WTP_ERR_BAD_ARG, "k must be >= 1");
+    ctx->timer.reset(ctx->stream);
+    ctx->timer.begin_total();
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
+    int64_t* d_idx = ctx->d_out_idx.as<int64_t>((size_t)(qe - qb) * k);
+    T* d_dist = out_dist ? ctx->d_out_dist.as<T>((size_t)(qe - qb) * k) : nullptr;
+    {
+        ScopedPhase ph(ctx->timer, PH_H2D);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int64_t rb, re;
+    knn_device<T>(ctx, d_pts, N, D, k, drop_first, d_idx, d_dist, &rb, &re);
+    wtp_timing keep = ctx->last_timing;
+    {
+        ScopedPhase ph(ctx->timer, PH_D2H);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(out_idx + rb * k, d_idx, (size_t)(re - rb) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(out_dist + rb * k, d_dist, (size_t)(re - rb) * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ctx->timer.end_total();
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_timing = keep;
+    API_END(ctx)
+}
+
+template <class T>
+static int32_t knn_dev(wtp_ctx* ctx, const T* d_pts, int64_t N, int32_t D, int32_t k, int64_t* d_out_idx, T* d_out_dist) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(d_pts && d_out_idx && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    ctx->timer.reset(ctx->stream);
+    ctx->timer.begin_total();
+    int64_t rb, re;
+    knn_device<T>(ctx, d_pts, N, D, k, true, d_out_idx, d_out_dist, &rb, &re);
+    ctx->timer.end_total();
+    API_END(ctx)
+}
+
+}  // namespace wtp
+
+extern "C" {
+
+int32_t wtp_knn_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_host<float>(c, p, N, D, k, true, oi, od); }
+int32_t wtp_knn_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_host<double>(c, p, N, D, k, true, oi, od); }
+int32_t wtp_knn_self_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_host<float>(c, p, N, D, k, false, oi, od); }
+int32_t wtp_knn_self_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_host<double>(c, p, N, D, k, false, oi, od); }
+int32_t wtp_knn_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_dev<float>(c, p, N, D, k, oi, od); }
+int32_t wtp_knn_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_dev<double>(c, p, N, D, k, oi, od); }
+
+}  // extern "C"

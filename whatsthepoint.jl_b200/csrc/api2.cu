@@ -1,0 +1,369 @@
+// api2.cu — C ABI entry points for radius topology, repel, spacing / force evaluation
+// and cloud metrics (include/wtp_cuda.h).
+#include <cmath>
+#include <new>
+
+#include "kernels.cuh"
+#include "knn_core.cuh"
+
+using namespace wtp;
+
+namespace wtp {
+int32_t fail(wtp_ctx* ctx, const Error& e);
+void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_cells, int64_t n_expanded);
+template <class T>
+void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int D, const wtp_spacing* sp_in, const T* d_bnd,
+                  const wtp_force* fm, const wtp_repel_params* prm, T* conv, wtp_trace_entry* trace, wtp_repel_result* res);
+}  // namespace wtp
+
+#define LAUNCH_CHECK(ctx)                         \
+    do {                                          \
+        (ctx)->launches++;                        \
+        WTP_CUDA_CHECK(cudaPeekAtLastError());    \
+    } while (0)
+
+#define API_BEGIN(ctx)                                                       \
+    if (!(ctx)) return WTP_ERR_BAD_ARG;                                      \
+    try {                                                                    \
+        WTP_CUDA_CHECK(cudaSetDevice((ctx)->device));
+#define API_END(ctx)                                                         \
+    }                                                                        \
+    catch (const Error& e) { return fail((ctx), e); }                        \
+    catch (const std::bad_alloc&) { return fail((ctx), Error{WTP_ERR_OOM, "host allocation failed"}); } \
+    catch (...) { return fail((ctx), Error{WTP_ERR_CUDA, "unknown failure"}); }  \
+    return WTP_OK;
+
+namespace wtp {
+
+// ----------------------------------------------------------------- radius
+template <class T>
+static void radius_count_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, T r, int64_t* d_offsets) {
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(r >= (T)0 && std::isfinite((double)r), WTP_ERR_BAD_ARG, "radius must be finite and >= 0");
+    IndexBuffers& ib = ctx->index[0];
+    double lo[3], hi[3];
+    compute_bbox<T>(ctx, ib, d_pts, N, D, lo, hi);
+    // cell size >= r (with margin) so the 3^D block around a query contains every hit
+    Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy, (double)r * 1.001);
+    int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
+    const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
+    const uint32_t* qlist = nullptr;
+    if (ctx->world > 1) {
+        build_query_list(ctx, ib, N, qb, qe, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
+        qlist = ctx->d_qlist.get<uint32_t>();
+    }
+    const int64_t nq = qe - qb;
+    uint32_t* counts = ctx->d_counts.as<uint32_t>((size_t)nq + 1);
+    radius_count<T>(ctx, ib, g, N, D, r, qlist, nq, qb, counts);
+    {
+        ScopedPhase ph(ctx->timer, PH_SCAN);
+        exclusive_scan_u32_to_i64(ctx, ib.scan_tmp, counts, d_offsets, nq);
+    }
+    int64_t* h_nnz = static_cast<int64_t*>(ctx->h_pinned);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(h_nnz, d_offsets + nq, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    auto& st = ctx->radius;
+    st.pending = true; st.f64 = sizeof(T) == 8; st.N = N; st.D = D; st.r = (double)r; st.nnz = *h_nnz;
+    st.q_begin = qb; st.q_end = qe;
+    static_assert(sizeof(Grid<T>) <= sizeof(ctx->grid_storage[0]), "grid storage too small");
+    memcpy(ctx->grid_storage[0], &g, sizeof(g));
+    finish_timing(ctx, passes, 1, g.ncells, 0);
+}
+
+template <class T>
+static void radius_fill_device(wtp_ctx* ctx, const int64_t* d_offsets, int64_t* d_indices) {
+    auto& st = ctx->radius;
+    Grid<T> g;
+    memcpy(&g, ctx->grid_storage[0], sizeof(g));
+    const uint32_t* qlist = ctx->world > 1 ? ctx->d_qlist.get<uint32_t>() : nullptr;
+    ctx->d_misc2.as<uint32_t>((size_t)std::max<int64_t>(st.nnz, 1));
+    radius_fill<T>(ctx, ctx->index[0], g, st.N, st.D, (T)st.r, qlist, st.q_end - st.q_begin, st.q_begin, d_offsets, d_indices);
+}
+
+template <class T>
+static int32_t radius_count_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, T r, int64_t* offsets) {
+    API_BEGIN(ctx)
+    ctx->radius.pending = false;
+    WTP_REQUIRE(pts && offsets && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    ctx->timer.reset(ctx->stream);
+    ctx->timer.begin_total();
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    {
+        ScopedPhase ph(ctx->timer, PH_H2D);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int64_t nq = wtp_shard_end(N, ctx->rank, ctx->world) - wtp_shard_begin(N, ctx->rank, ctx->world);
+    int64_t* d_off = ctx->d_offsets.as<int64_t>((size_t)nq + 1);
+    radius_count_device<T>(ctx, d_pts, N, D, r, d_off);
+    wtp_timing keep = ctx->last_timing;
+    {
+        ScopedPhase ph(ctx->timer, PH_D2H);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(offsets, d_off, (size_t)(nq + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ctx->timer.end_total();
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_timing = keep;
+    ctx->radius.dev_input = false;
+    API_END(ctx)
+}
+
+template <class T>
+static int32_t radius_count_dev(wtp_ctx* ctx, const T* d_pts, int64_t N, int32_t D, T r, int64_t* d_offsets) {
+    API_BEGIN(ctx)
+    ctx->radius.pending = false;
+    WTP_REQUIRE(d_pts && d_offsets && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    ctx->timer.reset(ctx->stream);
+    ctx->timer.begin_total();
+    radius_count_device<T>(ctx, d_pts, N, D, r, d_offsets);
+    ctx->timer.end_total();
+    ctx->radius.dev_input = true;
+    ctx->radius.pts = d_offsets;
+    API_END(ctx)
+}
+
+}  // namespace wtp
+
+extern "C" {
+
+int32_t wtp_radius_count_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, float r, int64_t* off) { return radius_count_host<float>(c, p, N, D, r, off); }
+int32_t wtp_radius_count_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, double r, int64_t* off) { return radius_count_host<double>(c, p, N, D, r, off); }
+int32_t wtp_radius_count_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, float r, int64_t* off) { return radius_count_dev<float>(c, p, N, D, r, off); }
+int32_t wtp_radius_count_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, double r, int64_t* off) { return radius_count_dev<double>(c, p, N, D, r, off); }
+
+int64_t wtp_radius_nnz(const wtp_ctx* ctx) { return ctx && ctx->radius.pending ? ctx->radius.nnz : -1; }
+
+int32_t wtp_radius_fill(wtp_ctx* ctx, int64_t* indices) {
+    API_BEGIN(ctx)
+    auto& st = ctx->radius;
+    WTP_REQUIRE(st.pending && !st.dev_input, WTP_ERR_STATE, "wtp_radius_fill must directly follow wtp_radius_count_* on the same context");
+    WTP_REQUIRE(indices || st.nnz == 0, WTP_ERR_BAD_ARG, "null indices");
+    st.pending = false;
+    if (st.nnz > 0) {
+        ctx->timer.reset(ctx->stream);
+        ctx->timer.begin_total();
+        int64_t* d_ind = ctx->d_indices.as<int64_t>((size_t)st.nnz);
+        if (st.f64) radius_fill_device<double>(ctx, ctx->d_offsets.get<int64_t>(), d_ind);
+        else radius_fill_device<float>(ctx, ctx->d_offsets.get<int64_t>(), d_ind);
+        {
+            ScopedPhase ph(ctx->timer, PH_D2H);
+            WTP_CUDA_CHECK(cudaMemcpyAsync(indices, d_ind, (size_t)st.nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        ctx->timer.end_total();
+        WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    API_END(ctx)
+}
+
+int32_t wtp_radius_fill_dev(wtp_ctx* ctx, int64_t* d_indices) {
+    API_BEGIN(ctx)
+    auto& st = ctx->radius;
+    WTP_REQUIRE(st.pending && st.dev_input, WTP_ERR_STATE, "wtp_radius_fill_dev must directly follow wtp_radius_count_dev_* on the same context");
+    WTP_REQUIRE(d_indices || st.nnz == 0, WTP_ERR_BAD_ARG, "null indices");
+    st.pending = false;
+    if (st.nnz > 0) {
+        ctx->timer.reset(ctx->stream);
+        ctx->timer.begin_total();
+        const int64_t* d_off = static_cast<const int64_t*>(st.pts);
+        if (st.f64) radius_fill_device<double>(ctx, d_off, d_indices);
+        else radius_fill_device<float>(ctx, d_off, d_indices);
+        ctx->timer.end_total();
+    }
+    API_END(ctx)
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ repel
+namespace wtp {
+
+template <class T>
+static int32_t repel_host(wtp_ctx* ctx, T* snap, int64_t n_fixed, int64_t n_move, int32_t D, const wtp_spacing* sp,
+                          const wtp_force* fm, const wtp_repel_params* prm, const wtp_wall_mesh* wall, T* conv,
+                          wtp_trace_entry* trace, wtp_repel_result* res) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(snap && sp && fm && prm && conv && res, WTP_ERR_BAD_ARG, "null pointer");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(n_fixed >= 0 && n_move >= 0 && n_fixed + n_move > 0, WTP_ERR_BAD_ARG, "empty snapshot");
+    WTP_REQUIRE(wall == nullptr && prm->wall == WTP_WALL_IDENTITY, WTP_ERR_UNSUPPORTED, "mesh wall rule is not available in this build");
+    ctx->timer.reset(ctx->stream);
+    ctx->timer.begin_total();
+    const int64_t n_all = n_fixed + n_move;
+    T* d_snap = ctx->d_pts.as<T>((size_t)n_all * D);
+    const T* d_bnd = nullptr;
+    {
+        ScopedPhase ph(ctx->timer, PH_H2D);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_snap, snap, (size_t)n_all * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        if (sp->kind != WTP_SPACING_CONSTANT) {
+            WTP_REQUIRE(sp->bnd_pts && sp->n_bnd > 0, WTP_ERR_BAD_ARG, "variable spacing needs its boundary point set");
+            T* b = ctx->d_spacing_pts.as<T>((size_t)sp->n_bnd * D);
+            WTP_CUDA_CHECK(cudaMemcpyAsync(b, sp->bnd_pts, (size_t)sp->n_bnd * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+            d_bnd = b;
+        }
+    }
+    relax_device<T>(ctx, d_snap, n_fixed, n_move, D, sp, d_bnd, fm, prm, conv, trace, res);
+    wtp_timing keep = ctx->last_timing;
+    {
+        ScopedPhase ph(ctx->timer, PH_D2H);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(snap + (size_t)n_fixed * D, d_snap + (size_t)n_fixed * D, (size_t)n_move * D * sizeof(T),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    ctx->timer.end_total();
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_timing = keep;
+    API_END(ctx)
+}
+
+template <class T>
+static int32_t repel_dev(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int32_t D, const wtp_spacing* sp,
+                         const wtp_force* fm, const wtp_repel_params* prm, T* conv, wtp_trace_entry* trace, wtp_repel_result* res) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(d_snap && sp && fm && prm && conv && res, WTP_ERR_BAD_ARG, "null pointer");
+    ctx->timer.reset(ctx->stream);
+    ctx->timer.begin_total();
+    relax_device<T>(ctx, d_snap, n_fixed, n_move, D, sp, static_cast<const T*>(sp->bnd_pts), fm, prm, conv, trace, res);
+    ctx->timer.end_total();
+    API_END(ctx)
+}
+
+template <class T>
+static int32_t spacing_eval_host(wtp_ctx* ctx, const wtp_spacing* sp, const T* pts, int64_t N, int32_t D, T* out) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(sp && pts && out && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(sp->kind >= WTP_SPACING_CONSTANT && sp->kind <= WTP_SPACING_BOUNDARY_LAYER, WTP_ERR_UNSUPPORTED, "user-defined spacing callable cannot cross the C ABI");
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    T* d_out = ctx->d_spacings.as<T>((size_t)N);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    if (sp->kind != WTP_SPACING_CONSTANT) {
+        WTP_REQUIRE(sp->bnd_pts && sp->n_bnd > 0, WTP_ERR_BAD_ARG, "variable spacing needs its boundary point set");
+        T* b = ctx->d_spacing_pts.as<T>((size_t)sp->n_bnd * D);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(b, sp->bnd_pts, (size_t)sp->n_bnd * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        bvh_build<T>(ctx, ctx->bvh, b, sp->n_bnd, D);
+    }
+    const SpacingP<T> spp{sp->kind, (T)sp->a, (T)sp->b, (T)sp->c};
+    spacing_eval<T>(ctx, spp, ctx->bvh, d_pts, N, D, d_out);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(out, d_out, (size_t)N * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+template <class T>
+static int32_t force_eval_host(wtp_ctx* ctx, const wtp_force* f, const T* u, int64_t n, T* out) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(f && u && out && n > 0, WTP_ERR_BAD_ARG, "null pointer or empty input");
+    WTP_REQUIRE(f->kind >= WTP_FORCE_INVERSE && f->kind <= WTP_FORCE_STRONG, WTP_ERR_UNSUPPORTED, "user-defined RepelForceModel cannot cross the C ABI");
+    T* d_u = ctx->d_misc.as<T>((size_t)n);
+    T* d_o = ctx->d_misc2.as<T>((size_t)n);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_u, u, (size_t)n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    const ForceP<T> fp{f->kind, (T)f->beta, (T)f->u0, (T)f->gamma};
+    force_eval<T>(ctx, fp, d_u, n, d_o);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(out, d_o, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+// ---------------------------------------------------------------- metrics
+struct MetricsPartial { double avg, sd, mx, mn, sep, fill; };
+
+// thread per point over its row of k sorted distances (rank 0 = self, dropped): the
+// per-point mean/std/max/min of src/metrics.jl:22-30, block-reduced in a fixed order
+template <class T>
+__global__ void __launch_bounds__(256) metrics_kernel(const T* __restrict__ dist, int64_t N, int k, MetricsPartial* __restrict__ partials) {
+    __shared__ MetricsPartial s[256];
+    MetricsPartial acc{0, 0, 0, 0, 1.0e300, 0};
+    const int m = k - 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const T* row = dist + i * k;
+        T sum = (T)0;
+        for (int j = 1; j < k; ++j) sum = sum + row[j];
+        const T mean = sum / (T)m;
+        T v = (T)0;
+        for (int j = 1; j < k; ++j) { const T e = row[j] - mean; v = v + e * e; }
+        const double sd = m > 1 ? (double)sqrt(v / (T)(m - 1)) : __longlong_as_double(0x7ff8000000000000LL);
+        const double nn = (double)row[1];
+        acc.avg += (double)mean; acc.sd += sd; acc.mx += (double)row[k - 1]; acc.mn += nn;
+        acc.sep = nn < acc.sep ? nn : acc.sep;
+        acc.fill = nn > acc.fill ? nn : acc.fill;
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            MetricsPartial a = s[threadIdx.x], b = s[threadIdx.x + o];
+            a.avg += b.avg; a.sd += b.sd; a.mx += b.mx; a.mn += b.mn;
+            a.sep = b.sep < a.sep ? b.sep : a.sep; a.fill = b.fill > a.fill ? b.fill : a.fill;
+            s[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = s[0];
+}
+
+}  // namespace wtp
+
+extern "C" {
+
+int32_t wtp_repel_f32(wtp_ctx* c, float* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
+                      const wtp_repel_params* prm, const wtp_wall_mesh* wall, float* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
+    return repel_host<float>(c, snap, nf, nm, D, sp, fm, prm, wall, conv, tr, res);
+}
+int32_t wtp_repel_f64(wtp_ctx* c, double* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
+                      const wtp_repel_params* prm, const wtp_wall_mesh* wall, double* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
+    return repel_host<double>(c, snap, nf, nm, D, sp, fm, prm, wall, conv, tr, res);
+}
+int32_t wtp_repel_dev_f32(wtp_ctx* c, float* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
+                          const wtp_repel_params* prm, float* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
+    return repel_dev<float>(c, snap, nf, nm, D, sp, fm, prm, conv, tr, res);
+}
+int32_t wtp_repel_dev_f64(wtp_ctx* c, double* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
+                          const wtp_repel_params* prm, double* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
+    return repel_dev<double>(c, snap, nf, nm, D, sp, fm, prm, conv, tr, res);
+}
+
+int32_t wtp_spacing_eval_f32(wtp_ctx* c, const wtp_spacing* sp, const float* p, int64_t N, int32_t D, float* out) { return spacing_eval_host<float>(c, sp, p, N, D, out); }
+int32_t wtp_spacing_eval_f64(wtp_ctx* c, const wtp_spacing* sp, const double* p, int64_t N, int32_t D, double* out) { return spacing_eval_host<double>(c, sp, p, N, D, out); }
+int32_t wtp_force_eval_f32(wtp_ctx* c, const wtp_force* f, const float* u, int64_t n, float* out) { return force_eval_host<float>(c, f, u, n, out); }
+int32_t wtp_force_eval_f64(wtp_ctx* c, const wtp_force* f, const double* u, int64_t n, double* out) { return force_eval_host<double>(c, f, u, n, out); }
+
+}  // extern "C"
+
+namespace wtp {
+// defined in api.cu
+template <class T>
+void knn_device_self(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, int64_t* d_out_idx, T* d_out_dist);
+
+template <class T>
+static int32_t metrics_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(pts && out && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(k >= 2 && (int64_t)k <= N, WTP_ERR_K_TOO_LARGE, "metrics needs 2 <= k <= N");
+    WTP_REQUIRE(ctx->world == 1, WTP_ERR_UNSUPPORTED, "metrics runs on a single-GPU context");
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    int64_t* d_idx = ctx->d_out_idx.as<int64_t>((size_t)N * k);
+    T* d_dist = ctx->d_out_dist.as<T>((size_t)N * k);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    knn_device_self<T>(ctx, d_pts, N, D, k, d_idx, d_dist);
+    const int nb = (int)std::min<int64_t>((N + 255) / 256, (int64_t)kNumSMs * 8);
+    MetricsPartial* d_part = ctx->d_reduce.as<MetricsPartial>((size_t)nb);
+    metrics_kernel<T><<<nb, 256, 0, ctx->stream>>>(d_dist, N, k, d_part);
+    LAUNCH_CHECK(ctx);
+    std::vector<MetricsPartial> h((size_t)nb);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(h.data(), d_part, sizeof(MetricsPartial) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    MetricsPartial a = h[0];
+    for (int i = 1; i < nb; ++i) {
+        a.avg += h[i].avg; a.sd += h[i].sd; a.mx += h[i].mx; a.mn += h[i].mn;
+        a.sep = std::min(a.sep, h[i].sep); a.fill = std::max(a.fill, h[i].fill);
+    }
+    out->avg = a.avg / (double)N; out->std = a.sd / (double)N; out->max = a.mx / (double)N; out->min = a.mn / (double)N;
+    out->separation = a.sep; out->fill = a.fill; out->mesh_ratio = a.fill / a.sep;
+    API_END(ctx)
+}
+}  // namespace wtp
+
+extern "C" {
+int32_t wtp_metrics_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<float>(c, p, N, D, k, out); }
+int32_t wtp_metrics_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<double>(c, p, N, D, k, out); }
+}

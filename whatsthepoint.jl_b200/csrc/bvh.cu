@@ -1,0 +1,226 @@
+// bvh.cu — spacing callables on the device (src/discretization/spacings.jl).
+//
+// The variable spacings (LogLike :67-72, BoundaryLayerSpacing :121-133) need the distance
+// from an arbitrary position to the nearest point of the spacing's own, static boundary
+// set (_min_distance :19-23, a KDTree 1-NN in the reference). Queries may lie far from
+// that set (deep interior points), where a uniform grid would walk many empty rings, so
+// the boundary set gets a Morton-sorted implicit BVH instead: 8-point leaves, complete
+// binary tree in heap layout, boxes built bottom-up; one thread answers one query with a
+// short explicit stack. Built once per repel / spacing_eval call on the device.
+#include "kernels.cuh"
+#include "knn_core.cuh"
+
+namespace wtp {
+
+#define LAUNCH_CHECK(ctx)                         \
+    do {                                          \
+        (ctx)->launches++;                        \
+        WTP_CUDA_CHECK(cudaPeekAtLastError());    \
+    } while (0)
+
+constexpr int BVH_LEAF = 8;
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t spread2(uint32_t v) {  // 16 bits -> every second bit
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(256) morton_key_kernel(const T* __restrict__ pts, int64_t n, T lox, T loy, T loz, T sx, T sy, T sz,
+                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int Q = D == 3 ? 1023 : 65535;
+    auto quant = [&](T v, T lo, T s) {
+        int q = (int)((v - lo) * s);
+        return (uint32_t)(q < 0 ? 0 : (q > Q ? Q : q));
+    };
+    uint32_t qx = quant(pts[i * D + 0], lox, sx), qy = quant(pts[i * D + 1], loy, sy);
+    uint32_t key;
+    if (D == 3) key = spread3(qx) | (spread3(qy) << 1) | (spread3(quant(pts[i * D + (D - 1)], loz, sz)) << 2);
+    else key = spread2(qx) | (spread2(qy) << 1);
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(256) bvh_gather_kernel(const T* __restrict__ pts, const uint32_t* __restrict__ vals, int64_t n,
+                                                         P4<T>* __restrict__ sorted) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t i = vals[j];
+    P4<T> p;
+    p.x = pts[(size_t)i * D + 0];
+    p.y = pts[(size_t)i * D + 1];
+    p.z = D == 3 ? pts[(size_t)i * D + (D - 1)] : (T)0;
+    p.w = idx_bits((T)0, i);
+    sorted[j] = p;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) bvh_leaf_kernel(const P4<T>* __restrict__ sorted, int64_t n, int64_t leaf_pow2, Box<T>* __restrict__ boxes) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= leaf_pow2) return;
+    Box<T> bx;
+    for (int d = 0; d < 3; ++d) { bx.lo[d] = t_inf<T>(); bx.hi[d] = -t_inf<T>(); }
+    const int64_t j0 = b * BVH_LEAF, j1 = j0 + BVH_LEAF < n ? j0 + BVH_LEAF : n;
+    for (int64_t j = j0; j < j1; ++j) {
+        const P4<T> p = sorted[j];
+        bx.lo[0] = p.x < bx.lo[0] ? p.x : bx.lo[0]; bx.hi[0] = p.x > bx.hi[0] ? p.x : bx.hi[0];
+        bx.lo[1] = p.y < bx.lo[1] ? p.y : bx.lo[1]; bx.hi[1] = p.y > bx.hi[1] ? p.y : bx.hi[1];
+        bx.lo[2] = p.z < bx.lo[2] ? p.z : bx.lo[2]; bx.hi[2] = p.z > bx.hi[2] ? p.z : bx.hi[2];
+    }
+    boxes[leaf_pow2 + b] = bx;
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) bvh_level_kernel(int64_t first, int64_t count, Box<T>* __restrict__ boxes) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int64_t i = first + t;
+    const Box<T> a = boxes[2 * i], b = boxes[2 * i + 1];
+    Box<T> o;
+    for (int d = 0; d < 3; ++d) { o.lo[d] = a.lo[d] < b.lo[d] ? a.lo[d] : b.lo[d]; o.hi[d] = a.hi[d] > b.hi[d] ? a.hi[d] : b.hi[d]; }
+    boxes[i] = o;
+}
+
+template <class T>
+void bvh_build(wtp_ctx* ctx, BvhBuffers& bv, const T* d_bnd, int64_t n, int D) {
+    WTP_REQUIRE(n > 0 && d_bnd, WTP_ERR_BAD_ARG, "variable spacing needs a non-empty boundary point set");
+    WTP_REQUIRE(n < (int64_t)0xfffffff0u, WTP_ERR_BAD_ARG, "boundary set too large");
+    double lo[3], hi[3];
+    compute_bbox<T>(ctx, bv.ib, d_bnd, n, D, lo, hi);
+    const double Q = D == 3 ? 1024.0 : 65536.0;
+    T s[3], l[3];
+    for (int d = 0; d < 3; ++d) {
+        double ext = d < D ? hi[d] - lo[d] : 0.0;
+        l[d] = (T)lo[d];
+        s[d] = (T)(ext > 0 ? Q / ext * (1.0 - 1e-6) : 0.0);
+    }
+    uint32_t* keys = bv.ib.keys_a.as<uint32_t>((size_t)n);
+    uint32_t* vals = bv.ib.vals_a.as<uint32_t>((size_t)n);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (D == 2) morton_key_kernel<T, 2><<<nb, 256, 0, ctx->stream>>>(d_bnd, n, l[0], l[1], l[2], s[0], s[1], s[2], keys, vals);
+    else morton_key_kernel<T, 3><<<nb, 256, 0, ctx->stream>>>(d_bnd, n, l[0], l[1], l[2], s[0], s[1], s[2], keys, vals);
+    LAUNCH_CHECK(ctx);
+    radix_sort_pairs(ctx, bv.ib, n, D == 3 ? 30 : 32);
+    P4<T>* sorted = bv.ib.sorted.as<P4<T>>((size_t)n);
+    if (D == 2) bvh_gather_kernel<T, 2><<<nb, 256, 0, ctx->stream>>>(d_bnd, bv.ib.vals_a.get<uint32_t>(), n, sorted);
+    else bvh_gather_kernel<T, 3><<<nb, 256, 0, ctx->stream>>>(d_bnd, bv.ib.vals_a.get<uint32_t>(), n, sorted);
+    LAUNCH_CHECK(ctx);
+    const int64_t nleaf = (n + BVH_LEAF - 1) / BVH_LEAF;
+    int64_t P = 1;
+    while (P < nleaf) P <<= 1;
+    Box<T>* boxes = bv.boxes.as<Box<T>>((size_t)2 * P);
+    bvh_leaf_kernel<T><<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(sorted, n, P, boxes);
+    LAUNCH_CHECK(ctx);
+    for (int64_t L = P / 2; L >= 1; L /= 2) {
+        bvh_level_kernel<T><<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(L, L, boxes);
+        LAUNCH_CHECK(ctx);
+    }
+    bv.n = n;
+    bv.leaf_pow2 = P;
+}
+template void bvh_build<float>(wtp_ctx*, BvhBuffers&, const float*, int64_t, int);
+template void bvh_build<double>(wtp_ctx*, BvhBuffers&, const double*, int64_t, int);
+
+template <class T>
+BvhView<T> bvh_view(const BvhBuffers& bv) {
+    return BvhView<T>{bv.ib.sorted.get<P4<T>>(), bv.boxes.get<Box<T>>(), bv.n, bv.leaf_pow2};
+}
+template BvhView<float> bvh_view<float>(const BvhBuffers&);
+template BvhView<double> bvh_view<double>(const BvhBuffers&);
+
+// squared distance from q to the nearest boundary point; same d2 arithmetic as the k-NN
+template <class T, int D>
+__device__ __forceinline__ T bvh_nearest_d2(const BvhView<T>& bv, T qx, T qy, T qz) {
+    auto box_lb = [&](int64_t i) -> T {
+        const Box<T> b = bv.boxes[i];
+        T gx = qx < b.lo[0] ? sub_rn(b.lo[0], qx) : (qx > b.hi[0] ? sub_rn(qx, b.hi[0]) : (T)0);
+        T gy = qy < b.lo[1] ? sub_rn(b.lo[1], qy) : (qy > b.hi[1] ? sub_rn(qy, b.hi[1]) : (T)0);
+        T s = add_rn(mul_rn(gx, gx), mul_rn(gy, gy));
+        if (D == 3) {
+            T gz = qz < b.lo[2] ? sub_rn(b.lo[2], qz) : (qz > b.hi[2] ? sub_rn(qz, b.hi[2]) : (T)0);
+            s = add_rn(s, mul_rn(gz, gz));
+        }
+        return s;  // +inf for empty nodes (lo = +inf)
+    };
+    T best = t_inf<T>();
+    int stack[48];  // node ids < 2^31
+    int sp = 0;
+    stack[sp++] = 1;
+    while (sp > 0) {
+        const int64_t i = stack[--sp];
+        if (i >= bv.leaf_pow2) {
+            const int64_t j0 = (i - bv.leaf_pow2) * BVH_LEAF, j1 = j0 + BVH_LEAF < bv.n ? j0 + BVH_LEAF : bv.n;
+            for (int64_t j = j0; j < j1; ++j) {
+                const P4<T> p = load_p4<T>(bv.pts + j);
+                const T d = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
+                best = d < best ? d : best;
+            }
+            continue;
+        }
+        const T ll = box_lb(2 * i), lr = box_lb(2 * i + 1);
+        // push the farther child first so the nearer one is popped first
+        if (ll <= lr) {
+            if (lr < best) stack[sp++] = (int)(2 * i + 1);
+            if (ll < best) stack[sp++] = (int)(2 * i);
+        } else {
+            if (ll < best) stack[sp++] = (int)(2 * i);
+            if (lr < best) stack[sp++] = (int)(2 * i + 1);
+        }
+    }
+    return best;
+}
+
+template <class T>
+__device__ __forceinline__ T spacing_from_dmin(const SpacingP<T>& sp, T dmin) {
+    if (sp.kind == WTP_SPACING_LOGLIKE) {                 // spacings.jl:67-72
+        const T inv_growth = (T)1 - (sp.b - (T)1);
+        const T aa = sp.a * inv_growth;
+        return sp.a * dmin / (aa + dmin);
+    }
+    const T delta = sp.c;                                  // spacings.jl:121-133
+    const T center = delta / (T)2, width = delta / (T)6;
+    const T sigma = (T)1 / ((T)1 + exp(-(dmin - center) / width));
+    return sp.a + (sp.b - sp.a) * sigma;
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(128) spacing_eval_kernel(const SpacingP<T> sp, const BvhView<T> bv, const T* __restrict__ pts,
+                                                           int64_t n, T* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (sp.kind == WTP_SPACING_CONSTANT) { out[i] = sp.a; return; }
+    const T qx = pts[i * D + 0], qy = pts[i * D + 1], qz = D == 3 ? pts[i * D + (D - 1)] : (T)0;
+    const T dmin = sqrt(bvh_nearest_d2<T, D>(bv, qx, qy, qz));
+    out[i] = spacing_from_dmin<T>(sp, dmin);
+}
+
+template <class T>
+void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out) {
+    if (n <= 0) return;
+    WTP_REQUIRE(sp.kind == WTP_SPACING_CONSTANT || sp.kind == WTP_SPACING_LOGLIKE || sp.kind == WTP_SPACING_BOUNDARY_LAYER,
+                WTP_ERR_UNSUPPORTED, "only ConstantSpacing, LogLike and BoundaryLayerSpacing run on the device");
+    const BvhView<T> v = bvh_view<T>(bv);
+    const unsigned nb = (unsigned)((n + 127) / 128);
+    if (D == 2) spacing_eval_kernel<T, 2><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, n, d_out);
+    else spacing_eval_kernel<T, 3><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, n, d_out);
+    LAUNCH_CHECK(ctx);
+}
+template void spacing_eval<float>(wtp_ctx*, const SpacingP<float>&, const BvhBuffers&, const float*, int64_t, int, float*);
+template void spacing_eval<double>(wtp_ctx*, const SpacingP<double>&, const BvhBuffers&, const double*, int64_t, int, double*);
+
+}  // namespace wtp

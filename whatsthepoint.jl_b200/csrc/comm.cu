@@ -1,0 +1,144 @@
+// comm.cu — multi-GPU plumbing: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2") so that the library shares the NCCL
+// the host program already loaded (torch's bundled copy under torchrun) and needs no
+// link-time dependency for single-GPU use. Collectives on the data path:
+//   k-NN / radius : none (queries shard by contiguous range, index replicated)
+//   repel         : per iteration one all-gather of the moved positions (grouped in-place
+//                   broadcasts, uneven shards allowed) + one all-gather of the per-rank
+//                   stop-test partials (a few dozen bytes)
+#include <dlfcn.h>
+
+#include "kernels.cuh"
+
+namespace wtp {
+
+typedef struct { char internal[128]; } nccl_unique_id;
+typedef void* nccl_comm_t;
+enum { NCCL_INT8 = 0 };
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(nccl_unique_id*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+static NcclApi* load_nccl() {
+    static NcclApi api;
+    if (api.handle) return &api;
+    const char* env = getenv("WTP_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) {
+        if (!n || !*n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) throw Error{WTP_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "not found")};
+#define BIND(field, sym)                                                                     \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(h, sym));                        \
+    if (!api.field) throw Error{WTP_ERR_NCCL, std::string("libnccl is missing symbol ") + sym};
+    BIND(GetUniqueId, "ncclGetUniqueId")
+    BIND(CommInitRank, "ncclCommInitRank")
+    BIND(CommDestroy, "ncclCommDestroy")
+    BIND(AllGather, "ncclAllGather")
+    BIND(Broadcast, "ncclBroadcast")
+    BIND(GroupStart, "ncclGroupStart")
+    BIND(GroupEnd, "ncclGroupEnd")
+    BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+    api.handle = h;
+    return &api;
+}
+
+#define NCCL_CHECK(api, expr)                                                                          \
+    do {                                                                                               \
+        int _r = (expr);                                                                               \
+        if (_r != 0) throw Error{WTP_ERR_NCCL, std::string(#expr) + ": " + (api)->GetErrorString(_r)}; \
+    } while (0)
+
+// every rank owns rows [shard_begin, shard_end) of d_buf; afterwards all ranks hold all rows
+void comm_allgather_rows(wtp_ctx* ctx, void* d_buf, int64_t n_rows, size_t row_bytes) {
+    if (ctx->world <= 1) return;
+    NcclApi* api = ctx->nccl;
+    NCCL_CHECK(api, api->GroupStart());
+    for (int r = 0; r < ctx->world; ++r) {
+        const int64_t b = wtp_shard_begin(n_rows, r, ctx->world), e = wtp_shard_end(n_rows, r, ctx->world);
+        if (e <= b) continue;
+        char* p = static_cast<char*>(d_buf) + (size_t)b * row_bytes;
+        NCCL_CHECK(api, api->Broadcast(p, p, (size_t)(e - b) * row_bytes, NCCL_INT8, r, ctx->nccl_comm, ctx->stream));
+    }
+    NCCL_CHECK(api, api->GroupEnd());
+}
+
+void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t bytes_per_rank) {
+    if (ctx->world <= 1) {
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_out, d_in, bytes_per_rank, cudaMemcpyDeviceToDevice, ctx->stream));
+        return;
+    }
+    NcclApi* api = ctx->nccl;
+    NCCL_CHECK(api, api->AllGather(d_in, d_out, bytes_per_rank, NCCL_INT8, ctx->nccl_comm, ctx->stream));
+}
+
+int32_t fail(wtp_ctx* ctx, const Error& e);
+
+}  // namespace wtp
+
+using namespace wtp;
+
+extern "C" {
+
+void wtp_comm_destroy_internal(wtp_ctx* ctx) {
+    if (ctx->nccl_comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    ctx->rank = 0;
+    ctx->world = 1;
+}
+
+int32_t wtp_comm_unique_id(void* out128) {
+    if (!out128) return WTP_ERR_BAD_ARG;
+    try {
+        NcclApi* api = load_nccl();
+        nccl_unique_id id;
+        int r = api->GetUniqueId(&id);
+        if (r != 0) return WTP_ERR_NCCL;
+        memcpy(out128, &id, sizeof(id));
+    } catch (const Error&) {
+        return WTP_ERR_NCCL;
+    }
+    return WTP_OK;
+}
+
+int32_t wtp_comm_init(wtp_ctx* ctx, int32_t rank, int32_t world, const void* unique_id128) {
+    if (!ctx) return WTP_ERR_BAD_ARG;
+    try {
+        WTP_REQUIRE(world >= 1 && rank >= 0 && rank < world, WTP_ERR_BAD_ARG, "bad rank/world");
+        WTP_CUDA_CHECK(cudaSetDevice(ctx->device));
+        wtp_comm_destroy_internal(ctx);
+        if (world == 1) return WTP_OK;
+        WTP_REQUIRE(unique_id128, WTP_ERR_BAD_ARG, "null NCCL unique id");
+        NcclApi* api = load_nccl();
+        nccl_unique_id id;
+        memcpy(&id, unique_id128, sizeof(id));
+        nccl_comm_t comm = nullptr;
+        NCCL_CHECK(api, api->CommInitRank(&comm, world, id, rank));
+        ctx->nccl = api;
+        ctx->nccl_comm = comm;
+        ctx->rank = rank;
+        ctx->world = world;
+    } catch (const Error& e) {
+        return fail(ctx, e);
+    }
+    return WTP_OK;
+}
+
+int32_t wtp_comm_rank(const wtp_ctx* ctx) { return ctx ? ctx->rank : -1; }
+int32_t wtp_comm_world(const wtp_ctx* ctx) { return ctx ? ctx->world : -1; }
+
+}  // extern "C"

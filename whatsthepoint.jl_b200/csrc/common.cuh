@@ -1,0 +1,210 @@
+// common.cuh — shared declarations of libwtp_cuda.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wtp_cuda.h"
+
+namespace wtp {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+constexpr int kWarp = 32;
+
+// ------------------------------------------------------------------ errors
+struct Error {
+    int32_t status;
+    std::string msg;
+};
+
+#define WTP_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            throw ::wtp::Error{_e == cudaErrorMemoryAllocation ? WTP_ERR_OOM : WTP_ERR_CUDA,     \
+                               std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +     \
+                                   __FILE__ + ":" + std::to_string(__LINE__)};                   \
+        }                                                                                        \
+    } while (0)
+
+#define WTP_REQUIRE(cond, status, message)                     \
+    do {                                                       \
+        if (!(cond)) throw ::wtp::Error{(status), (message)};  \
+    } while (0)
+
+// --------------------------------------------------------- device records
+// One sorted point: coordinates + the caller's index, 16 B (f32) / 32 B (f64), so that
+// any cell range is 16-byte aligned for cp.async.bulk and one LDG.128/LDS.128 per point.
+template <class T>
+struct alignas(16) P4 {
+    T x, y, z;
+    T w;  // bit pattern of the original (0-based) index, see idx_of / set_idx
+};
+
+__host__ __device__ inline uint32_t idx_of(const P4<float>& p) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(p.w);
+#else
+    uint32_t u; memcpy(&u, &p.w, 4); return u;
+#endif
+}
+__host__ __device__ inline uint32_t idx_of(const P4<double>& p) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__double_as_longlong(p.w);
+#else
+    uint64_t u; memcpy(&u, &p.w, 8); return (uint32_t)u;
+#endif
+}
+__device__ inline float idx_bits(float, uint32_t i) { return __uint_as_float(i); }
+__device__ inline double idx_bits(double, uint32_t i) { return __longlong_as_double((long long)i); }
+
+// Uniform grid over the bounding box; row-major cells (x fastest) so that the cells of
+// one x-row are contiguous in the sorted array.
+template <class T>
+struct Grid {
+    T lo[3];
+    T inv_c;     // 1 / cell size
+    T c;         // cell size
+    T slack;     // absolute safety margin for pruning bounds (few ulps of the extent)
+    int n[3];    // cells per dimension (n[2] = 1 in 2-D)
+    uint32_t ncells;
+};
+
+template <class T>
+__host__ __device__ inline int cell_coord(const Grid<T>& g, T v, int d) {
+    // monotone in v: floor(fl(fl(v - lo) * inv_c)), clamped (points outside the box of a
+    // stale grid land in the border cells, which are treated as unbounded outward).
+    T t = (v - g.lo[d]) * g.inv_c;
+    int i = (int)floor(t);
+    i = i < 0 ? 0 : i;
+    i = i > g.n[d] - 1 ? g.n[d] - 1 : i;
+    return i;
+}
+
+// ------------------------------------------------------------ device memory
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    void* reserve(size_t bytes) {
+        if (bytes > cap) {
+            if (p) { cudaFree(p); p = nullptr; cap = 0; }
+            size_t want = bytes + bytes / 8 + 256;
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {
+                p = nullptr; cap = 0;
+                (void)cudaGetLastError();
+                throw Error{WTP_ERR_OOM, "cudaMalloc(" + std::to_string(want) + " bytes): " + cudaGetErrorString(e)};
+            }
+            cap = want;
+        }
+        return p;
+    }
+    template <class U> U* as(size_t count) { return static_cast<U*>(reserve(count * sizeof(U))); }
+    template <class U> U* get() const { return static_cast<U*>(p); }
+};
+
+// --------------------------------------------------------------- timing
+enum Phase { PH_H2D = 0, PH_BBOX, PH_CELLKEY, PH_SORT, PH_REORDER, PH_QUERY, PH_SCAN, PH_REDUCE, PH_COMM, PH_D2H, PH_COUNT };
+
+struct PhaseTimer {
+    bool enabled = false;
+    cudaStream_t stream = nullptr;
+    struct Span { int phase; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    cudaEvent_t total_a = nullptr, total_b = nullptr;
+    bool have_total = false;
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+    void reset(cudaStream_t s) { stream = s; spans.clear(); used = 0; have_total = false; }
+    void begin_total() { if (enabled) { total_a = get(); cudaEventRecord(total_a, stream); } }
+    void end_total() { if (enabled) { total_b = get(); cudaEventRecord(total_b, stream); have_total = true; } }
+    int open(int phase) {
+        if (!enabled) return -1;
+        Span s{phase, get(), nullptr};
+        cudaEventRecord(s.a, stream);
+        spans.push_back(s);
+        return (int)spans.size() - 1;
+    }
+    void close(int h) {
+        if (h < 0) return;
+        spans[h].b = get();
+        cudaEventRecord(spans[h].b, stream);
+    }
+    ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); }
+};
+
+struct ScopedPhase {
+    PhaseTimer& t; int h;
+    ScopedPhase(PhaseTimer& t_, int phase) : t(t_), h(t_.open(phase)) {}
+    ~ScopedPhase() { t.close(h); }
+};
+
+// -------------------------------------------------------------- the index
+// Device-resident spatial index of one point set (all buffers owned by the context).
+struct IndexBuffers {
+    DevBuf keys_a, keys_b, vals_a, vals_b;  // radix sort ping-pong (u32)
+    DevBuf block_hist;                      // 256 x numBlocks digit histogram
+    DevBuf scan_tmp;                        // block sums of the scans
+    DevBuf sorted;                          // P4<T>[N]
+    DevBuf cell_start;                      // u32[ncells + 1]
+    DevBuf bbox_partial;                    // per-block min/max
+    DevBuf bbox;                            // 6 x T
+};
+
+// Implicit BVH over the Morton-sorted boundary set of a variable spacing (bvh.cu).
+struct BvhBuffers {
+    IndexBuffers ib;   // sort scratch + sorted P4 records
+    DevBuf boxes;      // Box<T>[2 * leaf_pow2], heap layout, node 1 = root
+    int64_t n = 0;
+    int64_t leaf_pow2 = 0;
+};
+
+struct NcclApi;  // comm.cu
+
+}  // namespace wtp
+
+// The opaque context of the C ABI.
+struct wtp_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    double cell_occupancy = 0.0;  // <= 0: default per dimension
+    int64_t launches = 0;
+    wtp::PhaseTimer timer;
+    wtp_timing last_timing{};
+    // spatial index of the queried point set / the repel snapshot
+    wtp::IndexBuffers index[1];
+    // 1-NN structure of a variable spacing's boundary set
+    wtp::BvhBuffers bvh;
+    wtp::DevBuf d_pts, d_out_idx, d_out_dist, d_offsets, d_counts, d_indices, d_misc, d_misc2;
+    wtp::DevBuf d_spacing_pts, d_spacings, d_p_new, d_reduce, d_qlist, d_nn;
+    // radius two-call state
+    struct {
+        bool pending = false; bool f64 = false; bool dev_input = false;
+        int64_t N = 0; int D = 0; double r = 0; int64_t nnz = -1;
+        const void* pts = nullptr;
+        int64_t q_begin = 0, q_end = 0;
+    } radius;
+    unsigned char grid_storage[2][128];  // last Grid<T> per index (host copy)
+    // multi-GPU
+    int rank = 0, world = 1;
+    void* nccl_comm = nullptr;
+    wtp::NcclApi* nccl = nullptr;
+    // pinned staging for scalar read-backs
+    void* h_pinned = nullptr;
+    size_t h_pinned_bytes = 0;
+};

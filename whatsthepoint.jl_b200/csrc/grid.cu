@@ -1,0 +1,453 @@
+// grid.cu — the device spatial index: bounding box, cell keys, LSD radix sort with one
+// byte (8-bit digit) per pass, exclusive scans, and the gather into sorted 16/32-byte
+// point records with per-cell start offsets.
+//
+// Replaces the per-call KDTree construction of the reference (Meshes KNearestSearch /
+// BallSearch at src/topology.jl:80,93 and KDTree(coords) at src/repel.jl:218,252).
+#include <cfloat>
+#include <cmath>
+
+#include "kernels.cuh"
+
+namespace wtp {
+
+#define LAUNCH_CHECK(ctx)                         \
+    do {                                          \
+        (ctx)->launches++;                        \
+        WTP_CUDA_CHECK(cudaPeekAtLastError());    \
+    } while (0)
+
+// =========================================================== bounding box
+template <class T> struct Lim;
+template <> struct Lim<float> { static __host__ __device__ float inf() { return __builtin_huge_valf(); } };
+template <> struct Lim<double> { static __host__ __device__ double inf() { return __builtin_huge_val(); } };
+
+constexpr int BBOX_THREADS = 256;
+
+template <class T, int D>
+__global__ void __launch_bounds__(BBOX_THREADS) bbox_partial_kernel(const T* __restrict__ pts, int64_t N, T* __restrict__ partial) {
+    T lo[3], hi[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { lo[d] = Lim<T>::inf(); hi[d] = -Lim<T>::inf(); }
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            T v = pts[i * D + d];
+            lo[d] = v < lo[d] ? v : lo[d];
+            hi[d] = v > hi[d] ? v : hi[d];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            T a = __shfl_xor_sync(0xffffffffu, lo[d], o), b = __shfl_xor_sync(0xffffffffu, hi[d], o);
+            lo[d] = a < lo[d] ? a : lo[d];
+            hi[d] = b > hi[d] ? b : hi[d];
+        }
+    }
+    __shared__ T s[BBOX_THREADS / 32][6];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { s[w][d] = lo[d]; s[w][3 + d] = hi[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        T v = s[0][threadIdx.x];
+        for (int i = 1; i < BBOX_THREADS / 32; ++i) {
+            T u = s[i][threadIdx.x];
+            v = threadIdx.x < 3 ? (u < v ? u : v) : (u > v ? u : v);
+        }
+        partial[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+template <class T>
+__global__ void bbox_final_kernel(const T* __restrict__ partial, int nblocks, T* __restrict__ bbox) {
+    // 6 warps: warp c reduces component c over all partials
+    int c = threadIdx.x >> 5, l = threadIdx.x & 31;
+    T v = c < 3 ? Lim<T>::inf() : -Lim<T>::inf();
+    for (int i = l; i < nblocks; i += 32) {
+        T u = partial[i * 6 + c];
+        v = c < 3 ? (u < v ? u : v) : (u > v ? u : v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        T u = __shfl_xor_sync(0xffffffffu, v, o);
+        v = c < 3 ? (u < v ? u : v) : (u > v ? u : v);
+    }
+    if (l == 0) bbox[c] = v;
+}
+
+template <class T>
+void compute_bbox(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, double lo[3], double hi[3]) {
+    ScopedPhase ph(ctx->timer, PH_BBOX);
+    int nblocks = (int)std::min<int64_t>((N + BBOX_THREADS - 1) / BBOX_THREADS, (int64_t)kNumSMs * 8);
+    if (nblocks < 1) nblocks = 1;
+    T* partial = ib.bbox_partial.as<T>((size_t)nblocks * 6);
+    T* bbox = ib.bbox.as<T>(6);
+    if (D == 2) bbox_partial_kernel<T, 2><<<nblocks, BBOX_THREADS, 0, ctx->stream>>>(d_pts, N, partial);
+    else bbox_partial_kernel<T, 3><<<nblocks, BBOX_THREADS, 0, ctx->stream>>>(d_pts, N, partial);
+    LAUNCH_CHECK(ctx);
+    bbox_final_kernel<T><<<1, 192, 0, ctx->stream>>>(partial, nblocks, bbox);
+    LAUNCH_CHECK(ctx);
+    T h[6];
+    WTP_CUDA_CHECK(cudaMemcpyAsync(h, bbox, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < 3; ++d) { lo[d] = d < D ? (double)h[d] : 0.0; hi[d] = d < D ? (double)h[3 + d] : 0.0; }
+}
+template void compute_bbox<float>(wtp_ctx*, IndexBuffers&, const float*, int64_t, int, double*, double*);
+template void compute_bbox<double>(wtp_ctx*, IndexBuffers&, const double*, int64_t, int, double*, double*);
+
+// =========================================================== grid parameters
+template <class T>
+Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], double occupancy, double min_cell) {
+    Grid<T> g;
+    double ext[3] = {0, 0, 0}, vol = 1.0, maxabs = 0.0, maxext = 0.0;
+    int deff = 0;
+    for (int d = 0; d < D; ++d) {
+        // extent in T arithmetic is what cell_coord sees; keep lo exactly as a T
+        ext[d] = (double)((T)hi[d] - (T)lo[d]);
+        if (!(ext[d] >= 0) || !std::isfinite(ext[d])) throw Error{WTP_ERR_BAD_ARG, "non-finite coordinates in point set"};
+        if (ext[d] > 0) { vol *= ext[d]; ++deff; }
+        maxabs = std::max(maxabs, std::max(std::fabs(lo[d]), std::fabs(hi[d])));
+        maxext = std::max(maxext, ext[d]);
+    }
+    if (occupancy <= 0) occupancy = (D == 3) ? 8.0 : 6.0;
+    double c = 1.0;
+    if (deff > 0 && N > 0) c = std::pow(vol * occupancy / (double)N, 1.0 / deff);
+    if (!(c > 0) || !std::isfinite(c)) c = maxext > 0 ? maxext : 1.0;
+    // keep the cell size representable relative to the extent (at most 2^20 cells per dimension)
+    c = std::max(c, maxext / 1048576.0);
+    if (min_cell > 0) c = std::max(c, min_cell);
+    const double cap = std::min(1073741824.0, std::max(4096.0, 4.0 * (double)N));
+    for (;;) {
+        double prod = 1.0;
+        for (int d = 0; d < 3; ++d) {
+            double nd = d < D ? std::floor(ext[d] / c) + 1.0 : 1.0;
+            g.n[d] = (int)std::min(nd, 1048576.0);
+            prod *= g.n[d];
+        }
+        if (prod <= cap) { g.ncells = (uint32_t)prod; break; }
+        c *= 1.1;
+    }
+    for (int d = 0; d < 3; ++d) g.lo[d] = d < D ? (T)lo[d] : (T)0;
+    g.c = (T)c;
+    g.inv_c = (T)1 / g.c;
+    const double eps = sizeof(T) == 4 ? (double)FLT_EPSILON : DBL_EPSILON;
+    // cell boundaries lo + i*c and the (v-lo)*inv_c rounding are each off by a few ulps of
+    // the coordinate magnitude; 16 ulps of slack keeps every pruning bound conservative.
+    g.slack = (T)(16.0 * eps * std::max(maxabs, maxext) + 4.0 * eps * c);
+    return g;
+}
+template Grid<float> make_grid<float>(int64_t, int, const double*, const double*, double, double);
+template Grid<double> make_grid<double>(int64_t, int, const double*, const double*, double, double);
+
+// ================================================================ cell keys
+template <class T, int D>
+__global__ void __launch_bounds__(256) cellkey_kernel(const T* __restrict__ pts, int64_t N, Grid<T> g,
+                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int cx = cell_coord(g, pts[i * D + 0], 0);
+    int cy = cell_coord(g, pts[i * D + 1], 1);
+    int cz = D == 3 ? cell_coord(g, pts[i * D + (D - 1)], 2) : 0;
+    keys[i] = ((uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy) * (uint32_t)g.n[0] + (uint32_t)cx;
+    vals[i] = (uint32_t)i;
+}
+
+// =============================================================== radix sort
+// Stable LSD radix sort of (cell key, point id) pairs, one byte per pass. Per pass:
+//   rs_hist_kernel    per-tile digit histogram            (reads 4 B/item)
+//   exclusive scan    over the digit-major histogram
+//   rs_scatter_kernel stable in-tile ranking in shared memory, coalesced run writes
+//                                                          (reads 8 B, writes 8 B/item)
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;   // 4096 keys per CTA
+constexpr int RS_WARP_ITEMS = RS_TILE / RS_WARPS;  // 512 consecutive keys per warp
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift,
+                                                             uint32_t* __restrict__ block_hist, int num_blocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        uint32_t i = base + r * RS_THREADS + threadIdx.x;
+        bool valid = i < n;
+        uint32_t digit = valid ? ((keys[i] >> shift) & 255u) : 256u;
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        if (valid && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&h[digit], __popc(peers));
+    }
+    __syncthreads();
+    block_hist[threadIdx.x * num_blocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                                                                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                                                                uint32_t n, int shift, const uint32_t* __restrict__ block_offsets,
+                                                                int num_blocks) {
+    __shared__ uint32_t warp_cnt[RS_WARPS][256];
+    __shared__ uint32_t digit_base[256];
+    __shared__ uint32_t global_base[256];
+    __shared__ uint32_t s_warp_tot[RS_WARPS];
+    __shared__ uint32_t s_keys[RS_TILE];
+    __shared__ uint32_t s_vals[RS_TILE];
+
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const uint32_t tile_base = blockIdx.x * RS_TILE;
+    const uint32_t n_valid = min((uint32_t)RS_TILE, n - tile_base);
+    for (int i = tid; i < RS_WARPS * 256; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    uint32_t key[RS_ITEMS];
+    uint16_t rank[RS_ITEMS];
+    // Warp w owns the 512 consecutive keys [w*512, (w+1)*512) of the tile, walked in 16
+    // rounds of 32: tile order = (warp, round, lane) = input order, which keeps the sort stable.
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        uint32_t local = w * RS_WARP_ITEMS + r * 32 + lane;
+        bool valid = local < n_valid;
+        key[r] = valid ? keys_in[tile_base + local] : 0xffffffffu;
+        // invalid tail entries sort as digit 255 behind every valid key of the tile
+        uint32_t digit = valid ? ((key[r] >> shift) & 255u) : 255u;
+        unsigned peers = __match_any_sync(0xffffffffu, digit);
+        uint32_t before = warp_cnt[w][digit];
+        rank[r] = (uint16_t)(before + __popc(peers & ((1u << lane) - 1)));
+        __syncwarp();
+        if ((peers & ((1u << lane) - 1)) == 0) warp_cnt[w][digit] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // thread d: exclusive scan over the warps of digit d, then exclusive scan over digits
+    uint32_t total = 0;
+    {
+        const int d = tid;
+#pragma unroll
+        for (int i = 0; i < RS_WARPS; ++i) {
+            uint32_t c = warp_cnt[i][d];
+            warp_cnt[i][d] = total;
+            total += c;
+        }
+        uint32_t incl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp_tot[w] = incl;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int i = 0; i < w; ++i) wbase += s_warp_tot[i];
+        uint32_t excl = wbase + incl - total;
+        digit_base[d] = excl;
+        global_base[d] = block_offsets[d * num_blocks + blockIdx.x] - excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        uint32_t local = w * RS_WARP_ITEMS + r * 32 + lane;
+        bool valid = local < n_valid;
+        uint32_t digit = valid ? ((key[r] >> shift) & 255u) : 255u;
+        uint32_t lp = digit_base[digit] + warp_cnt[w][digit] + rank[r];
+        s_keys[lp] = key[r];
+        s_vals[lp] = valid ? vals_in[tile_base + local] : 0u;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n_valid; i += RS_THREADS) {
+        uint32_t k = s_keys[i];
+        uint32_t out = global_base[(k >> shift) & 255u] + i;
+        keys_out[out] = k;
+        vals_out[out] = s_vals[i];
+    }
+}
+
+// ==================================================================== scans
+constexpr int SC_THREADS = 256;
+constexpr int SC_ITEMS = 8;
+constexpr int SC_TILE = SC_THREADS * SC_ITEMS;
+
+template <class A>
+__device__ inline A block_exclusive_scan(A v, A* s_warp /*[SC_THREADS/32]*/, A* block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    A incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        A t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    A base = 0, tot = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+        A c = s_warp[i];
+        if (i < w) base += c;
+        tot += c;
+    }
+    if (block_total) *block_total = tot;
+    return base + incl - v;
+}
+
+template <class A>
+__global__ void __launch_bounds__(SC_THREADS) scan_reduce_kernel(const uint32_t* __restrict__ in, int64_t n, A* __restrict__ block_sums) {
+    __shared__ A s_warp[SC_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    A v = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) if (base + i < n) v += (A)in[base + i];
+    A tot;
+    (void)block_exclusive_scan<A>(v, s_warp, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+template <class A>
+__global__ void __launch_bounds__(1024) scan_sums_kernel(A* __restrict__ block_sums, int64_t nb) {
+    // single CTA: in-place exclusive scan of nb block sums, chunk by chunk with a carry;
+    // block_sums[nb] receives the grand total.
+    __shared__ A s_warp[32];
+    __shared__ A s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t c0 = 0; c0 < nb; c0 += blockDim.x) {
+        int64_t i = c0 + threadIdx.x;
+        A v = i < nb ? block_sums[i] : (A)0;
+        A tot;
+        A ex = block_exclusive_scan<A>(v, s_warp, &tot);
+        A carry = s_carry;
+        if (i < nb) block_sums[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nb] = s_carry;
+}
+
+template <class A>
+__global__ void __launch_bounds__(SC_THREADS) scan_apply_kernel(const uint32_t* in, A* out, int64_t n,
+                                                                const A* __restrict__ block_sums, int64_t nb) {
+    // in and out may alias (in-place scan of the radix histogram): every thread reads all
+    // of its own items before it writes them, and touches nobody else's.
+    __shared__ A s_warp[SC_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SC_TILE + (int64_t)threadIdx.x * SC_ITEMS;
+    A item[SC_ITEMS];
+    A v = 0;
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) { item[i] = base + i < n ? (A)in[base + i] : (A)0; v += item[i]; }
+    A ex = block_exclusive_scan<A>(v, s_warp, nullptr) + block_sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SC_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = ex;
+        ex += item[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = block_sums[nb];
+}
+
+template <class A>
+static void exclusive_scan_impl(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, A* d_out, int64_t n) {
+    if (n <= 0) { WTP_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(A), ctx->stream)); return; }
+    int64_t nb = (n + SC_TILE - 1) / SC_TILE;
+    A* sums = tmp.as<A>((size_t)nb + 1);
+    scan_reduce_kernel<A><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(d_in, n, sums);
+    LAUNCH_CHECK(ctx);
+    scan_sums_kernel<A><<<1, 1024, 0, ctx->stream>>>(sums, nb);
+    LAUNCH_CHECK(ctx);
+    scan_apply_kernel<A><<<(unsigned)nb, SC_THREADS, 0, ctx->stream>>>(d_in, d_out, n, sums, nb);
+    LAUNCH_CHECK(ctx);
+}
+void exclusive_scan_u32(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, uint32_t* d_out, int64_t n) {
+    exclusive_scan_impl<uint32_t>(ctx, tmp, d_in, d_out, n);
+}
+void exclusive_scan_u32_to_i64(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, int64_t* d_out, int64_t n) {
+    exclusive_scan_impl<unsigned long long>(ctx, tmp, d_in, reinterpret_cast<unsigned long long*>(d_out), n);
+}
+
+// Sorts the (key, value) pairs held in ib.keys_a / ib.vals_a by the low `bits` bits of the
+// key; on return ib.keys_a / ib.vals_a hold the sorted pairs. Returns the passes run.
+int radix_sort_pairs(wtp_ctx* ctx, IndexBuffers& ib, int64_t N, int bits) {
+    ScopedPhase ph(ctx->timer, PH_SORT);
+    cudaStream_t st = ctx->stream;
+    uint32_t* keys_a = ib.keys_a.get<uint32_t>();
+    uint32_t* vals_a = ib.vals_a.get<uint32_t>();
+    uint32_t* keys_b = ib.keys_b.as<uint32_t>((size_t)N);
+    uint32_t* vals_b = ib.vals_b.as<uint32_t>((size_t)N);
+    const int passes = (bits + 7) / 8;
+    const int num_blocks = (int)((N + RS_TILE - 1) / RS_TILE);
+    uint32_t* hist = ib.block_hist.as<uint32_t>((size_t)256 * num_blocks + 1);
+    for (int p = 0; p < passes; ++p) {
+        rs_hist_kernel<<<num_blocks, RS_THREADS, 0, st>>>(keys_a, (uint32_t)N, 8 * p, hist, num_blocks);
+        LAUNCH_CHECK(ctx);
+        exclusive_scan_u32(ctx, ib.scan_tmp, hist, hist, (int64_t)256 * num_blocks);
+        rs_scatter_kernel<<<num_blocks, RS_THREADS, 0, st>>>(keys_a, vals_a, keys_b, vals_b, (uint32_t)N, 8 * p, hist, num_blocks);
+        LAUNCH_CHECK(ctx);
+        std::swap(keys_a, keys_b);
+        std::swap(vals_a, vals_b);
+    }
+    if (passes & 1) {
+        std::swap(ib.keys_a.p, ib.keys_b.p); std::swap(ib.keys_a.cap, ib.keys_b.cap);
+        std::swap(ib.vals_a.p, ib.vals_b.p); std::swap(ib.vals_a.cap, ib.vals_b.cap);
+    }
+    return passes;
+}
+
+// ====================================================== gather + cell starts
+template <class T, int D>
+__global__ void __launch_bounds__(256) reorder_kernel(const T* __restrict__ pts, const uint32_t* __restrict__ keys,
+                                                      const uint32_t* __restrict__ vals, uint32_t N, uint32_t ncells,
+                                                      P4<T>* __restrict__ sorted, uint32_t* __restrict__ cell_start) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    uint32_t i = vals[j];
+    P4<T> p;
+    p.x = pts[(size_t)i * D + 0];
+    p.y = pts[(size_t)i * D + 1];
+    p.z = D == 3 ? pts[(size_t)i * D + (D - 1)] : (T)0;
+    p.w = idx_bits((T)0, i);
+    sorted[j] = p;
+    uint32_t key = keys[j];
+    if (j == 0) {
+        for (uint32_t c = 0; c <= key; ++c) cell_start[c] = 0;
+    } else {
+        uint32_t prev = keys[j - 1];
+        for (uint32_t c = prev + 1; c <= key; ++c) cell_start[c] = j;  // empty cells in the gap start here too
+    }
+    if (j == N - 1)
+        for (uint32_t c = key + 1; c <= ncells; ++c) cell_start[c] = N;
+}
+
+template <class T>
+int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, const Grid<T>& g) {
+    WTP_REQUIRE(N > 0 && N < (int64_t)0xfffffff0u, WTP_ERR_BAD_ARG, "point count must be in [1, 2^32)");
+    cudaStream_t st = ctx->stream;
+    uint32_t* keys_a = ib.keys_a.as<uint32_t>((size_t)N);
+    uint32_t* vals_a = ib.vals_a.as<uint32_t>((size_t)N);
+    P4<T>* sorted = ib.sorted.as<P4<T>>((size_t)N);
+    uint32_t* cell_start = ib.cell_start.as<uint32_t>((size_t)g.ncells + 1);
+    const unsigned nb256 = (unsigned)((N + 255) / 256);
+    {
+        ScopedPhase ph(ctx->timer, PH_CELLKEY);
+        if (D == 2) cellkey_kernel<T, 2><<<nb256, 256, 0, st>>>(d_pts, N, g, keys_a, vals_a);
+        else cellkey_kernel<T, 3><<<nb256, 256, 0, st>>>(d_pts, N, g, keys_a, vals_a);
+        LAUNCH_CHECK(ctx);
+    }
+    int bits = 0;
+    while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)g.ncells) ++bits;
+    const int passes = radix_sort_pairs(ctx, ib, N, bits);
+    keys_a = ib.keys_a.get<uint32_t>();
+    vals_a = ib.vals_a.get<uint32_t>();
+    {
+        ScopedPhase ph(ctx->timer, PH_REORDER);
+        if (D == 2) reorder_kernel<T, 2><<<nb256, 256, 0, st>>>(d_pts, keys_a, vals_a, (uint32_t)N, g.ncells, sorted, cell_start);
+        else reorder_kernel<T, 3><<<nb256, 256, 0, st>>>(d_pts, keys_a, vals_a, (uint32_t)N, g.ncells, sorted, cell_start);
+        LAUNCH_CHECK(ctx);
+    }
+    return passes;
+}
+template int build_index<float>(wtp_ctx*, IndexBuffers&, const float*, int64_t, int, const Grid<float>&);
+template int build_index<double>(wtp_ctx*, IndexBuffers&, const double*, int64_t, int, const Grid<double>&);
+
+}  // namespace wtp

@@ -1,0 +1,68 @@
+// kernels.cuh — host-side entry points of the CUDA translation units.
+#pragma once
+#include "common.cuh"
+
+namespace wtp {
+
+// ---- grid.cu -------------------------------------------------------------
+// Bounding box of N x D points on the device (one small D2H + stream sync).
+template <class T>
+void compute_bbox(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, double lo[3], double hi[3]);
+
+// Grid parameters from a bounding box: cell size from the target occupancy, never
+// below min_cell (radius search), cell count capped.
+template <class T>
+Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], double occupancy, double min_cell);
+
+// cell keys -> radix sort -> sorted P4 tiles + cell starts. Returns radix passes run.
+template <class T>
+int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, const Grid<T>& g);
+
+// Stable LSD radix sort (8-bit digits) of the pairs in ib.keys_a / ib.vals_a on the low `bits` key bits.
+int radix_sort_pairs(wtp_ctx* ctx, IndexBuffers& ib, int64_t N, int bits);
+
+// Exclusive scans (count -> offsets). out has n+1 entries; out[n] = total.
+void exclusive_scan_u32(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, uint32_t* d_out, int64_t n);
+void exclusive_scan_u32_to_i64(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, int64_t* d_out, int64_t n);
+
+// ---- knn.cu --------------------------------------------------------------
+// Warp-per-query exact k-NN on a built index. Queries are the index's own points,
+// restricted to caller-order indices [q_begin, q_end) (d_qlist: their sorted positions,
+// or null = all). K1 = list length; drop_first drops rank 0 from the output.
+// Rows are written at (orig - q_begin) * (K1 - drop_first). idx_base: 1 for 1-based.
+template <class T>
+void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
+               const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, int64_t* d_out_idx, T* d_out_dist,
+               unsigned long long* d_expanded_counter);
+
+// Compact list of sorted positions whose original index is in [q_begin, q_end).
+void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q_begin, int64_t q_end,
+                      bool f64, DevBuf& flags, DevBuf& scan, DevBuf& qlist);
+
+// ---- radius.cu -----------------------------------------------------------
+template <class T>
+void radius_count(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, T r,
+                  const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, uint32_t* d_counts);
+template <class T>
+void radius_fill(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, T r,
+                 const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, const int64_t* d_offsets,
+                 int64_t* d_indices);
+
+// ---- bvh.cu --------------------------------------------------------------
+template <class T> struct ForceP { int kind; T beta, u0, gamma; };
+template <class T> struct SpacingP { int kind; T a, b, c; };
+template <class T> struct Box { T lo[3], hi[3]; };
+template <class T> struct BvhView { const P4<T>* pts; const Box<T>* boxes; int64_t n, leaf_pow2; };
+
+// Morton sort + bottom-up boxes over the spacing's boundary set (device pointer, n x D).
+template <class T>
+void bvh_build(wtp_ctx* ctx, BvhBuffers& bv, const T* d_bnd, int64_t n, int D);
+template <class T>
+BvhView<T> bvh_view(const BvhBuffers& bv);
+// out[i] = spacing(pts[i]) for i < n (thread per point; BVH 1-NN for the variable kinds).
+template <class T>
+void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out);
+template <class T>
+void force_eval(wtp_ctx* ctx, const ForceP<T>& f, const T* d_u, int64_t n, T* d_out);
+
+}  // namespace wtp

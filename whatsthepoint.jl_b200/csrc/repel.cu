@@ -1,0 +1,390 @@
+// repel.cu — the node-repulsion relaxation: _relax! (src/repel.jl:202-339).
+//
+// One fused sweep kernel per iteration (src/repel.jl:256-292): warp-per-point k-NN on the
+// snapshot grid, force accumulation in ascending (d2, index) order, adaptive step with
+// the one-spacing cap, wall rule, position update, and the block-reduced stopping
+// metrics (max |F|*s  :293, d_NN/s moments  :374-386, closest pair  :396-403) plus the
+// bounding box of the moved points for the next grid. A tiny second kernel folds the
+// per-CTA partials in a fixed order, the host replays the stop logic (:305-337).
+#include <cmath>
+#include <limits>
+
+#include "kernels.cuh"
+#include "knn_core.cuh"
+
+namespace wtp {
+
+#define LAUNCH_CHECK(ctx)                         \
+    do {                                          \
+        (ctx)->launches++;                        \
+        WTP_CUDA_CHECK(cudaPeekAtLastError());    \
+    } while (0)
+
+// comm.cu
+void comm_allgather_rows(wtp_ctx* ctx, void* d_buf, int64_t n_rows, size_t row_bytes);
+void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t bytes_per_rank);
+
+// ------------------------------------------------------------------ forces
+// src/repel_forces.jl:37, 57-60, 96-100, 124-127 (compiled with -fmad=false)
+template <class T>
+__device__ __forceinline__ T force_fn(const ForceP<T>& f, T u) {
+    const T u2 = u * u;
+    switch (f.kind) {
+        case WTP_FORCE_INVERSE: { const T t = u2 + f.beta; return (T)1 / (t * t); }
+        case WTP_FORCE_EQUILIBRIUM: { const T t = u2 + f.beta; return ((T)1 - u2) / (t * t); }
+        case WTP_FORCE_CLIPPED: { const T t = u2 + f.beta; const T F = (f.u0 * f.u0 - u2) / (t * t); return F > (T)0 ? F : (T)0; }
+        default: return ((T)1 - u2) / pow(u2 + f.beta, f.gamma);
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) force_eval_kernel(const ForceP<T> f, const T* __restrict__ u, int64_t n, T* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = force_fn<T>(f, u[i]);
+}
+template <class T>
+void force_eval(wtp_ctx* ctx, const ForceP<T>& f, const T* d_u, int64_t n, T* d_out) {
+    if (n <= 0) return;
+    force_eval_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(f, d_u, n, d_out);
+    LAUNCH_CHECK(ctx);
+}
+template void force_eval<float>(wtp_ctx*, const ForceP<float>&, const float*, int64_t, float*);
+template void force_eval<double>(wtp_ctx*, const ForceP<double>&, const double*, int64_t, double*);
+
+// ------------------------------------------------------------------- sweep
+template <class T> __host__ __device__ inline T t_max();
+template <> __host__ __device__ inline float t_max<float>() { return 3.402823466e+38f; }
+template <> __host__ __device__ inline double t_max<double>() { return 1.7976931348623157e+308; }
+
+template <class T>
+struct RepelPartial {
+    double s1, s2;              // sum u, sum u*u, u = d_NN / s     (_dnn_cv, :374-386)
+    unsigned long long n;       // points swept
+    T max_force;                // max |F|*s                        (:293)
+    T min_nn;                   // closest pair                     (:396-403)
+    uint32_t min_id;            // movable id of the pair's first point
+    uint32_t min_nn_idx;        // snapshot-global 0-based index of its nearest neighbour
+    T lo[3], hi[3];             // bounding box of the new positions
+};
+
+template <class T>
+__device__ __forceinline__ void partial_init(RepelPartial<T>& p) {
+    p.s1 = 0; p.s2 = 0; p.n = 0; p.max_force = (T)0; p.min_nn = t_inf<T>(); p.min_id = 0xffffffffu; p.min_nn_idx = 0xffffffffu;
+    for (int d = 0; d < 3; ++d) { p.lo[d] = t_inf<T>(); p.hi[d] = -t_inf<T>(); }
+}
+// fold b into a; b covers later points than a (sum order = point order within a CTA)
+template <class T>
+__host__ __device__ inline void partial_merge(RepelPartial<T>& a, const RepelPartial<T>& b) {
+    a.s1 += b.s1; a.s2 += b.s2; a.n += b.n;
+    a.max_force = b.max_force > a.max_force ? b.max_force : a.max_force;
+    if (b.min_nn < a.min_nn || (b.min_nn == a.min_nn && b.min_id < a.min_id)) { a.min_nn = b.min_nn; a.min_id = b.min_id; a.min_nn_idx = b.min_nn_idx; }
+    for (int d = 0; d < 3; ++d) { a.lo[d] = b.lo[d] < a.lo[d] ? b.lo[d] : a.lo[d]; a.hi[d] = b.hi[d] > a.hi[d] ? b.hi[d] : a.hi[d]; }
+}
+
+template <class T>
+struct SweepArgs {
+    Grid<T> g;
+    const P4<T>* sorted;
+    const uint32_t* cell_start;
+    const T* S;            // snapshot coordinates, n_all x D, caller order
+    const T* P_old;        // n_move x D
+    T* P_new;              // n_move x D
+    const T* s_cur;        // spacing at P_old per movable point (null: constant)
+    const T* spacings;     // n_all, snapshot-global, as of the last rebuild
+    T s_const;
+    uint32_t n_fixed, n_all, id_lo, id_hi;
+    const uint32_t* qlist; // sorted positions to sweep (null: all, filtered by id range)
+    uint32_t nq;
+    int kk, rebuild;
+    T a_lo, a_max;
+    ForceP<T> force;
+    RepelPartial<T>* partials;
+};
+
+constexpr int SW_THREADS = 256;
+constexpr int SW_WARPS = SW_THREADS / 32;
+
+template <class T, int D, int KPL>
+__global__ void __launch_bounds__(SW_THREADS) repel_sweep_kernel(const SweepArgs<T> a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ T s_term[SW_WARPS][32 * KPL][3];
+    __shared__ RepelPartial<T> s_part[SW_WARPS];
+    WarpKnn<T, D, KPL> knn(a.g, a.sorted, a.cell_start);
+    RepelPartial<T> acc;
+    partial_init(acc);
+
+    for (uint32_t chunk = blockIdx.x; (uint64_t)chunk * SW_WARPS < a.nq; chunk += gridDim.x) {
+        const uint32_t qi = chunk * SW_WARPS + warp;
+        if (qi >= a.nq) continue;
+        const uint32_t j = a.qlist ? a.qlist[qi] : qi;
+        const uint32_t self = idx_of(load_p4<T>(a.sorted + j));
+        if (self < a.n_fixed + a.id_lo || self >= a.n_fixed + a.id_hi) continue;   // fixed wall / other rank's point
+        const uint32_t id = self - a.n_fixed;
+        const T xi0 = a.P_old[(size_t)id * D + 0], xi1 = a.P_old[(size_t)id * D + 1];
+        const T xi2 = D == 3 ? a.P_old[(size_t)id * D + (D - 1)] : (T)0;
+        knn.run(xi0, xi1, xi2, a.kk, lane);                                       // :259
+        const T s = a.s_cur ? a.s_cur[id] : a.s_const;                            // :260
+
+        bool found = false;
+        T nn_d2 = (T)0; uint32_t nn_idx = 0xffffffffu;
+#pragma unroll
+        for (int e = 0; e < KPL; ++e) {                                           // :270-280
+            const int r = e * 32 + lane;
+            const uint32_t nj = knn.list.idx[e];
+            const bool valid = r < a.kk && nj != 0xffffffffu && nj != self;       // skip self BY INDEX (:271)
+            T t0 = (T)0, t1 = (T)0, t2 = (T)0;
+            if (valid) {
+                const T rr = sqrt(knn.list.d2[e]);
+                if (rr > (T)0) {                                                   // _safe_direction (:358-364)
+                    const T f = force_fn<T>(a.force, rr / s);
+                    t0 = f * ((xi0 - a.S[(size_t)nj * D + 0]) / rr);
+                    t1 = f * ((xi1 - a.S[(size_t)nj * D + 1]) / rr);
+                    if (D == 3) t2 = f * ((xi2 - a.S[(size_t)nj * D + (D - 1)]) / rr);
+                }
+            }
+            s_term[warp][r][0] = t0; s_term[warp][r][1] = t1; s_term[warp][r][2] = t2;
+            const unsigned m = __ballot_sync(FULL, valid);
+            if (!found && m) {                                                     // first non-self hit (:272-275)
+                const int src = __ffs(m) - 1;
+                nn_d2 = __shfl_sync(FULL, knn.list.d2[e], src);
+                nn_idx = __shfl_sync(FULL, nj, src);
+                found = true;
+            }
+        }
+        __syncwarp();
+        // F += term_j in ascending (d2, index) order: lanes 0..D-1 each add up one component
+        T Fc = (T)0;
+        if (lane < D) for (int r = 0; r < a.kk; ++r) Fc = Fc + s_term[warp][r][lane];
+        __syncwarp();
+        const T F0 = __shfl_sync(FULL, Fc, 0), F1 = __shfl_sync(FULL, Fc, 1), F2 = D == 3 ? __shfl_sync(FULL, Fc, 2) : (T)0;
+        T n2 = F0 * F0 + F1 * F1;
+        if (D == 3) n2 = n2 + F2 * F2;
+        const T Fn = sqrt(n2);                                                     // :282
+        const T fs = Fn * s;                                                       // :283
+        T ai = (T)1 / (Fn + (T)1.0e-30);                                           // :285
+        ai = ai > a.a_max ? a.a_max : (ai < a.a_lo ? a.a_lo : ai);
+        const T sa = s * ai;
+        T d0 = sa * F0, d1 = sa * F1, d2 = D == 3 ? sa * F2 : (T)0;                // :286
+        T dn2 = d0 * d0 + d1 * d1;
+        if (D == 3) dn2 = dn2 + d2 * d2;
+        const T dn = sqrt(dn2);
+        if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
+        const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;                       // :291 (identity wall)
+        if (lane == 0) {
+            a.P_new[(size_t)id * D + 0] = p0;
+            a.P_new[(size_t)id * D + 1] = p1;
+            if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
+        }
+        const T nn = found ? sqrt(nn_d2) : t_max<T>();
+        const T s_mon = a.spacings[self];   // spacing as of the last rebuild (:251, :379)
+        const T u = nn / s_mon;
+        acc.s1 += (double)u; acc.s2 += (double)(u * u); acc.n += 1;
+        acc.max_force = fs > acc.max_force ? fs : acc.max_force;
+        if (nn < acc.min_nn || (nn == acc.min_nn && id < acc.min_id)) { acc.min_nn = nn; acc.min_id = id; acc.min_nn_idx = nn_idx; }
+        acc.lo[0] = p0 < acc.lo[0] ? p0 : acc.lo[0]; acc.hi[0] = p0 > acc.hi[0] ? p0 : acc.hi[0];
+        acc.lo[1] = p1 < acc.lo[1] ? p1 : acc.lo[1]; acc.hi[1] = p1 > acc.hi[1] ? p1 : acc.hi[1];
+        if (D == 3) { acc.lo[2] = p2 < acc.lo[2] ? p2 : acc.lo[2]; acc.hi[2] = p2 > acc.hi[2] ? p2 : acc.hi[2]; }
+    }
+    if (lane == 0) s_part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        RepelPartial<T> tot = s_part[0];
+        for (int w = 1; w < SW_WARPS; ++w) partial_merge(tot, s_part[w]);
+        a.partials[blockIdx.x] = tot;
+    }
+}
+
+// fold the per-CTA partials in a fixed order (thread t takes partials t, t+256, ...; then
+// a fixed tree over the threads) so the stop test is reproducible run to run
+template <class T>
+__global__ void __launch_bounds__(256) repel_finalize_kernel(const RepelPartial<T>* __restrict__ partials, int n, RepelPartial<T>* __restrict__ out) {
+    __shared__ RepelPartial<T> s[256];
+    RepelPartial<T> acc;
+    partial_init(acc);
+    for (int i = threadIdx.x; i < n; i += 256) partial_merge(acc, partials[i]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { RepelPartial<T> x = s[threadIdx.x]; partial_merge(x, s[threadIdx.x + o]); s[threadIdx.x] = x; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s[0];
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) fill_kernel(T* __restrict__ out, int64_t n, T v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+template <class T, int D>
+static void launch_sweep(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
+    if (a.kk <= 32) repel_sweep_kernel<T, D, 1><<<nblocks, SW_THREADS, 0, ctx->stream>>>(a);
+    else if (a.kk <= 64) repel_sweep_kernel<T, D, 2><<<nblocks, SW_THREADS, 0, ctx->stream>>>(a);
+    else repel_sweep_kernel<T, D, 4><<<nblocks, SW_THREADS, 0, ctx->stream>>>(a);
+    LAUNCH_CHECK(ctx);
+}
+
+// ------------------------------------------------------------- host driver
+template <class T>
+void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int D, const wtp_spacing* sp_in, const T* d_bnd,
+                  const wtp_force* fm, const wtp_repel_params* prm, T* conv, wtp_trace_entry* trace, wtp_repel_result* res) {
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(n_fixed >= 0 && n_move >= 0 && n_fixed + n_move > 0, WTP_ERR_BAD_ARG, "empty snapshot");
+    WTP_REQUIRE(prm->rebuild_every >= 1, WTP_ERR_BAD_ARG, "rebuild_every must be >= 1");          // src/repel.jl:74
+    WTP_REQUIRE(prm->k >= 1 && prm->max_iters >= 0, WTP_ERR_BAD_ARG, "k must be >= 1 and max_iters >= 0");
+    WTP_REQUIRE(prm->kick_after == 0, WTP_ERR_UNSUPPORTED, "kick_after > 0 draws randn (src/repel.jl:430): not reproducible on the device");
+    WTP_REQUIRE(prm->wall == WTP_WALL_IDENTITY, WTP_ERR_UNSUPPORTED, "mesh wall rule is not available in this build");
+    WTP_REQUIRE(fm->kind >= WTP_FORCE_INVERSE && fm->kind <= WTP_FORCE_STRONG, WTP_ERR_UNSUPPORTED, "user-defined RepelForceModel cannot cross the C ABI");
+    WTP_REQUIRE(sp_in->kind >= WTP_SPACING_CONSTANT && sp_in->kind <= WTP_SPACING_BOUNDARY_LAYER, WTP_ERR_UNSUPPORTED, "user-defined spacing callable cannot cross the C ABI");
+    const int64_t n_all = n_fixed + n_move;
+    WTP_REQUIRE(n_all < (int64_t)0xfffffff0u, WTP_ERR_BAD_ARG, "snapshot too large");
+    const int kk = (int)std::min<int64_t>(prm->k, n_all);                                           // :208
+    WTP_REQUIRE(kk <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K");
+    res->iters = 0; res->stop_reason = WTP_STOP_MAX_ITERS; res->last_cv = std::numeric_limits<double>::quiet_NaN();
+    if (n_move == 0 || prm->max_iters == 0) {
+        // the reference still runs sweeps over zero points and records conv = 0 each time (:293)
+        if (n_move == 0) for (int i = 0; i < prm->max_iters; ++i) { conv[i] = (T)0; res->iters = i + 1; if (0.0 < prm->tol) { res->stop_reason = WTP_STOP_TOL; break; } }
+        return;
+    }
+    cudaStream_t st = ctx->stream;
+    IndexBuffers& ib = ctx->index[0];
+    const SpacingP<T> sp{sp_in->kind, (T)sp_in->a, (T)sp_in->b, (T)sp_in->c};
+    const ForceP<T> force{fm->kind, (T)fm->beta, (T)fm->u0, (T)fm->gamma};
+    const bool variable = sp.kind != WTP_SPACING_CONSTANT;
+    if (variable) bvh_build<T>(ctx, ctx->bvh, d_bnd, sp_in->n_bnd, D);
+
+    T* spacings = ctx->d_spacings.as<T>((size_t)n_all);
+    T* s_cur = variable ? ctx->d_nn.as<T>((size_t)n_move) : nullptr;
+    spacing_eval<T>(ctx, sp, ctx->bvh, d_snap, n_all, D, spacings);                                 // :209
+    T* Pa = ctx->d_p_new.as<T>((size_t)2 * n_move * D);
+    T* Pb = Pa + (size_t)n_move * D;
+    T* S_tail = d_snap + (size_t)n_fixed * D;
+    WTP_CUDA_CHECK(cudaMemcpyAsync(Pa, S_tail, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));
+
+    // bounding boxes: the fixed wall once, the movable tail from each sweep's partials
+    double flo[3] = {0, 0, 0}, fhi[3] = {0, 0, 0}, mlo[3], mhi[3];
+    if (n_fixed > 0) compute_bbox<T>(ctx, ib, d_snap, n_fixed, D, flo, fhi);
+    compute_bbox<T>(ctx, ib, S_tail, n_move, D, mlo, mhi);
+
+    const int32_t rank = ctx->rank, world = ctx->world;
+    const int64_t id_lo = wtp_shard_begin(n_move, rank, world), id_hi = wtp_shard_end(n_move, rank, world);
+    const int nblocks = (int)std::min<int64_t>((n_all + SW_WARPS - 1) / SW_WARPS, (int64_t)kNumSMs * 8);
+    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + 1 + world);
+    RepelPartial<T>* d_tot = partials + nblocks;
+    RepelPartial<T>* d_all = d_tot + 1;
+    RepelPartial<T>* h_tot = static_cast<RepelPartial<T>*>(ctx->h_pinned);
+    WTP_REQUIRE(sizeof(RepelPartial<T>) * (size_t)(world + 1) + 64 <= ctx->h_pinned_bytes, WTP_ERR_BAD_ARG, "world size too large for the staging buffer");
+
+    Grid<T> g{};
+    int passes = 0;
+    T best_cv_T = t_max<T>();
+    int64_t last_impr = 0;
+    int it = 1, n_conv = 0;
+    const uint32_t* qlist = nullptr;
+    uint32_t nq = (uint32_t)n_all;
+    while (it <= prm->max_iters) {                                                                   // :243
+        const bool rebuild = (it - 1) % prm->rebuild_every == 0;                                     // :245
+        if (variable) spacing_eval<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur);                      // spacing(xi), :260 (and :251)
+        if (rebuild) {
+            WTP_CUDA_CHECK(cudaMemcpyAsync(S_tail, Pa, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));   // :246
+            if (variable) WTP_CUDA_CHECK(cudaMemcpyAsync(spacings + n_fixed, s_cur, (size_t)n_move * sizeof(T), cudaMemcpyDeviceToDevice, st));   // :251
+            double lo[3], hi[3];
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = n_fixed > 0 ? std::min(flo[d], mlo[d]) : mlo[d];
+                hi[d] = n_fixed > 0 ? std::max(fhi[d], mhi[d]) : mhi[d];
+            }
+            g = make_grid<T>(n_all, D, lo, hi, ctx->cell_occupancy, 0.0);
+            passes = build_index<T>(ctx, ib, d_snap, n_all, D, g);                                   // :252
+            if (world > 1) {
+                build_query_list(ctx, ib, n_all, n_fixed + id_lo, n_fixed + id_hi, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
+                qlist = ctx->d_qlist.get<uint32_t>();
+                nq = (uint32_t)(id_hi - id_lo);
+            }
+        }
+        SweepArgs<T> a;
+        a.g = g; a.sorted = ib.sorted.get<P4<T>>(); a.cell_start = ib.cell_start.get<uint32_t>();
+        a.S = d_snap; a.P_old = Pa; a.P_new = Pb; a.s_cur = s_cur; a.spacings = spacings; a.s_const = sp.a;
+        a.n_fixed = (uint32_t)n_fixed; a.n_all = (uint32_t)n_all; a.id_lo = (uint32_t)id_lo; a.id_hi = (uint32_t)id_hi;
+        a.qlist = qlist; a.nq = nq; a.kk = kk; a.rebuild = rebuild ? 1 : 0;
+        a.a_lo = (T)prm->alpha_lo; a.a_max = (T)prm->alpha_max; a.force = force; a.partials = partials;
+        {
+            ScopedPhase ph(ctx->timer, PH_QUERY);
+            if (D == 2) launch_sweep<T, 2>(ctx, a, nblocks); else launch_sweep<T, 3>(ctx, a, nblocks);
+        }
+        {
+            ScopedPhase ph(ctx->timer, PH_REDUCE);
+            repel_finalize_kernel<T><<<1, 256, 0, st>>>(partials, nblocks, d_tot);
+            LAUNCH_CHECK(ctx);
+        }
+        RepelPartial<T> tot;
+        if (world > 1) {
+            ScopedPhase ph(ctx->timer, PH_COMM);
+            comm_allgather_rows(ctx, Pb, n_move, (size_t)D * sizeof(T));                            // moved positions of every rank
+            comm_allgather_fixed(ctx, d_tot, d_all, sizeof(RepelPartial<T>));
+            WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_all, sizeof(RepelPartial<T>) * world, cudaMemcpyDeviceToHost, st));
+            WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+            tot = h_tot[0];
+            for (int r = 1; r < world; ++r) partial_merge(tot, h_tot[r]);
+        } else {
+            WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_tot, sizeof(RepelPartial<T>), cudaMemcpyDeviceToHost, st));
+            WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+            tot = h_tot[0];
+        }
+        for (int d = 0; d < 3; ++d) { mlo[d] = d < D ? (double)tot.lo[d] : 0.0; mhi[d] = d < D ? (double)tot.hi[d] : 0.0; }
+        conv[n_conv++] = tot.max_force;                                                              // :293
+        if (trace) {                                                                                 // :294-296, 396-403
+            const int64_t ig = (int64_t)tot.min_id + n_fixed + 1;
+            const int64_t jg = tot.min_nn_idx == 0xffffffffu ? 0 : (int64_t)tot.min_nn_idx + 1;
+            T sa_, sb_;
+            WTP_CUDA_CHECK(cudaMemcpyAsync(&sa_, spacings + (ig - 1), sizeof(T), cudaMemcpyDeviceToHost, st));
+            WTP_CUDA_CHECK(cudaMemcpyAsync(&sb_, spacings + (jg > 0 ? jg - 1 : ig - 1), sizeof(T), cudaMemcpyDeviceToHost, st));
+            WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+            const T s_pair = (sa_ + sb_) / (T)2;
+            wtp_trace_entry& te = trace[n_conv - 1];
+            te.r = (double)tot.min_nn; te.s = (double)s_pair; te.r_over_s = (double)(tot.min_nn / s_pair);
+            te.idx_a = std::min(ig, jg); te.idx_b = std::max(ig, jg);
+        }
+        bool stopped = false, keep_old = false;
+        if (prm->stall_after > 0 || prm->cv_target > 0) {                                            // :305-327
+            const double nn_ = (double)tot.n;
+            const T mu = (T)(tot.s1 / nn_);
+            const T var = (T)(tot.s2 / nn_) - mu * mu;
+            const T cv = std::sqrt(var > (T)0 ? var : (T)0) / mu;
+            res->last_cv = (double)cv;
+            if (prm->cv_target > 0 && (double)cv <= prm->cv_target) {
+                stopped = true; keep_old = true; res->stop_reason = WTP_STOP_CV_TARGET;              // p .= p_old (:314)
+            } else if (prm->stall_after > 0) {
+                if ((double)cv < (double)best_cv_T * (1 - 1.0e-3)) { best_cv_T = cv; last_impr = it; }
+                else if (it - last_impr >= prm->stall_after) { stopped = true; res->stop_reason = WTP_STOP_STALL; }
+            }
+        }
+        if (!keep_old) std::swap(Pa, Pb);  // Pa = p after the sweep
+        if (stopped) break;
+        if ((double)conv[n_conv - 1] < prm->tol) { res->stop_reason = WTP_STOP_TOL; break; }          // :329-332
+        ++it;
+    }
+    WTP_CUDA_CHECK(cudaMemcpyAsync(S_tail, Pa, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+    res->iters = n_conv;
+    ctx->last_timing = wtp_timing{};
+    ctx->last_timing.sort_passes = passes;
+    ctx->last_timing.query_launches = n_conv;
+    ctx->last_timing.n_cells = g.ncells;
+}
+
+template void relax_device<float>(wtp_ctx*, float*, int64_t, int64_t, int, const wtp_spacing*, const float*, const wtp_force*,
+                                  const wtp_repel_params*, float*, wtp_trace_entry*, wtp_repel_result*);
+template void relax_device<double>(wtp_ctx*, double*, int64_t, int64_t, int, const wtp_spacing*, const double*, const wtp_force*,
+                                   const wtp_repel_params*, double*, wtp_trace_entry*, wtp_repel_result*);
+
+template <class T>
+void fill_device(wtp_ctx* ctx, T* d_out, int64_t n, T v) {
+    if (n <= 0) return;
+    fill_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_out, n, v);
+    LAUNCH_CHECK(ctx);
+}
+template void fill_device<float>(wtp_ctx*, float*, int64_t, float);
+template void fill_device<double>(wtp_ctx*, double*, int64_t, double);
+
+}  // namespace wtp
