@@ -1,0 +1,321 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against the CPU oracle on identical inputs.
+Bit-exact for neighbour lists (indices AND distances); repel positions within the north-star
+tolerance (1e-6*spacing Float64, 1e-3*spacing Float32 after 10 iterations) — in practice bit-exact
+for constant spacing, because the sweep evaluates the same operations in the same order."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-6, np.float32: 1e-3}
+
+
+def rows_of(off, ind):
+    return [ind[off[i]:off[i + 1]].tolist() for i in range(len(off) - 1)]
+
+
+# ------------------------------------------------------------------ k-NN
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("N,k", [(50, 5), (1000, 21), (30000, 21), (5000, 40), (3000, 100), (22, 21), (2, 1)])
+def test_knn_bit_exact(ctx, oracle, dt, D, N, k):
+    pts = np.random.default_rng(N + k + D).random((N, D)).astype(dt)
+    a, ad = ctx.knn(pts, k, dists=True)
+    b, bd = oracle.knn(pts, k, dists=True)
+    assert np.array_equal(a, b) and np.array_equal(ad, bd)
+    assert not (a == np.arange(1, N + 1)[:, None]).any()            # self excluded (test/topology.jl:40)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_knn_clustered_graded_duplicates(ctx, oracle, dt):
+    rng = np.random.default_rng(1)
+    clustered = np.concatenate([rng.normal(0, 0.01, (5000, 3)), rng.random((5000, 3)) * 10]).astype(dt)
+    assert np.array_equal(ctx.knn(clustered, 21), oracle.knn(clustered, 21))
+    assert ctx.timing()["n_ring_expanded"] > 0                       # the ring expansion path ran
+    graded = (rng.random((20000, 3)) ** 3).astype(dt)                # density varies by orders of magnitude
+    assert np.array_equal(ctx.knn(graded, 21), oracle.knn(graded, 21))
+    dup = np.repeat(rng.random((500, 3)), 4, axis=0).astype(dt)      # ties: order by index
+    assert np.array_equal(ctx.knn(dup, 9), oracle.knn(dup, 9))
+    flat = rng.random((4000, 3)).astype(dt); flat[:, 2] = 0.5        # degenerate extent
+    assert np.array_equal(ctx.knn(flat, 12), oracle.knn(flat, 12))
+    far = (rng.random((3000, 3)) + 1.0e4).astype(dt)                 # large offset: few mantissa bits left in f32
+    assert np.array_equal(ctx.knn(far, 10), oracle.knn(far, 10))
+
+
+def test_knn_real_geometry(ctx, oracle, stl_points):
+    for name, pts in stl_points.items():                             # STL face centres
+        a, ad = ctx.knn(pts, 21, dists=True)
+        b, bd = oracle.knn(pts, 21, dists=True)
+        assert np.array_equal(a, b) and np.array_equal(ad, bd), name
+
+
+def test_search_including_self_and_known_answers(ctx, oracle, known):
+    g = known["circle_k3"]                                           # test/neighbors.jl:36-56
+    idx, dist = ctx.knn(np.array(g["points"]), 3, include_self=True, dists=True)
+    assert (idx[:, 0] == np.arange(1, 21)).all()
+    assert [sorted(r) for r in idx.tolist()] == g["sets"]
+    assert (dist[:, 0] == 0).all() and (np.diff(dist, axis=1) >= 0).all()
+    pts = np.random.default_rng(2).random((5, 3))
+    assert ctx.knn(pts, 5, include_self=True).shape == (5, 5)        # k == N (test/neighbors.jl:158-166)
+    assert (ctx.knn(pts, 1, include_self=True)[:, 0] == np.arange(1, 6)).all()
+
+
+def test_knn_errors(ctx, pkg):
+    pts = np.random.default_rng(3).random((5, 3))
+    with pytest.raises(pkg.WtpArgumentError):                        # k + 1 > N
+        ctx.knn(pts, 5)
+    with pytest.raises(pkg.WtpArgumentError):
+        ctx.knn(np.random.rand(500, 3), 200)                         # above WTP_MAX_K
+    with pytest.raises(pkg.WtpArgumentError):
+        ctx.knn(np.random.rand(10, 4), 2)
+
+
+def test_knn_cell_occupancy_invariance(ctx, oracle):
+    pts = np.random.default_rng(4).random((20000, 3)).astype(np.float32)
+    ref = oracle.knn(pts, 21)
+    for m in (1.0, 3.0, 20.0, 100.0):                                # results must not depend on the grid
+        ctx.set_cell_occupancy(m)
+        assert np.array_equal(ctx.knn(pts, 21), ref), m
+    ctx.set_cell_occupancy(0.0)
+
+
+# ---------------------------------------------------------------- radius
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("D,r", [(2, 0.03), (3, 0.08), (2, 0.004), (3, 0.5)])
+def test_radius_csr_bit_exact(ctx, oracle, dt, D, r):
+    n = 20000 if r < 0.4 else 1500                                   # r = 0.5: rows of hundreds (rank path)
+    pts = np.random.default_rng(D).random((n, D)).astype(dt)
+    off, ind = ctx.radius(pts, r)
+    roff, rind = oracle.radius(pts, r)
+    assert np.array_equal(off, roff) and np.array_equal(ind, rind)
+
+
+def test_radius_known_answer_and_edges(ctx, oracle, known):
+    g = known["radius_grid5x5"]                                      # test/topology.jl:46-52
+    for dt in (np.float64, np.float32):
+        off, ind = ctx.radius(np.array(g["points"], dtype=dt), g["radius"])
+        assert rows_of(off, ind) == g["rows"]
+    pts = np.random.default_rng(5).random((1000, 3))
+    off, ind = ctx.radius(pts, 1e-9)                                 # nobody in range: empty CSR
+    assert off[-1] == 0 and ind.size == 0
+    dup = np.repeat(pts[:100], 2, axis=0)
+    off, ind = ctx.radius(dup, 0.0)                                  # r = 0: only the coincident twin, self removed by index
+    roff, rind = oracle.radius(dup, 0.0)
+    assert np.array_equal(off, roff) and np.array_equal(ind, rind) and (np.diff(off) == 1).all()
+
+
+# ------------------------------------------------------- forces, spacings
+def test_compute_force_known_answers(ctx, known):
+    g = known["compute_force"]                                       # test/repel.jl:117-170
+    for kind, key, u0 in (("inverse", "inverse", 1.0), ("equilibrium", "equilibrium", 1.0), ("clipped", "clipped_u0_1", 1.0),
+                          ("clipped", "clipped_u0_0.8", 0.8), ("strong", "strong_gamma3", 1.0)):
+        got = ctx.force_eval(ctx.make_force(kind, g["beta"], u0, 3.0), np.array(g["u"]))
+        np.testing.assert_allclose(got, g[key], rtol=1e-14, atol=0)
+        got32 = ctx.force_eval(ctx.make_force(kind, g["beta"], u0, 3.0), np.array(g["u"], dtype=np.float32))
+        assert got32.dtype == np.float32
+        np.testing.assert_allclose(got32, g[key], rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("D", [2, 3])
+def test_spacings_match_oracle(ctx, oracle, dt, D):
+    rng = np.random.default_rng(6)
+    bnd = rng.random((3000, D)); bnd[:, 0] = 0
+    q = (rng.random((20000, D)) * 3 - 1).astype(dt)                  # queries also far outside the boundary set's box
+    for kind, a, b, c in (("constant", 0.1, 0, 0), ("loglike", 0.1, 1.5, 0), ("boundary_layer", 0.01, 0.04, 0.2)):
+        sp, k1 = ctx.make_spacing(kind, a, b, c, bnd.astype(dt) if kind != "constant" else None)
+        osp, k2 = oracle.make_spacing(kind, a, b, c, bnd.astype(dt) if kind != "constant" else None)
+        x, y = ctx.spacing_eval(sp, q), oracle.spacing_eval(osp, q)
+        if kind == "boundary_layer":                                 # exp(): CUDA and glibc differ in the last ulp
+            np.testing.assert_allclose(x, y, rtol=4e-7 if dt == np.float32 else 1e-15)
+        else:
+            assert np.array_equal(x, y), kind
+
+
+# ----------------------------------------------------------------- repel
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("skind", ["constant", "boundary_layer", "loglike"])
+def test_repel_10_iterations_within_tolerance(ctx, oracle, dt, D, skind):
+    rng = np.random.default_rng(7)
+    N, nf = 6000, 800
+    snap = rng.random((N, D)).astype(dt)
+    h = N ** (-1.0 / D)
+    args = {"constant": ("constant", h, 0, 0, None), "boundary_layer": ("boundary_layer", 0.7 * h, 1.3 * h, 0.2, snap[:nf]),
+            "loglike": ("loglike", 2 * h, 1.5, 0, snap[:nf])}[skind]
+    sp, k1 = ctx.make_spacing(*args)
+    osp, k2 = oracle.make_spacing(*args)
+    smin = float(oracle.spacing_eval(osp, snap).min())
+    kw = dict(k=21, max_iters=10, tol=0.0, stall_after=0, alpha_lo=smin / 2000, alpha_max=smin / 20, trace=True)
+    out, conv, res, tr = ctx.repel(snap, nf, sp, ctx.make_force("clipped", 0.2), **kw)
+    oout, oconv, ores, otr = oracle.repel(snap, nf, osp, oracle.make_force("clipped", 0.2), **kw)
+    assert res["iters"] == ores["iters"] == 10 and res["stop_reason"] == "max_iters"
+    assert np.array_equal(out[:nf], snap[:nf])                       # the wall is untouched
+    assert np.abs(out - oout).max() <= TOL[dt] * smin
+    np.testing.assert_allclose(conv, oconv, rtol=1e-5 if dt == np.float32 else 1e-12)
+    assert [(t["idx_a"], t["idx_b"]) for t in tr] == [(t["idx_a"], t["idx_b"]) for t in otr]
+    if skind == "constant":
+        assert np.array_equal(out, oout) and np.array_equal(conv, oconv)   # same ops, same order
+
+
+@pytest.mark.parametrize("kind", ["inverse", "equilibrium", "clipped", "strong"])
+def test_repel_force_models(ctx, oracle, kind):
+    rng = np.random.default_rng(8)
+    snap = rng.random((3000, 3))
+    h = 3000 ** (-1 / 3)
+    sp, _ = ctx.make_spacing("constant", h)
+    osp, _ = oracle.make_spacing("constant", h)
+    kw = dict(max_iters=5, tol=0.0, stall_after=0, alpha_lo=h / 2000, alpha_max=h / 20)
+    out = ctx.repel(snap, 300, sp, ctx.make_force(kind, 0.2, 1.0, 3.0), **kw)[0]
+    oout = oracle.repel(snap, 300, osp, oracle.make_force(kind, 0.2, 1.0, 3.0), **kw)[0]
+    assert np.abs(out - oout).max() <= 1e-6 * h
+
+
+@pytest.mark.parametrize("kw", [dict(stall_after=1, tol=1e-12, max_iters=600), dict(cv_target=10.0, tol=1e-12, max_iters=50, stall_after=0),
+                                dict(tol=1e6, max_iters=50, stall_after=0), dict(rebuild_every=3, max_iters=12, tol=0.0, stall_after=0),
+                                dict(k=40, max_iters=4, tol=0.0, stall_after=0), dict(k=5000, max_iters=2, tol=0.0, stall_after=0)])
+def test_repel_stop_logic_and_options(ctx, oracle, pkg, kw):
+    rng = np.random.default_rng(9)
+    n = 100 if kw.get("k", 21) > 128 else 4000                       # k > N: kk = min(k, N) (src/repel.jl:208)
+    snap = rng.random((n, 3))
+    h = n ** (-1 / 3)
+    sp, _ = ctx.make_spacing("constant", h)
+    osp, _ = oracle.make_spacing("constant", h)
+    a = dict(alpha_lo=h / 2000, alpha_max=h / 20)
+    out, conv, res, _ = ctx.repel(snap, n // 8, sp, ctx.make_force("clipped", 0.2), **a, **kw)
+    oout, oconv, ores, _ = oracle.repel(snap, n // 8, osp, oracle.make_force("clipped", 0.2), **a, **kw)
+    assert (res["iters"], res["stop_reason"]) == (ores["iters"], ores["stop_reason"])
+    assert np.abs(out - oout).max() <= 1e-6 * h
+    if "cv_target" in kw:
+        assert res["iters"] == 1 and np.array_equal(out, snap)       # pre-sweep configuration (test/repel.jl:281-289)
+
+
+def test_repel_rejects_what_cannot_cross_the_abi(ctx, pkg):
+    snap = np.random.default_rng(10).random((500, 3))
+    sp, _ = ctx.make_spacing("constant", 0.1)
+    f = ctx.make_force("clipped", 0.2)
+    with pytest.raises(pkg.WtpArgumentError):
+        ctx.repel(snap, 50, sp, f, rebuild_every=0, alpha_lo=1e-4, alpha_max=1e-2)
+    with pytest.raises(pkg.WtpError):
+        ctx.repel(snap, 50, sp, f, kick_after=5, alpha_lo=1e-4, alpha_max=1e-2)           # randn on the device: unsupported
+    bad = pkg._lib.Force(9, 0.2, 1.0, 3.0)
+    with pytest.raises(pkg.WtpError):
+        ctx.repel(snap, 50, sp, bad, alpha_lo=1e-4, alpha_max=1e-2)
+
+
+def test_converged_metrics_agree(ctx, oracle):
+    """North star: after full convergence the metrics agree within 1 %."""
+    rng = np.random.default_rng(11)
+    snap = rng.random((3000, 3))
+    h = 3000 ** (-1 / 3)
+    sp, _ = ctx.make_spacing("constant", h)
+    osp, _ = oracle.make_spacing("constant", h)
+    kw = dict(max_iters=400, tol=1e-12, stall_after=1, alpha_lo=h / 2000, alpha_max=h / 20)
+    out, _, res, _ = ctx.repel(snap, 400, sp, ctx.make_force("clipped", 0.2), **kw)
+    oout, _, ores, _ = oracle.repel(snap, 400, osp, oracle.make_force("clipped", 0.2), **kw)
+    assert res["stop_reason"] == ores["stop_reason"] and abs(res["iters"] - ores["iters"]) <= 1
+    m, om = ctx.metrics(out, 20), oracle.metrics(oout, 20)
+    for key in om:
+        assert abs(m[key] - om[key]) <= 0.01 * abs(om[key]), key
+    m2 = oracle.metrics(out, 20)                                     # device metrics kernel vs oracle on the same cloud
+    for key in m2:
+        assert abs(m[key] - m2[key]) <= 1e-9 * abs(m2[key]), key
+
+
+# -------------------------------------------------- reference-facing layer
+def test_set_topology_api(ctx, pkg, oracle):
+    rng = np.random.default_rng(12)
+    pts = rng.random((20, 3))
+    cloud = pkg.PointCloud(pkg.PointBoundary(pts))
+    cloud = pkg.set_topology(cloud, pkg.KNNTopology, 5, ctx=ctx)     # test/topology.jl:12-41
+    assert pkg.hastopology(cloud) and isinstance(pkg.topology(cloud), pkg.KNNTopology) and pkg.topology(cloud).k == 5
+    nb = pkg.neighbors(cloud)
+    assert len(nb) == 20 and all(len(r) == 5 for r in nb)
+    assert all(i not in pkg.neighbors(cloud, i) for i in range(1, 21))
+    pkg.rebuild_topology_(cloud, ctx=ctx)                            # test/topology.jl:68-84
+    assert pkg.topology(cloud).k == 5 and len(pkg.neighbors(cloud, 1)) == 5
+    grid = np.array([[i * 0.1, j * 0.1] for i in range(5) for j in range(5)])
+    c2 = pkg.set_topology(pkg.PointCloud(grid), pkg.RadiusTopology, 0.15, ctx=ctx)   # test/topology.jl:43-66
+    assert pkg.topology(c2).radius == 0.15 and all(i not in pkg.neighbors(c2, i) for i in range(1, 26))
+    c3 = pkg.set_topology(pkg.PointCloud(grid), pkg.RadiusTopology, lambda p: 0.15, ctx=ctx)   # radius as f(points), src/topology.jl:100
+    assert [r.tolist() for r in pkg.neighbors(c3)] == [r.tolist() for r in pkg.neighbors(c2)]
+    vol = pkg.set_topology(pkg.PointVolume(pts), pkg.KNNTopology, 3, ctx=ctx)        # volume-level (test/topology.jl:165+)
+    assert np.array_equal(pkg.neighbors(vol).table, oracle.knn(pts, 3))
+
+
+def test_repel_api(ctx, pkg, oracle):
+    rng = np.random.default_rng(13)
+    bnd, vol = rng.random((300, 3)).astype(np.float32), rng.random((2000, 3)).astype(np.float32)
+    cloud = pkg.PointCloud(bnd, vol)
+    sp = pkg.ConstantSpacing(np.float32(0.08))
+    conv, trace = [], []
+    out = pkg.repel(cloud, sp, beta=np.float32(0.2), max_iters=3, convergence=conv, trace=trace, ctx=ctx)   # test/float32_pipeline.jl:44
+    assert pkg.points(out).dtype == np.float32 and len(conv) == 3 and len(trace) == 3
+    assert isinstance(pkg.topology(out), pkg.NoTopology) and len(out) == len(cloud)
+    assert all(np.isfinite(conv)) and all(c >= 0 for c in conv)
+    assert trace[0]["idx_a"] < trace[0]["idx_b"]
+    c2 = pkg.repel(cloud, sp, max_iters=100, tol=1.0e6, ctx=ctx)      # test/repel.jl:8-11
+    assert c2.repel_result["iters"] == 1
+
+
+# ------------------------------------------------------- BASELINE sizes
+def _brute_rows(pts, qi, k):
+    """Canonical (d2, index) brute force for a few queries in the input precision (no FMA in numpy)."""
+    out = np.empty((len(qi), k), dtype=np.int64)
+    for a, i in enumerate(qi):
+        d = pts - pts[i]
+        d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
+        if pts.shape[1] == 3:
+            d2 = d2 + d[:, 2] * d[:, 2]
+        cand = np.argpartition(d2, k + 8)[:k + 9]
+        order = sorted(cand.tolist(), key=lambda j: (d2[j], j))
+        out[a] = np.array(order[1:k + 1]) + 1
+    return out
+
+
+def test_knn_full_size_properties(ctx):
+    """BASELINE sizes (1 M and 10 M, k = 21): sampled brute-force agreement, self exclusion,
+    ascending distances, and symmetry of the nearest-neighbour relation's distances."""
+    rng = np.random.Generator(np.random.Philox(key=0x57545031))
+    for n in (1_000_000, 10_000_000):
+        pts = rng.random((n, 3)).astype(np.float32)
+        idx, dist = ctx.knn(pts, 21, dists=True)
+        qi = rng.integers(0, n, 64)
+        assert np.array_equal(idx[qi], _brute_rows(pts, qi, 21))
+        assert (np.diff(dist, axis=1) >= 0).all()
+        assert (idx != np.arange(1, n + 1)[:, None]).all() and idx.min() >= 1 and idx.max() <= n
+        d1 = np.sqrt(((pts - pts[idx[:, 0] - 1]) ** 2).sum(1, dtype=np.float64))
+        np.testing.assert_allclose(dist[:, 0], d1, rtol=1e-5)
+        del idx, dist
+
+
+def test_radius_full_size_properties(ctx):
+    """Config #4 shape (2-D, CSR): 2 M points, r = 2.5 h; sampled brute force + symmetry of the graph."""
+    rng = np.random.Generator(np.random.Philox(key=0x57545034))
+    n = 2_000_000
+    pts = rng.random((n, 2))
+    h = n ** -0.5
+    off, ind = ctx.radius(pts, 2.5 * h)
+    assert off[0] == 0 and (np.diff(off) >= 0).all() and off[-1] == ind.size
+    for i in rng.integers(0, n, 32):
+        d = pts - pts[i]
+        d2 = d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]
+        want = np.flatnonzero(d2 <= (2.5 * h) * (2.5 * h))
+        assert ind[off[i]:off[i + 1]].tolist() == [j + 1 for j in want.tolist() if j != i]
+    src = np.repeat(np.arange(1, n + 1), np.diff(off))               # an undirected graph: edge count is symmetric
+    assert np.array_equal(np.bincount(src, minlength=n + 1), np.bincount(ind, minlength=n + 1))
+
+
+def test_repel_large_invariants(ctx):
+    """2 M points (config #3 size), 5 iterations: wall untouched, conv finite and decreasing overall,
+    closest-pair distance does not collapse, displacement capped at one spacing per sweep."""
+    rng = np.random.Generator(np.random.Philox(key=0x57545033))
+    n, nf = 2_000_000, 100_000
+    snap = rng.random((n, 3)).astype(np.float32)
+    h = np.float32(n ** (-1 / 3))
+    sp, _ = ctx.make_spacing("constant", h)
+    out, conv, res, _ = ctx.repel(snap, nf, sp, ctx.make_force("clipped", 0.2), max_iters=5, tol=0.0, stall_after=0,
+                                  alpha_lo=h / 2000, alpha_max=h / 20)
+    assert res["iters"] == 5 and np.isfinite(conv).all() and (conv >= 0).all() and conv[-1] < conv[0]
+    assert np.array_equal(out[:nf], snap[:nf])
+    assert np.sqrt(((out - snap) ** 2).sum(1)).max() <= 5 * h * 1.0001

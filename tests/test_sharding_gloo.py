@@ -1,0 +1,59 @@
+"""CPU, world_size 2, gloo: the N>1 host logic. Queries shard by contiguous range with the
+point set replicated (no collective); a Jacobi repel sweep shards the movable points the same
+way and all-gathers the moved positions each iteration. The per-rank compute here is the CPU
+oracle standing in for the device kernels: what is tested is the sharding/gather logic."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    pkg, oracle = ge.load_package(), ge.load_oracle()
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(3)
+    pts = rng.random((4001, 3))
+    # --- k-NN: every rank answers its own contiguous rows; concatenation equals the full answer
+    b, e = pkg.shard_range(len(pts), rank, world)
+    mine = oracle.knn(pts, 9, threads=1)[b:e]
+    parts = [None] * world
+    dist.all_gather_object(parts, (b, e, mine))
+    full = np.concatenate([p[2] for p in sorted(parts, key=lambda t: t[0])])
+    ok_knn = np.array_equal(full, oracle.knn(pts, 9, threads=1))
+    # --- repel: owned movable range per rank, all-gather of moved positions per iteration
+    n_fixed, iters = 401, 4
+    h = len(pts) ** (-1 / 3)
+    sp, _ = oracle.make_spacing("constant", h)
+    f = oracle.make_force("clipped", 0.2)
+    kw = dict(alpha_lo=h / 2000, alpha_max=h / 20, tol=0.0, stall_after=0, threads=1)
+    snap = pts.copy()
+    n_move = len(pts) - n_fixed
+    mb, me = pkg.shard_range(n_move, rank, world)
+    convs = []
+    for _ in range(iters):
+        new, conv, _, _ = oracle.repel(snap, n_fixed, sp, f, max_iters=1, **kw)
+        owned = torch.from_numpy(new[n_fixed + mb:n_fixed + me].copy())
+        sizes = [pkg.shard_range(n_move, r, world) for r in range(world)]
+        bufs = [torch.empty((s[1] - s[0], 3), dtype=torch.float64) for s in sizes]
+        dist.all_gather(bufs, owned)
+        snap[n_fixed:] = torch.cat(bufs).numpy()
+        convs.append(conv[0])
+    ref, rconv, _, _ = oracle.repel(pts, n_fixed, sp, f, max_iters=iters, **kw)
+    ok_repel = np.array_equal(snap, ref)
+    ret[rank] = (ok_knn, ok_repel)
+    dist.destroy_process_group()
+
+
+def test_sharded_knn_and_repel_world2():
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world, 29611, ret), nprocs=world, join=True)
+    assert all(ret[r] == (True, True) for r in range(world)), dict(ret)
