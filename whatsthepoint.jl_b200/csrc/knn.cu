@@ -13,8 +13,12 @@ namespace wtp {
 
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_WARPS = KNN_THREADS / 32;
-constexpr int KNN_QPW = 4;                        // queries per warp
-constexpr int KNN_QPB = KNN_WARPS * KNN_QPW;      // 32 consecutive sorted queries per CTA
+constexpr int KNN_QPW = 8;                        // consecutive sorted queries per warp (tile reuse within a cell)
+constexpr int KNN_QPB = KNN_WARPS * KNN_QPW;      // 64 consecutive sorted queries per CTA
+constexpr int KNN_TILE_CAP = 288;                 // records per warp tile: 3^3 cells x ~8 points + 4.9 sigma
+
+template <class T, int KPL>
+__host__ __device__ constexpr int knn_tile_cap() { return KPL == 1 ? KNN_TILE_CAP : 0; }   // long lists (K > 32) use the general path
 
 template <class T, int D, int KPL>
 __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted,
@@ -22,28 +26,46 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const Grid<T> g, const
                                                           const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t q_begin,
                                                           int K1, int drop, int64_t* __restrict__ out_idx,
                                                           T* __restrict__ out_dist, unsigned long long* __restrict__ expanded) {
+    constexpr int CAP = knn_tile_cap<T, KPL>();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t s_bar[KNN_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpKnn<T, D, KPL> s(g, sorted, cell_start);
+    P4<T>* tile = reinterpret_cast<P4<T>*>(smem_raw) + (size_t)warp * CAP;
+    WarpKnn<T, D, KPL, CAP> s(g, sorted, cell_start, tile, &s_bar[warp], lane);
     const int k_out = K1 - drop;
+    const uint32_t q0 = (blockIdx.x * KNN_WARPS + warp) * KNN_QPW;
 #pragma unroll 1
     for (int it = 0; it < KNN_QPW; ++it) {
-        // at any time the CTA's 8 warps work on 8 neighbouring sorted queries (same cells -> L1 hits)
-        const uint32_t qi = blockIdx.x * KNN_QPB + it * KNN_WARPS + warp;
+        const uint32_t qi = q0 + it;
         if (qi >= nq) break;
         const uint32_t j = qlist ? qlist[qi] : qi;
         const P4<T> q = load_p4<T>(sorted + j);
-        const int rings = s.run(q.x, q.y, q.z, K1, lane);
+        const int rings = s.run(q.x, q.y, q.z, K1);
         if (rings > 1 && lane == 0 && expanded) atomicAdd(expanded, 1ULL);
         const int64_t row = (int64_t)(idx_of(q) - q_begin) * k_out;
 #pragma unroll
         for (int e = 0; e < KPL; ++e) {
             const int r = e * 32 + lane;
             if (r >= drop && r < K1) {
-                out_idx[row + r - drop] = (int64_t)s.list.idx[e] + 1;
-                if (out_dist) out_dist[row + r - drop] = sqrt(s.list.d2[e]);
+                out_idx[row + r - drop] = (int64_t)s.list.e[e].idx() + 1;
+                if (out_dist) out_dist[row + r - drop] = sqrt(s.list.e[e].d2());
             }
         }
     }
+}
+
+template <class T, int D, int KPL>
+static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, const P4<T>* sorted, const uint32_t* cs,
+                           const uint32_t* d_qlist, int64_t nq, int64_t q_begin, int K1, int drop, int64_t* d_out_idx,
+                           T* d_out_dist, unsigned long long* d_exp) {
+    constexpr size_t smem = (size_t)knn_tile_cap<T, KPL>() * sizeof(P4<T>) * KNN_WARPS;
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        WTP_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<T, D, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    knn_kernel<T, D, KPL><<<nblocks, KNN_THREADS, smem, ctx->stream>>>(g, sorted, cs, d_qlist, (uint32_t)nq, (uint32_t)q_begin,
+                                                                       K1, drop, d_out_idx, d_out_dist, d_exp);
 }
 
 template <class T, int D>
@@ -52,14 +74,9 @@ static void launch_knn(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, i
     const unsigned nblocks = (unsigned)((nq + KNN_QPB - 1) / KNN_QPB);
     const P4<T>* sorted = ib.sorted.get<P4<T>>();
     const uint32_t* cs = ib.cell_start.get<uint32_t>();
-#define GO(KPL)                                                                                                     \
-    knn_kernel<T, D, KPL><<<nblocks, KNN_THREADS, 0, ctx->stream>>>(g, sorted, cs, d_qlist, (uint32_t)nq,           \
-                                                                    (uint32_t)q_begin, K1, drop, d_out_idx,          \
-                                                                    d_out_dist, d_exp)
-    if (K1 <= 32) GO(1);
-    else if (K1 <= 64) GO(2);
-    else GO(4);
-#undef GO
+    if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, d_out_dist, d_exp);
+    else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, d_out_dist, d_exp);
+    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, d_out_dist, d_exp);
     LAUNCH_CHECK(ctx);
 }
 

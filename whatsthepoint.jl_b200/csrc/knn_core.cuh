@@ -1,12 +1,17 @@
 // knn_core.cuh — the warp-per-query exact k-NN search on the uniform grid.
 //
-// One warp answers one query. The K best candidates live in registers, distributed
-// over the warp as a sorted list (rank = row*32 + lane, KPL rows per lane) ordered by
-// the canonical key (d2, original index). The warp sweeps the 3^D block of cells around
-// the query row by row (cells of one x-row are contiguous in the sorted array, so a row
-// is one coalesced run of 16/32-byte records), prunes rows and end cells whose distance
-// lower bound already exceeds the current K-th best, and keeps expanding ring by ring
-// until the K-th best is provably inside the swept block.
+// One warp answers a run of consecutive sorted queries. For the cell of the current query
+// the warp stages the 3^D block of neighbouring cells into its private shared-memory
+// tile with TMA bulk copies (cp.async.bulk + mbarrier; the cells of one x-row are
+// contiguous in the sorted array, so the block is <= 9 runs of 16/32-byte records, and
+// every run is 16-byte aligned). Queries falling in the same cell reuse the tile. Each
+// query sweeps the tile with one LDS.128 per candidate and keeps the K best in registers,
+// distributed over the warp as a sorted list (rank = row*32 + lane) of canonical keys
+// (d2, original index). f32 keys are packed into one 64-bit integer so a comparison is a
+// single integer compare. After the sweep the K-th best is checked against the distance
+// to the block's shell; only if it is not provably inside does the warp fall back to the
+// general path, which walks further rings of cells straight from global memory with
+// row/cell pruning. Blocks too large for the tile use the general path from ring 1.
 //
 // d2 = ((dx*dx + dy*dy) + dz*dz) in T with explicit round-to-nearest mul/add (never
 // contracted into FMA), the arithmetic the CPU oracle and the reference's KD-tree use.
@@ -37,11 +42,6 @@ __device__ __forceinline__ T dist2_rn(T qx, T qy, T qz, T px, T py, T pz) {
 }
 
 template <class T>
-__device__ __forceinline__ bool key_less(T ad, uint32_t ai, T bd, uint32_t bi) {
-    return ad < bd || (ad == bd && ai < bi);
-}
-
-template <class T>
 __device__ __forceinline__ P4<T> load_p4(const P4<T>* p);
 template <>
 __device__ __forceinline__ P4<float> load_p4<float>(const P4<float>* p) {
@@ -54,90 +54,157 @@ __device__ __forceinline__ P4<double> load_p4<double>(const P4<double>* p) {
     double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
     P4<double> r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y; return r;
 }
+// shared-memory tile reads (LDS.128)
+__device__ __forceinline__ P4<float> lds_p4(const P4<float>* p) {
+    float4 v = *reinterpret_cast<const float4*>(p);
+    P4<float> r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+}
+__device__ __forceinline__ P4<double> lds_p4(const P4<double>* p) {
+    double2 a = *reinterpret_cast<const double2*>(p);
+    double2 b = *(reinterpret_cast<const double2*>(p) + 1);
+    P4<double> r; r.x = a.x; r.y = a.y; r.z = b.x; r.w = b.y; return r;
+}
+
+// --------------------------------------------------------------- canonical keys
+// Key<T>: total order (d2, idx). f32: one u64 = (bits(d2) << 32) | idx (d2 >= 0, so the
+// IEEE bit pattern is monotone). f64: (double, u32) pair.
+template <class T> struct Key;
+template <> struct Key<float> {
+    unsigned long long v;
+    static __device__ __forceinline__ Key make(float d2, uint32_t idx) { Key k; k.v = ((unsigned long long)__float_as_uint(d2) << 32) | idx; return k; }
+    static __device__ __forceinline__ Key sentinel() { Key k; k.v = 0x7f800000ffffffffULL; return k; }   // (+inf, 0xffffffff)
+    __device__ __forceinline__ float d2() const { return __uint_as_float((uint32_t)(v >> 32)); }
+    __device__ __forceinline__ uint32_t idx() const { return (uint32_t)v; }
+    __device__ __forceinline__ bool less(const Key& o) const { return v < o.v; }
+    __device__ __forceinline__ Key shfl(int src) const { Key k; k.v = __shfl_sync(FULL, v, src); return k; }
+    __device__ __forceinline__ Key shfl_up1() const { Key k; k.v = __shfl_up_sync(FULL, v, 1); return k; }
+    __device__ __forceinline__ Key shfl_xor(int m) const { Key k; k.v = __shfl_xor_sync(FULL, v, m); return k; }
+};
+template <> struct Key<double> {
+    double d; uint32_t i;
+    static __device__ __forceinline__ Key make(double d2, uint32_t idx) { Key k; k.d = d2; k.i = idx; return k; }
+    static __device__ __forceinline__ Key sentinel() { Key k; k.d = t_inf<double>(); k.i = 0xffffffffu; return k; }
+    __device__ __forceinline__ double d2() const { return d; }
+    __device__ __forceinline__ uint32_t idx() const { return i; }
+    __device__ __forceinline__ bool less(const Key& o) const { return d < o.d || (d == o.d && i < o.i); }
+    __device__ __forceinline__ Key shfl(int src) const { Key k; k.d = __shfl_sync(FULL, d, src); k.i = __shfl_sync(FULL, i, src); return k; }
+    __device__ __forceinline__ Key shfl_up1() const { Key k; k.d = __shfl_up_sync(FULL, d, 1); k.i = __shfl_up_sync(FULL, i, 1); return k; }
+    __device__ __forceinline__ Key shfl_xor(int m) const { Key k; k.d = __shfl_xor_sync(FULL, d, m); k.i = __shfl_xor_sync(FULL, i, m); return k; }
+};
 
 // ------------------------------------------------------------ warp top-K list
 template <class T, int KPL>
 struct WarpList {
-    T d2[KPL];
-    uint32_t idx[KPL];
-    T thr_d;          // key at rank K-1 (warp-uniform)
-    uint32_t thr_i;
+    Key<T> e[KPL];   // rank = row*32 + lane, ascending
+    Key<T> thr;      // key at rank K-1 (warp-uniform)
     int K;
 
     __device__ __forceinline__ void init(int K_) {
         K = K_;
 #pragma unroll
-        for (int e = 0; e < KPL; ++e) { d2[e] = t_inf<T>(); idx[e] = 0xffffffffu; }
-        thr_d = t_inf<T>(); thr_i = 0xffffffffu;
+        for (int r = 0; r < KPL; ++r) e[r] = Key<T>::sentinel();
+        thr = Key<T>::sentinel();
     }
     __device__ __forceinline__ void refresh_threshold() {
         const int e_thr = (K - 1) >> 5, l_thr = (K - 1) & 31;
-        T td = d2[0]; uint32_t ti = idx[0];
+        Key<T> t = e[0];
 #pragma unroll
-        for (int e = 1; e < KPL; ++e) if (e == e_thr) { td = d2[e]; ti = idx[e]; }
-        thr_d = __shfl_sync(FULL, td, l_thr);
-        thr_i = __shfl_sync(FULL, ti, l_thr);
+        for (int r = 1; r < KPL; ++r) if (r == e_thr) t = e[r];
+        thr = t.shfl(l_thr);
     }
-    // insert one warp-uniform candidate into the sorted list (drops the old last entry)
-    __device__ __forceinline__ void insert(T cd, uint32_t ci, int lane) {
-        T carry_d = (T)0; uint32_t carry_i = 0;
+    // insert one warp-uniform candidate into the sorted list (the old last entry drops off)
+    __device__ __forceinline__ void insert(const Key<T>& c, int lane) {
+        Key<T> carry = c;
 #pragma unroll
-        for (int e = 0; e < KPL; ++e) {
-            T up_d = __shfl_up_sync(FULL, d2[e], 1);
-            uint32_t up_i = __shfl_up_sync(FULL, idx[e], 1);
-            T last_d = (T)0; uint32_t last_i = 0;
-            if (e + 1 < KPL) { last_d = __shfl_sync(FULL, d2[e], 31); last_i = __shfl_sync(FULL, idx[e], 31); }
-            if (lane == 0) { up_d = carry_d; up_i = carry_i; }
-            const bool lt = key_less(cd, ci, d2[e], idx[e]);
-            const bool lt_prev = (e == 0 && lane == 0) ? false : key_less(cd, ci, up_d, up_i);
-            if (lt) { d2[e] = lt_prev ? up_d : cd; idx[e] = lt_prev ? up_i : ci; }
-            carry_d = last_d; carry_i = last_i;
+        for (int r = 0; r < KPL; ++r) {
+            Key<T> up = e[r].shfl_up1();
+            Key<T> last = c;
+            if (r + 1 < KPL) last = e[r].shfl(31);
+            if (lane == 0) up = carry;
+            const bool lt = c.less(e[r]);
+            const bool lt_prev = (r == 0 && lane == 0) ? false : c.less(up);
+            if (lt) e[r] = lt_prev ? up : c;
+            carry = last;
         }
     }
-    // offer one candidate per lane (cd = +inf on idle lanes)
-    __device__ __forceinline__ void offer(T cd, uint32_t ci, int lane) {
-        unsigned m = __ballot_sync(FULL, key_less(cd, ci, thr_d, thr_i));
+    // offer one candidate per lane (sentinel on idle lanes)
+    __device__ __forceinline__ void offer(const Key<T>& c, int lane) {
+        unsigned m = __ballot_sync(FULL, c.less(thr));
         while (m) {
             const int b = __ffs(m) - 1;
-            const T bd = __shfl_sync(FULL, cd, b);
-            const uint32_t bi = __shfl_sync(FULL, ci, b);
-            insert(bd, bi, lane);
+            insert(c.shfl(b), lane);
             refresh_threshold();
-            m = __ballot_sync(FULL, key_less(cd, ci, thr_d, thr_i)) & ~((2u << b) - 1u);
+            m = __ballot_sync(FULL, c.less(thr)) & ~((2u << b) - 1u);
         }
     }
     // first batch into an empty list: bitonic sort of the 32 candidates straight into row 0
-    __device__ __forceinline__ void seed(T cd, uint32_t ci, int lane) {
+    __device__ __forceinline__ void seed(Key<T> c, int lane) {
 #pragma unroll
         for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
             for (int j = k >> 1; j > 0; j >>= 1) {
-                const T od = __shfl_xor_sync(FULL, cd, j);
-                const uint32_t oi = __shfl_xor_sync(FULL, ci, j);
+                const Key<T> o = c.shfl_xor(j);
                 const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
-                const bool other_less = key_less(od, oi, cd, ci);
-                const bool mine_less = key_less(cd, ci, od, oi);
-                const bool take = keep_min ? other_less : mine_less;
-                if (take) { cd = od; ci = oi; }
+                const bool take = keep_min ? o.less(c) : c.less(o);
+                if (take) c = o;
             }
         }
-        d2[0] = cd; idx[0] = ci;
+        e[0] = c;
         refresh_threshold();
     }
 };
 
+// ------------------------------------------------------------------ TMA helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
+// row offsets of the 3^D block, centre row first, then face rows, then corner rows
+__device__ __forceinline__ int row_dy(int t) { return (int)((0x22161u >> (2 * t)) & 3u) - 1; }   // 0,-1,+1,0,0,-1,+1,-1,+1
+__device__ __forceinline__ int row_dz(int t) { return (int)((0x28215u >> (2 * t)) & 3u) - 1; }   // 0,0,0,-1,+1,-1,-1,+1,+1
+
 // ------------------------------------------------------------- the search
-template <class T, int D, int KPL>
+// TILE_CAP: points per warp tile (0 disables staging: general path only).
+template <class T, int D, int KPL, int TILE_CAP>
 struct WarpKnn {
+    static constexpr int NROWS = D == 3 ? 9 : 3;
     const Grid<T>& g;
     const P4<T>* __restrict__ sorted;
     const uint32_t* __restrict__ cell_start;
+    P4<T>* tile;        // this warp's shared-memory tile (TILE_CAP records)
+    uint64_t* bar;      // this warp's mbarrier
+    uint32_t phase;
+    int lane;
+    int scx, scy, scz;  // staged cell (-1: none)
+    uint32_t tile_n;    // staged candidates; 0xffffffff: block does not fit the tile
     T qx, qy, qz;
-    int cx, cy, cz, lane;
+    int cx, cy, cz;
     bool seeded;
     WarpList<T, KPL> list;
 
-    __device__ __forceinline__ WarpKnn(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs) : g(g_), sorted(s), cell_start(cs) {}
+    __device__ __forceinline__ WarpKnn(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs, P4<T>* tile_, uint64_t* bar_, int lane_)
+        : g(g_), sorted(s), cell_start(cs), tile(tile_), bar(bar_), phase(0), lane(lane_), scx(-1), scy(-1), scz(-1), tile_n(0) {
+        if (TILE_CAP > 0) {
+            if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+            __syncwarp();
+        }
+    }
 
     __device__ __forceinline__ T face(int d, int j) const { return add_rn(g.lo[d], mul_rn((T)j, g.c)); }
     // conservative gap from the query to the slab of cells at offset o (o != 0) along d
@@ -152,41 +219,88 @@ struct WarpKnn {
         if (D == 3) s = add_rn(s, mul_rn(gz, gz));
         return s;
     }
+    __device__ __forceinline__ void consume(bool valid, const P4<T>& p) {
+        Key<T> c = Key<T>::sentinel();
+        if (valid) c = Key<T>::make(dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z), idx_of(p));
+        if (!seeded) { list.seed(c, lane); seeded = true; }
+        else list.offer(c, lane);
+    }
+
+    // ---- staged path ---------------------------------------------------------
+    // Lanes 0..NROWS-1 each resolve one x-row of the block (two cell_start loads in
+    // parallel), a warp scan lays the rows out back to back in the tile, and each of those
+    // lanes issues the bulk copy of its own row; everyone waits on the warp's mbarrier.
+    __device__ __forceinline__ void stage() {
+        uint32_t begin = 0, len = 0;
+        if (lane < NROWS) {
+            const int ry = cy + row_dy(lane), rz = D == 3 ? cz + row_dz(lane) : 0;
+            if (ry >= 0 && ry < g.n[1] && rz >= 0 && rz < g.n[2]) {
+                const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < g.n[0] - 1 ? cx + 1 : g.n[0] - 1;
+                const uint32_t row = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
+                begin = cell_start[row + x0];
+                len = cell_start[row + x1 + 1] - begin;
+            }
+        }
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, NROWS - 1);
+        scx = cx; scy = cy; scz = cz;
+        if (total > (uint32_t)TILE_CAP) { tile_n = 0xffffffffu; return; }
+        tile_n = total;
+        if (total == 0) return;
+        __syncwarp();   // every lane is done reading the previous tile
+        if (lane == 0) mbar_expect_tx(bar, total * (uint32_t)sizeof(P4<T>));
+        __syncwarp();
+        if (len > 0) tma_bulk_g2s(tile + (incl - len), sorted + begin, len * (uint32_t)sizeof(P4<T>), bar);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+    }
+    __device__ __forceinline__ void sweep_tile() {
+        for (uint32_t j0 = 0; j0 < tile_n; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool valid = j < tile_n;
+            P4<T> p;
+            if (valid) p = lds_p4(tile + j);
+            consume(valid, p);
+        }
+    }
+
+    // ---- general path --------------------------------------------------------
     __device__ __forceinline__ void sweep(uint32_t begin, uint32_t end) {
         for (uint32_t j0 = begin; j0 < end; j0 += 32) {
             const uint32_t j = j0 + lane;
-            T cd = t_inf<T>(); uint32_t ci = 0xffffffffu;
-            if (j < end) {
-                const P4<T> p = load_p4<T>(sorted + j);
-                cd = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
-                ci = idx_of(p);
-            }
-            if (!seeded) { list.seed(cd, ci, lane); seeded = true; }
-            else list.offer(cd, ci, lane);
+            const bool valid = j < end;
+            P4<T> p;
+            if (valid) p = load_p4<T>(sorted + j);
+            consume(valid, p);
         }
     }
-    // cells [x0, x1] of row (ry, rz); the caller has clamped and pruned
     __device__ __forceinline__ void sweep_cells(int x0, int x1, int ry, int rz) {
         const uint32_t row = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
         sweep(cell_start[row + x0], cell_start[row + x1 + 1]);
     }
     // Row at offset (dy, dz) of ring R: the whole x-span if the row is on the ring's outer
-    // shell (or R == 1 centre row), else just the two end cells.
+    // shell (or R == 1), else just the two end cells; pruned by distance lower bounds.
     __device__ __forceinline__ void ring_row(int R, int dy, int dz) {
         const int ry = cy + dy, rz = cz + dz;
         if (ry < 0 || ry >= g.n[1] || rz < 0 || rz >= g.n[2]) return;
         const T gy = gap(1, qy, cy, dy), gz = D == 3 ? gap(2, qz, cz, dz) : (T)0;
         const int ady = dy < 0 ? -dy : dy, adz = dz < 0 ? -dz : dz;
         const bool outer = (ady > adz ? ady : adz) == R;
+        const T thr_d = list.thr.d2();
         if (outer || R == 1) {
-            if (lb3((T)0, gy, gz) > list.thr_d) return;
+            if (lb3((T)0, gy, gz) > thr_d) return;
             int x0 = cx - R, x1 = cx + R;
-            if (x0 < 0) x0 = 0; else if (lb3(gap(0, qx, cx, -R), gy, gz) > list.thr_d) ++x0;
-            if (x1 > g.n[0] - 1) x1 = g.n[0] - 1; else if (lb3(gap(0, qx, cx, R), gy, gz) > list.thr_d) --x1;
+            if (x0 < 0) x0 = 0; else if (lb3(gap(0, qx, cx, -R), gy, gz) > thr_d) ++x0;
+            if (x1 > g.n[0] - 1) x1 = g.n[0] - 1; else if (lb3(gap(0, qx, cx, R), gy, gz) > thr_d) --x1;
             if (x0 <= x1) sweep_cells(x0, x1, ry, rz);
         } else {
-            if (cx - R >= 0 && !(lb3(gap(0, qx, cx, -R), gy, gz) > list.thr_d)) sweep_cells(cx - R, cx - R, ry, rz);
-            if (cx + R <= g.n[0] - 1 && !(lb3(gap(0, qx, cx, R), gy, gz) > list.thr_d)) sweep_cells(cx + R, cx + R, ry, rz);
+            if (cx - R >= 0 && !(lb3(gap(0, qx, cx, -R), gy, gz) > thr_d)) sweep_cells(cx - R, cx - R, ry, rz);
+            if (cx + R <= g.n[0] - 1 && !(lb3(gap(0, qx, cx, R), gy, gz) > list.thr.d2())) sweep_cells(cx + R, cx + R, ry, rz);
         }
     }
     // true when every point outside the block of radius R is provably worse than the K-th best
@@ -203,28 +317,36 @@ struct WarpKnn {
         }
         if (!open) return true;            // the block covers the whole grid
         if (!(shell > (T)0)) return false;
-        return list.thr_d < mul_rn(shell, shell);
+        return list.thr.d2() < mul_rn(shell, shell);
     }
-    // Runs the search; returns the number of rings swept (1 = the 3^D block sufficed).
-    __device__ __forceinline__ int run(T x, T y, T z, int K, int lane_) {
-        qx = x; qy = y; qz = z; lane = lane_;
+
+    // Runs the search for one query; returns the number of rings swept (1 = the 3^D block sufficed).
+    __device__ __forceinline__ int run(T x, T y, T z, int K) {
+        qx = x; qy = y; qz = z;
         cx = cell_coord(g, qx, 0);
         cy = cell_coord(g, qy, 1);
         cz = D == 3 ? cell_coord(g, qz, 2) : 0;
         seeded = false;
         list.init(K);
-        // ring 1, centre row first, then face rows, then corner rows
-        ring_row(1, 0, 0);
-        ring_row(1, -1, 0); ring_row(1, 1, 0);
-        if (D == 3) {
-            ring_row(1, 0, -1); ring_row(1, 0, 1);
-            ring_row(1, -1, -1); ring_row(1, 1, -1); ring_row(1, -1, 1); ring_row(1, 1, 1);
+        bool staged = false;
+        if (TILE_CAP > 0) {
+            if (cx != scx || cy != scy || cz != scz) stage();
+            staged = tile_n != 0xffffffffu;
+        }
+        if (staged) {
+            sweep_tile();
+        } else {
+#pragma unroll 1
+            for (int t = 0; t < NROWS; ++t) ring_row(1, row_dy(t), D == 3 ? row_dz(t) : 0);
         }
         int R = 1;
+#pragma unroll 1
         while (!block_is_exact(R)) {
             ++R;
             const int Rz = D == 3 ? R : 0;
+#pragma unroll 1
             for (int dz = -Rz; dz <= Rz; ++dz)
+#pragma unroll 1
                 for (int dy = -R; dy <= R; ++dy) ring_row(R, dy, dz);
         }
         return R;

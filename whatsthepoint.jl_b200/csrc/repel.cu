@@ -103,26 +103,34 @@ struct SweepArgs {
 
 constexpr int SW_THREADS = 256;
 constexpr int SW_WARPS = SW_THREADS / 32;
+constexpr int SW_QPW = 8;                        // consecutive sorted points per warp and work item
+constexpr int SW_TILE_CAP = 288;
+template <int KPL> __host__ __device__ constexpr int sw_tile_cap() { return KPL == 1 ? SW_TILE_CAP : 0; }
 
 template <class T, int D, int KPL>
 __global__ void __launch_bounds__(SW_THREADS) repel_sweep_kernel(const SweepArgs<T> a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int CAP = sw_tile_cap<KPL>();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t s_bar[SW_WARPS];
     __shared__ T s_term[SW_WARPS][32 * KPL][3];
     __shared__ RepelPartial<T> s_part[SW_WARPS];
-    WarpKnn<T, D, KPL> knn(a.g, a.sorted, a.cell_start);
+    P4<T>* tile = reinterpret_cast<P4<T>*>(smem_raw) + (size_t)warp * CAP;
+    WarpKnn<T, D, KPL, CAP> knn(a.g, a.sorted, a.cell_start, tile, &s_bar[warp], lane);
     RepelPartial<T> acc;
     partial_init(acc);
 
-    for (uint32_t chunk = blockIdx.x; (uint64_t)chunk * SW_WARPS < a.nq; chunk += gridDim.x) {
-        const uint32_t qi = chunk * SW_WARPS + warp;
-        if (qi >= a.nq) continue;
+    // work item = SW_QPW consecutive sorted points for one warp; items are dealt round-robin
+    const uint32_t n_items = (a.nq + SW_QPW - 1) / SW_QPW;
+    for (uint32_t item = blockIdx.x * SW_WARPS + warp; item < n_items; item += gridDim.x * SW_WARPS)
+    for (uint32_t qi = item * SW_QPW; qi < min(a.nq, (item + 1) * SW_QPW); ++qi) {
         const uint32_t j = a.qlist ? a.qlist[qi] : qi;
         const uint32_t self = idx_of(load_p4<T>(a.sorted + j));
         if (self < a.n_fixed + a.id_lo || self >= a.n_fixed + a.id_hi) continue;   // fixed wall / other rank's point
         const uint32_t id = self - a.n_fixed;
         const T xi0 = a.P_old[(size_t)id * D + 0], xi1 = a.P_old[(size_t)id * D + 1];
         const T xi2 = D == 3 ? a.P_old[(size_t)id * D + (D - 1)] : (T)0;
-        knn.run(xi0, xi1, xi2, a.kk, lane);                                       // :259
+        knn.run(xi0, xi1, xi2, a.kk);                                             // :259
         const T s = a.s_cur ? a.s_cur[id] : a.s_const;                            // :260
 
         bool found = false;
@@ -130,11 +138,11 @@ __global__ void __launch_bounds__(SW_THREADS) repel_sweep_kernel(const SweepArgs
 #pragma unroll
         for (int e = 0; e < KPL; ++e) {                                           // :270-280
             const int r = e * 32 + lane;
-            const uint32_t nj = knn.list.idx[e];
+            const uint32_t nj = knn.list.e[e].idx();
             const bool valid = r < a.kk && nj != 0xffffffffu && nj != self;       // skip self BY INDEX (:271)
             T t0 = (T)0, t1 = (T)0, t2 = (T)0;
             if (valid) {
-                const T rr = sqrt(knn.list.d2[e]);
+                const T rr = sqrt(knn.list.e[e].d2());
                 if (rr > (T)0) {                                                   // _safe_direction (:358-364)
                     const T f = force_fn<T>(a.force, rr / s);
                     t0 = f * ((xi0 - a.S[(size_t)nj * D + 0]) / rr);
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(SW_THREADS) repel_sweep_kernel(const SweepArgs
             const unsigned m = __ballot_sync(FULL, valid);
             if (!found && m) {                                                     // first non-self hit (:272-275)
                 const int src = __ffs(m) - 1;
-                nn_d2 = __shfl_sync(FULL, knn.list.d2[e], src);
+                nn_d2 = __shfl_sync(FULL, knn.list.e[e].d2(), src);
                 nn_idx = __shfl_sync(FULL, nj, src);
                 found = true;
             }
@@ -217,11 +225,21 @@ __global__ void __launch_bounds__(256) fill_kernel(T* __restrict__ out, int64_t 
     if (i < n) out[i] = v;
 }
 
+template <class T, int D, int KPL>
+static void launch_sweep_kpl(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
+    constexpr size_t smem = (size_t)sw_tile_cap<KPL>() * sizeof(P4<T>) * SW_WARPS;
+    static bool configured = false;
+    if (!configured && smem > 0) {
+        WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_sweep_kernel<T, D, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    repel_sweep_kernel<T, D, KPL><<<nblocks, SW_THREADS, smem, ctx->stream>>>(a);
+}
 template <class T, int D>
 static void launch_sweep(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
-    if (a.kk <= 32) repel_sweep_kernel<T, D, 1><<<nblocks, SW_THREADS, 0, ctx->stream>>>(a);
-    else if (a.kk <= 64) repel_sweep_kernel<T, D, 2><<<nblocks, SW_THREADS, 0, ctx->stream>>>(a);
-    else repel_sweep_kernel<T, D, 4><<<nblocks, SW_THREADS, 0, ctx->stream>>>(a);
+    if (a.kk <= 32) launch_sweep_kpl<T, D, 1>(ctx, a, nblocks);
+    else if (a.kk <= 64) launch_sweep_kpl<T, D, 2>(ctx, a, nblocks);
+    else launch_sweep_kpl<T, D, 4>(ctx, a, nblocks);
     LAUNCH_CHECK(ctx);
 }
 
@@ -269,7 +287,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 
     const int32_t rank = ctx->rank, world = ctx->world;
     const int64_t id_lo = wtp_shard_begin(n_move, rank, world), id_hi = wtp_shard_end(n_move, rank, world);
-    const int nblocks = (int)std::min<int64_t>((n_all + SW_WARPS - 1) / SW_WARPS, (int64_t)kNumSMs * 8);
+    const int nblocks = (int)std::min<int64_t>((n_all + SW_WARPS * SW_QPW - 1) / (SW_WARPS * SW_QPW), (int64_t)kNumSMs * 8);
     RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + 1 + world);
     RepelPartial<T>* d_tot = partials + nblocks;
     RepelPartial<T>* d_all = d_tot + 1;
