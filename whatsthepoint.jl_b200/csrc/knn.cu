@@ -29,9 +29,10 @@ __global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const Grid<T> g, const
     constexpr int CAP = knn_tile_cap<T, KPL>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_bar[KNN_WARPS];
+    __shared__ __align__(16) unsigned char s_buf[KNN_WARPS * 64 * sizeof(Key<T>)];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     P4<T>* tile = reinterpret_cast<P4<T>*>(smem_raw) + (size_t)warp * CAP;
-    WarpKnn<T, D, KPL, CAP> s(g, sorted, cell_start, tile, &s_bar[warp], lane);
+    WarpKnn<T, D, KPL, CAP> s(g, sorted, cell_start, tile, reinterpret_cast<Key<T>*>(s_buf) + warp * 64, &s_bar[warp], lane);
     const int k_out = K1 - drop;
     const uint32_t q0 = (blockIdx.x * KNN_WARPS + warp) * KNN_QPW;
 #pragma unroll 1

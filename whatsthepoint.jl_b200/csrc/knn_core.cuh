@@ -137,19 +137,36 @@ struct WarpList {
             m = __ballot_sync(FULL, c.less(thr)) & ~((2u << b) - 1u);
         }
     }
-    // first batch into an empty list: bitonic sort of the 32 candidates straight into row 0
-    __device__ __forceinline__ void seed(Key<T> c, int lane) {
+    // 32 candidates (one per lane) into row 0 at once: bitonic-sort the batch, keep the 32
+    // smallest of (row 0, batch) with one reversed elementwise min, then a 5-stage bitonic
+    // merge. Cheaper than serial inserts once more than ~6 candidates qualify. KPL == 1 only.
+    __device__ __forceinline__ void merge32(Key<T> c, int lane) {
+        c = sort32(c, lane);
+        const Key<T> rb = c.shfl(31 - lane);
+        if (rb.less(e[0])) e[0] = rb;
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) {
+            const Key<T> o = e[0].shfl_xor(j);
+            const bool keep_min = (lane & j) == 0;
+            if (o.less(e[0]) == keep_min) e[0] = o;
+        }
+        refresh_threshold();
+    }
+    static __device__ __forceinline__ Key<T> sort32(Key<T> c, int lane) {
 #pragma unroll
         for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
             for (int j = k >> 1; j > 0; j >>= 1) {
                 const Key<T> o = c.shfl_xor(j);
                 const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
-                const bool take = keep_min ? o.less(c) : c.less(o);
-                if (take) c = o;
+                if (o.less(c) == keep_min) c = o;   // equal keys: either choice is the same value
             }
         }
-        e[0] = c;
+        return c;
+    }
+    // first batch into an empty list: bitonic sort of the 32 candidates straight into row 0
+    __device__ __forceinline__ void seed(Key<T> c, int lane) {
+        e[0] = sort32(c, lane);
         refresh_threshold();
     }
 };
@@ -188,6 +205,8 @@ struct WarpKnn {
     const P4<T>* __restrict__ sorted;
     const uint32_t* __restrict__ cell_start;
     P4<T>* tile;        // this warp's shared-memory tile (TILE_CAP records)
+    Key<T>* buf;        // this warp's pre-filter buffer (PF_CAP keys)
+    T r0sq;             // pre-filter radius^2 for the staged block (0: disabled)
     uint64_t* bar;      // this warp's mbarrier
     uint32_t phase;
     int lane;
@@ -198,8 +217,9 @@ struct WarpKnn {
     bool seeded;
     WarpList<T, KPL> list;
 
-    __device__ __forceinline__ WarpKnn(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs, P4<T>* tile_, uint64_t* bar_, int lane_)
-        : g(g_), sorted(s), cell_start(cs), tile(tile_), bar(bar_), phase(0), lane(lane_), scx(-1), scy(-1), scz(-1), tile_n(0) {
+    static constexpr int PF_CAP = 64;
+    __device__ __forceinline__ WarpKnn(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs, P4<T>* tile_, Key<T>* buf_, uint64_t* bar_, int lane_)
+        : g(g_), sorted(s), cell_start(cs), tile(tile_), buf(buf_), r0sq((T)0), bar(bar_), phase(0), lane(lane_), scx(-1), scy(-1), scz(-1), tile_n(0) {
         if (TILE_CAP > 0) {
             if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
             __syncwarp();
@@ -258,6 +278,48 @@ struct WarpKnn {
         if (len > 0) tma_bulk_g2s(tile + (incl - len), sorted + begin, len * (uint32_t)sizeof(P4<T>), bar);
         mbar_wait(bar, phase);
         phase ^= 1u;
+    }
+    // Pre-filter radius for the staged block: the local density is tile_n points in the
+    // block, so a ball holding `target` points has r^D = target * V_block / (V_unit_ball * tile_n).
+    // Only a guess — exactness never depends on it (prefilter_tile reports failure).
+    __device__ __forceinline__ void set_prefilter_radius(int K) {
+        const float target = (float)K + 2.5f * sqrtf((float)K) + 1.0f;
+        const float c = (float)g.c;
+        float r2;
+        if (D == 3) { const float r3 = target * 27.0f / (4.18879f * (float)tile_n); r2 = c * c * cbrtf(r3 * r3); }
+        else r2 = c * c * target * 9.0f / (3.14159265f * (float)tile_n);
+        r0sq = (T)r2;
+    }
+    // One pass over the tile: every candidate with d2 <= r0sq goes to the warp's buffer.
+    // If between K and PF_CAP candidates qualify, the K best of the block are among them:
+    // one bitonic sort (plus a merge of the second half) builds the whole list.
+    __device__ __forceinline__ bool prefilter_tile(int K) {
+        uint32_t cnt = 0;
+        for (uint32_t j0 = 0; j0 < tile_n; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            bool q = false;
+            Key<T> c = Key<T>::sentinel();
+            if (j < tile_n) {
+                const P4<T> p = lds_p4(tile + j);
+                const T d = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
+                c = Key<T>::make(d, idx_of(p));
+                q = !(d > r0sq);
+            }
+            const unsigned m = __ballot_sync(FULL, q);
+            const uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
+            if (q && pos < (uint32_t)PF_CAP) buf[pos] = c;
+            cnt += __popc(m);
+        }
+        if (cnt < (uint32_t)K || cnt > (uint32_t)PF_CAP) return false;
+        __syncwarp();
+        list.seed((uint32_t)lane < cnt ? buf[lane] : Key<T>::sentinel(), lane);
+        if (cnt > 32u) {
+            const Key<T> b = (uint32_t)lane + 32u < cnt ? buf[lane + 32] : Key<T>::sentinel();
+            if (cnt > 38u) list.merge32(b, lane); else list.offer(b, lane);
+        }
+        __syncwarp();
+        seeded = true;
+        return true;
     }
     __device__ __forceinline__ void sweep_tile() {
         for (uint32_t j0 = 0; j0 < tile_n; j0 += 32) {
@@ -334,7 +396,12 @@ struct WarpKnn {
             staged = tile_n != 0xffffffffu;
         }
         if (staged) {
-            sweep_tile();
+            if (KPL == 1 && tile_n >= (uint32_t)K) {
+                set_prefilter_radius(K);
+                if (!prefilter_tile(K)) sweep_tile();
+            } else {
+                sweep_tile();
+            }
         } else {
 #pragma unroll 1
             for (int t = 0; t < NROWS; ++t) ring_row(1, row_dy(t), D == 3 ? row_dz(t) : 0);

@@ -115,8 +115,9 @@ __global__ void __launch_bounds__(SW_THREADS) repel_sweep_kernel(const SweepArgs
     __shared__ uint64_t s_bar[SW_WARPS];
     __shared__ T s_term[SW_WARPS][32 * KPL][3];
     __shared__ RepelPartial<T> s_part[SW_WARPS];
+    __shared__ __align__(16) unsigned char s_buf[SW_WARPS * 64 * sizeof(Key<T>)];
     P4<T>* tile = reinterpret_cast<P4<T>*>(smem_raw) + (size_t)warp * CAP;
-    WarpKnn<T, D, KPL, CAP> knn(a.g, a.sorted, a.cell_start, tile, &s_bar[warp], lane);
+    WarpKnn<T, D, KPL, CAP> knn(a.g, a.sorted, a.cell_start, tile, reinterpret_cast<Key<T>*>(s_buf) + warp * 64, &s_bar[warp], lane);
     RepelPartial<T> acc;
     partial_init(acc);
 
