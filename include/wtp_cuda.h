@@ -74,7 +74,8 @@ int32_t wtp_set_stream(wtp_ctx* ctx, void* cuda_stream);
 int32_t wtp_host_register(wtp_ctx* ctx, void* ptr, int64_t bytes);
 int32_t wtp_host_unregister(wtp_ctx* ctx, void* ptr);
 
-/* Tuning knob: target number of points per grid cell (default 8 in 3-D, 6 in 2-D; <=0 restores). */
+/* Tuning knob: target number of points per grid cell (default 0.36*K in 3-D, 0.45*K in 2-D for a
+ * list of K entries, i.e. 8 / 10 at k = 21; <= 0 restores the default). */
 int32_t wtp_set_cell_occupancy(wtp_ctx* ctx, double points_per_cell);
 
 /* Multi-GPU, one process per GPU. The NCCL unique id (128 bytes) is created on one
@@ -99,7 +100,7 @@ typedef struct {
     float ms_sort;       /* radix sort (all passes) */
     float ms_reorder;    /* gather into sorted float4 tiles + cell starts */
     float ms_query;      /* k-NN query / radius count+fill / repel sweep */
-    float ms_scan;       /* exclusive scan (radius CSR) */
+    float ms_scan;       /* exclusive scan (radius CSR); spacing evaluation (repel) */
     float ms_reduce;     /* repel reductions + stop-test scalars */
     float ms_comm;       /* NCCL all-gather (multi-GPU repel) */
     float ms_d2h;        /* host entry points only */

@@ -165,7 +165,7 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     IndexBuffers& ib = ctx->index[0];
     double lo[3], hi[3];
     compute_bbox<T>(ctx, ib, d_pts, N, D, lo, hi);
-    Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy, 0.0);
+    Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy, 0.0, K1);
     int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
     const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
     const uint32_t* qlist = nullptr;

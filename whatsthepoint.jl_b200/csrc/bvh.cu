@@ -144,8 +144,11 @@ template BvhView<float> bvh_view<float>(const BvhBuffers&);
 template BvhView<double> bvh_view<double>(const BvhBuffers&);
 
 // squared distance from q to the nearest boundary point; same d2 arithmetic as the k-NN
+// `hint` (in/out): sorted position of a boundary point to start from (0xffffffff: none). A repel
+// point moves little per iteration, so last iteration's nearest point gives a tight initial bound
+// and the traversal prunes almost everything; the result is exact either way.
 template <class T, int D>
-__device__ __forceinline__ T bvh_nearest_d2(const BvhView<T>& bv, T qx, T qy, T qz) {
+__device__ __forceinline__ T bvh_nearest_d2(const BvhView<T>& bv, T qx, T qy, T qz, uint32_t& hint) {
     auto box_lb = [&](int64_t i) -> T {
         const Box<T> b = bv.boxes[i];
         T gx = qx < b.lo[0] ? sub_rn(b.lo[0], qx) : (qx > b.hi[0] ? sub_rn(qx, b.hi[0]) : (T)0);
@@ -158,6 +161,10 @@ __device__ __forceinline__ T bvh_nearest_d2(const BvhView<T>& bv, T qx, T qy, T 
         return s;  // +inf for empty nodes (lo = +inf)
     };
     T best = t_inf<T>();
+    if (hint != 0xffffffffu) {
+        const P4<T> p = load_p4<T>(bv.pts + hint);
+        best = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
+    }
     int stack[48];  // node ids < 2^31
     int sp = 0;
     stack[sp++] = 1;
@@ -168,7 +175,7 @@ __device__ __forceinline__ T bvh_nearest_d2(const BvhView<T>& bv, T qx, T qy, T 
             for (int64_t j = j0; j < j1; ++j) {
                 const P4<T> p = load_p4<T>(bv.pts + j);
                 const T d = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
-                best = d < best ? d : best;
+                if (d < best) { best = d; hint = (uint32_t)j; }
             }
             continue;
         }
@@ -200,27 +207,30 @@ __device__ __forceinline__ T spacing_from_dmin(const SpacingP<T>& sp, T dmin) {
 
 template <class T, int D>
 __global__ void __launch_bounds__(128) spacing_eval_kernel(const SpacingP<T> sp, const BvhView<T> bv, const T* __restrict__ pts,
-                                                           int64_t n, T* __restrict__ out) {
+                                                           int64_t n, T* __restrict__ out, uint32_t* __restrict__ cache, int use_cache) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (sp.kind == WTP_SPACING_CONSTANT) { out[i] = sp.a; return; }
     const T qx = pts[i * D + 0], qy = pts[i * D + 1], qz = D == 3 ? pts[i * D + (D - 1)] : (T)0;
-    const T dmin = sqrt(bvh_nearest_d2<T, D>(bv, qx, qy, qz));
+    uint32_t hint = (cache && use_cache) ? cache[i] : 0xffffffffu;
+    const T dmin = sqrt(bvh_nearest_d2<T, D>(bv, qx, qy, qz, hint));
+    if (cache) cache[i] = hint;
     out[i] = spacing_from_dmin<T>(sp, dmin);
 }
 
 template <class T>
-void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out) {
+void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out,
+                  uint32_t* d_nn_cache, bool use_cache) {
     if (n <= 0) return;
     WTP_REQUIRE(sp.kind == WTP_SPACING_CONSTANT || sp.kind == WTP_SPACING_LOGLIKE || sp.kind == WTP_SPACING_BOUNDARY_LAYER,
                 WTP_ERR_UNSUPPORTED, "only ConstantSpacing, LogLike and BoundaryLayerSpacing run on the device");
     const BvhView<T> v = bvh_view<T>(bv);
     const unsigned nb = (unsigned)((n + 127) / 128);
-    if (D == 2) spacing_eval_kernel<T, 2><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, n, d_out);
-    else spacing_eval_kernel<T, 3><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, n, d_out);
+    if (D == 2) spacing_eval_kernel<T, 2><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, n, d_out, d_nn_cache, use_cache ? 1 : 0);
+    else spacing_eval_kernel<T, 3><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, n, d_out, d_nn_cache, use_cache ? 1 : 0);
     LAUNCH_CHECK(ctx);
 }
-template void spacing_eval<float>(wtp_ctx*, const SpacingP<float>&, const BvhBuffers&, const float*, int64_t, int, float*);
-template void spacing_eval<double>(wtp_ctx*, const SpacingP<double>&, const BvhBuffers&, const double*, int64_t, int, double*);
+template void spacing_eval<float>(wtp_ctx*, const SpacingP<float>&, const BvhBuffers&, const float*, int64_t, int, float*, uint32_t*, bool);
+template void spacing_eval<double>(wtp_ctx*, const SpacingP<double>&, const BvhBuffers&, const double*, int64_t, int, double*, uint32_t*, bool);
 
 }  // namespace wtp

@@ -102,7 +102,7 @@ template void compute_bbox<double>(wtp_ctx*, IndexBuffers&, const double*, int64
 
 // =========================================================== grid parameters
 template <class T>
-Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], double occupancy, double min_cell) {
+Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], double occupancy, double min_cell, int K) {
     Grid<T> g;
     double ext[3] = {0, 0, 0}, vol = 1.0, maxabs = 0.0, maxext = 0.0;
     int deff = 0;
@@ -114,7 +114,12 @@ Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], doub
         maxabs = std::max(maxabs, std::max(std::fabs(lo[d]), std::fabs(hi[d])));
         maxext = std::max(maxext, ext[d]);
     }
-    if (occupancy <= 0) occupancy = (D == 3) ? 8.0 : 6.0;
+    // Default points per cell: large enough that the K-th neighbour of most queries lies inside the
+    // 3^D block (ball of radius ~c holds K + margin points), small enough that the block stays ~10 K.
+    if (occupancy <= 0) {
+        const double k = K > 0 ? (double)K : 22.0;
+        occupancy = std::max(2.0, (deff >= 3 ? 0.36 : deff == 2 ? 0.45 : 0.7) * k);
+    }
     double c = 1.0;
     if (deff > 0 && N > 0) c = std::pow(vol * occupancy / (double)N, 1.0 / deff);
     if (!(c > 0) || !std::isfinite(c)) c = maxext > 0 ? maxext : 1.0;
@@ -141,8 +146,8 @@ Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], doub
     g.slack = (T)(16.0 * eps * std::max(maxabs, maxext) + 4.0 * eps * c);
     return g;
 }
-template Grid<float> make_grid<float>(int64_t, int, const double*, const double*, double, double);
-template Grid<double> make_grid<double>(int64_t, int, const double*, const double*, double, double);
+template Grid<float> make_grid<float>(int64_t, int, const double*, const double*, double, double, int);
+template Grid<double> make_grid<double>(int64_t, int, const double*, const double*, double, double, int);
 
 // ================================================================ cell keys
 template <class T, int D>

@@ -12,7 +12,7 @@ void compute_bbox(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int
 // Grid parameters from a bounding box: cell size from the target occupancy, never
 // below min_cell (radius search), cell count capped.
 template <class T>
-Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], double occupancy, double min_cell);
+Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], double occupancy, double min_cell, int K);
 
 // cell keys -> radix sort -> sorted P4 tiles + cell starts. Returns radix passes run.
 template <class T>
@@ -61,7 +61,8 @@ template <class T>
 BvhView<T> bvh_view(const BvhBuffers& bv);
 // out[i] = spacing(pts[i]) for i < n (thread per point; BVH 1-NN for the variable kinds).
 template <class T>
-void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out);
+void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out,
+                  uint32_t* d_nn_cache = nullptr, bool use_cache = false);
 template <class T>
 void force_eval(wtp_ctx* ctx, const ForceP<T>& f, const T* d_u, int64_t n, T* d_out);
 

@@ -18,10 +18,11 @@ constexpr int KNN_QPB = KNN_WARPS * KNN_QPW;      // 64 consecutive sorted queri
 constexpr int KNN_TILE_CAP = 288;                 // records per warp tile: 3^3 cells x ~8 points + 4.9 sigma
 
 template <class T, int KPL>
-__host__ __device__ constexpr int knn_tile_cap() { return KPL == 1 ? KNN_TILE_CAP : 0; }   // long lists (K > 32) use the general path
+__host__ __device__ constexpr int knn_tile_cap() { return KPL != 1 ? 0 : (sizeof(T) == 8 ? 224 : KNN_TILE_CAP); }
+template <class T> __host__ __device__ constexpr int knn_min_blocks() { return sizeof(T) == 8 ? 3 : 4; }   // long lists (K > 32) use the general path
 
 template <class T, int D, int KPL>
-__global__ void __launch_bounds__(KNN_THREADS) knn_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted,
+__global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted,
                                                           const uint32_t* __restrict__ cell_start,
                                                           const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t q_begin,
                                                           int K1, int drop, int64_t* __restrict__ out_idx,

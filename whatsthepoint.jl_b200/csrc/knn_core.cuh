@@ -140,8 +140,7 @@ struct WarpList {
     // 32 candidates (one per lane) into row 0 at once: bitonic-sort the batch, keep the 32
     // smallest of (row 0, batch) with one reversed elementwise min, then a 5-stage bitonic
     // merge. Cheaper than serial inserts once more than ~6 candidates qualify. KPL == 1 only.
-    __device__ __forceinline__ void merge32(Key<T> c, int lane) {
-        c = sort32(c, lane);
+    __device__ __forceinline__ void merge_sorted32(const Key<T>& c, int lane) {   // c: ascending over the lanes
         const Key<T> rb = c.shfl(31 - lane);
         if (rb.less(e[0])) e[0] = rb;
 #pragma unroll
@@ -150,7 +149,6 @@ struct WarpList {
             const bool keep_min = (lane & j) == 0;
             if (o.less(e[0]) == keep_min) e[0] = o;
         }
-        refresh_threshold();
     }
     static __device__ __forceinline__ Key<T> sort32(Key<T> c, int lane) {
 #pragma unroll
@@ -212,6 +210,8 @@ struct WarpKnn {
     int lane;
     int scx, scy, scz;  // staged cell (-1: none)
     uint32_t tile_n;    // staged candidates; 0xffffffff: block does not fit the tile
+    uint32_t block_n;   // points in the 3^D block of the staged cell
+    uint32_t row_begin, row_len;   // lane t < NROWS: its row of the block in the sorted array
     T qx, qy, qz;
     int cx, cy, cz;
     bool seeded;
@@ -219,7 +219,7 @@ struct WarpKnn {
 
     static constexpr int PF_CAP = 64;
     __device__ __forceinline__ WarpKnn(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs, P4<T>* tile_, Key<T>* buf_, uint64_t* bar_, int lane_)
-        : g(g_), sorted(s), cell_start(cs), tile(tile_), buf(buf_), r0sq((T)0), bar(bar_), phase(0), lane(lane_), scx(-1), scy(-1), scz(-1), tile_n(0) {
+        : g(g_), sorted(s), cell_start(cs), tile(tile_), buf(buf_), r0sq((T)0), bar(bar_), phase(0), lane(lane_), scx(-1), scy(-1), scz(-1), tile_n(0), block_n(0), row_begin(0), row_len(0) {
         if (TILE_CAP > 0) {
             if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
             __syncwarp();
@@ -269,6 +269,7 @@ struct WarpKnn {
         }
         const uint32_t total = __shfl_sync(FULL, incl, NROWS - 1);
         scx = cx; scy = cy; scz = cz;
+        block_n = total; row_begin = begin; row_len = len;
         if (total > (uint32_t)TILE_CAP) { tile_n = 0xffffffffu; return; }
         tile_n = total;
         if (total == 0) return;
@@ -286,41 +287,81 @@ struct WarpKnn {
         const float target = (float)K + 2.5f * sqrtf((float)K) + 1.0f;
         const float c = (float)g.c;
         float r2;
-        if (D == 3) { const float r3 = target * 27.0f / (4.18879f * (float)tile_n); r2 = c * c * cbrtf(r3 * r3); }
-        else r2 = c * c * target * 9.0f / (3.14159265f * (float)tile_n);
+        if (D == 3) { const float r3 = target * 27.0f / (4.18879f * (float)block_n); r2 = c * c * cbrtf(r3 * r3); }
+        else r2 = c * c * target * 9.0f / (3.14159265f * (float)block_n);
         r0sq = (T)r2;
     }
-    // One pass over the tile: every candidate with d2 <= r0sq goes to the warp's buffer.
-    // If between K and PF_CAP candidates qualify, the K best of the block are among them:
-    // one bitonic sort (plus a merge of the second half) builds the whole list.
-    __device__ __forceinline__ bool prefilter_tile(int K) {
-        uint32_t cnt = 0;
-        for (uint32_t j0 = 0; j0 < tile_n; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            bool q = false;
-            Key<T> c = Key<T>::sentinel();
-            if (j < tile_n) {
-                const P4<T> p = lds_p4(tile + j);
-                const T d = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
-                c = Key<T>::make(d, idx_of(p));
-                q = !(d > r0sq);
-            }
-            const unsigned m = __ballot_sync(FULL, q);
-            const uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
-            if (q && pos < (uint32_t)PF_CAP) buf[pos] = c;
-            cnt += __popc(m);
+    // Pre-filter: every candidate with d2 <= r0sq goes to the warp's buffer. If between K and
+    // PF_CAP candidates qualify, the K best of the block are among them: one bitonic sort
+    // (plus a merge of the second half) builds the whole list.
+    __device__ __forceinline__ void prefilter_push(bool valid, const P4<T>& p, uint32_t& cnt) {
+        bool q = false;
+        Key<T> c = Key<T>::sentinel();
+        if (valid) {
+            const T d = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
+            c = Key<T>::make(d, idx_of(p));
+            q = !(d > r0sq);
         }
+        const unsigned m = __ballot_sync(FULL, q);
+        const uint32_t pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (q && pos < (uint32_t)PF_CAP) buf[pos] = c;
+        cnt += __popc(m);
+    }
+    __device__ __forceinline__ bool prefilter_finish(int K, uint32_t cnt) {
         if (cnt < (uint32_t)K || cnt > (uint32_t)PF_CAP) return false;
         __syncwarp();
-        list.seed((uint32_t)lane < cnt ? buf[lane] : Key<T>::sentinel(), lane);
-        if (cnt > 32u) {
-            const Key<T> b = (uint32_t)lane + 32u < cnt ? buf[lane + 32] : Key<T>::sentinel();
-            if (cnt > 38u) list.merge32(b, lane); else list.offer(b, lane);
+        // First half: bitonic sort straight into the list. Second half (if any): a handful of
+        // extras are inserted one by one, more are sorted (same code copy, second trip) and merged.
+#pragma unroll 1
+        for (uint32_t h = 0; h < cnt; h += 32) {
+            Key<T> c = h + (uint32_t)lane < cnt ? buf[h + lane] : Key<T>::sentinel();
+            if (h == 0 || cnt > 38u) {
+                c = WarpList<T, KPL>::sort32(c, lane);
+                if (h == 0) list.e[0] = c;
+                else list.merge_sorted32(c, lane);
+            } else {
+                list.refresh_threshold();
+                list.offer(c, lane);
+            }
         }
+        list.refresh_threshold();
         __syncwarp();
         seeded = true;
         return true;
     }
+    __device__ __forceinline__ bool prefilter_tile(int K) {
+        uint32_t cnt = 0;
+        for (uint32_t j0 = 0; j0 < tile_n; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool valid = j < tile_n;
+            P4<T> p;
+            if (valid) p = lds_p4(tile + j);
+            prefilter_push(valid, p, cnt);
+        }
+        return prefilter_finish(K, cnt);
+    }
+    // Same filter for blocks too large for the tile (dense regions of graded clouds): rows are
+    // read straight from global memory, and rows / end cells farther than the filter radius
+    // are skipped.
+    __device__ __forceinline__ bool prefilter_rows(int K) {
+        uint32_t cnt = 0;
+#pragma unroll 1
+        for (int t = 0; t < NROWS; ++t) {
+            const uint32_t begin = __shfl_sync(FULL, row_begin, t), len = __shfl_sync(FULL, row_len, t);
+            if (len == 0) continue;
+            const T gy = gap(1, qy, cy, row_dy(t)), gz = D == 3 ? gap(2, qz, cz, row_dz(t)) : (T)0;
+            if (lb3((T)0, gy, gz) > r0sq) continue;
+            for (uint32_t j0 = begin; j0 < begin + len && cnt <= (uint32_t)PF_CAP; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const bool valid = j < begin + len;
+                P4<T> p;
+                if (valid) p = load_p4<T>(sorted + j);
+                prefilter_push(valid, p, cnt);
+            }
+        }
+        return prefilter_finish(K, cnt);
+    }
+    // classic sweep of the staged tile (pre-filter count out of range): seed batch, then inserts
     __device__ __forceinline__ void sweep_tile() {
         for (uint32_t j0 = 0; j0 < tile_n; j0 += 32) {
             const uint32_t j = j0 + lane;
@@ -395,20 +436,17 @@ struct WarpKnn {
             if (cx != scx || cy != scy || cz != scz) stage();
             staged = tile_n != 0xffffffffu;
         }
-        if (staged) {
-            if (KPL == 1 && tile_n >= (uint32_t)K) {
-                set_prefilter_radius(K);
-                if (!prefilter_tile(K)) sweep_tile();
-            } else {
-                sweep_tile();
-            }
-        } else {
-#pragma unroll 1
-            for (int t = 0; t < NROWS; ++t) ring_row(1, row_dy(t), D == 3 ? row_dz(t) : 0);
+        bool done = false;
+        if (TILE_CAP > 0 && KPL == 1 && block_n >= (uint32_t)K) {
+            set_prefilter_radius(K);
+            done = staged ? prefilter_tile(K) : prefilter_rows(K);
         }
-        int R = 1;
+        // General path (one code copy): rings of cells from global memory with pruning. Ring 1 is
+        // swept here only when the pre-filter did not settle the 3^D block.
+        if (!done && staged) { sweep_tile(); done = true; }
+        int R = done ? 1 : 0;
 #pragma unroll 1
-        while (!block_is_exact(R)) {
+        while (R == 0 || !block_is_exact(R)) {
             ++R;
             const int Rz = D == 3 ? R : 0;
 #pragma unroll 1

@@ -27,7 +27,7 @@ void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t by
 // ------------------------------------------------------------------ forces
 // src/repel_forces.jl:37, 57-60, 96-100, 124-127 (compiled with -fmad=false)
 template <class T>
-__device__ __forceinline__ T force_fn(const ForceP<T>& f, T u) {
+__device__ __noinline__ T force_fn(const ForceP<T> f, T u) {
     const T u2 = u * u;
     switch (f.kind) {
         case WTP_FORCE_INVERSE: { const T t = u2 + f.beta; return (T)1 / (t * t); }
@@ -104,13 +104,13 @@ struct SweepArgs {
 constexpr int SW_THREADS = 256;
 constexpr int SW_WARPS = SW_THREADS / 32;
 constexpr int SW_QPW = 8;                        // consecutive sorted points per warp and work item
-constexpr int SW_TILE_CAP = 288;
-template <int KPL> __host__ __device__ constexpr int sw_tile_cap() { return KPL == 1 ? SW_TILE_CAP : 0; }
+template <class T, int KPL> __host__ __device__ constexpr int sw_tile_cap() { return KPL != 1 ? 0 : (sizeof(T) == 8 ? 224 : 288); }
+template <class T> __host__ __device__ constexpr int sw_min_blocks() { return sizeof(T) == 8 ? 3 : 4; }
 
 template <class T, int D, int KPL>
-__global__ void __launch_bounds__(SW_THREADS) repel_sweep_kernel(const SweepArgs<T> a) {
+__global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_kernel(const SweepArgs<T> a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int CAP = sw_tile_cap<KPL>();
+    constexpr int CAP = sw_tile_cap<T, KPL>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_bar[SW_WARPS];
     __shared__ T s_term[SW_WARPS][32 * KPL][3];
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) fill_kernel(T* __restrict__ out, int64_t 
 
 template <class T, int D, int KPL>
 static void launch_sweep_kpl(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
-    constexpr size_t smem = (size_t)sw_tile_cap<KPL>() * sizeof(P4<T>) * SW_WARPS;
+    constexpr size_t smem = (size_t)sw_tile_cap<T, KPL>() * sizeof(P4<T>) * SW_WARPS;
     static bool configured = false;
     if (!configured && smem > 0) {
         WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_sweep_kernel<T, D, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -275,6 +275,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 
     T* spacings = ctx->d_spacings.as<T>((size_t)n_all);
     T* s_cur = variable ? ctx->d_nn.as<T>((size_t)n_move) : nullptr;
+    uint32_t* nn_cache = variable ? ctx->d_counts.as<uint32_t>((size_t)n_move) : nullptr;   // per-point BVH start hint
     spacing_eval<T>(ctx, sp, ctx->bvh, d_snap, n_all, D, spacings);                                 // :209
     T* Pa = ctx->d_p_new.as<T>((size_t)2 * n_move * D);
     T* Pb = Pa + (size_t)n_move * D;
@@ -304,7 +305,10 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     uint32_t nq = (uint32_t)n_all;
     while (it <= prm->max_iters) {                                                                   // :243
         const bool rebuild = (it - 1) % prm->rebuild_every == 0;                                     // :245
-        if (variable) spacing_eval<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur);                      // spacing(xi), :260 (and :251)
+        if (variable) {                                                                              // spacing(xi), :260 (and :251)
+            ScopedPhase ph(ctx->timer, PH_SCAN);
+            spacing_eval<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, it > 1);
+        }
         if (rebuild) {
             WTP_CUDA_CHECK(cudaMemcpyAsync(S_tail, Pa, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));   // :246
             if (variable) WTP_CUDA_CHECK(cudaMemcpyAsync(spacings + n_fixed, s_cur, (size_t)n_move * sizeof(T), cudaMemcpyDeviceToDevice, st));   // :251
@@ -313,7 +317,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
                 lo[d] = n_fixed > 0 ? std::min(flo[d], mlo[d]) : mlo[d];
                 hi[d] = n_fixed > 0 ? std::max(fhi[d], mhi[d]) : mhi[d];
             }
-            g = make_grid<T>(n_all, D, lo, hi, ctx->cell_occupancy, 0.0);
+            g = make_grid<T>(n_all, D, lo, hi, ctx->cell_occupancy, 0.0, kk);
             passes = build_index<T>(ctx, ib, d_snap, n_all, D, g);                                   // :252
             if (world > 1) {
                 build_query_list(ctx, ib, n_all, n_fixed + id_lo, n_fixed + id_hi, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
