@@ -44,6 +44,8 @@ const char* wtp_status_string(int32_t s) {
     return "unknown status";
 }
 
+void wtp_comm_destroy_internal(wtp_ctx* ctx);
+
 int32_t wtp_create(wtp_ctx** out, int32_t device) {
     if (!out) return WTP_ERR_BAD_ARG;
     *out = nullptr;
@@ -63,11 +65,13 @@ int32_t wtp_create(wtp_ctx** out, int32_t device) {
     ctx->stream = ctx->own_stream;
     ctx->h_pinned_bytes = 4096;
     if (cudaMallocHost(&ctx->h_pinned, ctx->h_pinned_bytes) != cudaSuccess) { cudaStreamDestroy(ctx->own_stream); delete ctx; return WTP_ERR_CUDA; }
+    bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& e : ctx->ev_chunk) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { wtp_destroy(ctx); return WTP_ERR_CUDA; }
     *out = ctx;
     return WTP_OK;
 }
-
-void wtp_comm_destroy_internal(wtp_ctx* ctx);
 
 void wtp_destroy(wtp_ctx* ctx) {
     if (!ctx) return;
@@ -75,6 +79,9 @@ void wtp_destroy(wtp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     wtp_comm_destroy_internal(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -155,8 +162,8 @@ void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_
 
 // ------------------------------------------------------------------- k-NN
 template <class T>
-static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bool drop_first, int64_t* d_out_idx,
-                       T* d_out_dist, int64_t* rows_begin, int64_t* rows_end) {
+static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bool drop_first, int64_t* d_out_idx,
+                       T* d_out_dist, int64_t* rows_begin, int64_t* rows_end, int64_t* h_out_idx = nullptr, T* h_out_dist = nullptr) {
     WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
     WTP_REQUIRE(k >= 1, WTP_ERR_BAD_ARG, "k must be >= 1");
     const int K1 = k + (drop_first ? 1 : 0);
@@ -175,12 +182,34 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     }
     unsigned long long* d_exp = ctx->d_reduce.as<unsigned long long>(1);
     WTP_CUDA_CHECK(cudaMemsetAsync(d_exp, 0, sizeof(unsigned long long), ctx->stream));
-    knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, qlist, qe - qb, qb, d_out_idx, d_out_dist, d_exp);
+    // Host sink and a large result: answer the queries in caller-order chunks and overlap the D2H of
+    // chunk c (copy stream) with the kernel of chunk c+1. The result is PCIe-bound either way.
+    const bool pipelined = h_out_idx != nullptr && (qe - qb) * (int64_t)k >= ((int64_t)4 << 20);
+    if (pipelined) {
+        constexpr int C = 8;
+        for (int c = 0; c < C; ++c) {
+            const int64_t cb = qb + (qe - qb) * c / C, ce = qb + (qe - qb) * (c + 1) / C;
+            if (ce <= cb) continue;
+            build_query_list(ctx, ib, N, cb, ce, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
+            knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, ctx->d_qlist.get<uint32_t>(), ce - cb, qb, d_out_idx, d_out_dist, d_exp);
+            WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
+            WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
+            WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_idx + cb * k, d_out_idx + (cb - qb) * k, (size_t)(ce - cb) * k * sizeof(int64_t),
+                                           cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (h_out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist + cb * k, d_out_dist + (cb - qb) * k, (size_t)(ce - cb) * k * sizeof(T),
+                                                           cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+        WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
+    } else {
+        knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, qlist, qe - qb, qb, d_out_idx, d_out_dist, d_exp);
+    }
     unsigned long long* h_exp = static_cast<unsigned long long*>(ctx->h_pinned);
     WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    finish_timing(ctx, passes, 1, g.ncells, (int64_t)*h_exp);
+    finish_timing(ctx, passes, pipelined ? 8 : 1, g.ncells, (int64_t)*h_exp);
     *rows_begin = qb; *rows_end = qe;
+    return pipelined;
 }
 
 template <class T>
@@ -208,9 +237,9 @@ static int32_t knn_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_
         WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     }
     int64_t rb, re;
-    knn_device<T>(ctx, d_pts, N, D, k, drop_first, d_idx, d_dist, &rb, &re);
+    const bool copied = knn_device<T>(ctx, d_pts, N, D, k, drop_first, d_idx, d_dist, &rb, &re, out_idx, out_dist);
     wtp_timing keep = ctx->last_timing;
-    {
+    if (!copied) {
         ScopedPhase ph(ctx->timer, PH_D2H);
         WTP_CUDA_CHECK(cudaMemcpyAsync(out_idx + rb * k, d_idx, (size_t)(re - rb) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(out_dist + rb * k, d_dist, (size_t)(re - rb) * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));

@@ -181,6 +181,9 @@ struct wtp_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // D2H of finished chunks while the next chunk computes
+    cudaEvent_t ev_chunk[8] = {};
+    cudaEvent_t ev_copy_done = nullptr;
     std::string last_error;
     double cell_occupancy = 0.0;  // <= 0: default per dimension
     int64_t launches = 0;
