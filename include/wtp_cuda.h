@@ -183,17 +183,23 @@ typedef struct {
 enum { WTP_WALL_IDENTITY = 0,      /* repel(cloud, spacing): src/repel.jl:82         */
        WTP_WALL_MESH = 1 };        /* repel(cloud, spacing, octree): :158-160,448-469 */
 
-/* Triangle mesh for the wall rule of the 3-argument repel (3-D only). The library
- * builds its own device search structure; results equal the reference's octree
- * queries (nearest triangle, pseudonormal-signed inside test). HOST pointers. */
+/* Triangle mesh for the wall rule of the 3-argument repel (3-D only): the arrays of the
+ * reference's TriangleIndex (src/octree/triangle_octree.jl:22-31) flattened per triangle. The
+ * library builds its own device search structure (Morton BVH + a cell-class grid); results equal
+ * the reference's octree queries: nearest triangle by (d2, triangle index), closest point by
+ * Ericson's region tests (src/octree/geometric_utils.jl:68-136), inside test = sign of
+ * dot(p - cp, pseudonormal of the closest feature) < 0 inside the mesh bounding box
+ * (src/octree/triangle_octree.jl:71-99, 583-607). HOST pointers, coordinates in the cloud's T. */
 typedef struct {
-    const void* vertices;          /* n_tri x 3 x 3 of T: v1,v2,v3 per triangle        */
-    const void* face_normals;      /* n_tri x 3 of T (octree.index.face)               */
+    const void* triangles;         /* n_tri x 9 of T: v1, v2, v3                                  */
+    const void* feature_normals;   /* n_tri x 21 of T: face, vertex 1..3, edge 12, 13, 23          */
+                                   /*   (index.face / index.vertex / index.edge pseudonormals)    */
     int64_t n_tri;
-    double offset_dist;            /* 1e-6 * |bbox_max - bbox_min|  (src/repel.jl:150) */
-    const uint8_t* is_bnd;         /* n_move flags (src/repel.jl:155)                  */
-    int64_t* tri_indices;          /* out, n_move, 1-based landing triangle (0 = none) */
-    uint8_t* escaped;              /* out, n_move                                       */
+    double bbox_min[3], bbox_max[3]; /* index.bbox_min / bbox_max (domain_bounds)                 */
+    double offset_dist;            /* 1e-6 * |bbox_max - bbox_min|  (src/repel.jl:150)            */
+    const uint8_t* is_bnd;         /* n_move flags (src/repel.jl:155)                             */
+    int64_t* tri_indices;          /* out, n_move, 1-based landing triangle (0 = untouched)       */
+    uint8_t* escaped;              /* out, n_move                                                 */
 } wtp_wall_mesh;
 
 typedef struct {
@@ -248,6 +254,14 @@ int32_t wtp_spacing_eval_f32(wtp_ctx*, const wtp_spacing*, const float* pts, int
                              int32_t D, float* out);
 int32_t wtp_spacing_eval_f64(wtp_ctx*, const wtp_spacing*, const double* pts, int64_t N,
                              int32_t D, double* out);
+
+/* Batched geometry queries on the same mesh structure (is_bnd / tri_indices / escaped unused):
+ * isinside(points, octree) (src/octree/triangle_octree.jl:97-115) -> out[i] in {0,1};
+ * _project_to_boundary (src/repel.jl:522-537) -> out_pts N x 3, out_tri 1-based (0: none). */
+int32_t wtp_mesh_isinside_f32(wtp_ctx*, const wtp_wall_mesh*, const float* pts, int64_t N, uint8_t* out);
+int32_t wtp_mesh_isinside_f64(wtp_ctx*, const wtp_wall_mesh*, const double* pts, int64_t N, uint8_t* out);
+int32_t wtp_mesh_project_f32(wtp_ctx*, const wtp_wall_mesh*, const float* pts, int64_t N, float* out_pts, int64_t* out_tri);
+int32_t wtp_mesh_project_f64(wtp_ctx*, const wtp_wall_mesh*, const double* pts, int64_t N, double* out_pts, int64_t* out_tri);
 
 /* compute_force(model, u) elementwise on the device (src/repel_forces.jl:22). */
 int32_t wtp_force_eval_f32(wtp_ctx*, const wtp_force*, const float* u, int64_t n, float* out);

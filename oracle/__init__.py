@@ -55,6 +55,50 @@ class TraceEntry(C.Structure):
                 ("idx_a", C.c_int64), ("idx_b", C.c_int64)]
 
 
+class WallMesh(C.Structure):
+    _fields_ = [("triangles", C.c_void_p), ("feature_normals", C.c_void_p), ("n_tri", C.c_int64),
+                ("bbox_min", C.c_double * 3), ("bbox_max", C.c_double * 3), ("offset_dist", C.c_double),
+                ("is_bnd", C.c_void_p), ("tri_indices", C.c_void_p), ("escaped", C.c_void_p)]
+
+
+def make_wall(triangles, feature_normals, bbox_min, bbox_max, offset_dist, is_bnd=None, tri_indices=None, escaped=None):
+    """WallMesh from the flattened TriangleIndex arrays (n x 9, n x 21). Returns (struct, keepalive)."""
+    triangles, feature_normals = np.ascontiguousarray(triangles), np.ascontiguousarray(feature_normals)
+    w = WallMesh()
+    w.triangles, w.feature_normals, w.n_tri = triangles.ctypes.data, feature_normals.ctypes.data, triangles.shape[0]
+    for d in range(3):
+        w.bbox_min[d], w.bbox_max[d] = float(bbox_min[d]), float(bbox_max[d])
+    w.offset_dist = float(offset_dist)
+    w.is_bnd = is_bnd.ctypes.data if is_bnd is not None else None
+    w.tri_indices = tri_indices.ctypes.data if tri_indices is not None else None
+    w.escaped = escaped.ctypes.data if escaped is not None else None
+    return w, (triangles, feature_normals, is_bnd, tri_indices, escaped)
+
+
+def wall_from(mesh, dtype, is_bnd=None, tri_indices=None, escaped=None):
+    """Same, from any object with the TriangleIndex arrays (e.g. the host mirror's TriangleOctree)."""
+    m = mesh.astype(dtype)
+    return make_wall(m.triangles, m.feature_normals, m.bbox_min, m.bbox_max, m.offset_dist, is_bnd, tri_indices, escaped)
+
+
+def mesh_isinside(mesh, pts, *, threads=0):
+    pts = _pts(pts)
+    w, keep = wall_from(mesh, pts.dtype)
+    out = np.zeros(pts.shape[0], dtype=np.uint8)
+    getattr(lib(), "wtpo_mesh_isinside_" + _sfx(pts.dtype))(C.byref(w), pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]),
+                                                            C.c_int32(threads), out.ctypes.data_as(C.c_void_p))
+    return out.astype(bool)
+
+
+def mesh_project(mesh, pts, *, threads=0):
+    pts = _pts(pts)
+    w, keep = wall_from(mesh, pts.dtype)
+    out, tri = np.empty_like(pts), np.zeros(pts.shape[0], dtype=np.int64)
+    getattr(lib(), "wtpo_mesh_project_" + _sfx(pts.dtype))(C.byref(w), pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]),
+                                                           C.c_int32(threads), out.ctypes.data_as(C.c_void_p), tri.ctypes.data_as(C.c_void_p))
+    return out, tri
+
+
 class CloudMetrics(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("avg", "std", "max", "min", "separation", "fill", "mesh_ratio")]
 
@@ -158,19 +202,27 @@ def spacing_eval(sp: Spacing, pts):
 
 
 def repel(snap, n_fixed, sp: Spacing, f: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
-          stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, threads=0):
+          stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, threads=0, mesh=None, is_bnd=None):
     """_relax! on snap = [fixed head; movable tail]. Returns (new_snap, conv, result dict, trace)."""
     snap = np.array(_pts(snap), copy=True)
     n_all, d = snap.shape
     n_move = n_all - n_fixed
-    prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 0, 1 if trace else 0, 0,
+    prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0, 0,
                       float(alpha_lo), float(alpha_max), float(tol), float(cv_target))
     conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
     tr = (TraceEntry * max(max_iters, 1))() if trace else None
     res = RepelResult()
+    wall, keep = None, None
+    repel.last_wall = None
+    if mesh is not None:
+        flags = np.ascontiguousarray(is_bnd, dtype=np.uint8)
+        tri_idx, esc = np.zeros(n_move, dtype=np.int64), np.zeros(n_move, dtype=np.uint8)
+        w, keep = wall_from(mesh, snap.dtype, flags, tri_idx, esc)
+        wall = C.byref(w)
+        repel.last_wall = dict(tri_indices=tri_idx, escaped=esc)
     rc = getattr(lib(), "wtpo_repel_" + _sfx(snap.dtype))(
         snap.ctypes.data_as(C.c_void_p), C.c_int64(n_fixed), C.c_int64(n_move), C.c_int32(d),
-        C.byref(sp), C.byref(f), C.byref(prm), conv.ctypes.data_as(C.c_void_p),
+        C.byref(sp), C.byref(f), C.byref(prm), wall, conv.ctypes.data_as(C.c_void_p),
         tr, C.byref(res), C.c_int32(threads))
     if rc != 0:
         raise ValueError(f"oracle repel failed with status {rc}")
@@ -196,6 +248,7 @@ def metrics(pts, k=20, *, threads=0):
 def closest_point_on_triangle(p, a, b, c):
     p, a, b, c = (np.ascontiguousarray(x) for x in (p, a, b, c))
     out = np.empty(3, dtype=p.dtype)
-    getattr(lib(), "wtpo_closest_point_on_triangle_" + _sfx(p.dtype))(
+    feature = getattr(lib(), "wtpo_closest_point_on_triangle_" + _sfx(p.dtype))(
         *(x.ctypes.data_as(C.c_void_p) for x in (p, a, b, c)), out.ctypes.data_as(C.c_void_p))
+    closest_point_on_triangle.last_feature = int(feature)
     return out

@@ -23,7 +23,8 @@
 //   _relax!             src/repel.jl:202-339 (sweep :256-292, reductions :293, 374-403,
 //                       stop logic :305-337)
 //   metrics             src/metrics.jl:19-41
-//   closest point / wall rule   src/octree/geometric_utils.jl:68-136, src/repel.jl:448-469,522-537
+//   closest point / wall rule   src/octree/geometric_utils.jl:68-136, src/repel.jl:448-469,522-537,
+//                               src/octree/triangle_octree.jl:71-99,531-549,583-607 (brute force over triangles)
 //
 // Canonical order: candidates are ordered by (d2, index) ascending with
 // d2 = ((dx*dx + dy*dy) + dz*dz) evaluated in T; compile with -ffp-contract=off.
@@ -243,44 +244,88 @@ struct Spacing {
 };
 
 // ------------------------------------------------------ closest point (wall)
-// Ericson's closest point on triangle (src/octree/geometric_utils.jl:68-136).
+// Ericson's closest point on triangle with the feature code of the region
+// (src/octree/geometric_utils.jl:68-136): 0 face, 1..3 vertex, 4 edge12, 5 edge13, 6 edge23.
 template <class T>
-inline void closest_point_on_triangle(const T* p, const T* a, const T* b, const T* c, T* out) {
+inline int closest_point_on_triangle(const T* p, const T* a, const T* b, const T* c, T* out) {
     T ab[3], ac[3], ap[3];
     for (int i = 0; i < 3; ++i) { ab[i] = b[i] - a[i]; ac[i] = c[i] - a[i]; ap[i] = p[i] - a[i]; }
     auto dot = [](const T* x, const T* y) { return (x[0] * y[0] + x[1] * y[1]) + x[2] * y[2]; };
     T d1 = dot(ab, ap), d2 = dot(ac, ap);
-    if (d1 <= 0 && d2 <= 0) { for (int i = 0; i < 3; ++i) out[i] = a[i]; return; }
+    if (d1 <= 0 && d2 <= 0) { for (int i = 0; i < 3; ++i) out[i] = a[i]; return 1; }
     T bp[3]; for (int i = 0; i < 3; ++i) bp[i] = p[i] - b[i];
     T d3 = dot(ab, bp), d4 = dot(ac, bp);
-    if (d3 >= 0 && d4 <= d3) { for (int i = 0; i < 3; ++i) out[i] = b[i]; return; }
+    if (d3 >= 0 && d4 <= d3) { for (int i = 0; i < 3; ++i) out[i] = b[i]; return 2; }
     T vc = d1 * d4 - d3 * d2;
-    if (vc <= 0 && d1 >= 0 && d3 <= 0) { T v = d1 / (d1 - d3); for (int i = 0; i < 3; ++i) out[i] = a[i] + v * ab[i]; return; }
+    if (vc <= 0 && d1 >= 0 && d3 <= 0) { T v = d1 / (d1 - d3); for (int i = 0; i < 3; ++i) out[i] = a[i] + v * ab[i]; return 4; }
     T cp[3]; for (int i = 0; i < 3; ++i) cp[i] = p[i] - c[i];
     T d5 = dot(ab, cp), d6 = dot(ac, cp);
-    if (d6 >= 0 && d5 <= d6) { for (int i = 0; i < 3; ++i) out[i] = c[i]; return; }
+    if (d6 >= 0 && d5 <= d6) { for (int i = 0; i < 3; ++i) out[i] = c[i]; return 3; }
     T vb = d5 * d2 - d1 * d6;
-    if (vb <= 0 && d2 >= 0 && d6 <= 0) { T w = d2 / (d2 - d6); for (int i = 0; i < 3; ++i) out[i] = a[i] + w * ac[i]; return; }
+    if (vb <= 0 && d2 >= 0 && d6 <= 0) { T w = d2 / (d2 - d6); for (int i = 0; i < 3; ++i) out[i] = a[i] + w * ac[i]; return 5; }
     T va = d3 * d6 - d5 * d4;
     if (va <= 0 && (d4 - d3) >= 0 && (d5 - d6) >= 0) {
         T w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
         for (int i = 0; i < 3; ++i) out[i] = b[i] + w * (c[i] - b[i]);
-        return;
+        return 6;
     }
     T denom = T(1) / (va + vb + vc);
     T v = vb * denom, w = vc * denom;
     for (int i = 0; i < 3; ++i) out[i] = a[i] + ab[i] * v + ac[i] * w;
+    return 0;
+}
+
+// Brute-force nearest triangle (src/octree/triangle_octree.jl:531-549 without the tree):
+// canonical tie-break (d2, triangle index). Returns the 0-based triangle, -1 if none.
+template <class T>
+struct Nearest { T d2; int64_t tri; T cp[3]; int feature; };
+template <class T>
+inline Nearest<T> nearest_triangle(const T* tris, int64_t n_tri, const T* p) {
+    Nearest<T> best{std::numeric_limits<T>::max(), -1, {p[0], p[1], p[2]}, 0};
+    for (int64_t t = 0; t < n_tri; ++t) {
+        const T* v = tris + size_t(t) * 9;
+        T cp[3];
+        int f = closest_point_on_triangle<T>(p, v, v + 3, v + 6, cp);
+        T dv[3] = {p[0] - cp[0], p[1] - cp[1], p[2] - cp[2]};
+        T d2 = (dv[0] * dv[0] + dv[1] * dv[1]) + dv[2] * dv[2];
+        if (d2 < best.d2) { best.d2 = d2; best.tri = t; best.feature = f; for (int i = 0; i < 3; ++i) best.cp[i] = cp[i]; }
+    }
+    return best;
+}
+// isinside(p, octree) (src/octree/triangle_octree.jl:71-99, 583-607): mesh-bbox test, then the
+// sign of dot(p - cp, pseudonormal of the closest feature) < 0.
+template <class T>
+inline bool mesh_isinside(const wtp_wall_mesh* m, const T* p) {
+    for (int d = 0; d < 3; ++d) if (p[d] < T(m->bbox_min[d]) || p[d] > T(m->bbox_max[d])) return false;
+    const T* tris = static_cast<const T*>(m->triangles);
+    Nearest<T> nb = nearest_triangle<T>(tris, m->n_tri, p);
+    if (nb.tri < 0) return false;
+    const T* n = static_cast<const T*>(m->feature_normals) + size_t(nb.tri) * 21 + size_t(nb.feature) * 3;
+    T s = ((p[0] - nb.cp[0]) * n[0] + (p[1] - nb.cp[1]) * n[1]) + (p[2] - nb.cp[2]) * n[2];
+    return s < T(0);
+}
+// _project_to_boundary (src/repel.jl:522-537): closest point nudged inward along the face normal.
+template <class T>
+inline int64_t mesh_project(const wtp_wall_mesh* m, const T* p, T* out) {
+    const T* tris = static_cast<const T*>(m->triangles);
+    Nearest<T> nb = nearest_triangle<T>(tris, m->n_tri, p);
+    if (nb.tri < 0) { for (int i = 0; i < 3; ++i) out[i] = p[i]; return 0; }
+    const T* n = static_cast<const T*>(m->feature_normals) + size_t(nb.tri) * 21;
+    const T off = T(m->offset_dist);
+    for (int i = 0; i < 3; ++i) out[i] = nb.cp[i] - off * n[i];
+    return nb.tri + 1;
 }
 
 // ------------------------------------------------------------------- relax
 template <class T, int D>
 int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in, const wtp_force* fm,
-              const wtp_repel_params* prm, T* conv, wtp_trace_entry* trace, wtp_repel_result* res,
+              const wtp_repel_params* prm, const wtp_wall_mesh* wall, T* conv, wtp_trace_entry* trace, wtp_repel_result* res,
               int threads) {
     const int64_t n_all = n_fixed + n_move;
     if (prm->rebuild_every < 1) return WTP_ERR_BAD_ARG;                      // src/repel.jl:74
     if (prm->kick_after > 0) return WTP_ERR_UNSUPPORTED;                     // randn, :430
-    if (prm->wall != WTP_WALL_IDENTITY) return WTP_ERR_UNSUPPORTED;
+    if ((prm->wall == WTP_WALL_MESH) != (wall != nullptr)) return WTP_ERR_BAD_ARG;
+    if (wall && D != 3) return WTP_ERR_BAD_ARG;
     const int kk = int(std::min<int64_t>(prm->k, n_all));                   // :208
     Spacing<T, D> spacing;
     spacing.init(sp_in);
@@ -340,7 +385,22 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
                 for (int d = 0; d < D; ++d) { disp[d] = sa * F[d]; dn2 = dn2 + disp[d] * disp[d]; }
                 const T dn = std::sqrt(dn2);
                 if (dn > s) { const T sc = s / dn; for (int d = 0; d < D; ++d) disp[d] = disp[d] * sc; }  // :288-290
-                for (int d = 0; d < D; ++d) p[size_t(id) * D + d] = xi[d] + disp[d];  // :291 (identity wall)
+                T prop[3] = {T(0), T(0), T(0)};
+                for (int d = 0; d < D; ++d) prop[d] = xi[d] + disp[d];
+                if (wall && D == 3) {                                         // _constrain_octree :448-469
+                    T xi3[3] = {xi[0], xi[1], xi[D - 1]};
+                    if (wall->is_bnd[id]) {
+                        T sv[3];
+                        int64_t tri = mesh_project<T>(wall, prop, sv);
+                        if (tri == 0) tri = mesh_project<T>(wall, xi3, sv);
+                        wall->tri_indices[id] = tri;
+                        for (int d = 0; d < 3; ++d) prop[d] = sv[d];
+                    } else if (!mesh_isinside<T>(wall, prop)) {
+                        wall->escaped[id] = 1;
+                        for (int d = 0; d < 3; ++d) prop[d] = xi3[d];
+                    }
+                }
+                for (int d = 0; d < D; ++d) p[size_t(id) * D + d] = prop[d];  // :291
                 nn_id[size_t(id)] = nid; nn_dist[size_t(id)] = nd;
             }
         }
@@ -549,19 +609,33 @@ int32_t wtpo_spacing_f64(const wtp_spacing* sp, const double* pts, int64_t N, in
 }
 
 int32_t wtpo_repel_f32(float* snap, int64_t n_fixed, int64_t n_move, int32_t D, const wtp_spacing* sp,
-                       const wtp_force* fm, const wtp_repel_params* prm, float* conv, wtp_trace_entry* trace,
-                       wtp_repel_result* res, int32_t threads) {
+                       const wtp_force* fm, const wtp_repel_params* prm, const wtp_wall_mesh* wall, float* conv,
+                       wtp_trace_entry* trace, wtp_repel_result* res, int32_t threads) {
     threads = default_threads(threads);
-    return DISPATCH_D(float, D, (relax<float, 2>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)),
-                      (relax<float, 3>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)));
+    return DISPATCH_D(float, D, (relax<float, 2>(snap, n_fixed, n_move, sp, fm, prm, wall, conv, trace, res, threads)),
+                      (relax<float, 3>(snap, n_fixed, n_move, sp, fm, prm, wall, conv, trace, res, threads)));
 }
 int32_t wtpo_repel_f64(double* snap, int64_t n_fixed, int64_t n_move, int32_t D, const wtp_spacing* sp,
-                       const wtp_force* fm, const wtp_repel_params* prm, double* conv, wtp_trace_entry* trace,
-                       wtp_repel_result* res, int32_t threads) {
+                       const wtp_force* fm, const wtp_repel_params* prm, const wtp_wall_mesh* wall, double* conv,
+                       wtp_trace_entry* trace, wtp_repel_result* res, int32_t threads) {
     threads = default_threads(threads);
-    return DISPATCH_D(double, D, (relax<double, 2>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)),
-                      (relax<double, 3>(snap, n_fixed, n_move, sp, fm, prm, conv, trace, res, threads)));
+    return DISPATCH_D(double, D, (relax<double, 2>(snap, n_fixed, n_move, sp, fm, prm, wall, conv, trace, res, threads)),
+                      (relax<double, 3>(snap, n_fixed, n_move, sp, fm, prm, wall, conv, trace, res, threads)));
 }
+
+#define MESH_QUERIES(T, sfx)                                                                                        \
+    void wtpo_mesh_isinside_##sfx(const wtp_wall_mesh* m, const T* pts, int64_t N, int32_t threads, uint8_t* out) { \
+        threads = default_threads(threads);                                                                         \
+        _Pragma("omp parallel for num_threads(threads) schedule(dynamic, 64)")                                      \
+        for (int64_t i = 0; i < N; ++i) out[i] = mesh_isinside<T>(m, pts + size_t(i) * 3) ? 1 : 0;                  \
+    }                                                                                                               \
+    void wtpo_mesh_project_##sfx(const wtp_wall_mesh* m, const T* pts, int64_t N, int32_t threads, T* out_pts, int64_t* out_tri) { \
+        threads = default_threads(threads);                                                                         \
+        _Pragma("omp parallel for num_threads(threads) schedule(dynamic, 64)")                                      \
+        for (int64_t i = 0; i < N; ++i) out_tri[i] = mesh_project<T>(m, pts + size_t(i) * 3, out_pts + size_t(i) * 3); \
+    }
+MESH_QUERIES(float, f32)
+MESH_QUERIES(double, f64)
 
 int32_t wtpo_metrics_f32(const float* pts, int64_t N, int32_t D, int32_t k, int32_t threads, wtp_cloud_metrics* out) {
     threads = default_threads(threads);
@@ -572,11 +646,11 @@ int32_t wtpo_metrics_f64(const double* pts, int64_t N, int32_t D, int32_t k, int
     return DISPATCH_D(double, D, (metrics_impl<double, 2>(pts, N, k, threads, out)), (metrics_impl<double, 3>(pts, N, k, threads, out)));
 }
 
-void wtpo_closest_point_on_triangle_f64(const double* p, const double* a, const double* b, const double* c, double* out) {
-    closest_point_on_triangle<double>(p, a, b, c, out);
+int32_t wtpo_closest_point_on_triangle_f64(const double* p, const double* a, const double* b, const double* c, double* out) {
+    return closest_point_on_triangle<double>(p, a, b, c, out);
 }
-void wtpo_closest_point_on_triangle_f32(const float* p, const float* a, const float* b, const float* c, float* out) {
-    closest_point_on_triangle<float>(p, a, b, c, out);
+int32_t wtpo_closest_point_on_triangle_f32(const float* p, const float* a, const float* b, const float* c, float* out) {
+    return closest_point_on_triangle<float>(p, a, b, c, out);
 }
 
 }  // extern "C"

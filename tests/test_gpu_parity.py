@@ -258,6 +258,96 @@ def test_repel_api(ctx, pkg, oracle):
     assert c2.repel_result["iters"] == 1
 
 
+# ------------------------------------------------------- mesh wall rule (R6)
+def _mesh_queries(mesh, rng, n, dt):
+    """Points inside, outside, far away, hugging the surface, and exactly on vertices / edge midpoints."""
+    lo, hi = mesh.bbox_min.astype(np.float64), mesh.bbox_max.astype(np.float64)
+    ext = hi - lo
+    tri = mesh.triangles.reshape(-1, 3, 3).astype(np.float64)
+    box = lo + rng.random((n, 3)) * ext
+    wide = lo - ext + rng.random((n // 2, 3)) * 3 * ext
+    pick = rng.integers(0, len(tri), n)
+    bary = rng.dirichlet([1, 1, 1], n)
+    on = (tri[pick] * bary[:, :, None]).sum(1)
+    near = on + rng.normal(0, 1e-3, (n, 3)) * np.linalg.norm(ext)
+    verts = tri[pick[:200], 0]
+    mids = 0.5 * (tri[pick[:200], 0] + tri[pick[:200], 1])
+    return np.ascontiguousarray(np.concatenate([box, wide, near, on, verts, mids]).astype(dt))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", ["cube", "cuboid", "sphere", "torus"])
+def test_mesh_isinside_project_bit_exact(ctx, oracle, pkg, dt, shape):
+    mesh = {"cube": lambda: pkg.unit_cube_mesh(dt), "cuboid": lambda: pkg.cuboid_mesh(20.0, 7.0, 3.0, dt),
+            "sphere": lambda: pkg.icosphere_mesh(3, 2.5, (1.0, -2.0, 0.5), dt), "torus": lambda: pkg.torus_mesh(dtype=dt)}[shape]()
+    q = _mesh_queries(mesh, np.random.default_rng(len(shape)), 3000, dt)
+    assert np.array_equal(ctx.mesh_isinside(mesh, q), oracle.mesh_isinside(mesh, q))
+    p, tri = ctx.mesh_project(mesh, q)
+    op, otri = oracle.mesh_project(mesh, q)
+    assert np.array_equal(tri, otri) and np.array_equal(p, op)      # canonical (d2, triangle index) nearest triangle, same arithmetic
+
+
+def test_mesh_isinside_known_answers(ctx, pkg):
+    cube = pkg.unit_cube_mesh()                                      # test/octree_isinside.jl:7-11, 57-63, 106-137
+    assert pkg.isinside(np.array([[0.5, 0.5, 0.5], [-0.5, 0.5, 0.5], [0.3, 0.3, 0.3]]), cube, ctx=ctx).tolist() == [True, False, True]
+    d = 1.0e-3
+    assert pkg.isinside(np.array([[0.5, 0.5, d], [0.5, 0.5, -d], [d, 0.5, d], [-d, 0.5, -d]]), cube, ctx=ctx).tolist() == [True, False, True, False]
+    box = pkg.cuboid_mesh(20.0, 7.0, 3.0)                            # :66-103
+    assert pkg.isinside(np.array([[5, 3.5, 1.5], [5, 3.5, 10.0], [25, 3.5, 1.5]]), box, ctx=ctx).tolist() == [True, False, False]
+    assert pkg.isinside(np.array([0.5, 0.5, 0.5]), cube, ctx=ctx) is True
+
+
+def _wall_problem(pkg, rng, dt, n_vol=6000, sub=3):
+    sph = pkg.icosphere_mesh(sub, dtype=dt)
+    bnd = sph.triangles.reshape(-1, 3, 3).astype(np.float64).mean(axis=1)
+    vol = rng.normal(size=(n_vol, 3))
+    vol *= (0.97 * rng.random((n_vol, 1)) ** (1 / 3)) / np.linalg.norm(vol, axis=1, keepdims=True)   # some start right under the wall
+    snap = np.ascontiguousarray(np.concatenate([bnd, vol]).astype(dt))
+    return sph, snap, np.arange(len(snap)) < len(bnd)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("skind", ["constant", "boundary_layer"])
+def test_repel_mesh_wall_10_iterations(ctx, oracle, pkg, dt, skind):
+    """repel(cloud, spacing, octree): n_fixed = 0, boundary points re-projected, escapees reverted and flagged."""
+    sph, snap, is_bnd = _wall_problem(pkg, np.random.default_rng(21), dt)
+    h = 0.085
+    bset = np.ascontiguousarray(snap[is_bnd])
+    args = ("constant", h) if skind == "constant" else ("boundary_layer", 0.6 * h, 1.2 * h, 0.4, bset)
+    sp, keep = ctx.make_spacing(*args)
+    osp, okeep = oracle.make_spacing(*args)
+    kw = dict(max_iters=10, tol=0.0, stall_after=0, alpha_lo=h / 2000, alpha_max=h / 20)
+    out, conv, res, _ = ctx.repel(snap, 0, sp, ctx.make_force("clipped", dt(0.2)), mesh=sph, is_bnd=is_bnd, **kw)
+    wall = ctx.last_wall
+    oout, oconv, ores, _ = oracle.repel(snap, 0, osp, oracle.make_force("clipped", dt(0.2)), mesh=sph, is_bnd=is_bnd, **kw)
+    owall = oracle.repel.last_wall
+    assert res["iters"] == ores["iters"] == 10
+    assert np.array_equal(wall["escaped"], owall["escaped"]) and wall["escaped"].any()     # the wall rule actually fired
+    assert (wall["tri_indices"] == owall["tri_indices"]).mean() > 0.999                   # rounding of the position may flip a tie
+    assert np.abs(out.astype(np.float64) - oout).max() <= TOL[dt] * h
+    np.testing.assert_allclose(conv, oconv, rtol=1e-4 if dt == np.float32 else 1e-9)
+    assert oracle.mesh_isinside(sph, out[~is_bnd]).all()                                   # test/repel.jl:31-37
+
+
+def test_repel_octree_api(ctx, pkg, oracle):
+    sph, snap, is_bnd = _wall_problem(pkg, np.random.default_rng(22), np.float64, n_vol=2500, sub=2)
+    nb = int(is_bnd.sum())
+    normals = sph.face.copy()
+    surf = pkg.PointSurface(snap[:nb], normals, np.full(nb, 0.01))
+    cloud = pkg.PointCloud(pkg.PointBoundary({"wall": surf}), snap[nb:])
+    conv = []
+    out = pkg.repel(cloud, pkg.ConstantSpacing(0.11), sph, max_iters=6, stall_after=0, tol=0.0, convergence=conv, ctx=ctx)
+    assert len(out) == len(cloud) and len(conv) == 6                  # total point count preserved (test/repel.jl:31-33)
+    assert list(out.boundary.surfaces) == ["boundary"] and len(out.boundary) == nb          # _reconstruct_cloud :624-626
+    assert pkg.isinside(out.volume.points, sph, ctx=ctx).all()                              # :35-37
+    n = out.boundary.surfaces["boundary"].normals
+    np.testing.assert_allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-12)
+    with pytest.raises(pkg.WtpError):
+        pkg.repel(cloud, pkg.ConstantSpacing(0.11), sph, deposit_ratio=0.5, ctx=ctx)
+    with pytest.raises(TypeError):
+        pkg.repel(pkg.PointCloud(snap[:50, :2], snap[50:200, :2]), pkg.ConstantSpacing(0.1), sph, ctx=ctx)
+
+
 # ------------------------------------------------------- BASELINE sizes
 def _brute_rows(pts, qi, k):
     """Canonical (d2, index) brute force for a few queries in the input precision (no FMA in numpy)."""

@@ -8,7 +8,8 @@ from ._lib import Context, WtpArgumentError, WtpError, default_context, shard_ra
 from .api import (AbstractSpacing, AbstractTopology, BoundaryLayerSpacing, ClippedSpacingForce, ConstantSpacing, CSRRows,
                   FlatRows, InverseDistanceForce, KNNTopology, LogLike, NoTopology, PointBoundary, PointCloud,
                   PointSurface, PointVolume, RadiusTopology, RepelForceModel, SpacingEquilibriumForce,
-                  StrongSpacingForce, compute_force, hastopology, metrics, neighbors, points, rebuild_topology_, repel,
+                  StrongSpacingForce, compute_force, hastopology, isinside, metrics, neighbors, points, rebuild_topology_, repel,
                   search, searchdists, set_topology, topology)
+from .mesh import TriangleOctree, cuboid_mesh, icosphere_mesh, read_binary_stl, torus_mesh, unit_cube_mesh
 
 __all__ = [n for n in dir() if not n.startswith("_")]

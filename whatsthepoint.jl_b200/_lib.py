@@ -57,6 +57,12 @@ class TraceEntry(C.Structure):
                 ("idx_a", C.c_int64), ("idx_b", C.c_int64)]
 
 
+class WallMesh(C.Structure):
+    _fields_ = [("triangles", C.c_void_p), ("feature_normals", C.c_void_p), ("n_tri", C.c_int64),
+                ("bbox_min", C.c_double * 3), ("bbox_max", C.c_double * 3), ("offset_dist", C.c_double),
+                ("is_bnd", C.c_void_p), ("tri_indices", C.c_void_p), ("escaped", C.c_void_p)]
+
+
 class CloudMetrics(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("avg", "std", "max", "min", "separation", "fill", "mesh_ratio")]
 
@@ -241,20 +247,29 @@ class Context:
         return Spacing(SPACING_KINDS[kind], float(a), float(b), float(c), bnd_ptr, n_bnd), None
 
     def repel(self, snap, n_fixed: int, sp: Spacing, force: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
-              stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False):
+              stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, mesh=None, is_bnd=None):
         """_relax! on snap = [fixed head; movable tail] (host array, copied). Returns
         (new_snap, conv, result dict, trace list | None)."""
         snap = np.array(_as_points(snap), copy=True)
         n_all, d = snap.shape
         n_move = n_all - n_fixed
-        prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 0, 1 if trace else 0, 0,
+        prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0, 0,
                           float(alpha_lo), float(alpha_max), float(tol), float(cv_target))
         conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
         tr = (TraceEntry * max(max_iters, 1))() if trace else None
         res = RepelResult()
+        wall, keep = None, None
+        self.last_wall = None
+        if mesh is not None:   # repel(cloud, spacing, octree): boundary flags in, landing triangles / escape flags out
+            flags = np.ascontiguousarray(is_bnd, dtype=np.uint8)
+            tri_idx, esc = np.zeros(n_move, dtype=np.int64), np.zeros(n_move, dtype=np.uint8)
+            w, keep = mesh.astype(snap.dtype).wall(flags, tri_idx, esc)
+            wall = C.byref(w)
+            self.last_wall = dict(tri_indices=tri_idx, escaped=esc)
         fn = getattr(self._lib, "wtp_repel_" + _sfx(snap.dtype))
         self._check(fn(self._h, _vp(snap), C.c_int64(n_fixed), C.c_int64(n_move), C.c_int32(d), C.byref(sp), C.byref(force),
-                       C.byref(prm), None, _vp(conv), tr, C.byref(res)))
+                       C.byref(prm), wall, _vp(conv), tr, C.byref(res)))
+        del keep
         out_tr = None
         if trace:
             out_tr = [dict(iteration=i + 1, r=tr[i].r, s=tr[i].s, r_over_s=tr[i].r_over_s, idx_a=tr[i].idx_a, idx_b=tr[i].idx_b)
@@ -285,6 +300,22 @@ class Context:
         out = np.empty_like(u)
         self._check(getattr(self._lib, "wtp_force_eval_" + _sfx(u.dtype))(self._h, C.byref(force), _vp(u), C.c_int64(u.size), _vp(out)))
         return out
+
+    def mesh_isinside(self, mesh, pts) -> np.ndarray:
+        """isinside(points, octree) -> bool array (src/octree/triangle_octree.jl:97-115)."""
+        pts = _as_points(pts)
+        w, keep = mesh.astype(pts.dtype).wall()
+        out = np.zeros(pts.shape[0], dtype=np.uint8)
+        self._check(getattr(self._lib, "wtp_mesh_isinside_" + _sfx(pts.dtype))(self._h, C.byref(w), _vp(pts), C.c_int64(pts.shape[0]), _vp(out)))
+        return out.astype(bool)
+
+    def mesh_project(self, mesh, pts):
+        """_project_to_boundary for a batch -> (projected points, 1-based triangle ids)."""
+        pts = _as_points(pts)
+        w, keep = mesh.astype(pts.dtype).wall()
+        out, tri = np.empty_like(pts), np.zeros(pts.shape[0], dtype=np.int64)
+        self._check(getattr(self._lib, "wtp_mesh_project_" + _sfx(pts.dtype))(self._h, C.byref(w), _vp(pts), C.c_int64(pts.shape[0]), _vp(out), _vp(tri)))
+        return out, tri
 
     def metrics(self, pts, k=20) -> dict:
         pts = _as_points(pts)

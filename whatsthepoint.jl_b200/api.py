@@ -8,6 +8,8 @@ written in Python with the reference's names, argument meaning and error behavio
     rebuild_topology_(cloud)  (rebuild_topology!)   src/cloud.jl:224, src/topology.jl:109-129
     neighbors / hastopology / topology / points     src/cloud.jl:171-197,235
     repel(cloud, spacing; ...)                 src/repel.jl:56-95
+    repel(cloud, spacing, octree; ...)         src/repel.jl:122-181 (mesh wall rule, _reconstruct_cloud :590-629)
+    isinside(points, octree)                   src/octree/triangle_octree.jl:97-115
     metrics(cloud; k)                          src/metrics.jl:19-41
     ConstantSpacing / LogLike / BoundaryLayerSpacing   src/discretization/spacings.jl
     InverseDistanceForce / SpacingEquilibriumForce / ClippedSpacingForce / StrongSpacingForce
@@ -409,7 +411,7 @@ def compute_force(model: RepelForceModel, u, ctx=None):
 # --------------------------------------------------------------------- repel
 def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2, force_model: RepelForceModel | None = None,
           alpha=None, alpha_min=None, k=21, max_iters=1000, tol=1.0e-6, rebuild_every: int = 1, cull_ratio=0.0,
-          kick_after: int = 0, stall_after: int = 50, cv_target=0.0, convergence: list | None = None,
+          kick_after: int = 0, stall_after: int = 50, cv_target=0.0, deposit_ratio=0.0, convergence: list | None = None,
           trace: list | None = None, isinside: Callable | None = None, ctx=None) -> PointCloud:
     """repel(cloud, spacing; kwargs...) (src/repel.jl:56-95): volume points move, boundary
     points are the fixed wall; returns a new cloud with NoTopology.
@@ -421,8 +423,12 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
     """
     if rebuild_every < 1:
         raise WtpArgumentError(1, "rebuild_every must be ≥ 1")                     # src/repel.jl:74
-    if octree is not None:
-        raise WtpError(3, "repel(cloud, spacing, octree) needs the mesh wall rule, which this build does not provide")
+    if octree is not None and not hasattr(octree, "feature_normals"):
+        raise WtpError(3, "repel(cloud, spacing, octree): octree must be a TriangleOctree (only its TriangleIndex arrays cross the C ABI)")
+    if deposit_ratio < 0:
+        raise WtpArgumentError(1, "deposit_ratio must be ≥ 0")                     # src/repel.jl:143
+    if deposit_ratio > 0:
+        raise WtpError(3, "deposit_ratio > 0 (_deposit_escaped!, src/repel.jl:483-514, serial by design) is not provided by this build")
     if cull_ratio > 0:
         raise WtpError(3, "cull_ratio > 0 (_cull, src/repel.jl:549-580) is not provided by this build")
     if not isinstance(spacing, AbstractSpacing):
@@ -433,16 +439,22 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         raise WtpError(3, "user-defined RepelForceModel subtypes cannot cross the C ABI (no CPU fallback)")
     bnd_p = cloud.boundary._points()
     n_bnd = bnd_p.shape[0]
-    snap = np.concatenate([bnd_p, cloud.volume.points], axis=0)                    # :80
+    snap = np.concatenate([bnd_p, cloud.volume.points], axis=0)                    # :80 / :146-148
     dtype = snap.dtype
+    if octree is not None and snap.shape[1] != 3:
+        raise TypeError("repel(cloud, spacing, octree) is defined for 3-D clouds only")   # dispatch on 𝔼{3}, :123
     sp, keep = spacing._abi(dtype)
     if alpha is None:                                                              # :61  α = minimum(spacing.(to(cloud)))/20
         alpha = dtype.type(ctx.spacing_eval(sp, snap).min()) / dtype.type(20)
     if alpha_min is None:                                                          # :62
         alpha_min = alpha / 100
-    new_snap, conv, res, tr = ctx.repel(snap, n_bnd, sp, fm._abi(), k=k, max_iters=max_iters, tol=tol,
+    is_bnd = None
+    if octree is not None:                                                         # every point moves, :172; is_bnd :155
+        is_bnd = np.arange(snap.shape[0]) < n_bnd
+    new_snap, conv, res, tr = ctx.repel(snap, 0 if octree is not None else n_bnd, sp, fm._abi(), k=k, max_iters=max_iters, tol=tol,
                                         rebuild_every=rebuild_every, stall_after=stall_after, cv_target=cv_target,
-                                        alpha_lo=alpha_min, alpha_max=alpha, kick_after=kick_after, trace=trace is not None)
+                                        alpha_lo=alpha_min, alpha_max=alpha, kick_after=kick_after, trace=trace is not None,
+                                        mesh=octree, is_bnd=is_bnd)
     del keep
     if convergence is not None:
         convergence.extend(float(c) for c in conv)                                 # :88
@@ -457,12 +469,46 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         log.info("Node repel finished in %d iterations", i)
     elif max_iters > 0:
         log.warning("Node repel reached maximum iterations")
+    if octree is not None:
+        out = _reconstruct_cloud(cloud, new_snap, ctx.last_wall["tri_indices"], is_bnd, n_bnd, octree)
+        out.repel_result = res
+        out.escaped = ctx.last_wall["escaped"].astype(bool)
+        return out
     p = new_snap[n_bnd:]
     if isinside is not None:
         p = p[np.asarray(isinside(p), dtype=bool)]                                 # :90
     out = PointCloud(cloud.boundary, PointVolume(p), NoTopology())                 # :94
     out.repel_result = res
     return out
+
+
+def _reconstruct_cloud(cloud: PointCloud, p: np.ndarray, tri_indices: np.ndarray, is_bnd: np.ndarray, n_boundary: int, octree) -> PointCloud:
+    """src/repel.jl:590-629: kept points are split by is_bnd into one `boundary` surface and the
+    volume; projected boundary points take the landing triangle's normal, imported ones keep
+    their area."""
+    normals = [s.normals for s in cloud.boundary.surfaces.values()]
+    areas = [s.areas for s in cloud.boundary.surfaces.values()]
+    orig_normals = np.concatenate(normals, axis=0) if all(x is not None for x in normals) and normals else None
+    orig_areas = np.concatenate(areas, axis=0) if all(x is not None for x in areas) and areas else None
+    b = np.flatnonzero(is_bnd)
+    tri = tri_indices[b]
+    face = octree.astype(p.dtype).face
+    new_normals = face[np.maximum(tri, 1) - 1].copy()
+    if orig_normals is not None:
+        keep_orig = (tri == 0) & (b < n_boundary)
+        new_normals[keep_orig] = orig_normals[b[keep_orig]]
+    new_areas = orig_areas[b] if orig_areas is not None else None
+    surf = PointSurface(p[b], new_normals, new_areas)
+    return PointCloud(PointBoundary({"boundary": surf}), PointVolume(p[~is_bnd]), NoTopology())
+
+
+def isinside(pts, octree, ctx=None) -> np.ndarray:
+    """isinside(points, octree) on the device (src/octree/triangle_octree.jl:97-115)."""
+    ctx = ctx or default_context()
+    a = pts._points() if hasattr(pts, "_points") else np.asarray(pts)
+    single = a.ndim == 1
+    out = ctx.mesh_isinside(octree, a[None, :] if single else a)
+    return bool(out[0]) if single else out
 
 
 # ------------------------------------------------------------------- metrics

@@ -13,7 +13,8 @@ int32_t fail(wtp_ctx* ctx, const Error& e);
 void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_cells, int64_t n_expanded);
 template <class T>
 void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int D, const wtp_spacing* sp_in, const T* d_bnd,
-                  const wtp_force* fm, const wtp_repel_params* prm, T* conv, wtp_trace_entry* trace, wtp_repel_result* res);
+                  const wtp_force* fm, const wtp_repel_params* prm, MeshBuffers* mesh, T* conv, wtp_trace_entry* trace,
+                  wtp_repel_result* res);
 }  // namespace wtp
 
 #define LAUNCH_CHECK(ctx)                         \
@@ -185,7 +186,9 @@ static int32_t repel_host(wtp_ctx* ctx, T* snap, int64_t n_fixed, int64_t n_move
     WTP_REQUIRE(snap && sp && fm && prm && conv && res, WTP_ERR_BAD_ARG, "null pointer");
     WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
     WTP_REQUIRE(n_fixed >= 0 && n_move >= 0 && n_fixed + n_move > 0, WTP_ERR_BAD_ARG, "empty snapshot");
-    WTP_REQUIRE(wall == nullptr && prm->wall == WTP_WALL_IDENTITY, WTP_ERR_UNSUPPORTED, "mesh wall rule is not available in this build");
+    WTP_REQUIRE((wall != nullptr) == (prm->wall == WTP_WALL_MESH), WTP_ERR_BAD_ARG, "params.wall and the wall mesh argument disagree");
+    WTP_REQUIRE(!wall || D == 3, WTP_ERR_BAD_ARG, "the mesh wall rule is 3-D only (src/repel.jl:123)");
+    WTP_REQUIRE(!wall || n_move == 0 || wall->is_bnd, WTP_ERR_BAD_ARG, "mesh wall needs the is_bnd flags");
     ctx->timer.reset(ctx->stream);
     ctx->timer.begin_total();
     const int64_t n_all = n_fixed + n_move;
@@ -201,12 +204,24 @@ static int32_t repel_host(wtp_ctx* ctx, T* snap, int64_t n_fixed, int64_t n_move
             d_bnd = b;
         }
     }
-    relax_device<T>(ctx, d_snap, n_fixed, n_move, D, sp, d_bnd, fm, prm, conv, trace, res);
+    MeshBuffers* mesh = nullptr;
+    if (wall) {   // TriangleIndex arrays -> device BVH; per-point wall state (src/repel.jl:151-156)
+        mesh = &ctx->mesh;
+        mesh_build<T>(ctx, *mesh, wall);
+        const size_t nm = (size_t)std::max<int64_t>(n_move, 1);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(mesh->is_bnd.as<uint8_t>(nm), wall->is_bnd, (size_t)n_move, cudaMemcpyHostToDevice, ctx->stream));
+        WTP_CUDA_CHECK(cudaMemsetAsync(mesh->tri_idx.as<int64_t>(nm), 0, nm * sizeof(int64_t), ctx->stream));
+        WTP_CUDA_CHECK(cudaMemsetAsync(mesh->escaped.as<uint8_t>(nm), 0, nm, ctx->stream));
+        WTP_CUDA_CHECK(cudaMemsetAsync(mesh->hint.as<uint32_t>(nm), 0xff, nm * sizeof(uint32_t), ctx->stream));
+    }
+    relax_device<T>(ctx, d_snap, n_fixed, n_move, D, sp, d_bnd, fm, prm, mesh, conv, trace, res);
     wtp_timing keep = ctx->last_timing;
     {
         ScopedPhase ph(ctx->timer, PH_D2H);
         WTP_CUDA_CHECK(cudaMemcpyAsync(snap + (size_t)n_fixed * D, d_snap + (size_t)n_fixed * D, (size_t)n_move * D * sizeof(T),
                                        cudaMemcpyDeviceToHost, ctx->stream));
+        if (mesh && wall->tri_indices) WTP_CUDA_CHECK(cudaMemcpyAsync(wall->tri_indices, mesh->tri_idx.get<int64_t>(), (size_t)n_move * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (mesh && wall->escaped) WTP_CUDA_CHECK(cudaMemcpyAsync(wall->escaped, mesh->escaped.get<uint8_t>(), (size_t)n_move, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->timer.end_total();
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -221,7 +236,7 @@ static int32_t repel_dev(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_mov
     WTP_REQUIRE(d_snap && sp && fm && prm && conv && res, WTP_ERR_BAD_ARG, "null pointer");
     ctx->timer.reset(ctx->stream);
     ctx->timer.begin_total();
-    relax_device<T>(ctx, d_snap, n_fixed, n_move, D, sp, static_cast<const T*>(sp->bnd_pts), fm, prm, conv, trace, res);
+    relax_device<T>(ctx, d_snap, n_fixed, n_move, D, sp, static_cast<const T*>(sp->bnd_pts), fm, prm, nullptr, conv, trace, res);
     ctx->timer.end_total();
     API_END(ctx)
 }
@@ -259,6 +274,31 @@ static int32_t force_eval_host(wtp_ctx* ctx, const wtp_force* f, const T* u, int
     const ForceP<T> fp{f->kind, (T)f->beta, (T)f->u0, (T)f->gamma};
     force_eval<T>(ctx, fp, d_u, n, d_o);
     WTP_CUDA_CHECK(cudaMemcpyAsync(out, d_o, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+// ----------------------------------------------------------- mesh queries
+// isinside(points, octree) / _project_to_boundary for a batch of host points (3-D)
+template <class T>
+static int32_t mesh_query_host(wtp_ctx* ctx, const wtp_wall_mesh* wall, const T* pts, int64_t N, uint8_t* out_inside, T* out_pts, int64_t* out_tri) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(wall && pts && N > 0 && (out_inside || (out_pts && out_tri)), WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    MeshBuffers& mb = ctx->mesh;
+    mesh_build<T>(ctx, mb, wall);
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * 3);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    if (out_inside) {
+        uint8_t* d_o = ctx->d_misc.as<uint8_t>((size_t)N);
+        mesh_isinside<T>(ctx, mb, d_pts, N, d_o);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(out_inside, d_o, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        T* d_o = ctx->d_misc.as<T>((size_t)N * 3);
+        int64_t* d_t = ctx->d_misc2.as<int64_t>((size_t)N);
+        mesh_project<T>(ctx, mb, d_pts, N, d_o, d_t);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(out_pts, d_o, (size_t)N * 3 * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        WTP_CUDA_CHECK(cudaMemcpyAsync(out_tri, d_t, (size_t)N * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
 }
@@ -325,6 +365,11 @@ int32_t wtp_spacing_eval_f32(wtp_ctx* c, const wtp_spacing* sp, const float* p, 
 int32_t wtp_spacing_eval_f64(wtp_ctx* c, const wtp_spacing* sp, const double* p, int64_t N, int32_t D, double* out) { return spacing_eval_host<double>(c, sp, p, N, D, out); }
 int32_t wtp_force_eval_f32(wtp_ctx* c, const wtp_force* f, const float* u, int64_t n, float* out) { return force_eval_host<float>(c, f, u, n, out); }
 int32_t wtp_force_eval_f64(wtp_ctx* c, const wtp_force* f, const double* u, int64_t n, double* out) { return force_eval_host<double>(c, f, u, n, out); }
+
+int32_t wtp_mesh_isinside_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, uint8_t* out) { return mesh_query_host<float>(c, m, p, N, out, nullptr, nullptr); }
+int32_t wtp_mesh_isinside_f64(wtp_ctx* c, const wtp_wall_mesh* m, const double* p, int64_t N, uint8_t* out) { return mesh_query_host<double>(c, m, p, N, out, nullptr, nullptr); }
+int32_t wtp_mesh_project_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, float* op, int64_t* ot) { return mesh_query_host<float>(c, m, p, N, nullptr, op, ot); }
+int32_t wtp_mesh_project_f64(wtp_ctx* c, const wtp_wall_mesh* m, const double* p, int64_t N, double* op, int64_t* ot) { return mesh_query_host<double>(c, m, p, N, nullptr, op, ot); }
 
 }  // extern "C"
 

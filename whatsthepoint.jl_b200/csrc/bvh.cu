@@ -20,23 +20,6 @@ namespace wtp {
 
 constexpr int BVH_LEAF = 8;
 
-__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000ffu;
-    v = (v | (v << 8)) & 0x0300f00fu;
-    v = (v | (v << 4)) & 0x030c30c3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-__device__ __forceinline__ uint32_t spread2(uint32_t v) {  // 16 bits -> every second bit
-    v &= 0xffffu;
-    v = (v | (v << 8)) & 0x00ff00ffu;
-    v = (v | (v << 4)) & 0x0f0f0f0fu;
-    v = (v | (v << 2)) & 0x33333333u;
-    v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-
 template <class T, int D>
 __global__ void __launch_bounds__(256) morton_key_kernel(const T* __restrict__ pts, int64_t n, T lox, T loy, T loz, T sx, T sy, T sz,
                                                          uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
@@ -96,6 +79,17 @@ __global__ void __launch_bounds__(256) bvh_level_kernel(int64_t first, int64_t c
     boxes[i] = o;
 }
 
+// inner boxes of a complete binary tree in heap layout whose P leaves (boxes[P..2P)) are set
+template <class T>
+void bvh_build_levels(wtp_ctx* ctx, Box<T>* boxes, int64_t P) {
+    for (int64_t L = P / 2; L >= 1; L /= 2) {
+        bvh_level_kernel<T><<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(L, L, boxes);
+        LAUNCH_CHECK(ctx);
+    }
+}
+template void bvh_build_levels<float>(wtp_ctx*, Box<float>*, int64_t);
+template void bvh_build_levels<double>(wtp_ctx*, Box<double>*, int64_t);
+
 template <class T>
 void bvh_build(wtp_ctx* ctx, BvhBuffers& bv, const T* d_bnd, int64_t n, int D) {
     WTP_REQUIRE(n > 0 && d_bnd, WTP_ERR_BAD_ARG, "variable spacing needs a non-empty boundary point set");
@@ -126,10 +120,7 @@ void bvh_build(wtp_ctx* ctx, BvhBuffers& bv, const T* d_bnd, int64_t n, int D) {
     Box<T>* boxes = bv.boxes.as<Box<T>>((size_t)2 * P);
     bvh_leaf_kernel<T><<<(unsigned)((P + 255) / 256), 256, 0, ctx->stream>>>(sorted, n, P, boxes);
     LAUNCH_CHECK(ctx);
-    for (int64_t L = P / 2; L >= 1; L /= 2) {
-        bvh_level_kernel<T><<<(unsigned)((L + 255) / 256), 256, 0, ctx->stream>>>(L, L, boxes);
-        LAUNCH_CHECK(ctx);
-    }
+    bvh_build_levels<T>(ctx, boxes, P);
     bv.n = n;
     bv.leaf_pow2 = P;
 }

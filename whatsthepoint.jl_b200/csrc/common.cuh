@@ -86,6 +86,24 @@ __host__ __device__ inline int cell_coord(const Grid<T>& g, T v, int d) {
     return i;
 }
 
+// Morton bit spreading (bvh.cu, mesh.cu)
+__device__ __forceinline__ uint32_t spread3(uint32_t v) {  // 10 bits -> every third bit
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t spread2(uint32_t v) {  // 16 bits -> every second bit
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
 // ------------------------------------------------------------ device memory
 struct DevBuf {
     void* p = nullptr;
@@ -172,6 +190,21 @@ struct BvhBuffers {
     int64_t leaf_pow2 = 0;
 };
 
+// Triangle mesh of the wall rule (mesh.cu): sorted triangle records, implicit BVH, the
+// per-triangle feature pseudonormals in caller order, and the per-point wall state.
+struct MeshBuffers {
+    IndexBuffers ib;                   // sort scratch
+    DevBuf raw;                        // n_tri x 9 of T as uploaded
+    DevBuf tris;                       // TriRec<T>[n_tri], Morton order
+    DevBuf boxes;                      // Box<T>[2 * leaf_pow2]
+    DevBuf fnorm;                      // n_tri x 21 of T, caller order
+    DevBuf is_bnd, tri_idx, escaped;   // u8 / i64 / u8 per movable point
+    DevBuf hint;                       // u32 per movable point: sorted position of last nearest triangle
+    int64_t n = 0, leaf_pow2 = 0;
+    double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    double offset = 0, maxabs = 0;
+};
+
 struct NcclApi;  // comm.cu
 
 }  // namespace wtp
@@ -193,6 +226,8 @@ struct wtp_ctx {
     wtp::IndexBuffers index[1];
     // 1-NN structure of a variable spacing's boundary set
     wtp::BvhBuffers bvh;
+    // triangle mesh of the wall rule (3-argument repel) and of the batched mesh queries
+    wtp::MeshBuffers mesh;
     wtp::DevBuf d_pts, d_out_idx, d_out_dist, d_offsets, d_counts, d_indices, d_misc, d_misc2;
     wtp::DevBuf d_spacing_pts, d_spacings, d_p_new, d_reduce, d_qlist, d_nn;
     // radius two-call state

@@ -65,5 +65,24 @@ void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, con
                   uint32_t* d_nn_cache = nullptr, bool use_cache = false);
 template <class T>
 void force_eval(wtp_ctx* ctx, const ForceP<T>& f, const T* d_u, int64_t n, T* d_out);
+// inner boxes of a complete binary tree in heap layout whose P leaves (boxes[P..2P)) are set
+template <class T>
+void bvh_build_levels(wtp_ctx* ctx, Box<T>* boxes, int64_t P);
+
+// ---- mesh.cu -------------------------------------------------------------
+// Triangle-mesh queries of the wall rule (_constrain_octree, src/repel.jl:448-469): Morton BVH
+// over the triangles, exact nearest triangle by (d2, triangle index), Ericson closest point,
+// pseudonormal-signed inside test.
+// H2D of the TriangleIndex arrays (host pointers in `wall`) + BVH build on the device.
+template <class T>
+void mesh_build(wtp_ctx* ctx, MeshBuffers& mb, const wtp_wall_mesh* wall);
+template <class T>
+void mesh_isinside(wtp_ctx* ctx, const MeshBuffers& mb, const T* d_pts, int64_t n, uint8_t* d_out);
+template <class T>
+void mesh_project(wtp_ctx* ctx, const MeshBuffers& mb, const T* d_pts, int64_t n, T* d_out_pts, int64_t* d_out_tri);
+// Wall rule on the movable ids [id_lo, id_hi): P_new holds the proposals on entry and the
+// constrained positions on return; mb.tri_idx / mb.escaped (n_move entries) are updated.
+template <class T>
+void mesh_wall_apply(wtp_ctx* ctx, MeshBuffers& mb, const T* d_P_old, T* d_P_new, int64_t id_lo, int64_t id_hi);
 
 }  // namespace wtp

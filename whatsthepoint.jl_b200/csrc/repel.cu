@@ -247,13 +247,16 @@ static void launch_sweep(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
 // ------------------------------------------------------------- host driver
 template <class T>
 void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int D, const wtp_spacing* sp_in, const T* d_bnd,
-                  const wtp_force* fm, const wtp_repel_params* prm, T* conv, wtp_trace_entry* trace, wtp_repel_result* res) {
+                  const wtp_force* fm, const wtp_repel_params* prm, MeshBuffers* mesh, T* conv, wtp_trace_entry* trace,
+                  wtp_repel_result* res) {
     WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
     WTP_REQUIRE(n_fixed >= 0 && n_move >= 0 && n_fixed + n_move > 0, WTP_ERR_BAD_ARG, "empty snapshot");
     WTP_REQUIRE(prm->rebuild_every >= 1, WTP_ERR_BAD_ARG, "rebuild_every must be >= 1");          // src/repel.jl:74
     WTP_REQUIRE(prm->k >= 1 && prm->max_iters >= 0, WTP_ERR_BAD_ARG, "k must be >= 1 and max_iters >= 0");
     WTP_REQUIRE(prm->kick_after == 0, WTP_ERR_UNSUPPORTED, "kick_after > 0 draws randn (src/repel.jl:430): not reproducible on the device");
-    WTP_REQUIRE(prm->wall == WTP_WALL_IDENTITY, WTP_ERR_UNSUPPORTED, "mesh wall rule is not available in this build");
+    WTP_REQUIRE(prm->wall == WTP_WALL_IDENTITY || prm->wall == WTP_WALL_MESH, WTP_ERR_UNSUPPORTED, "user-defined constrain closure cannot cross the C ABI");
+    WTP_REQUIRE((prm->wall == WTP_WALL_MESH) == (mesh != nullptr), WTP_ERR_BAD_ARG, "params.wall and the wall mesh argument disagree");
+    WTP_REQUIRE(!mesh || D == 3, WTP_ERR_BAD_ARG, "the mesh wall rule is 3-D only (src/repel.jl:123)");
     WTP_REQUIRE(fm->kind >= WTP_FORCE_INVERSE && fm->kind <= WTP_FORCE_STRONG, WTP_ERR_UNSUPPORTED, "user-defined RepelForceModel cannot cross the C ABI");
     WTP_REQUIRE(sp_in->kind >= WTP_SPACING_CONSTANT && sp_in->kind <= WTP_SPACING_BOUNDARY_LAYER, WTP_ERR_UNSUPPORTED, "user-defined spacing callable cannot cross the C ABI");
     const int64_t n_all = n_fixed + n_move;
@@ -335,6 +338,10 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             ScopedPhase ph(ctx->timer, PH_QUERY);
             if (D == 2) launch_sweep<T, 2>(ctx, a, nblocks); else launch_sweep<T, 3>(ctx, a, nblocks);
         }
+        if (mesh) {                                                                                  // constrain(id, xi, xi + disp), :291, 448-469
+            ScopedPhase ph(ctx->timer, PH_SCAN);
+            mesh_wall_apply<T>(ctx, *mesh, Pa, Pb, id_lo, id_hi);
+        }
         {
             ScopedPhase ph(ctx->timer, PH_REDUCE);
             repel_finalize_kernel<T><<<1, 256, 0, st>>>(partials, nblocks, d_tot);
@@ -388,6 +395,10 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         ++it;
     }
     WTP_CUDA_CHECK(cudaMemcpyAsync(S_tail, Pa, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    if (mesh && world > 1) {   // every rank returns the landing triangles / escape flags of all points
+        comm_allgather_rows(ctx, mesh->tri_idx.get<int64_t>(), n_move, sizeof(int64_t));
+        comm_allgather_rows(ctx, mesh->escaped.get<uint8_t>(), n_move, sizeof(uint8_t));
+    }
     WTP_CUDA_CHECK(cudaStreamSynchronize(st));
     res->iters = n_conv;
     ctx->last_timing = wtp_timing{};
@@ -397,9 +408,9 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 }
 
 template void relax_device<float>(wtp_ctx*, float*, int64_t, int64_t, int, const wtp_spacing*, const float*, const wtp_force*,
-                                  const wtp_repel_params*, float*, wtp_trace_entry*, wtp_repel_result*);
+                                  const wtp_repel_params*, MeshBuffers*, float*, wtp_trace_entry*, wtp_repel_result*);
 template void relax_device<double>(wtp_ctx*, double*, int64_t, int64_t, int, const wtp_spacing*, const double*, const wtp_force*,
-                                   const wtp_repel_params*, double*, wtp_trace_entry*, wtp_repel_result*);
+                                   const wtp_repel_params*, MeshBuffers*, double*, wtp_trace_entry*, wtp_repel_result*);
 
 template <class T>
 void fill_device(wtp_ctx* ctx, T* d_out, int64_t n, T v) {
