@@ -3,6 +3,7 @@
 #include <cmath>
 #include <new>
 
+#include "host_pool.h"
 #include "kernels.cuh"
 
 using namespace wtp;
@@ -68,6 +69,7 @@ int32_t wtp_create(wtp_ctx** out, int32_t device) {
     bool ok = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (auto& e : ctx->ev_chunk) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->ev_copy_done, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& e : ctx->ev_copied) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { wtp_destroy(ctx); return WTP_ERR_CUDA; }
     *out = ctx;
     return WTP_OK;
@@ -78,6 +80,9 @@ void wtp_destroy(wtp_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     wtp_comm_destroy_internal(ctx);
+    delete ctx->pool;
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    for (auto e : ctx->ev_copied) if (e) cudaEventDestroy(e);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
@@ -182,22 +187,54 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     }
     unsigned long long* d_exp = ctx->d_reduce.as<unsigned long long>(1);
     WTP_CUDA_CHECK(cudaMemsetAsync(d_exp, 0, sizeof(unsigned long long), ctx->stream));
-    // Host sink and a large result: answer the queries in caller-order chunks and overlap the D2H of
-    // chunk c (copy stream) with the kernel of chunk c+1. The result is PCIe-bound either way.
+    // Host sink and a large result (the int64 table is PCIe-bound): answer the queries in caller-order
+    // chunks writing 4-byte indices, bring chunk c back into a pinned staging ring on the copy stream
+    // while chunk c+1 computes, and widen it into the caller's int64 rows on the host pool while chunk
+    // c+1 is on the wire. 4 B per neighbour cross PCIe instead of 8.
     const bool pipelined = h_out_idx != nullptr && (qe - qb) * (int64_t)k >= ((int64_t)4 << 20);
+    int n_chunks = 1;
     if (pipelined) {
-        constexpr int C = 8;
-        for (int c = 0; c < C; ++c) {
-            const int64_t cb = qb + (qe - qb) * c / C, ce = qb + (qe - qb) * (c + 1) / C;
-            if (ce <= cb) continue;
-            build_query_list(ctx, ib, N, cb, ce, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
-            knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, ctx->d_qlist.get<uint32_t>(), ce - cb, qb, d_out_idx, d_out_dist, d_exp);
-            WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[c], ctx->stream));
-            WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c], 0));
-            WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_idx + cb * k, d_out_idx + (cb - qb) * k, (size_t)(ce - cb) * k * sizeof(int64_t),
-                                           cudaMemcpyDeviceToHost, ctx->copy_stream));
-            if (h_out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist + cb * k, d_out_dist + (cb - qb) * k, (size_t)(ce - cb) * k * sizeof(T),
+        constexpr int S = 3;                                     // staging slots
+        constexpr size_t SLOT = (size_t)32 << 20;                // bytes per slot
+        if (!ctx->h_stage) {
+            WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, S * SLOT));
+            ctx->h_stage_slot_bytes = SLOT;
+        }
+        if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());
+        const int64_t nq = qe - qb;
+        const int64_t rows = std::max<int64_t>(1, (int64_t)(SLOT / ((size_t)k * sizeof(uint32_t))));
+        n_chunks = (int)((nq + rows - 1) / rows);
+        uint32_t* d_idx32 = reinterpret_cast<uint32_t*>(d_out_idx);   // the device table holds 4-byte indices in this mode
+        const uint32_t* lists = build_chunk_query_lists(ctx, ib, ctx->qsort, N, qb, qe, rows, n_chunks, sizeof(T) == 8);
+        auto enqueue_kernel = [&](int c) {
+            const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
+            knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, lists + cb, ce - cb, qb, d_idx32, d_out_dist, d_exp, true);
+            WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[c % 8], ctx->stream));
+        };
+        auto enqueue_copy = [&](int c) {
+            const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
+            WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c % 8], 0));
+            WTP_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT, d_idx32 + cb * k,
+                                           (size_t)(ce - cb) * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (h_out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist + (qb + cb) * k, d_out_dist + cb * k, (size_t)(ce - cb) * k * sizeof(T),
                                                            cudaMemcpyDeviceToHost, ctx->copy_stream));
+            WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[c % 4], ctx->copy_stream));
+        };
+        // kernels run four chunks ahead of the chunk being widened, copies two ahead (slots c, c+1, c+2 are distinct)
+        for (int c = 0; c < std::min(4, n_chunks); ++c) enqueue_kernel(c);
+        for (int c = 0; c < std::min(2, n_chunks); ++c) enqueue_copy(c);
+        for (int c = 0; c < n_chunks; ++c) {
+            if (c + 4 < n_chunks) enqueue_kernel(c + 4);
+            if (c + 2 < n_chunks) enqueue_copy(c + 2);
+            WTP_CUDA_CHECK(cudaEventSynchronize(ctx->ev_copied[c % 4]));
+            const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT);
+            int64_t* dst = h_out_idx + (qb + cb) * k;
+            const size_t total = (size_t)(ce - cb) * k;
+            ctx->pool->run([&](int part, int parts) {
+                const size_t a = (total * part / parts) & ~(size_t)3, b = part + 1 == parts ? total : ((total * (part + 1) / parts) & ~(size_t)3);
+                widen_u32_to_i64(src + a, dst + a, b - a);
+            });
         }
         WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
         WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
@@ -207,7 +244,7 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     unsigned long long* h_exp = static_cast<unsigned long long*>(ctx->h_pinned);
     WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    finish_timing(ctx, passes, pipelined ? 8 : 1, g.ncells, (int64_t)*h_exp);
+    finish_timing(ctx, passes, n_chunks, g.ncells, (int64_t)*h_exp);
     *rows_begin = qb; *rows_end = qe;
     return pipelined;
 }

@@ -206,6 +206,7 @@ struct MeshBuffers {
 };
 
 struct NcclApi;  // comm.cu
+class HostPool;  // host_pool.h
 
 }  // namespace wtp
 
@@ -242,6 +243,12 @@ struct wtp_ctx {
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
     wtp::NcclApi* nccl = nullptr;
+    // host k-NN pipeline: chunk query lists, 4-byte index staging (pinned ring) and the widening threads
+    wtp::IndexBuffers qsort;
+    void* h_stage = nullptr;
+    size_t h_stage_slot_bytes = 0;
+    cudaEvent_t ev_copied[4] = {};
+    wtp::HostPool* pool = nullptr;
     // pinned staging for scalar read-backs
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;

@@ -32,12 +32,17 @@ void exclusive_scan_u32_to_i64(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, 
 // Rows are written at (orig - q_begin) * (K1 - drop_first). idx_base: 1 for 1-based.
 template <class T>
 void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
-               const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, int64_t* d_out_idx, T* d_out_dist,
-               unsigned long long* d_expanded_counter);
+               const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+               unsigned long long* d_expanded_counter, bool out32 = false);   // out32: uint32 rows instead of int64
 
 // Compact list of sorted positions whose original index is in [q_begin, q_end).
 void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q_begin, int64_t q_end,
                       bool f64, DevBuf& flags, DevBuf& scan, DevBuf& qlist);
+
+// Query lists of all caller-order chunks [q_begin + c*rows_per_chunk, ...) in one stable radix pass;
+// returns the concatenated lists (chunk c starts at c*rows_per_chunk).
+const uint32_t* build_chunk_query_lists(wtp_ctx* ctx, const IndexBuffers& ib, IndexBuffers& scratch, int64_t N, int64_t q_begin,
+                                        int64_t q_end, int64_t rows_per_chunk, int n_chunks, bool f64);
 
 // ---- radius.cu -----------------------------------------------------------
 template <class T>

@@ -25,7 +25,7 @@ template <class T, int D, int KPL>
 __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted,
                                                           const uint32_t* __restrict__ cell_start,
                                                           const uint32_t* __restrict__ qlist, uint32_t nq, uint32_t q_begin,
-                                                          int K1, int drop, int64_t* __restrict__ out_idx,
+                                                          int K1, int drop, void* __restrict__ out_idx_v, int out32,
                                                           T* __restrict__ out_dist, unsigned long long* __restrict__ expanded) {
     constexpr int CAP = knn_tile_cap<T, KPL>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
     P4<T>* tile = reinterpret_cast<P4<T>*>(smem_raw) + (size_t)warp * CAP;
     WarpKnn<T, D, KPL, CAP> s(g, sorted, cell_start, tile, reinterpret_cast<Key<T>*>(s_buf) + warp * 64, &s_bar[warp], lane);
     const int k_out = K1 - drop;
+    int64_t* __restrict__ out_idx = static_cast<int64_t*>(out_idx_v);     // ABI layout: int64, 1-based
+    uint32_t* __restrict__ out_idx32 = static_cast<uint32_t*>(out_idx_v); // staging layout of the host entry points (widened on the host)
     const uint32_t q0 = (blockIdx.x * KNN_WARPS + warp) * KNN_QPW;
 #pragma unroll 1
     for (int it = 0; it < KNN_QPW; ++it) {
@@ -49,7 +51,8 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
         for (int e = 0; e < KPL; ++e) {
             const int r = e * 32 + lane;
             if (r >= drop && r < K1) {
-                out_idx[row + r - drop] = (int64_t)s.list.e[e].idx() + 1;
+                if (out32) out_idx32[row + r - drop] = s.list.e[e].idx() + 1u;
+                else out_idx[row + r - drop] = (int64_t)s.list.e[e].idx() + 1;
                 if (out_dist) out_dist[row + r - drop] = sqrt(s.list.e[e].d2());
             }
         }
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
 
 template <class T, int D, int KPL>
 static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, const P4<T>* sorted, const uint32_t* cs,
-                           const uint32_t* d_qlist, int64_t nq, int64_t q_begin, int K1, int drop, int64_t* d_out_idx,
+                           const uint32_t* d_qlist, int64_t nq, int64_t q_begin, int K1, int drop, void* d_out_idx, int out32,
                            T* d_out_dist, unsigned long long* d_exp) {
     constexpr size_t smem = (size_t)knn_tile_cap<T, KPL>() * sizeof(P4<T>) * KNN_WARPS;
     static bool configured = false;
@@ -67,36 +70,36 @@ static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, con
         configured = true;
     }
     knn_kernel<T, D, KPL><<<nblocks, KNN_THREADS, smem, ctx->stream>>>(g, sorted, cs, d_qlist, (uint32_t)nq, (uint32_t)q_begin,
-                                                                       K1, drop, d_out_idx, d_out_dist, d_exp);
+                                                                       K1, drop, d_out_idx, out32, d_out_dist, d_exp);
 }
 
 template <class T, int D>
 static void launch_knn(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int K1, int drop, const uint32_t* d_qlist,
-                       int64_t nq, int64_t q_begin, int64_t* d_out_idx, T* d_out_dist, unsigned long long* d_exp) {
+                       int64_t nq, int64_t q_begin, void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
     const unsigned nblocks = (unsigned)((nq + KNN_QPB - 1) / KNN_QPB);
     const P4<T>* sorted = ib.sorted.get<P4<T>>();
     const uint32_t* cs = ib.cell_start.get<uint32_t>();
-    if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, d_out_dist, d_exp);
-    else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, d_out_dist, d_exp);
-    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, d_out_dist, d_exp);
+    if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
+    else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
+    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, q_begin, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
     LAUNCH_CHECK(ctx);
 }
 
 template <class T>
 void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
-               const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, int64_t* d_out_idx, T* d_out_dist,
-               unsigned long long* d_expanded_counter) {
+               const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+               unsigned long long* d_expanded_counter, bool out32) {
     (void)N;
     WTP_REQUIRE(K1 >= 1 && K1 <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K (128 list entries)");
     if (n_queries <= 0) return;
     ScopedPhase ph(ctx->timer, PH_QUERY);
-    if (D == 2) launch_knn<T, 2>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, q_begin, d_out_idx, d_out_dist, d_expanded_counter);
-    else launch_knn<T, 3>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, q_begin, d_out_idx, d_out_dist, d_expanded_counter);
+    if (D == 2) launch_knn<T, 2>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
+    else launch_knn<T, 3>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
 }
 template void knn_query<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int64_t, int, int, int, const uint32_t*, int64_t,
-                               int64_t, int64_t*, float*, unsigned long long*);
+                               int64_t, void*, float*, unsigned long long*, bool);
 template void knn_query<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, const uint32_t*, int64_t,
-                                int64_t, int64_t*, double*, unsigned long long*);
+                                int64_t, void*, double*, unsigned long long*, bool);
 
 // ------------------------------------------------------------ query lists
 // Sharded mode: the sorted positions whose original index lies in [q_begin, q_end), in
@@ -128,6 +131,34 @@ void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q
     exclusive_scan_u32(ctx, const_cast<IndexBuffers&>(ib).scan_tmp, d_flags, d_pos, N);
     qcompact_kernel<<<nb, 256, 0, ctx->stream>>>(d_flags, d_pos, (uint32_t)N, d_q);
     LAUNCH_CHECK(ctx);
+}
+
+// All chunk query lists in one pass: key = chunk of the point's caller index ((i - q_begin) / rows_per_chunk;
+// points outside [q_begin, q_end) get the last bin), value = sorted position, one stable radix pass on
+// the few key bits. The sorted values are the chunk lists back to back, each in sorted (cell) order.
+template <class T>
+__global__ void __launch_bounds__(256) qchunk_key_kernel(const P4<T>* __restrict__ sorted, uint32_t N, uint32_t qb, uint32_t qe,
+                                                         uint32_t rows_per_chunk, uint32_t n_chunks, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ vals) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const uint32_t i = idx_of(sorted[j]);
+    keys[j] = (i >= qb && i < qe) ? (i - qb) / rows_per_chunk : n_chunks;
+    vals[j] = j;
+}
+
+const uint32_t* build_chunk_query_lists(wtp_ctx* ctx, const IndexBuffers& ib, IndexBuffers& scratch, int64_t N, int64_t q_begin,
+                                        int64_t q_end, int64_t rows_per_chunk, int n_chunks, bool f64) {
+    uint32_t* keys = scratch.keys_a.as<uint32_t>((size_t)N);
+    uint32_t* vals = scratch.vals_a.as<uint32_t>((size_t)N);
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    if (f64) qchunk_key_kernel<double><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<double>>(), (uint32_t)N, (uint32_t)q_begin, (uint32_t)q_end, (uint32_t)rows_per_chunk, (uint32_t)n_chunks, keys, vals);
+    else qchunk_key_kernel<float><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<float>>(), (uint32_t)N, (uint32_t)q_begin, (uint32_t)q_end, (uint32_t)rows_per_chunk, (uint32_t)n_chunks, keys, vals);
+    LAUNCH_CHECK(ctx);
+    int bits = 1;
+    while ((1 << bits) < n_chunks + 1) ++bits;
+    radix_sort_pairs(ctx, scratch, N, bits);
+    return scratch.vals_a.get<uint32_t>();
 }
 
 }  // namespace wtp
