@@ -1,6 +1,8 @@
 // api.cu — the C ABI of libwtp_cuda.so (include/wtp_cuda.h): context, instrumentation,
 // and the topology entry points. Repel lives in repel.cu, multi-GPU plumbing in comm.cu.
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "host_pool.h"
@@ -223,10 +225,15 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         // kernels run four chunks ahead of the chunk being widened, copies two ahead (slots c, c+1, c+2 are distinct)
         for (int c = 0; c < std::min(4, n_chunks); ++c) enqueue_kernel(c);
         for (int c = 0; c < std::min(2, n_chunks); ++c) enqueue_copy(c);
+        const bool dbg = std::getenv("WTP_PIPE_DEBUG") != nullptr;
+        double t_wait = 0, t_widen = 0;
+        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
         for (int c = 0; c < n_chunks; ++c) {
             if (c + 4 < n_chunks) enqueue_kernel(c + 4);
             if (c + 2 < n_chunks) enqueue_copy(c + 2);
+            const double t0 = dbg ? now() : 0;
             WTP_CUDA_CHECK(cudaEventSynchronize(ctx->ev_copied[c % 4]));
+            const double t1 = dbg ? now() : 0;
             const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT);
             int64_t* dst = h_out_idx + (qb + cb) * k;
@@ -235,7 +242,9 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
                 const size_t a = (total * part / parts) & ~(size_t)3, b = part + 1 == parts ? total : ((total * (part + 1) / parts) & ~(size_t)3);
                 widen_u32_to_i64(src + a, dst + a, b - a);
             });
+            if (dbg) { t_wait += t1 - t0; t_widen += now() - t1; }
         }
+        if (dbg) fprintf(stderr, "[wtp pipe] chunks=%d threads=%d wait_copy=%.2f ms widen=%.2f ms\n", n_chunks, ctx->pool->size(), t_wait, t_widen);
         WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
         WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
     } else {
