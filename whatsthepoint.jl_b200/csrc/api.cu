@@ -194,6 +194,9 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     // while chunk c+1 computes, and widen it into the caller's int64 rows on the host pool while chunk
     // c+1 is on the wire. 4 B per neighbour cross PCIe instead of 8.
     const bool pipelined = h_out_idx != nullptr && (qe - qb) * (int64_t)k >= ((int64_t)4 << 20);
+    // CTA-tiled front end (knn_tile.cuh) whenever the list fits one register row and this context answers
+    // every query; the general kernel alone otherwise (long lists, caller-order shards).
+    const bool tiled = K1 <= 32 && ctx->world == 1 && std::getenv("WTP_NO_TILED") == nullptr;
     int n_chunks = 1;
     if (pipelined) {
         constexpr int S = 3;                                     // staging slots
@@ -207,15 +210,22 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         const int64_t rows = std::max<int64_t>(1, (int64_t)(SLOT / ((size_t)k * sizeof(uint32_t))));
         n_chunks = (int)((nq + rows - 1) / rows);
         uint32_t* d_idx32 = reinterpret_cast<uint32_t*>(d_out_idx);   // the device table holds 4-byte indices in this mode
-        const uint32_t* lists = build_chunk_query_lists(ctx, ib, ctx->qsort, N, qb, qe, rows, n_chunks, sizeof(T) == 8);
+        // tiled: one pass over all queries in sorted order (rows land at their caller positions), then the
+        // copies; otherwise one kernel per caller-order chunk, overlapped with the copies
+        const uint32_t* lists = tiled ? nullptr : build_chunk_query_lists(ctx, ib, ctx->qsort, N, qb, qe, rows, n_chunks, sizeof(T) == 8);
         auto enqueue_kernel = [&](int c) {
-            const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
-            knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, lists + cb, ce - cb, qb, d_idx32, d_out_dist, d_exp, true);
+            if (tiled) {
+                if (c != 0) return;
+                knn_query_tiled<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, 0, N, qb, d_idx32, d_out_dist, d_exp, true);
+            } else {
+                const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
+                knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, lists + cb, ce - cb, qb, d_idx32, d_out_dist, d_exp, true);
+            }
             WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[c % 8], ctx->stream));
         };
         auto enqueue_copy = [&](int c) {
             const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
-            WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c % 8], 0));
+            if (!tiled || c == 0) WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c % 8], 0));
             WTP_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT, d_idx32 + cb * k,
                                            (size_t)(ce - cb) * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
             if (h_out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist + (qb + cb) * k, d_out_dist + cb * k, (size_t)(ce - cb) * k * sizeof(T),
@@ -247,6 +257,8 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         if (dbg) fprintf(stderr, "[wtp pipe] chunks=%d threads=%d wait_copy=%.2f ms widen=%.2f ms\n", n_chunks, ctx->pool->size(), t_wait, t_widen);
         WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
         WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
+    } else if (tiled) {
+        knn_query_tiled<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, 0, N, qb, d_out_idx, d_out_dist, d_exp);
     } else {
         knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, qlist, qe - qb, qb, d_out_idx, d_out_dist, d_exp);
     }

@@ -35,6 +35,12 @@ void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N
                const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, void* d_out_idx, T* d_out_dist,
                unsigned long long* d_expanded_counter, bool out32 = false);   // out32: uint32 rows instead of int64
 
+// CTA-tiled front end + general kernel for the leftovers, over the sorted positions [s_begin, s_end)
+// (K1 <= 32). Rows are written at (orig - q_begin) * (K1 - drop_first) like knn_query.
+template <class T>
+void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first, int64_t s_begin,
+                     int64_t s_end, int64_t q_begin, void* d_out_idx, T* d_out_dist, unsigned long long* d_expanded_counter, bool out32 = false);
+
 // Compact list of sorted positions whose original index is in [q_begin, q_end).
 void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q_begin, int64_t q_end,
                       bool f64, DevBuf& flags, DevBuf& scan, DevBuf& qlist);

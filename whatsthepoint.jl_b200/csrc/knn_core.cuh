@@ -76,6 +76,7 @@ template <> struct Key<float> {
     __device__ __forceinline__ float d2() const { return __uint_as_float((uint32_t)(v >> 32)); }
     __device__ __forceinline__ uint32_t idx() const { return (uint32_t)v; }
     __device__ __forceinline__ bool less(const Key& o) const { return v < o.v; }
+    __device__ __forceinline__ uint32_t coarse() const { return (uint32_t)(v >> 32); }    // monotone 32-bit image of d2
     __device__ __forceinline__ Key shfl(int src) const { Key k; k.v = __shfl_sync(FULL, v, src); return k; }
     __device__ __forceinline__ Key shfl_up1() const { Key k; k.v = __shfl_up_sync(FULL, v, 1); return k; }
     __device__ __forceinline__ Key shfl_xor(int m) const { Key k; k.v = __shfl_xor_sync(FULL, v, m); return k; }
@@ -87,6 +88,7 @@ template <> struct Key<double> {
     __device__ __forceinline__ double d2() const { return d; }
     __device__ __forceinline__ uint32_t idx() const { return i; }
     __device__ __forceinline__ bool less(const Key& o) const { return d < o.d || (d == o.d && i < o.i); }
+    __device__ __forceinline__ uint32_t coarse() const { return (uint32_t)__double2hiint(d); }   // d >= 0: high word is monotone
     __device__ __forceinline__ Key shfl(int src) const { Key k; k.d = __shfl_sync(FULL, d, src); k.i = __shfl_sync(FULL, i, src); return k; }
     __device__ __forceinline__ Key shfl_up1() const { Key k; k.d = __shfl_up_sync(FULL, d, 1); k.i = __shfl_up_sync(FULL, i, 1); return k; }
     __device__ __forceinline__ Key shfl_xor(int m) const { Key k; k.d = __shfl_xor_sync(FULL, d, m); k.i = __shfl_xor_sync(FULL, i, m); return k; }
@@ -161,6 +163,28 @@ struct WarpList {
             }
         }
         return c;
+    }
+    // Same result as sort32, cheaper: sort 32-bit images (the top 27 bits of d2's pattern, the lane in
+    // the low 5) with one SHFL + one min/max per stage, fetch the full keys through the sorted lane
+    // numbers, and check that neighbours are in strict canonical order. The images of two keys collide
+    // only when their d2 agree to ~18 bits (or on exact ties); then the order of that pair is decided
+    // by the full sort instead.
+    static __device__ __forceinline__ Key<T> sort32_fast(const Key<T>& c, int lane) {
+        uint32_t k = (c.coarse() & ~31u) | (uint32_t)lane;
+#pragma unroll
+        for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+                const uint32_t o = __shfl_xor_sync(FULL, k, j);
+                const bool keep_min = ((lane & j) == 0) == ((lane & kk) == 0);
+                k = keep_min ? min(k, o) : max(k, o);
+            }
+        }
+        const Key<T> s = c.shfl((int)(k & 31u));
+        const Key<T> prev = s.shfl_up1();
+        const bool bad = lane > 0 && !prev.less(s) && !(s.idx() == 0xffffffffu && prev.idx() == 0xffffffffu);   // sentinels tie with each other
+        if (__ballot_sync(FULL, bad)) return sort32(c, lane);
+        return s;
     }
     // first batch into an empty list: bitonic sort of the 32 candidates straight into row 0
     __device__ __forceinline__ void seed(Key<T> c, int lane) {
