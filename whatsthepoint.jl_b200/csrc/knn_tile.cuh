@@ -9,7 +9,7 @@
 //      3^D block (shared-memory broadcast reads, no cross-lane traffic), test
 //      d2 <= r0^2 (the density-guided radius of knn_core.cuh) and append the tile slot of
 //      every hit to the query's list in shared memory;
-//   B  warp per query: the <= 64 hits are turned into canonical (d2, index) keys, one
+//   B  warp per query: the hits are turned into canonical (d2, index) keys, one
 //      32-lane bitonic sort (+ merge) yields the sorted list, the K-th entry is checked against
 //      the shell of the block, and the row is written with coalesced stores.
 // Anything that does not fit this fast path (slab larger than the tile, fewer than K or more
@@ -134,9 +134,12 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
         const bool fits = total <= (uint32_t)CAP;
         if (fits && total > 0) { mbar_wait(&s_bar, phase); phase ^= 1u; }
 
-        // ---- phase A: thread per query
+        // ---- phase A: thread per query. The filter uses a fused (cheaper) distance and a radius padded by a
+        // few ulps, so the list holds at least every block point with canonical d2 <= r0sq.
         uint32_t cnt = 0;
         bool fail = !fits;
+        T r0sq = (T)0;
+        uint16_t* my = lists + tid * TK_LSTRIDE;
         if (in_group && fits) {
             uint32_t b[NROWS], e[NROWS], block_n = 0;
             const int xa = cx > 0 ? cx - 1 : 0, xb = cx < g.n[0] - 1 ? cx + 1 : g.n[0] - 1;
@@ -153,54 +156,66 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
             }
             if (block_n < (uint32_t)K1) fail = true;
             else {
-                const T r0sq = prefilter_radius2<T, D>(g, block_n, K1);
-                uint16_t* my = lists + tid * TK_LSTRIDE;
+                r0sq = prefilter_radius2<T, D>(g, block_n, K1);
+                const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));
+                const uint32_t my_s = smem_u32(my);
 #pragma unroll
                 for (int r = 0; r < NROWS; ++r) {
 #pragma unroll 2
                     for (uint32_t t = b[r]; t < e[r]; ++t) {
                         const P4<T> p = lds_p4(tile + t);
-                        const T d = dist2_rn<T, D>(q.x, q.y, q.z, p.x, p.y, p.z);
-                        // branch-free append: the slot is overwritten by the next candidate unless this one counts
-                        my[cnt < (uint32_t)TK_LCAP ? cnt : (uint32_t)TK_LCAP] = (uint16_t)t;
-                        cnt += d <= r0sq ? 1u : 0u;
+                        const T dx = q.x - p.x, dy = q.y - p.y;
+                        T d = fma(dy, dy, dx * dx);
+                        if (D == 3) { const T dz = q.z - p.z; d = fma(dz, dz, d); }
+                        const uint32_t slot = cnt < (uint32_t)TK_LCAP ? cnt : (uint32_t)TK_LCAP;
+                        const uint32_t hit = d <= r0pad ? 1u : 0u;
+                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t}"
+                                     ::"r"(my_s + slot * 2u), "h"((uint16_t)t), "r"(hit) : "memory");
+                        cnt += hit;
                     }
                 }
                 if (cnt < (uint32_t)K1 || cnt > (uint32_t)TK_LCAP) fail = true;
             }
         }
-        __syncwarp();
-        // ---- phase B: warp per query
-        unsigned todo = __ballot_sync(FULL, in_group && !fail);
-        unsigned failed = __ballot_sync(FULL, in_group && fail);
-        while (todo) {
-            const int qi = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const uint32_t c = __shfl_sync(FULL, cnt, qi);
-            const T x = __shfl_sync(FULL, q.x, qi), y = __shfl_sync(FULL, q.y, qi), z = D == 3 ? __shfl_sync(FULL, q.z, qi) : (T)0;
-            const uint16_t* ql = lists + (warp * 32 + qi) * TK_LSTRIDE;
-            Key<T> c0 = Key<T>::sentinel();
-            if ((uint32_t)lane < c) { const P4<T> p = lds_p4(tile + ql[lane]); c0 = Key<T>::make(dist2_rn<T, D>(x, y, z, p.x, p.y, p.z), idx_of(p)); }
-            WarpList<T, 1> list;
-            list.K = K1;
-            list.e[0] = WarpList<T, 1>::sort32_fast(c0, lane);
-            if (c > 32u) {
-                Key<T> c1 = Key<T>::sentinel();
-                if ((uint32_t)lane + 32u < c) { const P4<T> p = lds_p4(tile + ql[lane + 32]); c1 = Key<T>::make(dist2_rn<T, D>(x, y, z, p.x, p.y, p.z), idx_of(p)); }
-                if (c > 40u) list.merge_sorted32(WarpList<T, 1>::sort32_fast(c1, lane), lane);
-                else { list.refresh_threshold(); list.offer(c1, lane); }
+        // ---- phase B: still thread per query. Canonical keys of the hits, reduced to 32-bit images (top 26
+        // bits of d2's pattern, the list slot below), go through a fixed sorting network in registers; the
+        // K smallest are then re-read in that order, checked for strict canonical order (the images of two
+        // keys collide only when their d2 agree to ~17 bits, or on exact ties) and written out.
+        if (in_group && !fail) {
+            uint32_t k[TK_LCAP];
+#pragma unroll
+            for (int s = 0; s < TK_LCAP; ++s) {
+                const bool live = (uint32_t)s < cnt;
+                const uint32_t t = live ? (uint32_t)my[s] : 0u;
+                const P4<T> p = lds_p4(tile + t);
+                const Key<T> key = Key<T>::make(dist2_rn<T, D>(q.x, q.y, q.z, p.x, p.y, p.z), 0u);
+                k[s] = live ? ((key.coarse() & ~63u) | (uint32_t)s) : 0xffffffffu;
             }
-            list.refresh_threshold();
-            const T sh2 = __shfl_sync(FULL, shell2, qi);
-            if (!(list.thr.d2() < sh2)) { failed |= 1u << qi; continue; }
-            const uint32_t orig = __shfl_sync(FULL, idx_of(q), qi);
-            const int64_t row = (int64_t)(orig - q_begin) * k_out;
-            if (lane >= drop && lane < K1) {
-                if (out32) out_idx32[row + lane - drop] = list.e[0].idx() + 1u;
-                else out_idx[row + lane - drop] = (int64_t)list.e[0].idx() + 1;
-                if (out_dist) out_dist[row + lane - drop] = sqrt(list.e[0].d2());
+#define CE(i, j) { const uint32_t lo_ = min(k[i], k[j]); k[j] = max(k[i], k[j]); k[i] = lo_; }
+#include "sortnet48.inc"
+#undef CE
+            const int64_t row = (int64_t)(idx_of(q) - q_begin) * k_out;
+            Key<T> prev = Key<T>::make((T)0, 0u);
+            bool ok = true;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+                if (r < K1) {
+                    const P4<T> p = lds_p4(tile + my[k[r] & 63u]);
+                    const Key<T> key = Key<T>::make(dist2_rn<T, D>(q.x, q.y, q.z, p.x, p.y, p.z), idx_of(p));
+                    if (r > 0) ok = ok && prev.less(key);
+                    prev = key;
+                    if (r >= drop) {
+                        if (out32) out_idx32[row + r - drop] = key.idx() + 1u;
+                        else out_idx[row + r - drop] = (int64_t)key.idx() + 1;
+                        if (out_dist) out_dist[row + r - drop] = sqrt(key.d2());
+                    }
+                }
+                if (r + 1 == K1) ok = ok && (k[r] >> 6) != (k[r + 1] >> 6);   // the first key left out must not be a look-alike
             }
+            // prev is the K-th key: it must lie inside the guaranteed radius of the list and inside the block's shell
+            fail = !(ok && prev.d2() <= r0sq && prev.d2() < shell2);
         }
+        const unsigned failed = __ballot_sync(FULL, in_group && fail);
         if (failed) {                                        // hand the rest to the general kernel
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(fail_count, (uint32_t)__popc(failed));
