@@ -59,57 +59,87 @@ __device__ __forceinline__ T prefilter_radius2(const Grid<T>& g, uint32_t block_
     return (T)r2;
 }
 
+// predicated append used by the filter: if (d <= r) { *(u16*)addr = t; addr += 2; }
+__device__ __forceinline__ void append_if_le(uint32_t& addr, uint32_t t, float d, float r) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %2, %3;\n\t@p st.shared.u16 [%0], %1;\n\t@p add.u32 %0, %0, 2;\n\t}"
+                 : "+r"(addr) : "h"((uint16_t)t), "f"(d), "f"(r) : "memory");
+}
+__device__ __forceinline__ void append_if_le(uint32_t& addr, uint32_t t, double d, double r) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %2, %3;\n\t@p st.shared.u16 [%0], %1;\n\t@p add.u32 %0, %0, 2;\n\t}"
+                 : "+r"(addr) : "h"((uint16_t)t), "d"(d), "d"(r) : "memory");
+}
+
+// The search state of one thread (= one query) of a tiled CTA. Usage (all threads of the CTA together):
+//   TileSearch<T, D> ts(...); ts.init(j, active);
+//   while (ts.next_group()) {                     // stages the slab of the next x-row of queries
+//       bool ok = ts.select(K);                   // phases A + B: ts.my[0..K) = tile slots of the K best, ascending
+//       ... read ts.tile[ts.my[r]], r < K, check the order with ts.verify() ...
+//       ts.report(fail, ...);
+//   }
 template <class T, int D>
-__global__ void __launch_bounds__(TK_Q, sizeof(T) == 4 ? 5 : 3)
-knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_t* __restrict__ cell_start, uint32_t s_begin, uint32_t s_end,
-                uint32_t q_begin, int K1, int drop, void* __restrict__ out_idx_v, int out32, T* __restrict__ out_dist,
-                uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) {
-    constexpr int NROWS = D == 3 ? 9 : 3;
-    constexpr int CAP = tk_cap<T>();
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    P4<T>* tile = reinterpret_cast<P4<T>*>(smem_raw);
-    uint16_t* lists = reinterpret_cast<uint16_t*>(smem_raw + (size_t)CAP * sizeof(P4<T>));   // [thread][slot]
-    __shared__ uint64_t s_bar;
-    __shared__ uint32_t s_rowid[TK_Q];
-    __shared__ uint32_t s_next, s_total;
-    __shared__ int s_x0, s_x1;
-    __shared__ uint32_t s_run_begin[NROWS], s_run_off[NROWS], s_run_base[NROWS];   // base: first cell id of the row (0xffffffff: outside)
+struct TileSearch {
+    static constexpr int NROWS = D == 3 ? 9 : 3;
+    static constexpr int CAP = tk_cap<T>();
+    struct Shared {
+        uint64_t bar;
+        uint32_t rowid[TK_Q];
+        uint32_t next, total;
+        int x0, x1;
+        uint32_t run_begin[NROWS], run_off[NROWS], run_base[NROWS];   // base: first cell id of the row (0xffffffff: outside)
+    };
+    const Grid<T>& g;
+    const P4<T>* __restrict__ sorted;
+    const uint32_t* __restrict__ cell_start;
+    P4<T>* tile;
+    uint16_t* my;          // this thread's list: hits during phase A, sorted tile slots after select()
+    Shared& sh;
+    int tid, lane, warp;
+    uint32_t j;            // sorted position of the query
+    bool active, in_group, fits, last;
+    P4<T> q;
+    int cx, cy, cz;
+    uint32_t rowid, phase;
+    T shell2, r0sq;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t j = s_begin + blockIdx.x * TK_Q + tid;
-    const bool active = j < s_end;
-    P4<T> q; q.x = q.y = q.z = (T)0; q.w = idx_bits((T)0, 0u);
-    int cx = 0, cy = 0, cz = 0;
-    if (active) {
-        q = load_p4<T>(sorted + j);
-        cx = cell_coord(g, q.x, 0); cy = cell_coord(g, q.y, 1); cz = D == 3 ? cell_coord(g, q.z, 2) : 0;
+    __device__ __forceinline__ TileSearch(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs, unsigned char* smem_dyn, Shared& sh_)
+        : g(g_), sorted(s), cell_start(cs), tile(reinterpret_cast<P4<T>*>(smem_dyn)), sh(sh_) {
+        tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
+        my = reinterpret_cast<uint16_t*>(smem_dyn + (size_t)CAP * sizeof(P4<T>)) + tid * TK_LSTRIDE;
+        phase = 0; last = false; in_group = false; fits = false;
     }
-    const uint32_t rowid = active ? (uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy : 0xffffffffu;
-    s_rowid[tid] = rowid;
-    if (tid == 0) { s_next = 0; mbar_init(&s_bar, 1); fence_mbar_init(); }
-    const T shell2 = block_shell2<T, D>(g, q.x, q.y, q.z, cx, cy, cz);
-    const int k_out = K1 - drop;
-    int64_t* __restrict__ out_idx = static_cast<int64_t*>(out_idx_v);
-    uint32_t* __restrict__ out_idx32 = static_cast<uint32_t*>(out_idx_v);
-    uint32_t phase = 0;
-
-    for (;;) {
-        __syncthreads();                                   // previous group is done with the tile; s_next is final
-        const uint32_t first = s_next;
-        if (first >= TK_Q || s_rowid[first] == 0xffffffffu) break;
-        const uint32_t grp_row = s_rowid[first];
-        const bool in_group = active && (uint32_t)tid >= first && rowid == grp_row;
-        if ((uint32_t)tid == first) s_x0 = cx;
-        if (in_group && (tid == TK_Q - 1 || s_rowid[tid + 1] != grp_row)) { s_x1 = cx; }
+    // qpos: the position whose block is searched (the record's own coordinates unless the caller overrides them)
+    __device__ __forceinline__ void init(uint32_t j_, bool active_) {
+        j = j_; active = active_;
+        q.x = q.y = q.z = (T)0; q.w = idx_bits((T)0, 0u);
+        cx = cy = cz = 0;
+        if (active) {
+            q = load_p4<T>(sorted + j);
+            cx = cell_coord(g, q.x, 0); cy = cell_coord(g, q.y, 1); cz = D == 3 ? cell_coord(g, q.z, 2) : 0;
+        }
+        rowid = active ? (uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy : 0xffffffffu;
+        sh.rowid[tid] = rowid;
+        if (tid == 0) { sh.next = 0; mbar_init(&sh.bar, 1); fence_mbar_init(); }
+        shell2 = block_shell2<T, D>(g, q.x, q.y, q.z, cx, cy, cz);
+    }
+    // Stages the slab for the next group of queries (same x-row of cells). False when every query is done.
+    __device__ __forceinline__ bool next_group() {
+        if (last) return false;                            // no barrier on the way out: warps retire as they finish
+        __syncthreads();                                   // previous group is done with the tile; sh.next is final
+        const uint32_t first = sh.next;
+        if (first >= TK_Q || sh.rowid[first] == 0xffffffffu) return false;
+        const uint32_t grp_row = sh.rowid[first];
+        in_group = active && (uint32_t)tid >= first && rowid == grp_row;
+        const bool tail = in_group && (tid == TK_Q - 1 || sh.rowid[tid + 1] != grp_row);
+        if ((uint32_t)tid == first) sh.x0 = cx;
+        if (tail) sh.x1 = cx;
         __syncthreads();
-        // ---- stage the slab: rows (cy+dy, cz+dz), cells [x0-1, x1+1]
         if (warp == 0) {
             uint32_t begin = 0, len = 0, base = 0xffffffffu;
             if (lane < NROWS) {
                 const int gy = (int)(grp_row % (uint32_t)g.n[1]), gz = (int)(grp_row / (uint32_t)g.n[1]);
                 const int ry = gy + row_dy(lane), rz = D == 3 ? gz + row_dz(lane) : 0;
                 if (ry >= 0 && ry < g.n[1] && rz >= 0 && rz < g.n[2]) {
-                    const int x0 = s_x0 > 0 ? s_x0 - 1 : 0, x1 = s_x1 < g.n[0] - 1 ? s_x1 + 1 : g.n[0] - 1;
+                    const int x0 = sh.x0 > 0 ? sh.x0 - 1 : 0, x1 = sh.x1 < g.n[0] - 1 ? sh.x1 + 1 : g.n[0] - 1;
                     base = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
                     begin = cell_start[base + x0];
                     len = cell_start[base + x1 + 1] - begin;
@@ -122,106 +152,134 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
                 if (lane >= o) incl += t;
             }
             const uint32_t total = __shfl_sync(FULL, incl, NROWS - 1);
-            if (lane < NROWS) { s_run_begin[lane] = begin; s_run_off[lane] = incl - len; s_run_base[lane] = base; }
-            if (lane == 0) { s_total = total; if (total > 0 && total <= (uint32_t)CAP) mbar_expect_tx(&s_bar, total * (uint32_t)sizeof(P4<T>)); }
+            if (lane < NROWS) { sh.run_begin[lane] = begin; sh.run_off[lane] = incl - len; sh.run_base[lane] = base; }
+            if (lane == 0) { sh.total = total; if (total > 0 && total <= (uint32_t)CAP) mbar_expect_tx(&sh.bar, total * (uint32_t)sizeof(P4<T>)); }
             __syncwarp();
-            if (total > 0 && total <= (uint32_t)CAP && len > 0) tma_bulk_g2s(tile + (incl - len), sorted + begin, len * (uint32_t)sizeof(P4<T>), &s_bar);
+            if (total > 0 && total <= (uint32_t)CAP && len > 0) tma_bulk_g2s(tile + (incl - len), sorted + begin, len * (uint32_t)sizeof(P4<T>), &sh.bar);
         }
-        // the last member of the group hands over to the next group
-        if (in_group && (tid == TK_Q - 1 || s_rowid[tid + 1] != grp_row)) s_next = (uint32_t)tid + 1;
+        if (tail) sh.next = (uint32_t)tid + 1;             // hand over to the next group
         __syncthreads();
-        const uint32_t total = s_total;
-        const bool fits = total <= (uint32_t)CAP;
-        if (fits && total > 0) { mbar_wait(&s_bar, phase); phase ^= 1u; }
-
-        // ---- phase A: thread per query. The filter uses a fused (cheaper) distance and a radius padded by a
-        // few ulps, so the list holds at least every block point with canonical d2 <= r0sq.
-        uint32_t cnt = 0;
-        bool fail = !fits;
-        T r0sq = (T)0;
-        uint16_t* my = lists + tid * TK_LSTRIDE;
-        if (in_group && fits) {
-            uint32_t b[NROWS], e[NROWS], block_n = 0;
-            const int xa = cx > 0 ? cx - 1 : 0, xb = cx < g.n[0] - 1 ? cx + 1 : g.n[0] - 1;
+        const uint32_t nxt = sh.next;
+        last = nxt >= TK_Q || sh.rowid[nxt] == 0xffffffffu;
+        const uint32_t total = sh.total;
+        fits = total <= (uint32_t)CAP;
+        if (fits && total > 0) { mbar_wait(&sh.bar, phase); phase ^= 1u; }
+        return true;
+    }
+    // Phases A and B for the query at (x, y, z) in this thread's cell block. On success my[0..K) holds the tile
+    // slots of the K nearest candidates in ascending order of their 32-bit key images and the return value is
+    // true; the caller still has to confirm the order on full keys (verify) and the K-th key (accept).
+    __device__ __forceinline__ bool select(int K) {
+        if (!in_group || !fits) return false;
+        // ---- phase A. The filter uses a fused (cheaper) distance and a radius padded by a few ulps, so the
+        // list holds at least every block point with canonical d2 <= r0sq.
+        uint32_t b[NROWS], e[NROWS], block_n = 0;
+        const int xa = cx > 0 ? cx - 1 : 0, xb = cx < g.n[0] - 1 ? cx + 1 : g.n[0] - 1;
 #pragma unroll
-            for (int r = 0; r < NROWS; ++r) {
-                const uint32_t base = s_run_base[r];
-                b[r] = e[r] = 0;
-                if (base != 0xffffffffu) {
-                    const uint32_t shift = s_run_off[r] - s_run_begin[r];
-                    b[r] = __ldg(cell_start + base + xa) + shift;
-                    e[r] = __ldg(cell_start + base + xb + 1) + shift;
-                    block_n += e[r] - b[r];
-                }
-            }
-            if (block_n < (uint32_t)K1) fail = true;
-            else {
-                r0sq = prefilter_radius2<T, D>(g, block_n, K1);
-                const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));
-                const uint32_t my_s = smem_u32(my);
-#pragma unroll
-                for (int r = 0; r < NROWS; ++r) {
-#pragma unroll 2
-                    for (uint32_t t = b[r]; t < e[r]; ++t) {
-                        const P4<T> p = lds_p4(tile + t);
-                        const T dx = q.x - p.x, dy = q.y - p.y;
-                        T d = fma(dy, dy, dx * dx);
-                        if (D == 3) { const T dz = q.z - p.z; d = fma(dz, dz, d); }
-                        const uint32_t slot = cnt < (uint32_t)TK_LCAP ? cnt : (uint32_t)TK_LCAP;
-                        const uint32_t hit = d <= r0pad ? 1u : 0u;
-                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u16 [%0], %1;\n\t}"
-                                     ::"r"(my_s + slot * 2u), "h"((uint16_t)t), "r"(hit) : "memory");
-                        cnt += hit;
-                    }
-                }
-                if (cnt < (uint32_t)K1 || cnt > (uint32_t)TK_LCAP) fail = true;
+        for (int r = 0; r < NROWS; ++r) {
+            const uint32_t base = sh.run_base[r];
+            b[r] = e[r] = 0;
+            if (base != 0xffffffffu) {
+                const uint32_t shift = sh.run_off[r] - sh.run_begin[r];
+                b[r] = __ldg(cell_start + base + xa) + shift;
+                e[r] = __ldg(cell_start + base + xb + 1) + shift;
+                block_n += e[r] - b[r];
             }
         }
-        // ---- phase B: still thread per query. Canonical keys of the hits, reduced to 32-bit images (top 26
-        // bits of d2's pattern, the list slot below), go through a fixed sorting network in registers; the
-        // K smallest are then re-read in that order, checked for strict canonical order (the images of two
-        // keys collide only when their d2 agree to ~17 bits, or on exact ties) and written out.
-        if (in_group && !fail) {
-            uint32_t k[TK_LCAP];
+        if (block_n < (uint32_t)K) return false;
+        r0sq = prefilter_radius2<T, D>(g, block_n, K);
+        const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));
+        const uint32_t my_s = smem_u32(my), lim = my_s + (uint32_t)(TK_LCAP + 1) * 2u;
+        uint32_t addr = my_s;
 #pragma unroll
-            for (int s = 0; s < TK_LCAP; ++s) {
-                const bool live = (uint32_t)s < cnt;
-                const uint32_t t = live ? (uint32_t)my[s] : 0u;
+        for (int r = 0; r < NROWS; ++r) {
+#pragma unroll 4
+            for (uint32_t t = b[r]; t < e[r]; ++t) {
                 const P4<T> p = lds_p4(tile + t);
-                const Key<T> key = Key<T>::make(dist2_rn<T, D>(q.x, q.y, q.z, p.x, p.y, p.z), 0u);
-                k[s] = live ? ((key.coarse() & ~63u) | (uint32_t)s) : 0xffffffffu;
+                const T dx = q.x - p.x, dy = q.y - p.y;
+                T d = fma(dy, dy, dx * dx);
+                if (D == 3) { const T dz = q.z - p.z; d = fma(dz, dz, d); }
+                append_if_le(addr, t, d, r0pad);
+                addr = min(addr, lim);                     // slots LCAP, LCAP+1 absorb an overflowing list
             }
+        }
+        const uint32_t cnt = (addr - my_s) >> 1;
+        if (cnt < (uint32_t)K || cnt > (uint32_t)TK_LCAP) return false;
+        // ---- phase B. Canonical keys of the hits, reduced to 32-bit images (top 26 bits of d2's pattern, the
+        // list slot below), go through a fixed sorting network in registers.
+        uint32_t k[TK_LCAP];
+#pragma unroll
+        for (int s = 0; s < TK_LCAP; ++s) {
+            const bool live = (uint32_t)s < cnt;
+            const uint32_t t = live ? (uint32_t)my[s] : 0u;
+            const P4<T> p = lds_p4(tile + t);
+            const Key<T> key = Key<T>::make(dist2_rn<T, D>(q.x, q.y, q.z, p.x, p.y, p.z), 0u);
+            k[s] = live ? ((key.coarse() & ~63u) | (uint32_t)s) : 0xffffffffu;
+        }
 #define CE(i, j) { const uint32_t lo_ = min(k[i], k[j]); k[j] = max(k[i], k[j]); k[i] = lo_; }
 #include "sortnet48.inc"
 #undef CE
-            const int64_t row = (int64_t)(idx_of(q) - q_begin) * k_out;
-            Key<T> prev = Key<T>::make((T)0, 0u);
-            bool ok = true;
+        // sorted slots -> sorted tile positions, written back over the head of the list (all reads first), so
+        // that the caller's loop over the K best can stay rolled; look-alike mask of neighbouring images
+        uint16_t tt[33];
+        uint32_t alike = 0;
 #pragma unroll
-            for (int r = 0; r < 32; ++r) {
-                if (r < K1) {
-                    const P4<T> p = lds_p4(tile + my[k[r] & 63u]);
-                    const Key<T> key = Key<T>::make(dist2_rn<T, D>(q.x, q.y, q.z, p.x, p.y, p.z), idx_of(p));
-                    if (r > 0) ok = ok && prev.less(key);
-                    prev = key;
-                    if (r >= drop) {
-                        if (out32) out_idx32[row + r - drop] = key.idx() + 1u;
-                        else out_idx[row + r - drop] = (int64_t)key.idx() + 1;
-                        if (out_dist) out_dist[row + r - drop] = sqrt(key.d2());
-                    }
-                }
-                if (r + 1 == K1) ok = ok && (k[r] >> 6) != (k[r + 1] >> 6);   // the first key left out must not be a look-alike
-            }
-            // prev is the K-th key: it must lie inside the guaranteed radius of the list and inside the block's shell
-            fail = !(ok && prev.d2() <= r0sq && prev.d2() < shell2);
-        }
+        for (int r = 0; r < 33; ++r) tt[r] = my[min(k[r] & 63u, (uint32_t)TK_LCAP)];   // sentinels (slot 63) stay inside the list
+#pragma unroll
+        for (int r = 0; r < 32; ++r) alike |= ((k[r] >> 6) == (k[r + 1] >> 6) ? 1u : 0u) << r;
+#pragma unroll
+        for (int r = 0; r < 33; ++r) my[r] = tt[r];
+        return ((alike >> (K - 1)) & 1u) == 0u;            // the first key left out must not be a look-alike of the K-th
+    }
+    // the K-th key must lie inside the guaranteed radius of the list and inside the block's shell
+    __device__ __forceinline__ bool accept(const Key<T>& kth) const { return kth.d2() <= r0sq && kth.d2() < shell2; }
+    // queries that could not be settled here go to the general kernel
+    __device__ __forceinline__ void report(bool fail, uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) const {
         const unsigned failed = __ballot_sync(FULL, in_group && fail);
-        if (failed) {                                        // hand the rest to the general kernel
+        if (failed) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(fail_count, (uint32_t)__popc(failed));
             base = __shfl_sync(FULL, base, 0);
             if ((failed >> lane) & 1u) fail_list[base + __popc(failed & ((1u << lane) - 1u))] = j;
         }
+    }
+};
+
+template <class T, int D>
+__global__ void __launch_bounds__(TK_Q, sizeof(T) == 4 ? 5 : 3)
+knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_t* __restrict__ cell_start, uint32_t s_begin, uint32_t s_end,
+                uint32_t q_begin, int K1, int drop, void* __restrict__ out_idx_v, int out32, T* __restrict__ out_dist,
+                uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ typename TileSearch<T, D>::Shared sh;
+    TileSearch<T, D> ts(g, sorted, cell_start, smem_raw, sh);
+    const uint32_t j = s_begin + blockIdx.x * TK_Q + threadIdx.x;
+    ts.init(j, j < s_end);
+    const int k_out = K1 - drop;
+    int64_t* __restrict__ out_idx = static_cast<int64_t*>(out_idx_v);
+    uint32_t* __restrict__ out_idx32 = static_cast<uint32_t*>(out_idx_v);
+    while (ts.next_group()) {
+        bool ok = ts.select(K1);
+        if (ok) {
+            // re-read the K best in order, check strict canonical order (the images of two keys collide only when
+            // their d2 agree to ~17 bits, or on exact ties) and write the row
+            const int64_t row = (int64_t)(idx_of(ts.q) - q_begin) * k_out;
+            Key<T> prev = Key<T>::make((T)0, 0u);
+#pragma unroll 2
+            for (int r = 0; r < K1; ++r) {
+                const P4<T> p = lds_p4(ts.tile + ts.my[r]);
+                const Key<T> key = Key<T>::make(dist2_rn<T, D>(ts.q.x, ts.q.y, ts.q.z, p.x, p.y, p.z), idx_of(p));
+                if (r > 0) ok = ok && prev.less(key);
+                prev = key;
+                if (r >= drop) {
+                    if (out32) out_idx32[row + r - drop] = key.idx() + 1u;
+                    else out_idx[row + r - drop] = (int64_t)key.idx() + 1;
+                    if (out_dist) out_dist[row + r - drop] = sqrt(key.d2());
+                }
+            }
+            ok = ok && ts.accept(prev);
+        }
+        ts.report(!ok, fail_list, fail_count);
     }
 }
 
