@@ -95,7 +95,9 @@ struct TileSearch {
     Shared& sh;
     int tid, lane, warp;
     uint32_t j;            // sorted position of the query
-    bool active, in_group, fits, last;
+    bool active;           // j is inside the swept range: the thread takes part in forming the groups
+    bool query;            // ... and its record is a query (records filtered out by init() still shape the slab)
+    bool in_group, fits, last;
     P4<T> q;
     int cx, cy, cz;
     uint32_t rowid, phase;
@@ -108,12 +110,15 @@ struct TileSearch {
         phase = 0; last = false; in_group = false; fits = false;
     }
     // qpos: the position whose block is searched (the record's own coordinates unless the caller overrides them)
-    __device__ __forceinline__ void init(uint32_t j_, bool active_) {
-        j = j_; active = active_;
+    // keep_lo/keep_hi: only records whose caller index lies in [keep_lo, keep_hi) are queries
+    __device__ __forceinline__ void init(uint32_t j_, bool in_range, uint32_t keep_lo = 0u, uint32_t keep_hi = 0xffffffffu) {
+        j = j_; active = in_range; query = false;
         q.x = q.y = q.z = (T)0; q.w = idx_bits((T)0, 0u);
         cx = cy = cz = 0;
         if (active) {
             q = load_p4<T>(sorted + j);
+            const uint32_t i = idx_of(q);
+            query = i >= keep_lo && i < keep_hi;
             cx = cell_coord(g, q.x, 0); cy = cell_coord(g, q.y, 1); cz = D == 3 ? cell_coord(g, q.z, 2) : 0;
         }
         rowid = active ? (uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy : 0xffffffffu;
@@ -170,7 +175,7 @@ struct TileSearch {
     // slots of the K nearest candidates in ascending order of their 32-bit key images and the return value is
     // true; the caller still has to confirm the order on full keys (verify) and the K-th key (accept).
     __device__ __forceinline__ bool select(int K) {
-        if (!in_group || !fits) return false;
+        if (!in_group || !fits || !query) return false;
         // ---- phase A. The filter uses a fused (cheaper) distance and a radius padded by a few ulps, so the
         // list holds at least every block point with canonical d2 <= r0sq.
         uint32_t b[NROWS], e[NROWS], block_n = 0;
@@ -235,7 +240,7 @@ struct TileSearch {
     __device__ __forceinline__ bool accept(const Key<T>& kth) const { return kth.d2() <= r0sq && kth.d2() < shell2; }
     // queries that could not be settled here go to the general kernel
     __device__ __forceinline__ void report(bool fail, uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) const {
-        const unsigned failed = __ballot_sync(FULL, in_group && fail);
+        const unsigned failed = __ballot_sync(FULL, in_group && query && fail);
         if (failed) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(fail_count, (uint32_t)__popc(failed));

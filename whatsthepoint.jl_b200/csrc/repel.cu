@@ -7,10 +7,12 @@
 // bounding box of the moved points for the next grid. A tiny second kernel folds the
 // per-CTA partials in a fixed order, the host replays the stop logic (:305-337).
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 
 #include "kernels.cuh"
 #include "knn_core.cuh"
+#include "knn_tile.cuh"
 
 namespace wtp {
 
@@ -95,6 +97,7 @@ struct SweepArgs {
     uint32_t n_fixed, n_all, id_lo, id_hi;
     const uint32_t* qlist; // sorted positions to sweep (null: all, filtered by id range)
     uint32_t nq;
+    const uint32_t* nq_ptr; // device-side length of qlist (the tiled sweep's fail list), or null
     int kk, rebuild;
     T a_lo, a_max;
     ForceP<T> force;
@@ -122,9 +125,10 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
     partial_init(acc);
 
     // work item = SW_QPW consecutive sorted points for one warp; items are dealt round-robin
-    const uint32_t n_items = (a.nq + SW_QPW - 1) / SW_QPW;
+    const uint32_t nq = a.nq_ptr ? *a.nq_ptr : a.nq;
+    const uint32_t n_items = (nq + SW_QPW - 1) / SW_QPW;
     for (uint32_t item = blockIdx.x * SW_WARPS + warp; item < n_items; item += gridDim.x * SW_WARPS)
-    for (uint32_t qi = item * SW_QPW; qi < min(a.nq, (item + 1) * SW_QPW); ++qi) {
+    for (uint32_t qi = item * SW_QPW; qi < min(nq, (item + 1) * SW_QPW); ++qi) {
         const uint32_t j = a.qlist ? a.qlist[qi] : qi;
         const uint32_t self = idx_of(load_p4<T>(a.sorted + j));
         if (self < a.n_fixed + a.id_lo || self >= a.n_fixed + a.id_hi) continue;   // fixed wall / other rank's point
@@ -203,6 +207,103 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
     }
 }
 
+// ------------------------------------------------------------ tiled sweep
+// The same iteration on the CTA-tiled search (knn_tile.cuh): one thread per point. After the selection
+// the K nearest snapshot points are read back from the staged slab in ascending (d2, index) order, so the
+// force terms are added in the reference's serial order without leaving the thread, and the neighbour
+// coordinates come from shared memory instead of a gather from the snapshot. Only valid right after a
+// rebuild (the sorted records then carry the current positions). Points the fast path cannot settle go
+// to the fail list and through repel_sweep_kernel.
+template <class T>
+__device__ __forceinline__ void partial_warp_reduce(RepelPartial<T>& p) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        RepelPartial<T> b;
+        b.s1 = __shfl_down_sync(FULL, p.s1, o); b.s2 = __shfl_down_sync(FULL, p.s2, o); b.n = __shfl_down_sync(FULL, p.n, o);
+        b.max_force = __shfl_down_sync(FULL, p.max_force, o); b.min_nn = __shfl_down_sync(FULL, p.min_nn, o);
+        b.min_id = __shfl_down_sync(FULL, p.min_id, o); b.min_nn_idx = __shfl_down_sync(FULL, p.min_nn_idx, o);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { b.lo[d] = __shfl_down_sync(FULL, p.lo[d], o); b.hi[d] = __shfl_down_sync(FULL, p.hi[d], o); }
+        partial_merge(p, b);   // lanes >= 32 - o fold garbage, never read: lane 0 ends up with the fixed tree over all 32
+    }
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(TK_Q, sizeof(T) == 4 ? 5 : 3)
+repel_tile_kernel(const SweepArgs<T> a, uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ typename TileSearch<T, D>::Shared sh;
+    __shared__ RepelPartial<T> s_part[TK_WARPS];
+    TileSearch<T, D> ts(a.g, a.sorted, a.cell_start, smem_raw, sh);
+    const uint32_t j = blockIdx.x * TK_Q + threadIdx.x;
+    ts.init(j, j < a.n_all, a.n_fixed + a.id_lo, a.n_fixed + a.id_hi);      // fixed wall / other rank's points are not swept
+    RepelPartial<T> acc;
+    partial_init(acc);
+    while (ts.next_group()) {
+        bool ok = ts.select(a.kk);                                            // :259
+        if (ok) {
+            const uint32_t self = idx_of(ts.q), id = self - a.n_fixed;
+            const T xi0 = ts.q.x, xi1 = ts.q.y, xi2 = ts.q.z;                 // == P_old[id] right after a rebuild (:246, :257)
+            const T s = a.s_cur ? a.s_cur[id] : a.s_const;                    // :260
+            T F0 = (T)0, F1 = (T)0, F2 = (T)0, nn_d2 = (T)0;
+            uint32_t nn_idx = 0xffffffffu;
+            Key<T> prev = Key<T>::make((T)0, 0u);
+#pragma unroll 2
+            for (int r = 0; r < a.kk; ++r) {                                  // :270-280, ascending (d2, index)
+                const P4<T> p = lds_p4(ts.tile + ts.my[r]);
+                const Key<T> key = Key<T>::make(dist2_rn<T, D>(xi0, xi1, xi2, p.x, p.y, p.z), idx_of(p));
+                if (r > 0) ok = ok && prev.less(key);
+                prev = key;
+                if (key.idx() == self) continue;                              // skip self BY INDEX (:271)
+                if (nn_idx == 0xffffffffu) { nn_idx = key.idx(); nn_d2 = key.d2(); }   // :272-275
+                const T rr = sqrt(key.d2());
+                if (rr > (T)0) {                                              // _safe_direction (:358-364)
+                    const T f = force_fn<T>(a.force, rr / s);
+                    F0 = F0 + f * ((xi0 - p.x) / rr);
+                    F1 = F1 + f * ((xi1 - p.y) / rr);
+                    if (D == 3) F2 = F2 + f * ((xi2 - p.z) / rr);
+                }
+            }
+            ok = ok && ts.accept(prev);
+            if (ok) {
+                T n2 = F0 * F0 + F1 * F1;
+                if (D == 3) n2 = n2 + F2 * F2;
+                const T Fn = sqrt(n2);                                        // :282
+                const T fs = Fn * s;                                          // :283
+                T ai = (T)1 / (Fn + (T)1.0e-30);                              // :285
+                ai = ai > a.a_max ? a.a_max : (ai < a.a_lo ? a.a_lo : ai);
+                const T sa = s * ai;
+                T d0 = sa * F0, d1 = sa * F1, d2 = D == 3 ? sa * F2 : (T)0;   // :286
+                T dn2 = d0 * d0 + d1 * d1;
+                if (D == 3) dn2 = dn2 + d2 * d2;
+                const T dn = sqrt(dn2);
+                if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
+                const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;          // :291 (the wall rule follows in its own kernel)
+                a.P_new[(size_t)id * D + 0] = p0;
+                a.P_new[(size_t)id * D + 1] = p1;
+                if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
+                const T nn = nn_idx != 0xffffffffu ? sqrt(nn_d2) : t_max<T>();
+                const T u = nn / a.spacings[self];                            // spacing as of the last rebuild (:251, :379)
+                RepelPartial<T> one;
+                one.s1 = (double)u; one.s2 = (double)(u * u); one.n = 1; one.max_force = fs;
+                one.min_nn = nn; one.min_id = id; one.min_nn_idx = nn_idx;
+                one.lo[0] = one.hi[0] = p0; one.lo[1] = one.hi[1] = p1;
+                one.lo[2] = D == 3 ? p2 : t_inf<T>(); one.hi[2] = D == 3 ? p2 : -t_inf<T>();
+                partial_merge(acc, one);
+            }
+        }
+        ts.report(!ok, fail_list, fail_count);
+    }
+    partial_warp_reduce(acc);
+    if (ts.lane == 0) s_part[ts.warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        RepelPartial<T> tot = s_part[0];
+        for (int w = 1; w < TK_WARPS; ++w) partial_merge(tot, s_part[w]);
+        a.partials[blockIdx.x] = tot;
+    }
+}
+
 // fold the per-CTA partials in a fixed order (thread t takes partials t, t+256, ...; then
 // a fixed tree over the threads) so the stop test is reproducible run to run
 template <class T>
@@ -241,6 +342,18 @@ static void launch_sweep(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
     if (a.kk <= 32) launch_sweep_kpl<T, D, 1>(ctx, a, nblocks);
     else if (a.kk <= 64) launch_sweep_kpl<T, D, 2>(ctx, a, nblocks);
     else launch_sweep_kpl<T, D, 4>(ctx, a, nblocks);
+    LAUNCH_CHECK(ctx);
+}
+
+template <class T, int D>
+static void launch_sweep_tiled(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks, uint32_t* fail_list, uint32_t* fail_count) {
+    constexpr size_t smem = tk_smem<T>();
+    static bool configured = false;
+    if (!configured) {
+        WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_tile_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    repel_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(a, fail_list, fail_count);
     LAUNCH_CHECK(ctx);
 }
 
@@ -293,8 +406,12 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     const int32_t rank = ctx->rank, world = ctx->world;
     const int64_t id_lo = wtp_shard_begin(n_move, rank, world), id_hi = wtp_shard_end(n_move, rank, world);
     const int nblocks = (int)std::min<int64_t>((n_all + SW_WARPS * SW_QPW - 1) / (SW_WARPS * SW_QPW), (int64_t)kNumSMs * 8);
-    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + 1 + world);
-    RepelPartial<T>* d_tot = partials + nblocks;
+    // tiled sweep (one thread per point) whenever the list fits one register row and this rank sweeps every point
+    const bool tiled_ok = kk <= 32 && world == 1 && std::getenv("WTP_NO_TILED") == nullptr;
+    const int n_tiled_blocks = tiled_ok ? (int)((n_all + TK_Q - 1) / TK_Q) : 0;
+    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + n_tiled_blocks + 1 + world);
+    RepelPartial<T>* partials_tiled = partials + nblocks;       // [general sweep | tiled sweep], folded together
+    RepelPartial<T>* d_tot = partials_tiled + n_tiled_blocks;
     RepelPartial<T>* d_all = d_tot + 1;
     RepelPartial<T>* h_tot = static_cast<RepelPartial<T>*>(ctx->h_pinned);
     WTP_REQUIRE(sizeof(RepelPartial<T>) * (size_t)(world + 1) + 64 <= ctx->h_pinned_bytes, WTP_ERR_BAD_ARG, "world size too large for the staging buffer");
@@ -334,8 +451,21 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         a.n_fixed = (uint32_t)n_fixed; a.n_all = (uint32_t)n_all; a.id_lo = (uint32_t)id_lo; a.id_hi = (uint32_t)id_hi;
         a.qlist = qlist; a.nq = nq; a.kk = kk; a.rebuild = rebuild ? 1 : 0;
         a.a_lo = (T)prm->alpha_lo; a.a_max = (T)prm->alpha_max; a.force = force; a.partials = partials;
+        a.nq_ptr = nullptr;
+        int n_partials = nblocks;
         {
             ScopedPhase ph(ctx->timer, PH_QUERY);
+            if (rebuild && tiled_ok) {
+                // tiled sweep over every sorted position, then the general sweep over what it handed back
+                SweepArgs<T> at = a;
+                at.qlist = nullptr; at.nq = (uint32_t)n_all; at.partials = partials_tiled;
+                uint32_t* d_fail = ctx->d_fail.as<uint32_t>((size_t)n_all + 4);
+                WTP_CUDA_CHECK(cudaMemsetAsync(d_fail, 0, sizeof(uint32_t), st));
+                if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, d_fail + 4, d_fail);
+                else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, d_fail + 4, d_fail);
+                a.qlist = d_fail + 4; a.nq = (uint32_t)n_all; a.nq_ptr = d_fail;
+                n_partials = nblocks + n_tiled_blocks;
+            }
             if (D == 2) launch_sweep<T, 2>(ctx, a, nblocks); else launch_sweep<T, 3>(ctx, a, nblocks);
         }
         if (mesh) {                                                                                  // constrain(id, xi, xi + disp), :291, 448-469
@@ -344,7 +474,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         }
         {
             ScopedPhase ph(ctx->timer, PH_REDUCE);
-            repel_finalize_kernel<T><<<1, 256, 0, st>>>(partials, nblocks, d_tot);
+            repel_finalize_kernel<T><<<1, 256, 0, st>>>(partials, n_partials, d_tot);
             LAUNCH_CHECK(ctx);
         }
         RepelPartial<T> tot;
