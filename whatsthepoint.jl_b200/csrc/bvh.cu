@@ -209,6 +209,39 @@ __global__ void __launch_bounds__(128) spacing_eval_kernel(const SpacingP<T> sp,
     out[i] = spacing_from_dmin<T>(sp, dmin);
 }
 
+// Same evaluation, one thread per record of a (slightly stale) spatially sorted copy of the snapshot:
+// thread t takes the point whose caller index is stored in order[t] (movable points only), so that the
+// lanes of a warp are neighbours in space and walk the BVH together instead of diverging.
+template <class T, int D>
+__global__ void __launch_bounds__(128) spacing_eval_ordered_kernel(const SpacingP<T> sp, const BvhView<T> bv, const T* __restrict__ pts,
+                                                                   const P4<T>* __restrict__ order, int64_t n_order, uint32_t n_fixed, int64_t n,
+                                                                   T* __restrict__ out, uint32_t* __restrict__ cache, int use_cache) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_order) return;
+    const uint32_t g = idx_of(order[t]);
+    if (g < n_fixed) return;
+    const int64_t i = (int64_t)g - n_fixed;
+    if (i >= n) return;
+    const T qx = pts[i * D + 0], qy = pts[i * D + 1], qz = D == 3 ? pts[i * D + (D - 1)] : (T)0;
+    uint32_t hint = (cache && use_cache) ? cache[i] : 0xffffffffu;
+    const T dmin = sqrt(bvh_nearest_d2<T, D>(bv, qx, qy, qz, hint));
+    if (cache) cache[i] = hint;
+    out[i] = spacing_from_dmin<T>(sp, dmin);
+}
+
+template <class T>
+void spacing_eval_ordered(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out,
+                          uint32_t* d_nn_cache, bool use_cache, const P4<T>* d_order, int64_t n_order, int64_t n_fixed) {
+    if (n <= 0 || n_order <= 0) return;
+    const BvhView<T> v = bvh_view<T>(bv);
+    const unsigned nb = (unsigned)((n_order + 127) / 128);
+    if (D == 2) spacing_eval_ordered_kernel<T, 2><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, d_order, n_order, (uint32_t)n_fixed, n, d_out, d_nn_cache, use_cache ? 1 : 0);
+    else spacing_eval_ordered_kernel<T, 3><<<nb, 128, 0, ctx->stream>>>(sp, v, d_pts, d_order, n_order, (uint32_t)n_fixed, n, d_out, d_nn_cache, use_cache ? 1 : 0);
+    LAUNCH_CHECK(ctx);
+}
+template void spacing_eval_ordered<float>(wtp_ctx*, const SpacingP<float>&, const BvhBuffers&, const float*, int64_t, int, float*, uint32_t*, bool, const P4<float>*, int64_t, int64_t);
+template void spacing_eval_ordered<double>(wtp_ctx*, const SpacingP<double>&, const BvhBuffers&, const double*, int64_t, int, double*, uint32_t*, bool, const P4<double>*, int64_t, int64_t);
+
 template <class T>
 void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out,
                   uint32_t* d_nn_cache, bool use_cache) {

@@ -205,6 +205,17 @@ struct MeshBuffers {
     double offset = 0, maxabs = 0;
 };
 
+// Why a query left the fast path of a tiled k-NN pass (knn_tile.cuh). TK_SPARSE: too few candidates in its block,
+// or the K-th neighbour is not provably inside it (the grid is too fine there). TK_DENSE: the slab does not fit the
+// tile, or more than TK_LCAP hits (too coarse there). TK_OTHER: look-alike key images or exact ties. Anything but
+// TK_OK is appended to one list of sorted positions and answered by the general kernel; the per-kind counters are
+// statistics.
+enum { TK_OK = 0, TK_SPARSE = 1, TK_DENSE = 2, TK_OTHER = 3 };
+struct TileFails {
+    uint32_t* counters;    // [0] length of the list, [1] sparse, [2] dense, [3] other
+    uint32_t* list;        // sorted positions
+};
+
 struct NcclApi;  // comm.cu
 class HostPool;  // host_pool.h
 
@@ -239,6 +250,7 @@ struct wtp_ctx {
         int64_t q_begin = 0, q_end = 0;
     } radius;
     unsigned char grid_storage[2][128];  // last Grid<T> per index (host copy)
+    int64_t last_tile_sparse = 0, last_tile_dense = 0, last_tile_other = 0;   // leftovers of the last tiled sweep, by kind
     // multi-GPU
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;

@@ -36,10 +36,14 @@ void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N
                unsigned long long* d_expanded_counter, bool out32 = false);   // out32: uint32 rows instead of int64
 
 // CTA-tiled front end + general kernel for the leftovers, over the sorted positions [s_begin, s_end)
-// (K1 <= 32). Rows are written at (orig - q_begin) * (K1 - drop_first) like knn_query.
+// (K1 <= 32). Rows are written at (orig - q_begin) * (K1 - drop_first) like knn_query. Fully asynchronous.
 template <class T>
-void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first, int64_t s_begin,
-                     int64_t s_end, int64_t q_begin, void* d_out_idx, T* d_out_dist, unsigned long long* d_expanded_counter, bool out32 = false);
+void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
+                     int64_t s_begin, int64_t s_end, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+                     unsigned long long* d_expanded_counter, bool out32 = false);
+
+// Sinks of a tiled pass inside ctx->d_fail: 16 counters (zeroed here), then the list of up to n sorted positions.
+TileFails tile_fails(wtp_ctx* ctx, int64_t n);
 
 // Compact list of sorted positions whose original index is in [q_begin, q_end).
 void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q_begin, int64_t q_end,
@@ -74,6 +78,10 @@ BvhView<T> bvh_view(const BvhBuffers& bv);
 template <class T>
 void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out,
                   uint32_t* d_nn_cache = nullptr, bool use_cache = false);
+// the same for the movable points [n_fixed, n_fixed + n) visited in the order of a sorted copy of the snapshot
+template <class T>
+void spacing_eval_ordered(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, const T* d_pts, int64_t n, int D, T* d_out,
+                          uint32_t* d_nn_cache, bool use_cache, const P4<T>* d_order, int64_t n_order, int64_t n_fixed);
 template <class T>
 void force_eval(wtp_ctx* ctx, const ForceP<T>& f, const T* d_u, int64_t n, T* d_out);
 // inner boxes of a complete binary tree in heap layout whose P leaves (boxes[P..2P)) are set

@@ -1,5 +1,9 @@
 // knn.cu — k-NN topology kernel: _build_knn_neighbors (src/topology.jl:79-84) and
 // search/searchdists (src/neighbors.jl:9-21) for every point of the indexed set.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "knn_core.cuh"
 #include "knn_tile.cuh"
@@ -14,8 +18,8 @@ namespace wtp {
 
 constexpr int KNN_THREADS = 256;
 constexpr int KNN_WARPS = KNN_THREADS / 32;
-constexpr int KNN_QPW = 8;                        // consecutive sorted queries per warp (tile reuse within a cell)
-constexpr int KNN_QPB = KNN_WARPS * KNN_QPW;      // 64 consecutive sorted queries per CTA
+constexpr int KNN_RUN = 8;                        // consecutive entries per warp and trip (tile reuse within a cell)
+constexpr int KNN_QPB = KNN_WARPS * KNN_RUN;      // entries per CTA and trip
 constexpr int KNN_TILE_CAP = 288;                 // records per warp tile: 3^3 cells x ~8 points + 4.9 sigma
 
 template <class T, int KPL>
@@ -25,7 +29,7 @@ template <class T> __host__ __device__ constexpr int knn_min_blocks() { return s
 template <class T, int D, int KPL>
 __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted,
                                                           const uint32_t* __restrict__ cell_start,
-                                                          const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ nq_ptr,
+                                                          const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ nq_dev,
                                                           uint32_t q_begin, int K1, int drop, void* __restrict__ out_idx_v, int out32,
                                                           T* __restrict__ out_dist, unsigned long long* __restrict__ expanded) {
     constexpr int CAP = knn_tile_cap<T, KPL>();
@@ -38,14 +42,7 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
     const int k_out = K1 - drop;
     int64_t* __restrict__ out_idx = static_cast<int64_t*>(out_idx_v);     // ABI layout: int64, 1-based
     uint32_t* __restrict__ out_idx32 = static_cast<uint32_t*>(out_idx_v); // staging layout of the host entry points (widened on the host)
-    if (nq_ptr) nq = *nq_ptr;                           // length of a device-built list (the tiled kernel's fail list)
-#pragma unroll 1
-    for (uint32_t item = blockIdx.x * KNN_WARPS + warp; item * KNN_QPW < nq; item += gridDim.x * KNN_WARPS)
-#pragma unroll 1
-    for (int it = 0; it < KNN_QPW; ++it) {
-        const uint32_t qi = item * KNN_QPW + it;
-        if (qi >= nq) break;
-        const uint32_t j = qlist ? qlist[qi] : qi;
+    auto answer = [&](uint32_t j) {
         const P4<T> q = load_p4<T>(sorted + j);
         const int rings = s.run(q.x, q.y, q.z, K1);
         if (rings > 1 && lane == 0 && expanded) atomicAdd(expanded, 1ULL);
@@ -59,13 +56,22 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
                 if (out_dist) out_dist[row + r - drop] = sqrt(s.list.e[e].d2());
             }
         }
+    };
+    // every warp takes runs of KNN_RUN consecutive entries (sorted positions, or entries of qlist), dealt round-robin:
+    // neighbours in space reuse the staged cell block. nq_dev: length of a device-built list (the tiled pass's leftovers).
+    if (nq_dev) nq = *nq_dev;
+#pragma unroll 1
+    for (uint32_t first = (blockIdx.x * KNN_WARPS + warp) * KNN_RUN; first < nq; first += gridDim.x * KNN_WARPS * KNN_RUN) {
+        const uint32_t end = min(nq, first + KNN_RUN);
+#pragma unroll 1
+        for (uint32_t qi = first; qi < end; ++qi) answer(qlist ? qlist[qi] : qi);
     }
 }
 
 template <class T, int D, int KPL>
 static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, const P4<T>* sorted, const uint32_t* cs,
-                           const uint32_t* d_qlist, int64_t nq, const uint32_t* d_nq, int64_t q_begin, int K1, int drop, void* d_out_idx,
-                           int out32, T* d_out_dist, unsigned long long* d_exp) {
+                           const uint32_t* d_qlist, int64_t nq, const uint32_t* d_nq, int64_t q_begin, int K1, int drop,
+                           void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
     constexpr size_t smem = (size_t)knn_tile_cap<T, KPL>() * sizeof(P4<T>) * KNN_WARPS;
     static bool configured = false;
     if (!configured && smem > 48 * 1024) {
@@ -78,8 +84,9 @@ static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, con
 
 template <class T, int D>
 static void launch_knn(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int K1, int drop, const uint32_t* d_qlist,
-                       int64_t nq, const uint32_t* d_nq, int64_t q_begin, void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
-    // a device-side count (fail list): a fixed grid strides over however many entries there are
+                       int64_t nq, const uint32_t* d_nq, int64_t q_begin, void* d_out_idx, int out32, T* d_out_dist,
+                       unsigned long long* d_exp) {
+    // a device-side count (the tiled pass's leftovers): a fixed grid strides over however many entries there are
     const unsigned nblocks = (unsigned)std::min<int64_t>((nq + KNN_QPB - 1) / KNN_QPB, d_nq ? (int64_t)kNumSMs * 4 : (int64_t)0x7fffffff);
     const P4<T>* sorted = ib.sorted.get<P4<T>>();
     const uint32_t* cs = ib.cell_start.get<uint32_t>();
@@ -101,49 +108,50 @@ void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N
     else launch_knn<T, 3>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, nullptr, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
 }
 
+template void knn_query<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int64_t, int, int, int, const uint32_t*, int64_t,
+                               int64_t, void*, float*, unsigned long long*, bool);
+template void knn_query<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, const uint32_t*, int64_t,
+                                int64_t, void*, double*, unsigned long long*, bool);
+
+TileFails tile_fails(wtp_ctx* ctx, int64_t n) {
+    uint32_t* base = ctx->d_fail.as<uint32_t>(16 + (size_t)n);
+    WTP_CUDA_CHECK(cudaMemsetAsync(base, 0, 16 * sizeof(uint32_t), ctx->stream));
+    return TileFails{base, base + 16};
+}
+
 // Tiled front end (knn_tile.cuh) over the sorted positions [s_begin, s_end), then the general kernel over
-// whatever it handed back. K1 <= 32 only. Returns nothing on the host: the fail count stays on the device
-// (d_fail[0]) so the call is fully asynchronous.
+// whatever it handed back.
 template <class T, int D>
-static void launch_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int K1, int drop, int64_t s_begin, int64_t s_end,
-                         int64_t q_begin, void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp, uint32_t* d_fail) {
+static void run_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int K1, int drop, int64_t s_begin, int64_t s_end,
+                      int64_t q_begin, void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
     constexpr size_t smem = tk_smem<T>();
     static bool configured = false;
     if (!configured) {
         WTP_CUDA_CHECK(cudaFuncSetAttribute(knn_tile_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const int64_t nq = s_end - s_begin;
-    const unsigned nblocks = (unsigned)((nq + TK_Q - 1) / TK_Q);
-    uint32_t* fail_count = d_fail, *fail_list = d_fail + 4;
-    WTP_CUDA_CHECK(cudaMemsetAsync(fail_count, 0, sizeof(uint32_t), ctx->stream));
+    const TileFails f = tile_fails(ctx, s_end - s_begin);
+    const unsigned nblocks = (unsigned)((s_end - s_begin + TK_Q - 1) / TK_Q);
     knn_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cell_start.get<uint32_t>(), (uint32_t)s_begin,
-                                                               (uint32_t)s_end, (uint32_t)q_begin, K1, drop, d_out_idx, out32, d_out_dist,
-                                                               fail_list, fail_count);
+                                                               (uint32_t)s_end, (uint32_t)q_begin, K1, drop, d_out_idx, out32, d_out_dist, f);
     LAUNCH_CHECK(ctx);
-    launch_knn<T, D>(ctx, ib, g, K1, drop, fail_list, nq, fail_count, q_begin, d_out_idx, out32, d_out_dist, d_exp);
+    launch_knn<T, D>(ctx, ib, g, K1, drop, f.list, s_end - s_begin, f.counters, q_begin, d_out_idx, out32, d_out_dist, d_exp);
 }
 
 template <class T>
-void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first, int64_t s_begin,
-                     int64_t s_end, int64_t q_begin, void* d_out_idx, T* d_out_dist, unsigned long long* d_expanded_counter, bool out32) {
-    (void)N;
+void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
+                     int64_t s_begin, int64_t s_end, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+                     unsigned long long* d_expanded_counter, bool out32) {
     WTP_REQUIRE(K1 >= 1 && K1 <= 32, WTP_ERR_K_TOO_LARGE, "the tiled k-NN front end holds lists of at most 32 entries");
     if (s_end <= s_begin) return;
     ScopedPhase ph(ctx->timer, PH_QUERY);
-    uint32_t* d_fail = ctx->d_fail.as<uint32_t>((size_t)(s_end - s_begin) + 4);
-    if (D == 2) launch_tiled<T, 2>(ctx, ib, g, K1, drop_first, s_begin, s_end, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter, d_fail);
-    else launch_tiled<T, 3>(ctx, ib, g, K1, drop_first, s_begin, s_end, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter, d_fail);
+    if (D == 2) run_tiled<T, 2>(ctx, ib, g, N, K1, drop_first, s_begin, s_end, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
+    else run_tiled<T, 3>(ctx, ib, g, N, K1, drop_first, s_begin, s_end, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
 }
-template void knn_query_tiled<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int64_t, int, int, int, int64_t, int64_t, int64_t, void*,
-                                     float*, unsigned long long*, bool);
-template void knn_query_tiled<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, int64_t, int64_t, int64_t, void*,
-                                      double*, unsigned long long*, bool);
-
-template void knn_query<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int64_t, int, int, int, const uint32_t*, int64_t,
-                               int64_t, void*, float*, unsigned long long*, bool);
-template void knn_query<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, const uint32_t*, int64_t,
-                                int64_t, void*, double*, unsigned long long*, bool);
+template void knn_query_tiled<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int64_t, int, int, int, int64_t, int64_t,
+                                     int64_t, void*, float*, unsigned long long*, bool);
+template void knn_query_tiled<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, int64_t, int64_t,
+                                      int64_t, void*, double*, unsigned long long*, bool);
 
 // ------------------------------------------------------------ query lists
 // Sharded mode: the sorted positions whose original index lies in [q_begin, q_end), in

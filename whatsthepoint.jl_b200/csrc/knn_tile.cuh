@@ -83,7 +83,7 @@ struct TileSearch {
     struct Shared {
         uint64_t bar;
         uint32_t rowid[TK_Q];
-        uint32_t next, total;
+        uint32_t next[2], total;       // next[p]: first thread of the group formed in pass p (double-buffered)
         int x0, x1;
         uint32_t run_begin[NROWS], run_off[NROWS], run_base[NROWS];   // base: first cell id of the row (0xffffffff: outside)
     };
@@ -100,19 +100,19 @@ struct TileSearch {
     bool in_group, fits, last;
     P4<T> q;
     int cx, cy, cz;
-    uint32_t rowid, phase;
+    uint32_t rowid, phase, block_n, pass;
     T shell2, r0sq;
 
     __device__ __forceinline__ TileSearch(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs, unsigned char* smem_dyn, Shared& sh_)
         : g(g_), sorted(s), cell_start(cs), tile(reinterpret_cast<P4<T>*>(smem_dyn)), sh(sh_) {
         tid = threadIdx.x; lane = tid & 31; warp = tid >> 5;
         my = reinterpret_cast<uint16_t*>(smem_dyn + (size_t)CAP * sizeof(P4<T>)) + tid * TK_LSTRIDE;
-        phase = 0; last = false; in_group = false; fits = false;
+        phase = 0; pass = 0; last = false; in_group = false; fits = false;
     }
     // qpos: the position whose block is searched (the record's own coordinates unless the caller overrides them)
     // keep_lo/keep_hi: only records whose caller index lies in [keep_lo, keep_hi) are queries
     __device__ __forceinline__ void init(uint32_t j_, bool in_range, uint32_t keep_lo = 0u, uint32_t keep_hi = 0xffffffffu) {
-        j = j_; active = in_range; query = false;
+        j = j_; active = in_range; query = false; block_n = 0;
         q.x = q.y = q.z = (T)0; q.w = idx_bits((T)0, 0u);
         cx = cy = cz = 0;
         if (active) {
@@ -123,62 +123,66 @@ struct TileSearch {
         }
         rowid = active ? (uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy : 0xffffffffu;
         sh.rowid[tid] = rowid;
-        if (tid == 0) { sh.next = 0; mbar_init(&sh.bar, 1); fence_mbar_init(); }
+        if (tid == 0) { sh.next[0] = 0; mbar_init(&sh.bar, 1); fence_mbar_init(); }
         shell2 = block_shell2<T, D>(g, q.x, q.y, q.z, cx, cy, cz);
     }
     // Stages the slab for the next group of queries (same x-row of cells). False when every query is done.
     __device__ __forceinline__ bool next_group() {
-        if (last) return false;                            // no barrier on the way out: warps retire as they finish
-        __syncthreads();                                   // previous group is done with the tile; sh.next is final
-        const uint32_t first = sh.next;
-        if (first >= TK_Q || sh.rowid[first] == 0xffffffffu) return false;
-        const uint32_t grp_row = sh.rowid[first];
-        in_group = active && (uint32_t)tid >= first && rowid == grp_row;
-        const bool tail = in_group && (tid == TK_Q - 1 || sh.rowid[tid + 1] != grp_row);
-        if ((uint32_t)tid == first) sh.x0 = cx;
-        if (tail) sh.x1 = cx;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t begin = 0, len = 0, base = 0xffffffffu;
-            if (lane < NROWS) {
-                const int gy = (int)(grp_row % (uint32_t)g.n[1]), gz = (int)(grp_row / (uint32_t)g.n[1]);
-                const int ry = gy + row_dy(lane), rz = D == 3 ? gz + row_dz(lane) : 0;
-                if (ry >= 0 && ry < g.n[1] && rz >= 0 && rz < g.n[2]) {
-                    const int x0 = sh.x0 > 0 ? sh.x0 - 1 : 0, x1 = sh.x1 < g.n[0] - 1 ? sh.x1 + 1 : g.n[0] - 1;
-                    base = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
-                    begin = cell_start[base + x0];
-                    len = cell_start[base + x1 + 1] - begin;
+        for (;;) {
+            if (last) return false;                        // no barrier on the way out: warps retire as they finish
+            __syncthreads();                               // previous group is done with the tile; sh.next[pass] is final
+            const uint32_t first = sh.next[pass & 1u];
+            if (first >= TK_Q || sh.rowid[first] == 0xffffffffu) return false;
+            const uint32_t grp_row = sh.rowid[first];
+            in_group = active && (uint32_t)tid >= first && rowid == grp_row;
+            const bool tail = in_group && (tid == TK_Q - 1 || sh.rowid[tid + 1] != grp_row);
+            if ((uint32_t)tid == first) sh.x0 = cx;
+            if (tail) { sh.x1 = cx; sh.next[(pass + 1u) & 1u] = (uint32_t)tid + 1; }   // the other slot: nobody reads it in this pass
+            const bool any_query = __syncthreads_or(in_group && query) != 0;
+            ++pass;
+            const uint32_t nxt = sh.next[pass & 1u];
+            last = nxt >= TK_Q || sh.rowid[nxt] == 0xffffffffu;
+            if (!any_query) { in_group = false; continue; }          // nothing to answer in this row: no staging
+            if (warp == 0) {
+                uint32_t begin = 0, len = 0, base = 0xffffffffu;
+                if (lane < NROWS) {
+                    const int gy = (int)(grp_row % (uint32_t)g.n[1]), gz = (int)(grp_row / (uint32_t)g.n[1]);
+                    const int ry = gy + row_dy(lane), rz = D == 3 ? gz + row_dz(lane) : 0;
+                    if (ry >= 0 && ry < g.n[1] && rz >= 0 && rz < g.n[2]) {
+                        const int x0 = sh.x0 > 0 ? sh.x0 - 1 : 0, x1 = sh.x1 < g.n[0] - 1 ? sh.x1 + 1 : g.n[0] - 1;
+                        base = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
+                        begin = cell_start[base + x0];
+                        len = cell_start[base + x1 + 1] - begin;
+                    }
                 }
-            }
-            uint32_t incl = len;
+                uint32_t incl = len;
 #pragma unroll
-            for (int o = 1; o < 16; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += t;
+                for (int o = 1; o < 16; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const uint32_t total = __shfl_sync(FULL, incl, NROWS - 1);
+                if (lane < NROWS) { sh.run_begin[lane] = begin; sh.run_off[lane] = incl - len; sh.run_base[lane] = base; }
+                if (lane == 0) { sh.total = total; if (total > 0 && total <= (uint32_t)CAP) mbar_expect_tx(&sh.bar, total * (uint32_t)sizeof(P4<T>)); }
+                __syncwarp();
+                if (total > 0 && total <= (uint32_t)CAP && len > 0) tma_bulk_g2s(tile + (incl - len), sorted + begin, len * (uint32_t)sizeof(P4<T>), &sh.bar);
             }
-            const uint32_t total = __shfl_sync(FULL, incl, NROWS - 1);
-            if (lane < NROWS) { sh.run_begin[lane] = begin; sh.run_off[lane] = incl - len; sh.run_base[lane] = base; }
-            if (lane == 0) { sh.total = total; if (total > 0 && total <= (uint32_t)CAP) mbar_expect_tx(&sh.bar, total * (uint32_t)sizeof(P4<T>)); }
-            __syncwarp();
-            if (total > 0 && total <= (uint32_t)CAP && len > 0) tma_bulk_g2s(tile + (incl - len), sorted + begin, len * (uint32_t)sizeof(P4<T>), &sh.bar);
+            __syncthreads();
+            const uint32_t total = sh.total;
+            fits = total <= (uint32_t)CAP;
+            if (fits && total > 0) { mbar_wait(&sh.bar, phase); phase ^= 1u; }
+            return true;
         }
-        if (tail) sh.next = (uint32_t)tid + 1;             // hand over to the next group
-        __syncthreads();
-        const uint32_t nxt = sh.next;
-        last = nxt >= TK_Q || sh.rowid[nxt] == 0xffffffffu;
-        const uint32_t total = sh.total;
-        fits = total <= (uint32_t)CAP;
-        if (fits && total > 0) { mbar_wait(&sh.bar, phase); phase ^= 1u; }
-        return true;
     }
     // Phases A and B for the query at (x, y, z) in this thread's cell block. On success my[0..K) holds the tile
     // slots of the K nearest candidates in ascending order of their 32-bit key images and the return value is
     // true; the caller still has to confirm the order on full keys (verify) and the K-th key (accept).
-    __device__ __forceinline__ bool select(int K) {
-        if (!in_group || !fits || !query) return false;
+    __device__ __forceinline__ int select(int K) {
+        if (!in_group || !query) return TK_SPARSE;         // not this thread's turn (never reported)
         // ---- phase A. The filter uses a fused (cheaper) distance and a radius padded by a few ulps, so the
         // list holds at least every block point with canonical d2 <= r0sq.
-        uint32_t b[NROWS], e[NROWS], block_n = 0;
+        uint32_t b[NROWS], e[NROWS];
+        block_n = 0;
         const int xa = cx > 0 ? cx - 1 : 0, xb = cx < g.n[0] - 1 ? cx + 1 : g.n[0] - 1;
 #pragma unroll
         for (int r = 0; r < NROWS; ++r) {
@@ -191,7 +195,8 @@ struct TileSearch {
                 block_n += e[r] - b[r];
             }
         }
-        if (block_n < (uint32_t)K) return false;
+        if (!fits) return TK_DENSE;
+        if (block_n < (uint32_t)K) return TK_SPARSE;
         r0sq = prefilter_radius2<T, D>(g, block_n, K);
         const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));
         const uint32_t my_s = smem_u32(my), lim = my_s + (uint32_t)(TK_LCAP + 1) * 2u;
@@ -209,7 +214,8 @@ struct TileSearch {
             }
         }
         const uint32_t cnt = (addr - my_s) >> 1;
-        if (cnt < (uint32_t)K || cnt > (uint32_t)TK_LCAP) return false;
+        if (cnt < (uint32_t)K) return TK_SPARSE;
+        if (cnt > (uint32_t)TK_LCAP) return TK_DENSE;
         // ---- phase B. Canonical keys of the hits, reduced to 32-bit images (top 26 bits of d2's pattern, the
         // list slot below), go through a fixed sorting network in registers.
         uint32_t k[TK_LCAP];
@@ -234,18 +240,25 @@ struct TileSearch {
         for (int r = 0; r < 32; ++r) alike |= ((k[r] >> 6) == (k[r + 1] >> 6) ? 1u : 0u) << r;
 #pragma unroll
         for (int r = 0; r < 33; ++r) my[r] = tt[r];
-        return ((alike >> (K - 1)) & 1u) == 0u;            // the first key left out must not be a look-alike of the K-th
+        return ((alike >> (K - 1)) & 1u) == 0u ? TK_OK : TK_OTHER;   // the first key left out must not be a look-alike of the K-th
     }
-    // the K-th key must lie inside the guaranteed radius of the list and inside the block's shell
-    __device__ __forceinline__ bool accept(const Key<T>& kth) const { return kth.d2() <= r0sq && kth.d2() < shell2; }
-    // queries that could not be settled here go to the general kernel
-    __device__ __forceinline__ void report(bool fail, uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) const {
-        const unsigned failed = __ballot_sync(FULL, in_group && query && fail);
-        if (failed) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(fail_count, (uint32_t)__popc(failed));
-            base = __shfl_sync(FULL, base, 0);
-            if ((failed >> lane) & 1u) fail_list[base + __popc(failed & ((1u << lane) - 1u))] = j;
+    // the K-th key must lie inside the guaranteed radius of the list and inside the block's shell; the order of
+    // the K best must have been confirmed on full keys
+    __device__ __forceinline__ int accept(bool ordered, const Key<T>& kth) const {
+        if (!ordered) return TK_OTHER;
+        return kth.d2() <= r0sq && kth.d2() < shell2 ? TK_OK : TK_SPARSE;
+    }
+    // queries that could not be settled here go to the general kernel's list (warp-aggregated append)
+    __device__ __forceinline__ void report(int status, const TileFails& f) const {
+        const bool failed_here = in_group && query && status != TK_OK;
+        const unsigned m = __ballot_sync(FULL, failed_here);
+        if (m == 0) return;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(f.counters, (uint32_t)__popc(m));
+        base = __shfl_sync(FULL, base, 0);
+        if (failed_here) {
+            f.list[base + __popc(m & ((1u << lane) - 1u))] = j;
+            atomicAdd(f.counters + status, 1u);
         }
     }
 };
@@ -254,7 +267,7 @@ template <class T, int D>
 __global__ void __launch_bounds__(TK_Q, sizeof(T) == 4 ? 5 : 3)
 knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_t* __restrict__ cell_start, uint32_t s_begin, uint32_t s_end,
                 uint32_t q_begin, int K1, int drop, void* __restrict__ out_idx_v, int out32, T* __restrict__ out_dist,
-                uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) {
+                const TileFails fails) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ typename TileSearch<T, D>::Shared sh;
     TileSearch<T, D> ts(g, sorted, cell_start, smem_raw, sh);
@@ -264,12 +277,13 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
     int64_t* __restrict__ out_idx = static_cast<int64_t*>(out_idx_v);
     uint32_t* __restrict__ out_idx32 = static_cast<uint32_t*>(out_idx_v);
     while (ts.next_group()) {
-        bool ok = ts.select(K1);
-        if (ok) {
+        int status = ts.select(K1);
+        if (status == TK_OK) {
             // re-read the K best in order, check strict canonical order (the images of two keys collide only when
             // their d2 agree to ~17 bits, or on exact ties) and write the row
             const int64_t row = (int64_t)(idx_of(ts.q) - q_begin) * k_out;
             Key<T> prev = Key<T>::make((T)0, 0u);
+            bool ok = true;
 #pragma unroll 2
             for (int r = 0; r < K1; ++r) {
                 const P4<T> p = lds_p4(ts.tile + ts.my[r]);
@@ -282,9 +296,9 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
                     if (out_dist) out_dist[row + r - drop] = sqrt(key.d2());
                 }
             }
-            ok = ok && ts.accept(prev);
+            status = ts.accept(ok, prev);
         }
-        ts.report(!ok, fail_list, fail_count);
+        ts.report(status, fails);
     }
 }
 

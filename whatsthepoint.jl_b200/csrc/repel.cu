@@ -97,7 +97,7 @@ struct SweepArgs {
     uint32_t n_fixed, n_all, id_lo, id_hi;
     const uint32_t* qlist; // sorted positions to sweep (null: all, filtered by id range)
     uint32_t nq;
-    const uint32_t* nq_ptr; // device-side length of qlist (the tiled sweep's fail list), or null
+    const uint32_t* nq_dev; // device-side length of qlist (the tiled sweep's leftovers), or null
     int kk, rebuild;
     T a_lo, a_max;
     ForceP<T> force;
@@ -106,7 +106,7 @@ struct SweepArgs {
 
 constexpr int SW_THREADS = 256;
 constexpr int SW_WARPS = SW_THREADS / 32;
-constexpr int SW_QPW = 8;                        // consecutive sorted points per warp and work item
+constexpr int SW_RUN = 8;                        // consecutive entries per warp and trip
 template <class T, int KPL> __host__ __device__ constexpr int sw_tile_cap() { return KPL != 1 ? 0 : (sizeof(T) == 8 ? 224 : 288); }
 template <class T> __host__ __device__ constexpr int sw_min_blocks() { return sizeof(T) == 8 ? 3 : 4; }
 
@@ -124,11 +124,10 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
     RepelPartial<T> acc;
     partial_init(acc);
 
-    // work item = SW_QPW consecutive sorted points for one warp; items are dealt round-robin
-    const uint32_t nq = a.nq_ptr ? *a.nq_ptr : a.nq;
-    const uint32_t n_items = (nq + SW_QPW - 1) / SW_QPW;
-    for (uint32_t item = blockIdx.x * SW_WARPS + warp; item < n_items; item += gridDim.x * SW_WARPS)
-    for (uint32_t qi = item * SW_QPW; qi < min(nq, (item + 1) * SW_QPW); ++qi) {
+    // every warp takes runs of SW_RUN consecutive entries (sorted positions, or entries of qlist), dealt round-robin
+    const uint32_t nq = a.nq_dev ? *a.nq_dev : a.nq;
+    for (uint32_t first = (blockIdx.x * SW_WARPS + warp) * SW_RUN; first < nq; first += gridDim.x * SW_WARPS * SW_RUN)
+      for (uint32_t qi = first; qi < min(nq, first + SW_RUN); ++qi) {
         const uint32_t j = a.qlist ? a.qlist[qi] : qi;
         const uint32_t self = idx_of(load_p4<T>(a.sorted + j));
         if (self < a.n_fixed + a.id_lo || self >= a.n_fixed + a.id_hi) continue;   // fixed wall / other rank's point
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
         acc.lo[0] = p0 < acc.lo[0] ? p0 : acc.lo[0]; acc.hi[0] = p0 > acc.hi[0] ? p0 : acc.hi[0];
         acc.lo[1] = p1 < acc.lo[1] ? p1 : acc.lo[1]; acc.hi[1] = p1 > acc.hi[1] ? p1 : acc.hi[1];
         if (D == 3) { acc.lo[2] = p2 < acc.lo[2] ? p2 : acc.lo[2]; acc.hi[2] = p2 > acc.hi[2] ? p2 : acc.hi[2]; }
-    }
+      }
     if (lane == 0) s_part[warp] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -230,18 +229,19 @@ __device__ __forceinline__ void partial_warp_reduce(RepelPartial<T>& p) {
 
 template <class T, int D>
 __global__ void __launch_bounds__(TK_Q, sizeof(T) == 4 ? 5 : 3)
-repel_tile_kernel(const SweepArgs<T> a, uint32_t* __restrict__ fail_list, uint32_t* __restrict__ fail_count) {
+repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ typename TileSearch<T, D>::Shared sh;
     __shared__ RepelPartial<T> s_part[TK_WARPS];
     TileSearch<T, D> ts(a.g, a.sorted, a.cell_start, smem_raw, sh);
     const uint32_t j = blockIdx.x * TK_Q + threadIdx.x;
-    ts.init(j, j < a.n_all, a.n_fixed + a.id_lo, a.n_fixed + a.id_hi);      // fixed wall / other rank's points are not swept
+    ts.init(j, j < a.n_all, a.n_fixed + a.id_lo, a.n_fixed + a.id_hi);   // fixed wall / other rank's points are not swept
     RepelPartial<T> acc;
     partial_init(acc);
     while (ts.next_group()) {
-        bool ok = ts.select(a.kk);                                            // :259
-        if (ok) {
+        int status = ts.select(a.kk);                                         // :259
+        if (status == TK_OK) {
+            bool ok = true;
             const uint32_t self = idx_of(ts.q), id = self - a.n_fixed;
             const T xi0 = ts.q.x, xi1 = ts.q.y, xi2 = ts.q.z;                 // == P_old[id] right after a rebuild (:246, :257)
             const T s = a.s_cur ? a.s_cur[id] : a.s_const;                    // :260
@@ -264,8 +264,8 @@ repel_tile_kernel(const SweepArgs<T> a, uint32_t* __restrict__ fail_list, uint32
                     if (D == 3) F2 = F2 + f * ((xi2 - p.z) / rr);
                 }
             }
-            ok = ok && ts.accept(prev);
-            if (ok) {
+            status = ts.accept(ok, prev);
+            if (status == TK_OK) {
                 T n2 = F0 * F0 + F1 * F1;
                 if (D == 3) n2 = n2 + F2 * F2;
                 const T Fn = sqrt(n2);                                        // :282
@@ -292,7 +292,7 @@ repel_tile_kernel(const SweepArgs<T> a, uint32_t* __restrict__ fail_list, uint32
                 partial_merge(acc, one);
             }
         }
-        ts.report(!ok, fail_list, fail_count);
+        ts.report(status, fails);
     }
     partial_warp_reduce(acc);
     if (ts.lane == 0) s_part[ts.warp] = acc;
@@ -346,14 +346,14 @@ static void launch_sweep(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
 }
 
 template <class T, int D>
-static void launch_sweep_tiled(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks, uint32_t* fail_list, uint32_t* fail_count) {
+static void launch_sweep_tiled(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks, const TileFails& fails) {
     constexpr size_t smem = tk_smem<T>();
     static bool configured = false;
     if (!configured) {
         WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_tile_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    repel_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(a, fail_list, fail_count);
+    repel_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(a, fails);
     LAUNCH_CHECK(ctx);
 }
 
@@ -405,16 +405,17 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 
     const int32_t rank = ctx->rank, world = ctx->world;
     const int64_t id_lo = wtp_shard_begin(n_move, rank, world), id_hi = wtp_shard_end(n_move, rank, world);
-    const int nblocks = (int)std::min<int64_t>((n_all + SW_WARPS * SW_QPW - 1) / (SW_WARPS * SW_QPW), (int64_t)kNumSMs * 8);
+    const int nblocks = (int)std::min<int64_t>((n_all + SW_WARPS * SW_RUN - 1) / (SW_WARPS * SW_RUN), (int64_t)kNumSMs * 8);
     // tiled sweep (one thread per point) whenever the list fits one register row and this rank sweeps every point
     const bool tiled_ok = kk <= 32 && world == 1 && std::getenv("WTP_NO_TILED") == nullptr;
     const int n_tiled_blocks = tiled_ok ? (int)((n_all + TK_Q - 1) / TK_Q) : 0;
-    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + n_tiled_blocks + 1 + world);
-    RepelPartial<T>* partials_tiled = partials + nblocks;       // [general sweep | tiled sweep], folded together
-    RepelPartial<T>* d_tot = partials_tiled + n_tiled_blocks;
+    // per-CTA partials of the sweep launches of an iteration (general sweep | tiled sweep), folded together
+    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + (size_t)n_tiled_blocks + 1 + world);
+    RepelPartial<T>* d_tot = partials + (size_t)nblocks + (size_t)n_tiled_blocks;
     RepelPartial<T>* d_all = d_tot + 1;
     RepelPartial<T>* h_tot = static_cast<RepelPartial<T>*>(ctx->h_pinned);
-    WTP_REQUIRE(sizeof(RepelPartial<T>) * (size_t)(world + 1) + 64 <= ctx->h_pinned_bytes, WTP_ERR_BAD_ARG, "world size too large for the staging buffer");
+    WTP_REQUIRE(sizeof(RepelPartial<T>) * (size_t)(world + 1) + 64 <= 3072, WTP_ERR_BAD_ARG, "world size too large for the staging buffer");
+    uint32_t* h_cnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 3072);
 
     Grid<T> g{};
     int passes = 0;
@@ -427,7 +428,9 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         const bool rebuild = (it - 1) % prm->rebuild_every == 0;                                     // :245
         if (variable) {                                                                              // spacing(xi), :260 (and :251)
             ScopedPhase ph(ctx->timer, PH_SCAN);
-            spacing_eval<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, it > 1);
+            // after the first build the previous iteration's sorted records give a spatially coherent visiting order
+            if (it > 1) spacing_eval_ordered<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, true, ib.sorted.get<P4<T>>(), n_all, n_fixed);
+            else spacing_eval<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, false);
         }
         if (rebuild) {
             WTP_CUDA_CHECK(cudaMemcpyAsync(S_tail, Pa, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));   // :246
@@ -451,19 +454,19 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         a.n_fixed = (uint32_t)n_fixed; a.n_all = (uint32_t)n_all; a.id_lo = (uint32_t)id_lo; a.id_hi = (uint32_t)id_hi;
         a.qlist = qlist; a.nq = nq; a.kk = kk; a.rebuild = rebuild ? 1 : 0;
         a.a_lo = (T)prm->alpha_lo; a.a_max = (T)prm->alpha_max; a.force = force; a.partials = partials;
-        a.nq_ptr = nullptr;
+        a.nq_dev = nullptr;
         int n_partials = nblocks;
+        const bool tiled_now = rebuild && tiled_ok;
+        TileFails fails{};
         {
             ScopedPhase ph(ctx->timer, PH_QUERY);
-            if (rebuild && tiled_ok) {
+            if (tiled_now) {
                 // tiled sweep over every sorted position, then the general sweep over what it handed back
+                fails = tile_fails(ctx, n_all);
                 SweepArgs<T> at = a;
-                at.qlist = nullptr; at.nq = (uint32_t)n_all; at.partials = partials_tiled;
-                uint32_t* d_fail = ctx->d_fail.as<uint32_t>((size_t)n_all + 4);
-                WTP_CUDA_CHECK(cudaMemsetAsync(d_fail, 0, sizeof(uint32_t), st));
-                if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, d_fail + 4, d_fail);
-                else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, d_fail + 4, d_fail);
-                a.qlist = d_fail + 4; a.nq = (uint32_t)n_all; a.nq_ptr = d_fail;
+                at.qlist = nullptr; at.nq = (uint32_t)n_all; at.partials = partials + nblocks;
+                if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, fails); else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, fails);
+                a.qlist = fails.list; a.nq = (uint32_t)n_all; a.nq_dev = fails.counters;
                 n_partials = nblocks + n_tiled_blocks;
             }
             if (D == 2) launch_sweep<T, 2>(ctx, a, nblocks); else launch_sweep<T, 3>(ctx, a, nblocks);
@@ -488,8 +491,10 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             for (int r = 1; r < world; ++r) partial_merge(tot, h_tot[r]);
         } else {
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_tot, sizeof(RepelPartial<T>), cudaMemcpyDeviceToHost, st));
+            if (tiled_now) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, fails.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             WTP_CUDA_CHECK(cudaStreamSynchronize(st));
             tot = h_tot[0];
+            if (tiled_now) { ctx->last_tile_sparse = h_cnt[1]; ctx->last_tile_dense = h_cnt[2]; ctx->last_tile_other = h_cnt[3]; }
         }
         for (int d = 0; d < 3; ++d) { mlo[d] = d < D ? (double)tot.lo[d] : 0.0; mhi[d] = d < D ? (double)tot.hi[d] : 0.0; }
         conv[n_conv++] = tot.max_force;                                                              // :293
