@@ -79,10 +79,15 @@ int32_t wtp_host_unregister(wtp_ctx* ctx, void* ptr);
 int32_t wtp_set_cell_occupancy(wtp_ctx* ctx, double points_per_cell);
 
 /* Multi-GPU, one process per GPU. The NCCL unique id (128 bytes) is created on one
- * rank with wtp_comm_unique_id and distributed by the host program. After wtp_comm_init
- * the k-NN / radius entry points answer only this rank's contiguous query range
- * [wtp_shard_begin, wtp_shard_end) of the caller's point order (no collective), and
- * wtp_repel_* all-gathers the moved positions over NCCL every iteration. */
+ * rank with wtp_comm_unique_id and distributed by the host program. After wtp_comm_init:
+ *  - k-NN: every rank builds the (replicated) index and answers the contiguous run
+ *    [wtp_shard_begin(N), wtp_shard_end(N)) of the SPATIALLY SORTED order, no collective.
+ *    Host entry points write those rows into the caller's N x k table at their caller
+ *    positions (other rows untouched); device entry points write a compact
+ *    wtp_shard_owned_count() x k table. wtp_shard_owned gives the caller index of each row.
+ *  - radius: the contiguous range [wtp_shard_begin, wtp_shard_end) of the caller's order.
+ *  - wtp_repel_*: the same kind of range of the movable points, all-gathering the moved
+ *    positions over NCCL every iteration. */
 int32_t wtp_comm_unique_id(void* out128);
 int32_t wtp_comm_init(wtp_ctx* ctx, int32_t rank, int32_t world, const void* unique_id128);
 int32_t wtp_comm_rank(const wtp_ctx* ctx);
@@ -90,6 +95,11 @@ int32_t wtp_comm_world(const wtp_ctx* ctx);
 /* Contiguous block partition of n items: rank r owns [begin, end). */
 int64_t wtp_shard_begin(int64_t n, int32_t rank, int32_t world);
 int64_t wtp_shard_end(int64_t n, int32_t rank, int32_t world);
+/* Rows answered by the last k-NN call of a sharded context: their number, and their caller
+ * indices (int64, 1-based) in the order of the compact device table. */
+int64_t wtp_shard_owned_count(const wtp_ctx* ctx);
+int32_t wtp_shard_owned(wtp_ctx* ctx, int64_t* ids /* host */);
+int32_t wtp_shard_owned_dev(wtp_ctx* ctx, int64_t* d_ids);
 
 /* ------------------------------------------------------------ instrumentation */
 
@@ -123,7 +133,7 @@ int64_t wtp_launch_count(const wtp_ctx* ctx);
 /* _build_knn_neighbors (src/topology.jl:79-84): for every point the k nearest OTHER
  * points. Queries k+1, orders by (d2, index), drops position 1 (the reference's
  * n[2:end]). out_idx: N x k int64, 1-based. out_dist (nullable): N x k distances
- * sqrt(d2) in T. Requires N >= k+1. In sharded mode only rows [begin,end) are written. */
+ * sqrt(d2) in T. Requires N >= k+1. Sharded contexts: see wtp_comm_init above. */
 int32_t wtp_knn_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_t k,
                     int64_t* out_idx, float* out_dist);
 int32_t wtp_knn_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k,

@@ -28,7 +28,12 @@ for dt in (np.float32, np.float64):
         idx = np.zeros((len(pts), 21), dtype=np.int64)
         ctx.knn(pts, 21, out_idx=idx)
         ref = oracle.knn(pts, 21)
-        check(f"knn shard rows {dt.__name__} D={D}", np.array_equal(idx[b:e], ref[b:e]) and (idx[:b] == 0).all() and (idx[e:] == 0).all())
+        own = ctx.owned() - 1                                   # this rank's points: a contiguous run of the sorted order
+        rest = np.ones(len(pts), dtype=bool); rest[own] = False
+        counts = torch.zeros(len(pts), dtype=torch.int32, device=dev); counts[torch.from_numpy(own).to(dev)] += 1
+        dist.all_reduce(counts)                                 # every point is owned by exactly one rank
+        check(f"knn shard rows {dt.__name__} D={D}", len(own) == e - b and np.array_equal(idx[own], ref[own]) and (idx[rest] == 0).all()
+              and bool((counts == 1).all().item()))
         off, ind = ctx.radius(pts, 0.02 if D == 2 else 0.06)
         roff, rind = oracle.radius(pts, 0.02 if D == 2 else 0.06)
         check(f"radius shard CSR {dt.__name__} D={D}", np.array_equal(off, roff[b:e + 1] - roff[b]) and np.array_equal(ind, rind[roff[b]:roff[e]]))

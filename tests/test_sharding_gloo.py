@@ -1,6 +1,7 @@
-"""CPU, world_size 2, gloo: the N>1 host logic. Queries shard by contiguous range with the
-point set replicated (no collective); a Jacobi repel sweep shards the movable points the same
-way and all-gathers the moved positions each iteration. The per-rank compute here is the CPU
+"""CPU, world_size 2, gloo: the N>1 host logic. k-NN queries shard by contiguous runs of a spatial
+(cell-sorted) order with the point set replicated (no collective), every rank returning the rows of
+the points it owns plus their caller indices; a Jacobi repel sweep shards the movable points by
+contiguous caller-order range and all-gathers the moved positions each iteration. The per-rank compute here is the CPU
 oracle standing in for the device kernels: what is tested is the sharding/gather logic."""
 import os
 import sys
@@ -21,13 +22,21 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(3)
     pts = rng.random((4001, 3))
-    # --- k-NN: every rank answers its own contiguous rows; concatenation equals the full answer
+    # --- k-NN: every rank answers a contiguous run of the cell-sorted order (wtp_shard_owned: caller ids of its
+    # rows); scattering every rank's (ids, rows) gives the full table, each row exactly once
+    cells = np.floor(pts * 12).astype(np.int64)
+    order = np.lexsort((np.arange(len(pts)), cells[:, 0], cells[:, 1], cells[:, 2]))   # row-major cells, stable
     b, e = pkg.shard_range(len(pts), rank, world)
-    mine = oracle.knn(pts, 9, threads=1)[b:e]
+    own = order[b:e]
+    mine = oracle.knn(pts, 9, threads=1)[own]
     parts = [None] * world
-    dist.all_gather_object(parts, (b, e, mine))
-    full = np.concatenate([p[2] for p in sorted(parts, key=lambda t: t[0])])
-    ok_knn = np.array_equal(full, oracle.knn(pts, 9, threads=1))
+    dist.all_gather_object(parts, (own, mine))
+    full = np.zeros((len(pts), 9), dtype=np.int64)
+    hits = np.zeros(len(pts), dtype=np.int64)
+    for ids, rows in parts:
+        full[ids] = rows
+        hits[ids] += 1
+    ok_knn = np.array_equal(full, oracle.knn(pts, 9, threads=1)) and (hits == 1).all()
     # --- repel: owned movable range per rank, all-gather of moved positions per iteration
     n_fixed, iters = 401, 4
     h = len(pts) ** (-1 / 3)

@@ -91,6 +91,8 @@ def load() -> C.CDLL:
         lib.wtp_radius_nnz.restype = C.c_int64
         lib.wtp_shard_begin.restype = C.c_int64
         lib.wtp_shard_end.restype = C.c_int64
+        lib.wtp_shard_owned_count.restype = C.c_int64
+        lib.wtp_shard_owned_count.argtypes = [C.c_void_p]
         lib.wtp_shard_begin.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         lib.wtp_shard_end.argtypes = [C.c_int64, C.c_int32, C.c_int32]
         _lib = lib
@@ -193,10 +195,18 @@ class Context:
     def shard(self, n: int):
         return shard_range(n, self.rank, self.world)
 
+    def owned(self) -> np.ndarray:
+        """Caller indices (1-based) of the rows the last k-NN call of a sharded context answered, in the
+        order of the compact device table (a contiguous run of the spatially sorted order)."""
+        n = int(self._lib.wtp_shard_owned_count(self._h))
+        ids = np.empty(max(n, 0), dtype=np.int64)
+        self._check(self._lib.wtp_shard_owned(self._h, _vp(ids)))
+        return ids
+
     # ------------------------------------------------------------ topology
     def knn(self, pts, k: int, *, dists: bool = False, include_self: bool = False, out_idx=None, out_dist=None):
         """_build_knn_neighbors (default) or search/searchdists (include_self). 1-based int64 N x k.
-        On a sharded context only rows [shard) are filled."""
+        On a sharded context only the rows of the points this rank owns (`owned()`) are filled."""
         pts = _as_points(pts)
         n, d = pts.shape
         idx = out_idx if out_idx is not None else np.empty((n, k), dtype=np.int64)

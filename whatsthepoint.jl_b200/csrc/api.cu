@@ -168,9 +168,17 @@ void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_
 }
 
 // ------------------------------------------------------------------- k-NN
+// Index build + queries. Single context: every point is a query and rows go by caller index. Sharded context
+// (wtp_comm_init): this rank answers the contiguous run [sb, se) of the spatially sorted order (the sorted set is
+// replicated, no collective) and writes a compact table, row t = sorted position sb + t; wtp_shard_owned tells
+// which caller index each row belongs to.
+//   device sink (h_out_idx == null): d_out_idx / d_out_dist are the caller's device tables (int64 / T);
+//   host sink: the rows are computed as 4-byte indices into a context buffer, brought back chunk by chunk into a
+//   pinned staging ring on the copy stream and widened (and, when sharded, scattered by caller index) into the
+//   caller's int64 table on the host pool while the next chunk is on the wire: 4 B per neighbour cross PCIe, not 8.
 template <class T>
-static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bool drop_first, int64_t* d_out_idx,
-                       T* d_out_dist, int64_t* rows_begin, int64_t* rows_end, int64_t* h_out_idx = nullptr, T* h_out_dist = nullptr) {
+static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bool drop_first, int64_t* d_out_idx, T* d_out_dist,
+                       int64_t* h_out_idx = nullptr, T* h_out_dist = nullptr) {
     WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
     WTP_REQUIRE(k >= 1, WTP_ERR_BAD_ARG, "k must be >= 1");
     const int K1 = k + (drop_first ? 1 : 0);
@@ -180,25 +188,32 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     double lo[3], hi[3];
     compute_bbox<T>(ctx, ib, d_pts, N, D, lo, hi);
     Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy, 0.0, K1);
-    int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
-    const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
-    const uint32_t* qlist = nullptr;
-    if (ctx->world > 1) {
-        build_query_list(ctx, ib, N, qb, qe, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
-        qlist = ctx->d_qlist.get<uint32_t>();
-    }
+    const int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
+    const bool sharded = ctx->world > 1;
+    const int64_t sb = wtp_shard_begin(N, ctx->rank, ctx->world), se = wtp_shard_end(N, ctx->rank, ctx->world);
+    const int64_t nq = se - sb;
+    ctx->owned_begin = sb; ctx->owned_end = se; ctx->owned_f64 = sizeof(T) == 8;
+    const RowMap rows{0u, (uint32_t)sb, sharded ? 1 : 0};
     unsigned long long* d_exp = ctx->d_reduce.as<unsigned long long>(1);
     WTP_CUDA_CHECK(cudaMemsetAsync(d_exp, 0, sizeof(unsigned long long), ctx->stream));
-    // Host sink and a large result (the int64 table is PCIe-bound): answer the queries in caller-order
-    // chunks writing 4-byte indices, bring chunk c back into a pinned staging ring on the copy stream
-    // while chunk c+1 computes, and widen it into the caller's int64 rows on the host pool while chunk
-    // c+1 is on the wire. 4 B per neighbour cross PCIe instead of 8.
-    const bool pipelined = h_out_idx != nullptr && (qe - qb) * (int64_t)k >= ((int64_t)4 << 20);
-    // CTA-tiled front end (knn_tile.cuh) whenever the list fits one register row and this context answers
-    // every query; the general kernel alone otherwise (long lists, caller-order shards).
-    const bool tiled = K1 <= 32 && ctx->world == 1 && std::getenv("WTP_NO_TILED") == nullptr;
+    // CTA-tiled front end (knn_tile.cuh) whenever the list fits one register row, the general kernel alone otherwise
+    const bool tiled = K1 <= 32 && std::getenv("WTP_NO_TILED") == nullptr;
+    auto compute = [&](void* d_idx, T* d_dist, bool out32) {
+        if (tiled) knn_query_tiled<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, sb, se, rows, d_idx, d_dist, d_exp, out32);
+        else knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, nullptr, nq, rows, d_idx, d_dist, d_exp, out32);
+    };
     int n_chunks = 1;
-    if (pipelined) {
+    if (!h_out_idx) {
+        compute(d_out_idx, d_out_dist, false);
+    } else if (!sharded && nq * (int64_t)k < ((int64_t)4 << 20)) {
+        // small result: int64 rows straight from the device table
+        int64_t* d_idx = ctx->d_out_idx.as<int64_t>((size_t)nq * k);
+        T* d_dist = h_out_dist ? ctx->d_out_dist.as<T>((size_t)nq * k) : nullptr;
+        compute(d_idx, d_dist, false);
+        ScopedPhase ph(ctx->timer, PH_D2H);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_idx, d_idx, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (h_out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist, d_dist, (size_t)nq * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
         constexpr int S = 3;                                     // staging slots
         constexpr size_t SLOT = (size_t)32 << 20;                // bytes per slot
         if (!ctx->h_stage) {
@@ -206,74 +221,78 @@ static bool knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
             ctx->h_stage_slot_bytes = SLOT;
         }
         if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());
-        const int64_t nq = qe - qb;
-        const int64_t rows = std::max<int64_t>(1, (int64_t)(SLOT / ((size_t)k * sizeof(uint32_t))));
-        n_chunks = (int)((nq + rows - 1) / rows);
-        uint32_t* d_idx32 = reinterpret_cast<uint32_t*>(d_out_idx);   // the device table holds 4-byte indices in this mode
-        // tiled: one pass over all queries in sorted order (rows land at their caller positions), then the
-        // copies; otherwise one kernel per caller-order chunk, overlapped with the copies
-        const uint32_t* lists = tiled ? nullptr : build_chunk_query_lists(ctx, ib, ctx->qsort, N, qb, qe, rows, n_chunks, sizeof(T) == 8);
-        auto enqueue_kernel = [&](int c) {
-            if (tiled) {
-                if (c != 0) return;
-                knn_query_tiled<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, 0, N, qb, d_idx32, d_out_dist, d_exp, true);
-            } else {
-                const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
-                knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, lists + cb, ce - cb, qb, d_idx32, d_out_dist, d_exp, true);
+        uint32_t* d_idx32 = ctx->d_out_idx.as<uint32_t>((size_t)nq * k);
+        T* d_dist = h_out_dist ? ctx->d_out_dist.as<T>((size_t)nq * k) : nullptr;
+        compute(d_idx32, d_dist, true);
+        // sharded: row t belongs to caller index ids[t]
+        std::vector<int64_t> ids;
+        std::vector<T> dist_tmp;
+        if (sharded) {
+            int64_t* d_ids = ctx->d_misc.as<int64_t>((size_t)std::max<int64_t>(nq, 1));
+            owned_ids(ctx, ib, sizeof(T) == 8, sb, se, d_ids);
+            ids.resize((size_t)nq);
+            WTP_CUDA_CHECK(cudaMemcpyAsync(ids.data(), d_ids, (size_t)nq * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (h_out_dist) {
+                dist_tmp.resize((size_t)nq * k);
+                WTP_CUDA_CHECK(cudaMemcpyAsync(dist_tmp.data(), d_dist, (size_t)nq * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
             }
-            WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[c % 8], ctx->stream));
-        };
+        } else if (h_out_dist) {
+            WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist, d_dist, (size_t)nq * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
+        WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0));
+        const int64_t rows_per = std::max<int64_t>(1, (int64_t)(SLOT / ((size_t)k * sizeof(uint32_t))));
+        n_chunks = (int)((nq + rows_per - 1) / rows_per);
         auto enqueue_copy = [&](int c) {
-            const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
-            if (!tiled || c == 0) WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[c % 8], 0));
+            const int64_t cb = (int64_t)c * rows_per, ce = std::min<int64_t>(nq, cb + rows_per);
             WTP_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT, d_idx32 + cb * k,
                                            (size_t)(ce - cb) * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
-            if (h_out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist + (qb + cb) * k, d_out_dist + cb * k, (size_t)(ce - cb) * k * sizeof(T),
-                                                           cudaMemcpyDeviceToHost, ctx->copy_stream));
             WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[c % 4], ctx->copy_stream));
         };
-        // kernels run four chunks ahead of the chunk being widened, copies two ahead (slots c, c+1, c+2 are distinct)
-        for (int c = 0; c < std::min(4, n_chunks); ++c) enqueue_kernel(c);
-        for (int c = 0; c < std::min(2, n_chunks); ++c) enqueue_copy(c);
+        for (int c = 0; c < std::min(2, n_chunks); ++c) enqueue_copy(c);   // two copies ahead of the chunk being widened
         const bool dbg = std::getenv("WTP_PIPE_DEBUG") != nullptr;
         double t_wait = 0, t_widen = 0;
         auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        if (sharded) WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));       // ids (and distances) are on the host
         for (int c = 0; c < n_chunks; ++c) {
-            if (c + 4 < n_chunks) enqueue_kernel(c + 4);
-            if (c + 2 < n_chunks) enqueue_copy(c + 2);
+            if (c + 2 < n_chunks) enqueue_copy(c + 2);                         // slots c, c+1, c+2 are distinct
             const double t0 = dbg ? now() : 0;
             WTP_CUDA_CHECK(cudaEventSynchronize(ctx->ev_copied[c % 4]));
             const double t1 = dbg ? now() : 0;
-            const int64_t cb = (int64_t)c * rows, ce = std::min<int64_t>(nq, cb + rows);
+            const int64_t cb = (int64_t)c * rows_per, ce = std::min<int64_t>(nq, cb + rows_per);
             const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT);
-            int64_t* dst = h_out_idx + (qb + cb) * k;
-            const size_t total = (size_t)(ce - cb) * k;
-            ctx->pool->run([&](int part, int parts) {
-                const size_t a = (total * part / parts) & ~(size_t)3, b = part + 1 == parts ? total : ((total * (part + 1) / parts) & ~(size_t)3);
-                widen_u32_to_i64(src + a, dst + a, b - a);
-            });
+            if (!sharded) {
+                int64_t* dst = h_out_idx + cb * k;
+                const size_t total = (size_t)(ce - cb) * k;
+                ctx->pool->run([&](int part, int parts) {
+                    const size_t a = (total * part / parts) & ~(size_t)3, b = part + 1 == parts ? total : ((total * (part + 1) / parts) & ~(size_t)3);
+                    widen_u32_to_i64(src + a, dst + a, b - a);
+                });
+            } else {
+                const int64_t nrow = ce - cb;
+                ctx->pool->run([&](int part, int parts) {
+                    for (int64_t t = nrow * part / parts; t < nrow * (part + 1) / parts; ++t) {
+                        int64_t* dst = h_out_idx + (ids[(size_t)(cb + t)] - 1) * k;
+                        for (int r = 0; r < k; ++r) dst[r] = (int64_t)src[t * k + r];
+                        if (h_out_dist) memcpy(h_out_dist + (ids[(size_t)(cb + t)] - 1) * k, dist_tmp.data() + (size_t)(cb + t) * k, (size_t)k * sizeof(T));
+                    }
+                });
+            }
             if (dbg) { t_wait += t1 - t0; t_widen += now() - t1; }
         }
         if (dbg) fprintf(stderr, "[wtp pipe] chunks=%d threads=%d wait_copy=%.2f ms widen=%.2f ms\n", n_chunks, ctx->pool->size(), t_wait, t_widen);
         WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
         WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
-    } else if (tiled) {
-        knn_query_tiled<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, 0, N, qb, d_out_idx, d_out_dist, d_exp);
-    } else {
-        knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, qlist, qe - qb, qb, d_out_idx, d_out_dist, d_exp);
     }
     unsigned long long* h_exp = static_cast<unsigned long long*>(ctx->h_pinned);
     WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     finish_timing(ctx, passes, n_chunks, g.ncells, (int64_t)*h_exp);
-    *rows_begin = qb; *rows_end = qe;
-    return pipelined;
 }
 
 template <class T>
 void knn_device_self(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, int64_t* d_out_idx, T* d_out_dist) {
-    int64_t rb, re;
-    knn_device<T>(ctx, d_pts, N, D, k, false, d_out_idx, d_out_dist, &rb, &re);
+    knn_device<T>(ctx, d_pts, N, D, k, false, d_out_idx, d_out_dist);
 }
 template void knn_device_self<float>(wtp_ctx*, const float*, int64_t, int, int, int64_t*, float*);
 template void knn_device_self<double>(wtp_ctx*, const double*, int64_t, int, int, int64_t*, double*);
@@ -287,21 +306,12 @@ static int32_t knn_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_
     ctx->timer.reset(ctx->stream);
     ctx->timer.begin_total();
     T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
-    const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
-    int64_t* d_idx = ctx->d_out_idx.as<int64_t>((size_t)(qe - qb) * k);
-    T* d_dist = out_dist ? ctx->d_out_dist.as<T>((size_t)(qe - qb) * k) : nullptr;
     {
         ScopedPhase ph(ctx->timer, PH_H2D);
         WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     }
-    int64_t rb, re;
-    const bool copied = knn_device<T>(ctx, d_pts, N, D, k, drop_first, d_idx, d_dist, &rb, &re, out_idx, out_dist);
+    knn_device<T>(ctx, d_pts, N, D, k, drop_first, nullptr, nullptr, out_idx, out_dist);
     wtp_timing keep = ctx->last_timing;
-    if (!copied) {
-        ScopedPhase ph(ctx->timer, PH_D2H);
-        WTP_CUDA_CHECK(cudaMemcpyAsync(out_idx + rb * k, d_idx, (size_t)(re - rb) * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(out_dist + rb * k, d_dist, (size_t)(re - rb) * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-    }
     ctx->timer.end_total();
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     ctx->last_timing = keep;
@@ -314,8 +324,7 @@ static int32_t knn_dev(wtp_ctx* ctx, const T* d_pts, int64_t N, int32_t D, int32
     WTP_REQUIRE(d_pts && d_out_idx && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
     ctx->timer.reset(ctx->stream);
     ctx->timer.begin_total();
-    int64_t rb, re;
-    knn_device<T>(ctx, d_pts, N, D, k, true, d_out_idx, d_out_dist, &rb, &re);
+    knn_device<T>(ctx, d_pts, N, D, k, true, d_out_idx, d_out_dist);
     ctx->timer.end_total();
     API_END(ctx)
 }
@@ -330,5 +339,25 @@ int32_t wtp_knn_self_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32
 int32_t wtp_knn_self_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_host<double>(c, p, N, D, k, false, oi, od); }
 int32_t wtp_knn_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_dev<float>(c, p, N, D, k, oi, od); }
 int32_t wtp_knn_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_dev<double>(c, p, N, D, k, oi, od); }
+
+int64_t wtp_shard_owned_count(const wtp_ctx* ctx) { return ctx ? ctx->owned_end - ctx->owned_begin : -1; }
+int32_t wtp_shard_owned_dev(wtp_ctx* ctx, int64_t* d_ids) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(d_ids || ctx->owned_end == ctx->owned_begin, WTP_ERR_BAD_ARG, "null output");
+    owned_ids(ctx, ctx->index[0], ctx->owned_f64, ctx->owned_begin, ctx->owned_end, d_ids);
+    API_END(ctx)
+}
+int32_t wtp_shard_owned(wtp_ctx* ctx, int64_t* ids) {
+    API_BEGIN(ctx)
+    const int64_t n = ctx->owned_end - ctx->owned_begin;
+    WTP_REQUIRE(ids || n == 0, WTP_ERR_BAD_ARG, "null output");
+    if (n > 0) {
+        int64_t* d_ids = ctx->d_misc.as<int64_t>((size_t)n);
+        owned_ids(ctx, ctx->index[0], ctx->owned_f64, ctx->owned_begin, ctx->owned_end, d_ids);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(ids, d_ids, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    API_END(ctx)
+}
 
 }  // extern "C"

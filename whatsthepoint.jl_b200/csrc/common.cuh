@@ -205,6 +205,16 @@ struct MeshBuffers {
     double offset = 0, maxabs = 0;
 };
 
+// Where the row of a query goes in the output table: at its caller index (minus q_begin), or, for the compact
+// table of a sharded host call, at its sorted position (minus pos_base).
+struct RowMap {
+    uint32_t q_begin, pos_base;
+    int by_position;
+    __host__ __device__ int64_t row(uint32_t sorted_pos, uint32_t caller_idx) const {
+        return by_position ? (int64_t)(sorted_pos - pos_base) : (int64_t)(caller_idx - q_begin);
+    }
+};
+
 // Why a query left the fast path of a tiled k-NN pass (knn_tile.cuh). TK_SPARSE: too few candidates in its block,
 // or the K-th neighbour is not provably inside it (the grid is too fine there). TK_DENSE: the slab does not fit the
 // tile, or more than TK_LCAP hits (too coarse there). TK_OTHER: look-alike key images or exact ties. Anything but
@@ -250,13 +260,13 @@ struct wtp_ctx {
         int64_t q_begin = 0, q_end = 0;
     } radius;
     unsigned char grid_storage[2][128];  // last Grid<T> per index (host copy)
+    int64_t owned_begin = 0, owned_end = 0; bool owned_f64 = false;   // sorted range answered by the last sharded k-NN call
     int64_t last_tile_sparse = 0, last_tile_dense = 0, last_tile_other = 0;   // leftovers of the last tiled sweep, by kind
     // multi-GPU
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
     wtp::NcclApi* nccl = nullptr;
-    // host k-NN pipeline: chunk query lists, 4-byte index staging (pinned ring) and the widening threads
-    wtp::IndexBuffers qsort;
+    // host k-NN pipeline: 4-byte index staging (pinned ring) and the widening threads
     void* h_stage = nullptr;
     size_t h_stage_slot_bytes = 0;
     cudaEvent_t ev_copied[4] = {};

@@ -29,18 +29,20 @@ void exclusive_scan_u32_to_i64(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, 
 // Warp-per-query exact k-NN on a built index. Queries are the index's own points,
 // restricted to caller-order indices [q_begin, q_end) (d_qlist: their sorted positions,
 // or null = all). K1 = list length; drop_first drops rank 0 from the output.
-// Rows are written at (orig - q_begin) * (K1 - drop_first). idx_base: 1 for 1-based.
+// Rows are written where `rows` says (RowMap, common.cuh).
 template <class T>
 void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
-               const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+               const uint32_t* d_qlist, int64_t n_queries, const RowMap& rows, void* d_out_idx, T* d_out_dist,
                unsigned long long* d_expanded_counter, bool out32 = false);   // out32: uint32 rows instead of int64
 
 // CTA-tiled front end + general kernel for the leftovers, over the sorted positions [s_begin, s_end)
 // (K1 <= 32). Rows are written at (orig - q_begin) * (K1 - drop_first) like knn_query. Fully asynchronous.
 template <class T>
 void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
-                     int64_t s_begin, int64_t s_end, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+                     int64_t s_begin, int64_t s_end, const RowMap& rows, void* d_out_idx, T* d_out_dist,
                      unsigned long long* d_expanded_counter, bool out32 = false);
+// caller indices (1-based) of the sorted positions [s_begin, s_end)
+void owned_ids(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, int64_t* d_ids);
 
 // Sinks of a tiled pass inside ctx->d_fail: 16 counters (zeroed here), then the list of up to n sorted positions.
 TileFails tile_fails(wtp_ctx* ctx, int64_t n);
@@ -48,11 +50,6 @@ TileFails tile_fails(wtp_ctx* ctx, int64_t n);
 // Compact list of sorted positions whose original index is in [q_begin, q_end).
 void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q_begin, int64_t q_end,
                       bool f64, DevBuf& flags, DevBuf& scan, DevBuf& qlist);
-
-// Query lists of all caller-order chunks [q_begin + c*rows_per_chunk, ...) in one stable radix pass;
-// returns the concatenated lists (chunk c starts at c*rows_per_chunk).
-const uint32_t* build_chunk_query_lists(wtp_ctx* ctx, const IndexBuffers& ib, IndexBuffers& scratch, int64_t N, int64_t q_begin,
-                                        int64_t q_end, int64_t rows_per_chunk, int n_chunks, bool f64);
 
 // ---- radius.cu -----------------------------------------------------------
 template <class T>

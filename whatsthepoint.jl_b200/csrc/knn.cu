@@ -30,7 +30,7 @@ template <class T, int D, int KPL>
 __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted,
                                                           const uint32_t* __restrict__ cell_start,
                                                           const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ nq_dev,
-                                                          uint32_t q_begin, int K1, int drop, void* __restrict__ out_idx_v, int out32,
+                                                          const RowMap rows, int K1, int drop, void* __restrict__ out_idx_v, int out32,
                                                           T* __restrict__ out_dist, unsigned long long* __restrict__ expanded) {
     constexpr int CAP = knn_tile_cap<T, KPL>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
         const P4<T> q = load_p4<T>(sorted + j);
         const int rings = s.run(q.x, q.y, q.z, K1);
         if (rings > 1 && lane == 0 && expanded) atomicAdd(expanded, 1ULL);
-        const int64_t row = (int64_t)(idx_of(q) - q_begin) * k_out;
+        const int64_t row = rows.row(j, idx_of(q)) * k_out;
 #pragma unroll
         for (int e = 0; e < KPL; ++e) {
             const int r = e * 32 + lane;
@@ -64,13 +64,13 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
     for (uint32_t first = (blockIdx.x * KNN_WARPS + warp) * KNN_RUN; first < nq; first += gridDim.x * KNN_WARPS * KNN_RUN) {
         const uint32_t end = min(nq, first + KNN_RUN);
 #pragma unroll 1
-        for (uint32_t qi = first; qi < end; ++qi) answer(qlist ? qlist[qi] : qi);
+        for (uint32_t qi = first; qi < end; ++qi) answer(qlist ? qlist[qi] : qi + rows.pos_base);   // no list: the run [pos_base, pos_base + nq)
     }
 }
 
 template <class T, int D, int KPL>
 static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, const P4<T>* sorted, const uint32_t* cs,
-                           const uint32_t* d_qlist, int64_t nq, const uint32_t* d_nq, int64_t q_begin, int K1, int drop,
+                           const uint32_t* d_qlist, int64_t nq, const uint32_t* d_nq, const RowMap& rows, int K1, int drop,
                            void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
     constexpr size_t smem = (size_t)knn_tile_cap<T, KPL>() * sizeof(P4<T>) * KNN_WARPS;
     static bool configured = false;
@@ -78,40 +78,40 @@ static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, con
         WTP_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<T, D, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    knn_kernel<T, D, KPL><<<nblocks, KNN_THREADS, smem, ctx->stream>>>(g, sorted, cs, d_qlist, (uint32_t)nq, d_nq, (uint32_t)q_begin,
+    knn_kernel<T, D, KPL><<<nblocks, KNN_THREADS, smem, ctx->stream>>>(g, sorted, cs, d_qlist, (uint32_t)nq, d_nq, rows,
                                                                        K1, drop, d_out_idx, out32, d_out_dist, d_exp);
 }
 
 template <class T, int D>
 static void launch_knn(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int K1, int drop, const uint32_t* d_qlist,
-                       int64_t nq, const uint32_t* d_nq, int64_t q_begin, void* d_out_idx, int out32, T* d_out_dist,
+                       int64_t nq, const uint32_t* d_nq, const RowMap& rows, void* d_out_idx, int out32, T* d_out_dist,
                        unsigned long long* d_exp) {
     // a device-side count (the tiled pass's leftovers): a fixed grid strides over however many entries there are
     const unsigned nblocks = (unsigned)std::min<int64_t>((nq + KNN_QPB - 1) / KNN_QPB, d_nq ? (int64_t)kNumSMs * 4 : (int64_t)0x7fffffff);
     const P4<T>* sorted = ib.sorted.get<P4<T>>();
     const uint32_t* cs = ib.cell_start.get<uint32_t>();
-    if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, q_begin, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
-    else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, q_begin, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
-    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, q_begin, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
+    if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
+    else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
+    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
     LAUNCH_CHECK(ctx);
 }
 
 template <class T>
 void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
-               const uint32_t* d_qlist, int64_t n_queries, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+               const uint32_t* d_qlist, int64_t n_queries, const RowMap& rows, void* d_out_idx, T* d_out_dist,
                unsigned long long* d_expanded_counter, bool out32) {
     (void)N;
     WTP_REQUIRE(K1 >= 1 && K1 <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K (128 list entries)");
     if (n_queries <= 0) return;
     ScopedPhase ph(ctx->timer, PH_QUERY);
-    if (D == 2) launch_knn<T, 2>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, nullptr, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
-    else launch_knn<T, 3>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, nullptr, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
+    if (D == 2) launch_knn<T, 2>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, nullptr, rows, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
+    else launch_knn<T, 3>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, nullptr, rows, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
 }
 
 template void knn_query<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int64_t, int, int, int, const uint32_t*, int64_t,
-                               int64_t, void*, float*, unsigned long long*, bool);
+                               const RowMap&, void*, float*, unsigned long long*, bool);
 template void knn_query<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, const uint32_t*, int64_t,
-                                int64_t, void*, double*, unsigned long long*, bool);
+                                const RowMap&, void*, double*, unsigned long long*, bool);
 
 TileFails tile_fails(wtp_ctx* ctx, int64_t n) {
     uint32_t* base = ctx->d_fail.as<uint32_t>(16 + (size_t)n);
@@ -123,7 +123,7 @@ TileFails tile_fails(wtp_ctx* ctx, int64_t n) {
 // whatever it handed back.
 template <class T, int D>
 static void run_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int K1, int drop, int64_t s_begin, int64_t s_end,
-                      int64_t q_begin, void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
+                      const RowMap& rows, void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
     constexpr size_t smem = tk_smem<T>();
     static bool configured = false;
     if (!configured) {
@@ -133,25 +133,39 @@ static void run_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, in
     const TileFails f = tile_fails(ctx, s_end - s_begin);
     const unsigned nblocks = (unsigned)((s_end - s_begin + TK_Q - 1) / TK_Q);
     knn_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cell_start.get<uint32_t>(), (uint32_t)s_begin,
-                                                               (uint32_t)s_end, (uint32_t)q_begin, K1, drop, d_out_idx, out32, d_out_dist, f);
+                                                               (uint32_t)s_end, rows, K1, drop, d_out_idx, out32, d_out_dist, f);
     LAUNCH_CHECK(ctx);
-    launch_knn<T, D>(ctx, ib, g, K1, drop, f.list, s_end - s_begin, f.counters, q_begin, d_out_idx, out32, d_out_dist, d_exp);
+    launch_knn<T, D>(ctx, ib, g, K1, drop, f.list, s_end - s_begin, f.counters, rows, d_out_idx, out32, d_out_dist, d_exp);
 }
 
 template <class T>
 void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
-                     int64_t s_begin, int64_t s_end, int64_t q_begin, void* d_out_idx, T* d_out_dist,
+                     int64_t s_begin, int64_t s_end, const RowMap& rows, void* d_out_idx, T* d_out_dist,
                      unsigned long long* d_expanded_counter, bool out32) {
     WTP_REQUIRE(K1 >= 1 && K1 <= 32, WTP_ERR_K_TOO_LARGE, "the tiled k-NN front end holds lists of at most 32 entries");
     if (s_end <= s_begin) return;
     ScopedPhase ph(ctx->timer, PH_QUERY);
-    if (D == 2) run_tiled<T, 2>(ctx, ib, g, N, K1, drop_first, s_begin, s_end, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
-    else run_tiled<T, 3>(ctx, ib, g, N, K1, drop_first, s_begin, s_end, q_begin, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
+    if (D == 2) run_tiled<T, 2>(ctx, ib, g, N, K1, drop_first, s_begin, s_end, rows, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
+    else run_tiled<T, 3>(ctx, ib, g, N, K1, drop_first, s_begin, s_end, rows, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
 }
 template void knn_query_tiled<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int64_t, int, int, int, int64_t, int64_t,
-                                     int64_t, void*, float*, unsigned long long*, bool);
+                                     const RowMap&, void*, float*, unsigned long long*, bool);
 template void knn_query_tiled<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, int64_t, int64_t,
-                                      int64_t, void*, double*, unsigned long long*, bool);
+                                      const RowMap&, void*, double*, unsigned long long*, bool);
+
+// caller indices (1-based) of the sorted positions [s_begin, s_end): the rows a sharded call wrote
+template <class T>
+__global__ void __launch_bounds__(256) owned_ids_kernel(const P4<T>* __restrict__ sorted, uint32_t s_begin, uint32_t s_end, int64_t* __restrict__ ids) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s_begin + t < s_end) ids[t] = (int64_t)idx_of(sorted[s_begin + t]) + 1;
+}
+void owned_ids(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, int64_t* d_ids) {
+    if (s_end <= s_begin) return;
+    const unsigned nb = (unsigned)((s_end - s_begin + 255) / 256);
+    if (f64) owned_ids_kernel<double><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<double>>(), (uint32_t)s_begin, (uint32_t)s_end, d_ids);
+    else owned_ids_kernel<float><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<float>>(), (uint32_t)s_begin, (uint32_t)s_end, d_ids);
+    LAUNCH_CHECK(ctx);
+}
 
 // ------------------------------------------------------------ query lists
 // Sharded mode: the sorted positions whose original index lies in [q_begin, q_end), in
@@ -183,34 +197,6 @@ void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q
     exclusive_scan_u32(ctx, const_cast<IndexBuffers&>(ib).scan_tmp, d_flags, d_pos, N);
     qcompact_kernel<<<nb, 256, 0, ctx->stream>>>(d_flags, d_pos, (uint32_t)N, d_q);
     LAUNCH_CHECK(ctx);
-}
-
-// All chunk query lists in one pass: key = chunk of the point's caller index ((i - q_begin) / rows_per_chunk;
-// points outside [q_begin, q_end) get the last bin), value = sorted position, one stable radix pass on
-// the few key bits. The sorted values are the chunk lists back to back, each in sorted (cell) order.
-template <class T>
-__global__ void __launch_bounds__(256) qchunk_key_kernel(const P4<T>* __restrict__ sorted, uint32_t N, uint32_t qb, uint32_t qe,
-                                                         uint32_t rows_per_chunk, uint32_t n_chunks, uint32_t* __restrict__ keys,
-                                                         uint32_t* __restrict__ vals) {
-    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= N) return;
-    const uint32_t i = idx_of(sorted[j]);
-    keys[j] = (i >= qb && i < qe) ? (i - qb) / rows_per_chunk : n_chunks;
-    vals[j] = j;
-}
-
-const uint32_t* build_chunk_query_lists(wtp_ctx* ctx, const IndexBuffers& ib, IndexBuffers& scratch, int64_t N, int64_t q_begin,
-                                        int64_t q_end, int64_t rows_per_chunk, int n_chunks, bool f64) {
-    uint32_t* keys = scratch.keys_a.as<uint32_t>((size_t)N);
-    uint32_t* vals = scratch.vals_a.as<uint32_t>((size_t)N);
-    const unsigned nb = (unsigned)((N + 255) / 256);
-    if (f64) qchunk_key_kernel<double><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<double>>(), (uint32_t)N, (uint32_t)q_begin, (uint32_t)q_end, (uint32_t)rows_per_chunk, (uint32_t)n_chunks, keys, vals);
-    else qchunk_key_kernel<float><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<float>>(), (uint32_t)N, (uint32_t)q_begin, (uint32_t)q_end, (uint32_t)rows_per_chunk, (uint32_t)n_chunks, keys, vals);
-    LAUNCH_CHECK(ctx);
-    int bits = 1;
-    while ((1 << bits) < n_chunks + 1) ++bits;
-    radix_sort_pairs(ctx, scratch, N, bits);
-    return scratch.vals_a.get<uint32_t>();
 }
 
 }  // namespace wtp

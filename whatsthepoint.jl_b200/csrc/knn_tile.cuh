@@ -266,7 +266,7 @@ struct TileSearch {
 template <class T, int D>
 __global__ void __launch_bounds__(TK_Q, sizeof(T) == 4 ? 5 : 3)
 knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_t* __restrict__ cell_start, uint32_t s_begin, uint32_t s_end,
-                uint32_t q_begin, int K1, int drop, void* __restrict__ out_idx_v, int out32, T* __restrict__ out_dist,
+                const RowMap rows, int K1, int drop, void* __restrict__ out_idx_v, int out32, T* __restrict__ out_dist,
                 const TileFails fails) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ typename TileSearch<T, D>::Shared sh;
@@ -281,7 +281,7 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
         if (status == TK_OK) {
             // re-read the K best in order, check strict canonical order (the images of two keys collide only when
             // their d2 agree to ~17 bits, or on exact ties) and write the row
-            const int64_t row = (int64_t)(idx_of(ts.q) - q_begin) * k_out;
+            const int64_t row = rows.row(ts.j, idx_of(ts.q)) * k_out;
             Key<T> prev = Key<T>::make((T)0, 0u);
             bool ok = true;
 #pragma unroll 2
