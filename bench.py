@@ -294,11 +294,11 @@ def main():
             "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(pts_h.nbytes),
                     "d2h_bytes_per_step": int(nq * K * 8), "api": "wtp_knn_f32 (host pointers, pinned)"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "knn_kernel<float,3,1>", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "knn_tile_kernel<float,3> (+ knn_kernel<float,3,1> for its leftovers)", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": ncu_traffic, "peak_source": how,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_QUERY_F32 * nq, "kernel_ms": q_ms_avg,
                          "kernel_share_of_step": q_ms_avg / ms_step,
-                         "note": "k-NN is issue/shared-memory bound, not DRAM bound: 96 B/query is compulsory traffic only (SURVEY.md §8d)"},
+                         "note": "k-NN is bound by instruction issue and the shared-memory pipe, not by DRAM: 96 B/query is compulsory traffic only (SURVEY.md §8d); kernel_ms = tiled pass + leftover pass"},
             "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("ms_bbox", "ms_cellkey", "ms_sort", "ms_reorder", "ms_query")},
             "ring_expanded_queries": expanded,
             "cpu_baseline": cpu,

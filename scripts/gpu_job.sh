@@ -18,7 +18,7 @@ for s in $steps; do
       timeout 600 $cmd > $out/plain_$tag.log 2>&1 &&
       timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_$tag.csv $cmd > $out/ncu_list_$tag.log 2>&1
       echo "ncu_list_rc=$?"
-      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'knn_kernel|repel_sweep_kernel' -s 3 -c 2 -f -o $out/prof_$tag $cmd > $out/ncu_full_$tag.log 2>&1
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'knn_tile_kernel|repel_tile_kernel' -s 4 -c 3 -f -o $out/prof_$tag $cmd > $out/ncu_full_$tag.log 2>&1
       echo "ncu_full_rc=$?" ;;
     extra)
       timeout 900 python scripts/bench_extra.py > $out/extra_$tag.log 2>&1; echo "extra_rc=$?"; tail -5 $out/extra_$tag.log ;;

@@ -176,20 +176,30 @@ constexpr int RS_WARP_ITEMS = RS_TILE / RS_WARPS;  // 512 consecutive keys per w
 
 __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const uint32_t* __restrict__ keys, uint32_t n, int shift,
                                                              uint32_t* __restrict__ block_hist, int num_blocks) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+    // one private histogram per warp (shared-memory atomics, a few-way conflicts at most), 16-byte key loads
+    __shared__ uint32_t h[RS_WARPS][256];
+    const int w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&h[0][0])[i] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * RS_TILE;
-#pragma unroll 4
-    for (int r = 0; r < RS_ITEMS; ++r) {
-        uint32_t i = base + r * RS_THREADS + threadIdx.x;
-        bool valid = i < n;
-        uint32_t digit = valid ? ((keys[i] >> shift) & 255u) : 256u;
-        unsigned peers = __match_any_sync(0xffffffffu, digit);
-        if (valid && (peers & ((1u << (threadIdx.x & 31)) - 1)) == 0) atomicAdd(&h[digit], __popc(peers));
+    if (base + RS_TILE <= n) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(keys + base);     // RS_TILE is a multiple of 4: 16-byte aligned
+#pragma unroll
+        for (int r = 0; r < RS_ITEMS / 4; ++r) {
+            const uint4 v = k4[r * RS_THREADS + threadIdx.x];
+            atomicAdd(&h[w][(v.x >> shift) & 255u], 1u);
+            atomicAdd(&h[w][(v.y >> shift) & 255u], 1u);
+            atomicAdd(&h[w][(v.z >> shift) & 255u], 1u);
+            atomicAdd(&h[w][(v.w >> shift) & 255u], 1u);
+        }
+    } else {
+        for (uint32_t i = base + threadIdx.x; i < n; i += RS_THREADS) atomicAdd(&h[w][(keys[i] >> shift) & 255u], 1u);
     }
     __syncthreads();
-    block_hist[threadIdx.x * num_blocks + blockIdx.x] = h[threadIdx.x];
+    uint32_t tot = 0;
+#pragma unroll
+    for (int i = 0; i < RS_WARPS; ++i) tot += h[i][threadIdx.x];
+    block_hist[threadIdx.x * num_blocks + blockIdx.x] = tot;
 }
 
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,

@@ -306,12 +306,17 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
 
 // fold the per-CTA partials in a fixed order (thread t takes partials t, t+256, ...; then
 // a fixed tree over the threads) so the stop test is reproducible run to run
+// (CTA b of a grid folds the contiguous slice b of the partials, so a large sweep is folded in two launches:
+// many slices -> one partial each, then those -> the total; slices and trees are fixed, so is the result)
 template <class T>
 __global__ void __launch_bounds__(256) repel_finalize_kernel(const RepelPartial<T>* __restrict__ partials, int n, RepelPartial<T>* __restrict__ out) {
     __shared__ RepelPartial<T> s[256];
     RepelPartial<T> acc;
     partial_init(acc);
-    for (int i = threadIdx.x; i < n; i += 256) partial_merge(acc, partials[i]);
+    const int per = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * per, hi = min(n, lo + per);
+    out += blockIdx.x;
+    for (int i = lo + (int)threadIdx.x; i < hi; i += 256) partial_merge(acc, partials[i]);
     s[threadIdx.x] = acc;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -410,8 +415,9 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     const bool tiled_ok = kk <= 32 && world == 1 && std::getenv("WTP_NO_TILED") == nullptr;
     const int n_tiled_blocks = tiled_ok ? (int)((n_all + TK_Q - 1) / TK_Q) : 0;
     // per-CTA partials of the sweep launches of an iteration (general sweep | tiled sweep), folded together
-    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + (size_t)n_tiled_blocks + 1 + world);
-    RepelPartial<T>* d_tot = partials + (size_t)nblocks + (size_t)n_tiled_blocks;
+    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + (size_t)n_tiled_blocks + 256 + 1 + world);
+    RepelPartial<T>* d_fold = partials + (size_t)nblocks + (size_t)n_tiled_blocks;   // first stage of a two-stage fold
+    RepelPartial<T>* d_tot = d_fold + 256;
     RepelPartial<T>* d_all = d_tot + 1;
     RepelPartial<T>* h_tot = static_cast<RepelPartial<T>*>(ctx->h_pinned);
     WTP_REQUIRE(sizeof(RepelPartial<T>) * (size_t)(world + 1) + 64 <= 3072, WTP_ERR_BAD_ARG, "world size too large for the staging buffer");
@@ -477,7 +483,13 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         }
         {
             ScopedPhase ph(ctx->timer, PH_REDUCE);
-            repel_finalize_kernel<T><<<1, 256, 0, st>>>(partials, n_partials, d_tot);
+            if (n_partials > 4096) {   // two-stage fold: 256 slices first
+                repel_finalize_kernel<T><<<256, 256, 0, st>>>(partials, n_partials, d_fold);
+                LAUNCH_CHECK(ctx);
+                repel_finalize_kernel<T><<<1, 256, 0, st>>>(d_fold, 256, d_tot);
+            } else {
+                repel_finalize_kernel<T><<<1, 256, 0, st>>>(partials, n_partials, d_tot);
+            }
             LAUNCH_CHECK(ctx);
         }
         RepelPartial<T> tot;
