@@ -301,6 +301,7 @@ def main():
                          "note": "k-NN is bound by instruction issue and the shared-memory pipe, not by DRAM: 96 B/query is compulsory traffic only (SURVEY.md §8d); kernel_ms = tiled pass + leftover pass"},
             "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("ms_bbox", "ms_cellkey", "ms_sort", "ms_reorder", "ms_query")},
             "ring_expanded_queries": expanded,
+            "tiled_pass_leftovers": {k: int(phases[-1][k]) for k in ("n_leftover_sparse", "n_leftover_dense", "n_leftover_other")},
             "cpu_baseline": cpu,
             "repel": repel,
             "clocks": clocks.summary(),

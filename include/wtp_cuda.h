@@ -119,6 +119,9 @@ typedef struct {
     int32_t query_launches;
     int64_t n_cells;
     int64_t n_ring_expanded; /* queries that needed more than the 3^D block */
+    /* queries the tiled front end handed to the general kernel, by reason: block too sparse / too dense for
+     * the tile / look-alike keys or exact ties (k-NN: last call; repel: last iteration) */
+    int64_t n_leftover_sparse, n_leftover_dense, n_leftover_other;
 } wtp_timing;
 
 /* enable != 0: record CUDA events around each phase of subsequent calls. */

@@ -71,7 +71,8 @@ class Timing(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("ms_h2d", "ms_bbox", "ms_cellkey", "ms_sort", "ms_reorder", "ms_query",
                                          "ms_scan", "ms_reduce", "ms_comm", "ms_d2h", "ms_total")] + \
                [("sort_passes", C.c_int32), ("query_launches", C.c_int32), ("n_cells", C.c_int64),
-                ("n_ring_expanded", C.c_int64)]
+                ("n_ring_expanded", C.c_int64), ("n_leftover_sparse", C.c_int64), ("n_leftover_dense", C.c_int64),
+                ("n_leftover_other", C.c_int64)]
 
 
 _lib = None

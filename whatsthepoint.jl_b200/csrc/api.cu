@@ -165,6 +165,9 @@ void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_
     ctx->last_timing.query_launches = query_launches;
     ctx->last_timing.n_cells = n_cells;
     ctx->last_timing.n_ring_expanded = n_expanded;
+    ctx->last_timing.n_leftover_sparse = ctx->last_tile_sparse;
+    ctx->last_timing.n_leftover_dense = ctx->last_tile_dense;
+    ctx->last_timing.n_leftover_other = ctx->last_tile_other;
 }
 
 // ------------------------------------------------------------------- k-NN
@@ -285,8 +288,11 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
     }
     unsigned long long* h_exp = static_cast<unsigned long long*>(ctx->h_pinned);
+    uint32_t* h_cnt = reinterpret_cast<uint32_t*>(h_exp + 1);
     WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    if (tiled) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, ctx->d_fail.get<uint32_t>(), 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_tile_sparse = tiled ? h_cnt[1] : 0; ctx->last_tile_dense = tiled ? h_cnt[2] : 0; ctx->last_tile_other = tiled ? h_cnt[3] : 0;
     finish_timing(ctx, passes, n_chunks, g.ncells, (int64_t)*h_exp);
 }
 

@@ -340,7 +340,7 @@ struct WarpKnn {
         for (uint32_t h = 0; h < cnt; h += 32) {
             Key<T> c = h + (uint32_t)lane < cnt ? buf[h + lane] : Key<T>::sentinel();
             if (h == 0 || cnt > 38u) {
-                c = WarpList<T, KPL>::sort32(c, lane);
+                c = WarpList<T, KPL>::sort32_fast(c, lane);
                 if (h == 0) list.e[0] = c;
                 else list.merge_sorted32(c, lane);
             } else {

@@ -552,6 +552,9 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     ctx->last_timing.sort_passes = passes;
     ctx->last_timing.query_launches = n_conv;
     ctx->last_timing.n_cells = g.ncells;
+    ctx->last_timing.n_leftover_sparse = ctx->last_tile_sparse;
+    ctx->last_timing.n_leftover_dense = ctx->last_tile_dense;
+    ctx->last_timing.n_leftover_other = ctx->last_tile_other;
 }
 
 template void relax_device<float>(wtp_ctx*, float*, int64_t, int64_t, int, const wtp_spacing*, const float*, const wtp_force*,

@@ -15,7 +15,7 @@
 module WTPCuda
 
 using Meshes, Unitful, StaticArrays
-import ..WhatsThePoint: _build_knn_neighbors, _build_radius_neighbors, _relax!, _get_radius,
+import ..WhatsThePoint: _build_knn_neighbors, _build_radius_neighbors, _relax!, _get_radius, _edge_key,
     RepelForceModel, InverseDistanceForce, SpacingEquilibriumForce, ClippedSpacingForce, StrongSpacingForce,
     ConstantSpacing, LogLike, BoundaryLayerSpacing
 
@@ -110,32 +110,78 @@ end
 cspacing(s, ::Type) = error("libwtp_cuda: spacing callable $(typeof(s)) cannot cross the C ABI (no CPU fallback)")
 
 const IDENTITY_WALL = 0
+const MESH_WALL = 1
+
+# wtp_wall_mesh (include/wtp_cuda.h): the TriangleIndex arrays flattened per triangle, in the cloud's machine type
+struct CWallMesh
+    triangles::Ptr{Cvoid}; feature_normals::Ptr{Cvoid}; n_tri::Int64
+    bbox_min::NTuple{3, Float64}; bbox_max::NTuple{3, Float64}; offset_dist::Float64
+    is_bnd::Ptr{UInt8}; tri_indices::Ptr{Int64}; escaped::Ptr{UInt8}
+end
+
+# index.vertices / triangles / face / vertex / edge (src/octree/triangle_octree.jl:22-31) -> 9 x n vertex
+# coordinates and 21 x n pseudonormals (face, vertex 1..3, edge 12, 13, 23; _feature_pseudonormal :322-337)
+function flatten_index(index, ::Type{T}) where {T}
+    n = length(index.triangles)
+    tri = Matrix{T}(undef, 9, n)
+    fn = Matrix{T}(undef, 21, n)
+    for i in 1:n
+        t = index.triangles[i]
+        v1, v2, v3 = index.vertices[t[1]], index.vertices[t[2]], index.vertices[t[3]]
+        f = index.face[i]
+        tri[1:3, i] .= v1; tri[4:6, i] .= v2; tri[7:9, i] .= v3
+        fn[1:3, i] .= f
+        fn[4:6, i] .= get(index.vertex, v1, f); fn[7:9, i] .= get(index.vertex, v2, f); fn[10:12, i] .= get(index.vertex, v3, f)
+        fn[13:15, i] .= get(index.edge, _edge_key(v1, v2), f)
+        fn[16:18, i] .= get(index.edge, _edge_key(v1, v3), f)
+        fn[19:21, i] .= get(index.edge, _edge_key(v2, v3), f)
+    end
+    return tri, fn
+end
 
 function _relax!(
         p, p_old, snap, spacing, force_model, constrain;
         n_fixed, n_protected, α_lo, α_max, k, max_iters, tol, rebuild_every,
         kick_after, trace, stall_after = 0, cv_target = 0.0, (deposit!) = nothing,
     )
-    isnothing(deposit!) || error("libwtp_cuda: deposit! is not available on the device path")
-    # repel(cloud, spacing, octree) calls with n_fixed = 0, n_protected = n_boundary (src/repel.jl:172):
-    # its constrain closure is the octree wall rule, which this build does not provide.
-    (n_fixed == 0 && n_protected > 0) && error("libwtp_cuda: the octree wall rule (_constrain_octree) is not available on the device path")
+    isnothing(deposit!) || error("libwtp_cuda: deposit! (_deposit_escaped!, serial by design) is not available on the device path")
     T, D = machine_type(snap), dimension(snap)
     n_move = length(p)
+    # repel(cloud, spacing, octree) calls with n_fixed = 0, n_protected = n_boundary (src/repel.jl:172) and a
+    # constrain closure over (is_bnd, escaped, tri_indices, octree, offset_dist, len_unit) (:158-160): the octree
+    # wall rule. Its captured variables are the closure's fields; the mesh crosses the ABI as flat arrays in T
+    # (the reference queries the octree in the octree's own machine type, :453 — identical when the two agree).
+    wall_mode = (n_fixed == 0 && n_protected > 0)
+    wall_mode || constrain === identity || error("libwtp_cuda: only identity and the octree wall rule can cross the C ABI as `constrain`")
+    tri = fn = nothing
+    is_bnd = UInt8[]; tri_idx = Int64[]; esc = UInt8[]
+    wall = Ref{CWallMesh}()
+    if wall_mode
+        index = constrain.octree.index
+        tri, fn = flatten_index(index, T)
+        is_bnd = UInt8.(constrain.is_bnd); tri_idx = zeros(Int64, n_move); esc = zeros(UInt8, n_move)
+        wall[] = CWallMesh(pointer(tri), pointer(fn), size(tri, 2), Tuple(Float64.(index.bbox_min)), Tuple(Float64.(index.bbox_max)),
+                           Float64(constrain.offset_dist), pointer(is_bnd), pointer(tri_idx), pointer(esc))
+    end
     @views snap[(n_fixed + 1):end] .= p
     sp, keep = cspacing(spacing, T)
     fm = cforce(force_model)
-    prm = CParams(k, max_iters, rebuild_every, stall_after, kick_after, IDENTITY_WALL, isnothing(trace) ? 0 : 1, 0,
+    prm = CParams(k, max_iters, rebuild_every, stall_after, kick_after, wall_mode ? MESH_WALL : IDENTITY_WALL, isnothing(trace) ? 0 : 1, 0,
                   Float64(α_lo), Float64(α_max), Float64(tol), Float64(cv_target))
     conv = Vector{T}(undef, max(max_iters, 1))
     tr = isnothing(trace) ? CTrace[] : Vector{CTrace}(undef, max(max_iters, 1))
     res = Ref(CResult(0, 0, NaN))
     s = raw(snap, T)
-    GC.@preserve s keep conv tr begin
+    GC.@preserve s keep conv tr tri fn is_bnd tri_idx esc wall begin
         rc = ccall((T === Float32 ? :wtp_repel_f32 : :wtp_repel_f64, LIB), Int32,
                    (Ptr{Cvoid}, Ptr{T}, Int64, Int64, Int32, Ref{CSpacing}, Ref{CForce}, Ref{CParams}, Ptr{Cvoid}, Ptr{T}, Ptr{CTrace}, Ref{CResult}),
-                   ctx(), s, n_fixed, n_move, D, Ref(sp), Ref(fm), Ref(prm), C_NULL, conv, isnothing(trace) ? C_NULL : pointer(tr), res)
+                   ctx(), s, n_fixed, n_move, D, Ref(sp), Ref(fm), Ref(prm),
+                   wall_mode ? Base.unsafe_convert(Ptr{Cvoid}, wall) : C_NULL, conv, isnothing(trace) ? C_NULL : pointer(tr), res)
         check(rc)
+    end
+    if wall_mode                                        # side arrays written from inside the sweep (src/repel.jl:462,467)
+        constrain.tri_indices .= tri_idx
+        constrain.escaped .|= (esc .!= 0)
     end
     @views p .= snap[(n_fixed + 1):end]                 # final positions (pre-sweep ones on a cv_target stop)
     r = res[]
