@@ -276,6 +276,17 @@ int32_t wtp_mesh_isinside_f64(wtp_ctx*, const wtp_wall_mesh*, const double* pts,
 int32_t wtp_mesh_project_f32(wtp_ctx*, const wtp_wall_mesh*, const float* pts, int64_t N, float* out_pts, int64_t* out_tri);
 int32_t wtp_mesh_project_f64(wtp_ctx*, const wtp_wall_mesh*, const double* pts, int64_t N, double* out_pts, int64_t* out_tri);
 
+/* isinside(points, cloud) against the boundary POINT cloud (src/isinside.jl), the survivor filter of
+ * repel(cloud, spacing) (src/repel.jl:90). D = 3: Green's-function sum over the boundary elements
+ * (positions M x 3, unit normals M x 3, areas M; all surfaces concatenated), inside iff the sum < -2*pi
+ * (:86-106). D = 2: winding number over the M polygon points, which must be ordered around the boundary
+ * (:18-35; WTP_ERR_BAD_ARG when M < 3 or the signed area vanishes, :37-69); normals and areas are unused.
+ * out: N flags; sums (nullable): the raw N sums in T. HOST pointers. */
+int32_t wtp_isinside_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, const float* bnd_pts, const float* bnd_normals,
+                         const float* bnd_areas, int64_t M, uint8_t* out, float* sums);
+int32_t wtp_isinside_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, const double* bnd_pts, const double* bnd_normals,
+                         const double* bnd_areas, int64_t M, uint8_t* out, double* sums);
+
 /* compute_force(model, u) elementwise on the device (src/repel_forces.jl:22). */
 int32_t wtp_force_eval_f32(wtp_ctx*, const wtp_force*, const float* u, int64_t n, float* out);
 int32_t wtp_force_eval_f64(wtp_ctx*, const wtp_force*, const double* u, int64_t n, double* out);

@@ -99,6 +99,21 @@ def mesh_project(mesh, pts, *, threads=0):
     return out, tri
 
 
+def isinside(pts, bnd_pts, bnd_normals=None, bnd_areas=None, *, threads=0):
+    """isinside(points, cloud) (src/isinside.jl): 3-D Green's function / 2-D winding number. Returns (flags, sums)."""
+    pts = _pts(pts)
+    d = pts.shape[1]
+    bx = np.ascontiguousarray(bnd_pts, dtype=pts.dtype)
+    bn = np.ascontiguousarray(bnd_normals, dtype=pts.dtype) if bnd_normals is not None else None
+    ba = np.ascontiguousarray(bnd_areas, dtype=pts.dtype) if bnd_areas is not None else None
+    out = np.zeros(pts.shape[0], dtype=np.uint8)
+    sums = np.zeros(pts.shape[0], dtype=pts.dtype)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    getattr(lib(), "wtpo_isinside_" + _sfx(pts.dtype))(vp(pts), C.c_int64(pts.shape[0]), C.c_int32(d), vp(bx), vp(bn), vp(ba),
+                                                        C.c_int64(bx.shape[0]), C.c_int32(threads), vp(out), vp(sums))
+    return out.astype(bool), sums
+
+
 class CloudMetrics(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("avg", "std", "max", "min", "separation", "fill", "mesh_ratio")]
 

@@ -23,6 +23,7 @@
 //   _relax!             src/repel.jl:202-339 (sweep :256-292, reductions :293, 374-403,
 //                       stop logic :305-337)
 //   metrics             src/metrics.jl:19-41
+//   isinside(p, cloud)  src/isinside.jl:18-35, 86-106 (winding number / Green's function over the boundary points)
 //   closest point / wall rule   src/octree/geometric_utils.jl:68-136, src/repel.jl:448-469,522-537,
 //                               src/octree/triangle_octree.jl:71-99,531-549,583-607 (brute force over triangles)
 //
@@ -556,6 +557,40 @@ int default_threads(int threads) {
 
 #define DISPATCH_D(T, D, call2, call3) ((D) == 2 ? (call2) : (D) == 3 ? (call3) : int32_t(WTP_ERR_BAD_ARG))
 
+// isinside(p, cloud) against the boundary point cloud (src/isinside.jl): 3-D Green's-function sum (:86-106),
+// 2-D winding number (:18-35, the signed angle A-p-B is atan(u x v, u . v)). Serial sums in element order.
+template <class T>
+static void isinside_points(const T* pts, int64_t N, int D, const T* bx, const T* bn, const T* ba, int64_t M, int threads, uint8_t* out, T* sums) {
+    const T eps = std::numeric_limits<T>::epsilon();
+    #pragma omp parallel for num_threads(threads) schedule(static)
+    for (int64_t i = 0; i < N; ++i) {
+        T g = T(0);
+        bool in;
+        if (D == 3) {
+            const T* p = pts + size_t(i) * 3;
+            for (int64_t j = 0; j < M; ++j) {
+                const T dx = p[0] - bx[j * 3], dy = p[1] - bx[j * 3 + 1], dz = p[2] - bx[j * 3 + 2];
+                const T dn = std::sqrt((dx * dx + dy * dy) + dz * dz);
+                const T dot = (dx * bn[j * 3] + dy * bn[j * 3 + 1]) + dz * bn[j * 3 + 2];
+                g = g + ba[j] * dot / (dn * dn * dn);
+            }
+            in = g < T(-6.283185307179586);
+        } else {
+            const T* p = pts + size_t(i) * 2;
+            bool on = false;
+            for (int64_t j = 0; j < M; ++j) {
+                const int64_t k = j + 1 == M ? 0 : j + 1;
+                const T ux = bx[j * 2] - p[0], uy = bx[j * 2 + 1] - p[1], vx = bx[k * 2] - p[0], vy = bx[k * 2 + 1] - p[1];
+                on = on || std::sqrt(ux * ux + uy * uy) < T(1.0e2) * eps;
+                g = g + std::atan2(ux * vy - uy * vx, ux * vx + uy * vy);
+            }
+            in = on || !(std::fabs(g) < T(1.0e3) * eps);
+        }
+        out[i] = in ? 1 : 0;
+        if (sums) sums[i] = g;
+    }
+}
+
 extern "C" {
 
 int32_t wtpo_max_threads(void) { return default_threads(0); }
@@ -634,6 +669,12 @@ int32_t wtpo_repel_f64(double* snap, int64_t n_fixed, int64_t n_move, int32_t D,
         _Pragma("omp parallel for num_threads(threads) schedule(dynamic, 64)")                                      \
         for (int64_t i = 0; i < N; ++i) out_tri[i] = mesh_project<T>(m, pts + size_t(i) * 3, out_pts + size_t(i) * 3); \
     }
+void wtpo_isinside_f32(const float* pts, int64_t N, int32_t D, const float* bx, const float* bn, const float* ba, int64_t M, int32_t threads, uint8_t* out, float* sums) {
+    isinside_points<float>(pts, N, D, bx, bn, ba, M, default_threads(threads), out, sums);
+}
+void wtpo_isinside_f64(const double* pts, int64_t N, int32_t D, const double* bx, const double* bn, const double* ba, int64_t M, int32_t threads, uint8_t* out, double* sums) {
+    isinside_points<double>(pts, N, D, bx, bn, ba, M, default_threads(threads), out, sums);
+}
 MESH_QUERIES(float, f32)
 MESH_QUERIES(double, f64)
 

@@ -348,6 +348,61 @@ def test_repel_octree_api(ctx, pkg, oracle):
         pkg.repel(pkg.PointCloud(snap[:50, :2], snap[50:200, :2]), pkg.ConstantSpacing(0.1), sph, ctx=ctx)
 
 
+# -------------------------------------- isinside(points, cloud) (src/isinside.jl)
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_isinside_greens_matches_oracle(ctx, oracle, pkg, dt):
+    rng = np.random.default_rng(31)
+    sph = pkg.icosphere_mesh(3)
+    tri = sph.triangles.reshape(-1, 3, 3)
+    c, n = tri.mean(1).astype(dt), sph.face.astype(dt)
+    a = (0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)).astype(dt)
+    q = (rng.random((20000, 3)) * 3 - 1.5).astype(dt)
+    f, g = ctx.isinside(q, c, n, a, sums=True)
+    of, og = oracle.isinside(q, c, n, a)
+    tol = 2e-4 if dt == np.float32 else 1e-11                        # same terms, different summation grouping (tiles of 256)
+    np.testing.assert_allclose(g, og, rtol=tol, atol=tol)
+    clear = np.abs(og + 2 * np.pi) > 1e-2
+    assert np.array_equal(f[clear], of[clear]) and clear.mean() > 0.99
+    r = np.linalg.norm(q.astype(np.float64), axis=1)
+    assert f[r < 0.93].all() and not f[r > 1.05].any()
+
+
+def test_isinside_polygon_known_answers_and_errors(ctx, pkg, oracle):
+    sq = np.array([[0.0, 0], [1, 0], [1, 1], [0, 1]])                 # test/isinside.jl:1-16
+    q = np.array([[0.5, 0.5], [0.5, 1.5], [0.5, 1 + np.finfo(float).eps], [1.5, 0.5], [0.5, -0.5]])
+    assert pkg.isinside(q, pkg.PointSurface(sq), ctx=ctx).tolist() == [True, False, False, False, False]
+    cloud = pkg.PointCloud(pkg.PointBoundary(sq * 3))                  # :29-40
+    assert pkg.isinside(np.array([[1.5, 1.5], [4.0, 1.5], [1.5, -1.0]]), cloud, ctx=ctx).tolist() == [True, False, False]
+    with pytest.raises(pkg.WtpArgumentError):                          # unordered points (:54-57)
+        pkg.isinside(np.array([[0.5, 0.5]]), pkg.PointSurface(np.array([[0.0, 0], [1, 1], [1, 0], [0, 1]])), ctx=ctx)
+    with pytest.raises(pkg.WtpArgumentError):                          # too few points (:59-62)
+        pkg.isinside(np.array([[0.5, 0.5]]), pkg.PointSurface(np.array([[0.0, 0], [1, 0]])), ctx=ctx)
+    rng = np.random.default_rng(32)
+    th = np.sort(rng.random(500)) * 2 * np.pi
+    poly = np.stack([(1 + 0.3 * np.sin(5 * th)) * np.cos(th), (1 + 0.3 * np.sin(5 * th)) * np.sin(th)], 1)   # non-convex star
+    qq = rng.random((20000, 2)) * 3 - 1.5
+    f, w = ctx.isinside(qq, poly, sums=True)
+    of, ow = oracle.isinside(qq, poly)
+    np.testing.assert_allclose(w, ow, atol=1e-9)
+    assert np.array_equal(f, of) and 0.2 < f.mean() < 0.6
+
+
+def test_repel_survivor_filter(ctx, pkg, oracle):
+    """repel(cloud, spacing) filters the moved points with isinside(x, cloud) (src/repel.jl:90)."""
+    rng = np.random.default_rng(33)
+    sph = pkg.icosphere_mesh(2)
+    tri = sph.triangles.reshape(-1, 3, 3)
+    c = tri.mean(1)
+    a = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    vol = rng.normal(size=(3000, 3)); vol *= (1.1 * rng.random((3000, 1)) ** (1 / 3)) / np.linalg.norm(vol, axis=1, keepdims=True)   # some start outside
+    cloud = pkg.PointCloud(pkg.PointBoundary({"wall": pkg.PointSurface(c, sph.face, a)}), vol)
+    out = pkg.repel(cloud, pkg.ConstantSpacing(0.12), max_iters=3, stall_after=0, tol=0.0, isinside=True, ctx=ctx)
+    kept = out.volume.points
+    assert 0 < len(kept) < len(vol)
+    assert pkg.isinside(kept, cloud, ctx=ctx).all()
+    assert (np.linalg.norm(kept, axis=1) < 1.02).all()
+
+
 # ------------------------------------------------------- BASELINE sizes
 def _brute_rows(pts, qi, k):
     """Canonical (d2, index) brute force for a few queries in the input precision (no FMA in numpy)."""

@@ -312,6 +312,20 @@ class Context:
         self._check(getattr(self._lib, "wtp_force_eval_" + _sfx(u.dtype))(self._h, C.byref(force), _vp(u), C.c_int64(u.size), _vp(out)))
         return out
 
+    def isinside(self, pts, bnd_pts, bnd_normals=None, bnd_areas=None, *, sums=False):
+        """isinside(points, cloud) (src/isinside.jl): Green's function over the boundary elements in 3-D, winding
+        number over the ordered boundary polygon in 2-D. Returns flags (and the raw sums)."""
+        pts = _as_points(pts)
+        d = pts.shape[1]
+        bx = np.ascontiguousarray(bnd_pts, dtype=pts.dtype)
+        bn = np.ascontiguousarray(bnd_normals, dtype=pts.dtype) if bnd_normals is not None else None
+        ba = np.ascontiguousarray(bnd_areas, dtype=pts.dtype) if bnd_areas is not None else None
+        out = np.zeros(pts.shape[0], dtype=np.uint8)
+        s = np.zeros(pts.shape[0], dtype=pts.dtype) if sums else None
+        fn = getattr(self._lib, "wtp_isinside_" + _sfx(pts.dtype))
+        self._check(fn(self._h, _vp(pts), C.c_int64(pts.shape[0]), C.c_int32(d), _vp(bx), _vp(bn), _vp(ba), C.c_int64(bx.shape[0]), _vp(out), _vp(s)))
+        return (out.astype(bool), s) if sums else out.astype(bool)
+
     def mesh_isinside(self, mesh, pts) -> np.ndarray:
         """isinside(points, octree) -> bool array (src/octree/triangle_octree.jl:97-115)."""
         pts = _as_points(pts)

@@ -417,9 +417,10 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
     points are the fixed wall; returns a new cloud with NoTopology.
 
     The relaxation (_relax!, src/repel.jl:202-339) runs in libwtp_cuda.so. The survivor
-    filter `filter(x -> isinside(x, cloud), p)` (:90) and the optional cull (:91-93) are
-    rows "next" of the scope table: pass `isinside` (a predicate on an N x D array) to
-    apply a filter, otherwise every moved point is kept.
+    filter `filter(x -> isinside(x, cloud), p)` (:90) runs on the device too when `isinside=True`
+    (Green's function over the boundary elements in 3-D, which needs their normals and areas;
+    winding number in 2-D) or with a caller's predicate on an N x D array; by default every
+    moved point is kept. The optional cull (:91-93) is a row "next" of the scope table.
     """
     if rebuild_every < 1:
         raise WtpArgumentError(1, "rebuild_every must be ≥ 1")                     # src/repel.jl:74
@@ -475,8 +476,10 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         out.escaped = ctx.last_wall["escaped"].astype(bool)
         return out
     p = new_snap[n_bnd:]
-    if isinside is not None:
-        p = p[np.asarray(isinside(p), dtype=bool)]                                 # :90
+    if isinside is not None:                                                       # :90  filter(x -> isinside(x, cloud), p)
+        keep_mask = isinside(p) if callable(isinside) else (globals()["isinside"](p, cloud, ctx=ctx) if isinside else None)
+        if keep_mask is not None:
+            p = p[np.asarray(keep_mask, dtype=bool)]
     out = PointCloud(cloud.boundary, PointVolume(p), NoTopology())                 # :94
     out.repel_result = res
     return out
@@ -502,12 +505,31 @@ def _reconstruct_cloud(cloud: PointCloud, p: np.ndarray, tri_indices: np.ndarray
     return PointCloud(PointBoundary({"boundary": surf}), PointVolume(p[~is_bnd]), NoTopology())
 
 
-def isinside(pts, octree, ctx=None) -> np.ndarray:
-    """isinside(points, octree) on the device (src/octree/triangle_octree.jl:97-115)."""
+def _boundary_elements(domain):
+    """(points, normals, areas) of all surfaces of a PointCloud / PointBoundary / PointSurface, concatenated."""
+    if isinstance(domain, PointCloud):
+        domain = domain.boundary
+    surfaces = list(domain.surfaces.values()) if isinstance(domain, PointBoundary) else [domain]
+    pts = np.concatenate([s.points for s in surfaces], axis=0)
+    if pts.shape[1] == 2:
+        return pts, None, None
+    if any(s.normals is None or s.areas is None for s in surfaces):
+        raise WtpArgumentError(1, "the 3-D isinside needs the normal and area of every boundary element")
+    return pts, np.concatenate([s.normals for s in surfaces], axis=0), np.concatenate([s.areas for s in surfaces], axis=0)
+
+
+def isinside(pts, domain, ctx=None) -> np.ndarray:
+    """isinside(points, octree) (src/octree/triangle_octree.jl:97-115) or isinside(points, cloud | boundary | surface)
+    (src/isinside.jl: Green's function over the boundary elements in 3-D, winding number in 2-D), on the device."""
     ctx = ctx or default_context()
     a = pts._points() if hasattr(pts, "_points") else np.asarray(pts)
     single = a.ndim == 1
-    out = ctx.mesh_isinside(octree, a[None, :] if single else a)
+    q = a[None, :] if single else a
+    if hasattr(domain, "feature_normals"):
+        out = ctx.mesh_isinside(domain, q)
+    else:
+        bx, bn, ba = _boundary_elements(domain)
+        out = ctx.isinside(q.astype(bx.dtype, copy=False), bx, bn, ba)
     return bool(out[0]) if single else out
 
 

@@ -303,6 +303,47 @@ static int32_t mesh_query_host(wtp_ctx* ctx, const wtp_wall_mesh* wall, const T*
     API_END(ctx)
 }
 
+// ------------------------------------------------- isinside(points, cloud)
+template <class T>
+static int32_t isinside_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, const T* bx, const T* bn, const T* ba, int64_t M,
+                             uint8_t* out, T* sums) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(pts && bx && out && N > 0 && M > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(D == 2 || (bn && ba), WTP_ERR_BAD_ARG, "the 3-D test needs the boundary normals and areas");
+    if (D == 2) {                                                    // _validate_polygon_ordering (src/isinside.jl:37-69)
+        WTP_REQUIRE(M >= 3, WTP_ERR_BAD_ARG, "need at least 3 points to define a polygon");
+        T sa = (T)0, xmin = bx[0], xmax = bx[0], ymin = bx[1], ymax = bx[1];
+        for (int64_t i = 0; i < M; ++i) {
+            const int64_t j = i + 1 == M ? 0 : i + 1;
+            sa += bx[i * 2] * bx[j * 2 + 1] - bx[j * 2] * bx[i * 2 + 1];
+            xmin = std::min(xmin, bx[i * 2]); xmax = std::max(xmax, bx[i * 2]);
+            ymin = std::min(ymin, bx[i * 2 + 1]); ymax = std::max(ymax, bx[i * 2 + 1]);
+        }
+        sa /= (T)2;
+        const T bbox_area = (xmax - xmin) * (ymax - ymin);
+        WTP_REQUIRE(!(bbox_area > (T)0 && std::fabs(sa) < (T)1.0e-10 * bbox_area), WTP_ERR_BAD_ARG,
+                    "polygon points do not appear to be ordered sequentially around the boundary");
+    }
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    T* d_b = ctx->d_spacing_pts.as<T>((size_t)M * (D == 3 ? 7 : 2));
+    uint8_t* d_o = ctx->d_misc.as<uint8_t>((size_t)N);
+    T* d_s = sums ? ctx->d_misc2.as<T>((size_t)N) : nullptr;
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_b, bx, (size_t)M * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    if (D == 3) {
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_b + M * 3, bn, (size_t)M * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_b + M * 6, ba, (size_t)M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        greens_isinside<T>(ctx, d_pts, N, d_b, d_b + M * 3, d_b + M * 6, M, d_s, d_o);
+    } else {
+        winding_isinside<T>(ctx, d_pts, N, d_b, M, d_s, d_o);
+    }
+    WTP_CUDA_CHECK(cudaMemcpyAsync(out, d_o, (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    if (sums) WTP_CUDA_CHECK(cudaMemcpyAsync(sums, d_s, (size_t)N * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
 // ---------------------------------------------------------------- metrics
 struct MetricsPartial { double avg, sd, mx, mn, sep, fill; };
 
@@ -366,6 +407,12 @@ int32_t wtp_spacing_eval_f64(wtp_ctx* c, const wtp_spacing* sp, const double* p,
 int32_t wtp_force_eval_f32(wtp_ctx* c, const wtp_force* f, const float* u, int64_t n, float* out) { return force_eval_host<float>(c, f, u, n, out); }
 int32_t wtp_force_eval_f64(wtp_ctx* c, const wtp_force* f, const double* u, int64_t n, double* out) { return force_eval_host<double>(c, f, u, n, out); }
 
+int32_t wtp_isinside_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, const float* bx, const float* bn, const float* ba, int64_t M, uint8_t* out, float* sums) {
+    return isinside_host<float>(c, p, N, D, bx, bn, ba, M, out, sums);
+}
+int32_t wtp_isinside_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, const double* bx, const double* bn, const double* ba, int64_t M, uint8_t* out, double* sums) {
+    return isinside_host<double>(c, p, N, D, bx, bn, ba, M, out, sums);
+}
 int32_t wtp_mesh_isinside_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, uint8_t* out) { return mesh_query_host<float>(c, m, p, N, out, nullptr, nullptr); }
 int32_t wtp_mesh_isinside_f64(wtp_ctx* c, const wtp_wall_mesh* m, const double* p, int64_t N, uint8_t* out) { return mesh_query_host<double>(c, m, p, N, out, nullptr, nullptr); }
 int32_t wtp_mesh_project_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, float* op, int64_t* ot) { return mesh_query_host<float>(c, m, p, N, nullptr, op, ot); }

@@ -101,4 +101,12 @@ void mesh_project(wtp_ctx* ctx, const MeshBuffers& mb, const T* d_pts, int64_t n
 template <class T>
 void mesh_wall_apply(wtp_ctx* ctx, MeshBuffers& mb, const T* d_P_old, T* d_P_new, int64_t id_lo, int64_t id_hi);
 
+// ---- inside.cu -----------------------------------------------------------
+// isinside(points, cloud): 3-D Green's-function sum over the boundary elements (positions, unit normals, areas);
+// 2-D winding number over the ordered boundary polygon (src/isinside.jl). d_g / d_w (nullable): the raw sums.
+template <class T>
+void greens_isinside(wtp_ctx* ctx, const T* d_pts, int64_t n, const T* d_bx, const T* d_bn, const T* d_ba, int64_t m, T* d_g, uint8_t* d_inside);
+template <class T>
+void winding_isinside(wtp_ctx* ctx, const T* d_pts, int64_t n, const T* d_poly, int64_t m, T* d_w, uint8_t* d_inside);
+
 }  // namespace wtp
