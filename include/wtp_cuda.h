@@ -304,6 +304,22 @@ int32_t wtp_metrics_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_
 int32_t wtp_metrics_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k,
                         wtp_cloud_metrics* out);
 
+/* spacing_metrics(cloud, spacing; k) (src/metrics.jl:56-71): error_i = |mean distance to the k-1 nearest
+ * others - s(x_i)| / s(x_i); max, mean and (sample) standard deviation over the points. */
+typedef struct { double max_error, mean_error, std_error; } wtp_spacing_metrics_t;
+int32_t wtp_spacing_metrics_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_t k, const wtp_spacing*, wtp_spacing_metrics_t* out);
+int32_t wtp_spacing_metrics_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k, const wtp_spacing*, wtp_spacing_metrics_t* out);
+
+/* spacing_fidelity_metrics(cloud, spacing; k, coord_radius) (src/metrics.jl:88-129): u_i = d_NN(i) / h(x_i)
+ * (nearest OTHER point by index among the k nearest); mean, cv = std/mean, the 5/50/95 % quantiles (linear
+ * interpolation between order statistics, Julia's default), and the mean number of neighbours within
+ * coord_radius * h(x_i). k is clamped to N. */
+typedef struct { double mean_dnn_h, cv, p05, p50, p95, coordination; } wtp_spacing_fidelity_t;
+int32_t wtp_spacing_fidelity_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_t k, double coord_radius, const wtp_spacing*,
+                                 wtp_spacing_fidelity_t* out);
+int32_t wtp_spacing_fidelity_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k, double coord_radius, const wtp_spacing*,
+                                 wtp_spacing_fidelity_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -260,6 +260,34 @@ def metrics(pts, k=20, *, threads=0):
     return {n: getattr(out, n) for n, _ in CloudMetrics._fields_}
 
 
+class SpacingMetrics(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("max_error", "mean_error", "std_error")]
+
+
+class SpacingFidelity(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("mean_dnn_h", "cv", "p05", "p50", "p95", "coordination")]
+
+
+def spacing_metrics(pts, sp: Spacing, k=20, *, threads=0):
+    pts = _pts(pts)
+    out = SpacingMetrics()
+    rc = getattr(lib(), "wtpo_spacing_metrics_" + _sfx(pts.dtype))(pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]),
+                                                                   C.c_int32(k), C.byref(sp), C.c_int32(threads), C.byref(out))
+    if rc != 0:
+        raise ValueError(f"oracle spacing_metrics failed with status {rc}")
+    return {n: getattr(out, n) for n, _ in SpacingMetrics._fields_}
+
+
+def spacing_fidelity_metrics(pts, sp: Spacing, k=30, coord_radius=1.4, *, threads=0):
+    pts = _pts(pts)
+    out = SpacingFidelity()
+    rc = getattr(lib(), "wtpo_spacing_fidelity_" + _sfx(pts.dtype))(pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]),
+                                                                    C.c_int32(k), C.c_double(coord_radius), C.byref(sp), C.c_int32(threads), C.byref(out))
+    if rc != 0:
+        raise ValueError(f"oracle spacing_fidelity_metrics failed with status {rc}")
+    return {n: getattr(out, n) for n, _ in SpacingFidelity._fields_}
+
+
 def closest_point_on_triangle(p, a, b, c):
     p, a, b, c = (np.ascontiguousarray(x) for x in (p, a, b, c))
     out = np.empty(3, dtype=p.dtype)

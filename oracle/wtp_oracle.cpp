@@ -22,7 +22,7 @@
 //   spacings x3         src/discretization/spacings.jl:19-23, 35-39, 67-72, 121-133
 //   _relax!             src/repel.jl:202-339 (sweep :256-292, reductions :293, 374-403,
 //                       stop logic :305-337)
-//   metrics             src/metrics.jl:19-41
+//   metrics             src/metrics.jl:19-41, spacing_metrics :56-71, spacing_fidelity_metrics :88-129
 //   isinside(p, cloud)  src/isinside.jl:18-35, 86-106 (winding number / Green's function over the boundary points)
 //   closest point / wall rule   src/octree/geometric_utils.jl:68-136, src/repel.jl:448-469,522-537,
 //                               src/octree/triangle_octree.jl:71-99,531-549,583-607 (brute force over triangles)
@@ -545,6 +545,85 @@ int32_t metrics_impl(const T* pts, int64_t N, int k, int threads, wtp_cloud_metr
     return WTP_OK;
 }
 
+// spacing_metrics (src/metrics.jl:56-71) and spacing_fidelity_metrics (:88-129)
+template <class T, int D>
+int32_t spacing_metrics_impl(const T* pts, int64_t N, int k, const wtp_spacing* sp_in, int threads, wtp_spacing_metrics_t* out) {
+    if (k > N || k < 2) return WTP_ERR_K_TOO_LARGE;
+    KDTree<T, D> tree;
+    tree.build(pts, N);
+    Spacing<T, D> spacing;
+    spacing.init(sp_in);
+    std::vector<T> err(static_cast<size_t>(N));
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<Cand<T>> buf(static_cast<size_t>(k));
+#pragma omp for schedule(dynamic, 1024)
+        for (int64_t i = 0; i < N; ++i) {
+            tree.knn(&pts[size_t(i) * D], k, buf.data());
+            T s = T(0);
+            for (int j = 1; j < k; ++j) s = s + std::sqrt(buf[size_t(j)].d2);
+            const T actual = s / T(k - 1), target = spacing(&pts[size_t(i) * D]);
+            err[size_t(i)] = std::fabs(actual - target) / target;
+        }
+    }
+    double mx = 0, sum = 0;
+    for (T e : err) { mx = std::max(mx, double(e)); sum += double(e); }
+    const double mu = sum / double(N);
+    double ss = 0;
+    for (T e : err) ss += (double(e) - mu) * (double(e) - mu);
+    out->max_error = mx; out->mean_error = mu; out->std_error = N > 1 ? std::sqrt(ss / double(N - 1)) : std::numeric_limits<double>::quiet_NaN();
+    return WTP_OK;
+}
+
+template <class T, int D>
+int32_t spacing_fidelity_impl(const T* pts, int64_t N, int k, double coord_radius, const wtp_spacing* sp_in, int threads, wtp_spacing_fidelity_t* out) {
+    k = int(std::min<int64_t>(k, N));                                              // :93
+    if (k < 1) return WTP_ERR_BAD_ARG;
+    KDTree<T, D> tree;
+    tree.build(pts, N);
+    Spacing<T, D> spacing;
+    spacing.init(sp_in);
+    std::vector<T> u(static_cast<size_t>(N));
+    std::vector<int> coord(static_cast<size_t>(N));
+    const T cr = T(coord_radius);
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<Cand<T>> buf(static_cast<size_t>(k));
+#pragma omp for schedule(dynamic, 1024)
+        for (int64_t i = 0; i < N; ++i) {
+            tree.knn(&pts[size_t(i) * D], k, buf.data());
+            const T h = spacing(&pts[size_t(i) * D]);
+            T dmin = std::numeric_limits<T>::max();
+            int c = 0;
+            for (int j = 0; j < k; ++j) {
+                if (buf[size_t(j)].idx == i) continue;                              // skip self BY INDEX (:106)
+                const T d = std::sqrt(buf[size_t(j)].d2);
+                dmin = std::min(dmin, d);
+                if (d <= cr * h) ++c;
+            }
+            u[size_t(i)] = dmin / h;
+            coord[size_t(i)] = c;
+        }
+    }
+    double sum = 0, csum = 0;
+    for (int64_t i = 0; i < N; ++i) { sum += double(u[size_t(i)]); csum += coord[size_t(i)]; }
+    const double mu = sum / double(N);
+    double ss = 0;
+    for (T x : u) ss += (double(x) - mu) * (double(x) - mu);
+    std::sort(u.begin(), u.end());
+    auto quant = [&](double p) {                                                    // Julia quantile, type 7
+        const double hh = double(N - 1) * p;
+        const int64_t lo = int64_t(std::floor(hh));
+        const int64_t hi = std::min<int64_t>(lo + 1, N - 1);
+        return double(u[size_t(lo)]) + (hh - double(lo)) * (double(u[size_t(hi)]) - double(u[size_t(lo)]));
+    };
+    out->mean_dnn_h = mu;
+    out->cv = (N > 1 ? std::sqrt(ss / double(N - 1)) : std::numeric_limits<double>::quiet_NaN()) / mu;
+    out->p05 = quant(0.05); out->p50 = quant(0.5); out->p95 = quant(0.95);
+    out->coordination = csum / double(N);
+    return WTP_OK;
+}
+
 int default_threads(int threads) {
 #ifdef _OPENMP
     return threads > 0 ? threads : omp_get_max_threads();
@@ -685,6 +764,23 @@ int32_t wtpo_metrics_f32(const float* pts, int64_t N, int32_t D, int32_t k, int3
 int32_t wtpo_metrics_f64(const double* pts, int64_t N, int32_t D, int32_t k, int32_t threads, wtp_cloud_metrics* out) {
     threads = default_threads(threads);
     return DISPATCH_D(double, D, (metrics_impl<double, 2>(pts, N, k, threads, out)), (metrics_impl<double, 3>(pts, N, k, threads, out)));
+}
+
+int32_t wtpo_spacing_metrics_f32(const float* pts, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, int32_t threads, wtp_spacing_metrics_t* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (spacing_metrics_impl<float, 2>(pts, N, k, sp, threads, out)), (spacing_metrics_impl<float, 3>(pts, N, k, sp, threads, out)));
+}
+int32_t wtpo_spacing_metrics_f64(const double* pts, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, int32_t threads, wtp_spacing_metrics_t* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (spacing_metrics_impl<double, 2>(pts, N, k, sp, threads, out)), (spacing_metrics_impl<double, 3>(pts, N, k, sp, threads, out)));
+}
+int32_t wtpo_spacing_fidelity_f32(const float* pts, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, int32_t threads, wtp_spacing_fidelity_t* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (spacing_fidelity_impl<float, 2>(pts, N, k, cr, sp, threads, out)), (spacing_fidelity_impl<float, 3>(pts, N, k, cr, sp, threads, out)));
+}
+int32_t wtpo_spacing_fidelity_f64(const double* pts, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, int32_t threads, wtp_spacing_fidelity_t* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (spacing_fidelity_impl<double, 2>(pts, N, k, cr, sp, threads, out)), (spacing_fidelity_impl<double, 3>(pts, N, k, cr, sp, threads, out)));
 }
 
 int32_t wtpo_closest_point_on_triangle_f64(const double* p, const double* a, const double* b, const double* c, double* out) {

@@ -403,6 +403,29 @@ def test_repel_survivor_filter(ctx, pkg, oracle):
     assert (np.linalg.norm(kept, axis=1) < 1.02).all()
 
 
+# ------------------------------------------ spacing_metrics / spacing_fidelity_metrics
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("D", [2, 3])
+def test_spacing_metrics_match_oracle(ctx, oracle, pkg, dt, D):
+    rng = np.random.default_rng(40 + D)
+    p = rng.random((30000, D)).astype(dt)
+    h = len(p) ** (-1.0 / D)
+    bnd = np.ascontiguousarray(p[:2000])
+    for args in (("constant", h), ("boundary_layer", 0.6 * h, 1.4 * h, 0.3, bnd)):
+        sp, k1 = ctx.make_spacing(*args); osp, k2 = oracle.make_spacing(*args)
+        a, b = ctx.spacing_metrics(p, sp, 20), oracle.spacing_metrics(p, osp, 20)
+        tol = 2e-5 if dt == np.float32 else 1e-11
+        for key in b:
+            np.testing.assert_allclose(a[key], b[key], rtol=tol, err_msg=key)
+        a, b = ctx.spacing_fidelity_metrics(p, sp, 30, 1.4), oracle.spacing_fidelity_metrics(p, osp, 30, 1.4)
+        for key in b:
+            np.testing.assert_allclose(a[key], b[key], rtol=tol, err_msg=key)
+    api = pkg.spacing_fidelity_metrics(pkg.PointCloud(p[:100], p[100:]), pkg.ConstantSpacing(dt(h)), ctx=ctx)
+    assert set(api) == {"mean_dnn_h", "cv", "p05", "p50", "p95", "coordination", "k", "coord_radius"} and api["p05"] <= api["p50"] <= api["p95"]
+    api = pkg.spacing_metrics(pkg.PointCloud(p[:100], p[100:]), pkg.ConstantSpacing(dt(h)), ctx=ctx)
+    assert set(api) == {"max_error", "mean_error", "std_error", "k"} and api["max_error"] >= api["mean_error"] >= 0
+
+
 # ------------------------------------------------------- BASELINE sizes
 def _brute_rows(pts, qi, k):
     """Canonical (d2, index) brute force for a few queries in the input precision (no FMA in numpy)."""

@@ -9,7 +9,7 @@ from .api import (AbstractSpacing, AbstractTopology, BoundaryLayerSpacing, Clipp
                   FlatRows, InverseDistanceForce, KNNTopology, LogLike, NoTopology, PointBoundary, PointCloud,
                   PointSurface, PointVolume, RadiusTopology, RepelForceModel, SpacingEquilibriumForce,
                   StrongSpacingForce, compute_force, hastopology, isinside, metrics, neighbors, points, rebuild_topology_, repel,
-                  search, searchdists, set_topology, topology)
+                  search, searchdists, set_topology, spacing_fidelity_metrics, spacing_metrics, topology)
 from .mesh import TriangleOctree, cuboid_mesh, icosphere_mesh, read_binary_stl, torus_mesh, unit_cube_mesh
 
 __all__ = [n for n in dir() if not n.startswith("_")]

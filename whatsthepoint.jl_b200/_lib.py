@@ -63,6 +63,14 @@ class WallMesh(C.Structure):
                 ("is_bnd", C.c_void_p), ("tri_indices", C.c_void_p), ("escaped", C.c_void_p)]
 
 
+class SpacingMetrics(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("max_error", "mean_error", "std_error")]
+
+
+class SpacingFidelity(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("mean_dnn_h", "cv", "p05", "p50", "p95", "coordination")]
+
+
 class CloudMetrics(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("avg", "std", "max", "min", "separation", "fill", "mesh_ratio")]
 
@@ -341,6 +349,23 @@ class Context:
         out, tri = np.empty_like(pts), np.zeros(pts.shape[0], dtype=np.int64)
         self._check(getattr(self._lib, "wtp_mesh_project_" + _sfx(pts.dtype))(self._h, C.byref(w), _vp(pts), C.c_int64(pts.shape[0]), _vp(out), _vp(tri)))
         return out, tri
+
+    def spacing_metrics(self, pts, sp: Spacing, k=20) -> dict:
+        """spacing_metrics(cloud, spacing; k) (src/metrics.jl:56-71)."""
+        pts = _as_points(pts)
+        out = SpacingMetrics()
+        fn = getattr(self._lib, "wtp_spacing_metrics_" + _sfx(pts.dtype))
+        self._check(fn(self._h, _vp(pts), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]), C.c_int32(k), C.byref(sp), C.byref(out)))
+        return {n: getattr(out, n) for n, _ in SpacingMetrics._fields_}
+
+    def spacing_fidelity_metrics(self, pts, sp: Spacing, k=30, coord_radius=1.4) -> dict:
+        """spacing_fidelity_metrics(cloud, spacing; k, coord_radius) (src/metrics.jl:88-129)."""
+        pts = _as_points(pts)
+        out = SpacingFidelity()
+        fn = getattr(self._lib, "wtp_spacing_fidelity_" + _sfx(pts.dtype))
+        self._check(fn(self._h, _vp(pts), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]), C.c_int32(k), C.c_double(coord_radius),
+                       C.byref(sp), C.byref(out)))
+        return {n: getattr(out, n) for n, _ in SpacingFidelity._fields_}
 
     def metrics(self, pts, k=20) -> dict:
         pts = _as_points(pts)

@@ -549,3 +549,30 @@ def metrics(cloud, k: int = 20, ctx=None, verbose: bool = True) -> dict:
         print(f"fill (max nearest-neighbor distance):       {m['fill']}")
         print(f"mesh ratio (fill / separation, ≥1):         {m['mesh_ratio']}")
     return m
+
+
+def spacing_metrics(cloud, spacing: AbstractSpacing, k: int = 20, ctx=None) -> dict:
+    """spacing_metrics(cloud, spacing; k) (src/metrics.jl:56-71) -> max_error, mean_error, std_error, k."""
+    if not isinstance(spacing, AbstractSpacing):
+        raise WtpError(3, "only ConstantSpacing, LogLike and BoundaryLayerSpacing can cross the C ABI (no CPU fallback)")
+    ctx = ctx or default_context()
+    pts = cloud._points() if hasattr(cloud, "_points") else _coords(cloud)
+    sp, keep = spacing._abi(pts.dtype)
+    m = ctx.spacing_metrics(pts, sp, int(k))
+    del keep
+    m["k"] = int(k)
+    return m
+
+
+def spacing_fidelity_metrics(cloud, spacing: AbstractSpacing, k: int = 30, coord_radius: float = 1.4, ctx=None) -> dict:
+    """spacing_fidelity_metrics(cloud, spacing; k, coord_radius) (src/metrics.jl:88-129) -> mean_dnn_h, cv, p05, p50, p95,
+    coordination, k, coord_radius."""
+    if not isinstance(spacing, AbstractSpacing):
+        raise WtpError(3, "only ConstantSpacing, LogLike and BoundaryLayerSpacing can cross the C ABI (no CPU fallback)")
+    ctx = ctx or default_context()
+    pts = cloud._points() if hasattr(cloud, "_points") else _coords(cloud)
+    sp, keep = spacing._abi(pts.dtype)
+    m = ctx.spacing_fidelity_metrics(pts, sp, int(k), float(coord_radius))
+    del keep
+    m["k"], m["coord_radius"] = min(int(k), len(pts)), coord_radius
+    return m

@@ -455,6 +455,207 @@ static int32_t metrics_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, in
 }
 }  // namespace wtp
 
+// ------------------------------------------- spacing_metrics / spacing_fidelity_metrics
+namespace wtp {
+
+struct StatPartial { double sum, mx; };
+
+// sum and max of (x[i] - shift)^power, power in {1, 2}: grid-stride, fixed block tree (mean / centred second moment)
+template <class T>
+__global__ void __launch_bounds__(256) stat_kernel(const T* __restrict__ x, int64_t n, double shift, int power, StatPartial* __restrict__ partials) {
+    __shared__ StatPartial s[256];
+    StatPartial acc{0.0, -1.0e300};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)x[i] - shift;
+        acc.sum += power == 2 ? v * v : v;
+        acc.mx = v > acc.mx ? v : acc.mx;
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s[threadIdx.x].sum += s[threadIdx.x + o].sum; s[threadIdx.x].mx = fmax(s[threadIdx.x].mx, s[threadIdx.x + o].mx); }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = s[0];
+}
+
+template <class T>
+static StatPartial stat_reduce(wtp_ctx* ctx, const T* d_x, int64_t n, double shift, int power) {
+    const int nb = (int)std::min<int64_t>((n + 255) / 256, (int64_t)kNumSMs * 8);
+    StatPartial* d_part = ctx->d_reduce.as<StatPartial>((size_t)nb);
+    stat_kernel<T><<<nb, 256, 0, ctx->stream>>>(d_x, n, shift, power, d_part);
+    LAUNCH_CHECK(ctx);
+    std::vector<StatPartial> h((size_t)nb);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(h.data(), d_part, sizeof(StatPartial) * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    StatPartial a = h[0];
+    for (int i = 1; i < nb; ++i) { a.sum += h[i].sum; a.mx = std::max(a.mx, h[i].mx); }
+    return a;
+}
+
+// error_i = |mean(dist[i][1:]) - s_i| / s_i      (src/metrics.jl:61-63)
+template <class T>
+__global__ void __launch_bounds__(256) spacing_error_kernel(const T* __restrict__ dist, int64_t N, int k, const T* __restrict__ spacing, T* __restrict__ err) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const T* row = dist + i * k;
+    T sum = (T)0;
+    for (int j = 1; j < k; ++j) sum = sum + row[j];
+    const T actual = sum / (T)(k - 1), target = spacing[i];
+    err[i] = fabs(actual - target) / target;
+}
+
+// u_i = d_NN(i) / h_i with self skipped BY INDEX, coordination count within coord_radius * h_i   (src/metrics.jl:98-113)
+template <class T>
+__global__ void __launch_bounds__(256) fidelity_kernel(const int64_t* __restrict__ idx, const T* __restrict__ dist, int64_t N, int k,
+                                                       const T* __restrict__ spacing, T coord_radius, T* __restrict__ u, float* __restrict__ coord) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const T h = spacing[i];
+    T dmin = sizeof(T) == 4 ? (T)3.402823466e+38f : (T)1.7976931348623157e+308;
+    int c = 0;
+    for (int j = 0; j < k; ++j) {
+        if (idx[i * k + j] == i + 1) continue;
+        const T d = dist[i * k + j];
+        dmin = d < dmin ? d : dmin;
+        c += d <= coord_radius * h ? 1 : 0;
+    }
+    u[i] = dmin / h;
+    coord[i] = (float)c;
+}
+
+// order statistics of non-negative values: radix sort of the bit patterns (two stable 32-bit sorts for doubles)
+template <class T>
+__global__ void __launch_bounds__(256) bits_key_kernel(const T* __restrict__ x, const uint32_t* __restrict__ order, int64_t n, int word,
+                                                       uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t i = order ? order[t] : (uint32_t)t;
+    uint32_t key;
+    if (sizeof(T) == 4) key = __float_as_uint((float)x[i]);
+    else { const unsigned long long b = (unsigned long long)__double_as_longlong((double)x[i]); key = word == 0 ? (uint32_t)b : (uint32_t)(b >> 32); }
+    keys[t] = key;
+    vals[t] = i;
+}
+template <class T>
+__global__ void pick_kernel(const T* __restrict__ x, const uint32_t* __restrict__ order, const int64_t* __restrict__ pos, int npos, double* __restrict__ out) {
+    if ((int)threadIdx.x < npos) out[threadIdx.x] = (double)x[order[pos[threadIdx.x]]];
+}
+
+// q[j] = quantile(x, p[j]) with linear interpolation between order statistics (Julia's default, type 7)
+template <class T>
+static void quantiles(wtp_ctx* ctx, const T* d_x, int64_t n, const double* p, int np, double* q) {
+    IndexBuffers& ib = ctx->index[0];
+    uint32_t* keys = ib.keys_a.as<uint32_t>((size_t)n);
+    uint32_t* vals = ib.vals_a.as<uint32_t>((size_t)n);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    const int words = sizeof(T) == 4 ? 1 : 2;
+    for (int w = 0; w < words; ++w) {
+        // second word: keys are gathered in the order the first sort produced (LSD on 64 bits)
+        const uint32_t* order = w == 0 ? nullptr : ctx->d_misc2.get<uint32_t>();
+        bits_key_kernel<T><<<nb, 256, 0, ctx->stream>>>(d_x, order, n, w, keys, vals);
+        LAUNCH_CHECK(ctx);
+        radix_sort_pairs(ctx, ib, n, 32);
+        vals = ib.vals_a.get<uint32_t>(); keys = ib.keys_a.get<uint32_t>();
+        if (w + 1 < words) WTP_CUDA_CHECK(cudaMemcpyAsync(ctx->d_misc2.as<uint32_t>((size_t)n), vals, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    std::vector<int64_t> pos((size_t)2 * np);
+    std::vector<double> frac((size_t)np);
+    for (int j = 0; j < np; ++j) {
+        const double hh = (double)(n - 1) * p[j];
+        const int64_t lo = (int64_t)std::floor(hh);
+        pos[2 * j] = lo; pos[2 * j + 1] = std::min<int64_t>(lo + 1, n - 1);
+        frac[j] = hh - (double)lo;
+    }
+    int64_t* d_pos = ctx->d_offsets.as<int64_t>((size_t)2 * np + 2 * np);
+    double* d_out = reinterpret_cast<double*>(d_pos + 2 * np);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_pos, pos.data(), sizeof(int64_t) * 2 * np, cudaMemcpyHostToDevice, ctx->stream));
+    pick_kernel<T><<<1, 32, 0, ctx->stream>>>(d_x, vals, d_pos, 2 * np, d_out);
+    LAUNCH_CHECK(ctx);
+    std::vector<double> v((size_t)2 * np);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(v.data(), d_out, sizeof(double) * 2 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < np; ++j) q[j] = v[2 * j] + frac[j] * (v[2 * j + 1] - v[2 * j]);
+}
+
+// uploads the cloud (and the spacing's boundary set), runs the k-NN with distances (k nearest including self) and
+// evaluates the spacing at every point: the common front of the two spacing metrics
+template <class T>
+static void spacing_metrics_front(wtp_ctx* ctx, const T* pts, int64_t N, int D, int k, const wtp_spacing* sp, int64_t** d_idx, T** d_dist, T** d_spacing) {
+    WTP_REQUIRE(sp->kind >= WTP_SPACING_CONSTANT && sp->kind <= WTP_SPACING_BOUNDARY_LAYER, WTP_ERR_UNSUPPORTED, "user-defined spacing callable cannot cross the C ABI");
+    WTP_REQUIRE(ctx->world == 1, WTP_ERR_UNSUPPORTED, "metrics run on a single-GPU context");
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    *d_idx = ctx->d_out_idx.as<int64_t>((size_t)N * k);
+    *d_dist = ctx->d_out_dist.as<T>((size_t)N * k);
+    *d_spacing = ctx->d_spacings.as<T>((size_t)N);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    if (sp->kind != WTP_SPACING_CONSTANT) {
+        WTP_REQUIRE(sp->bnd_pts && sp->n_bnd > 0, WTP_ERR_BAD_ARG, "variable spacing needs its boundary point set");
+        T* b = ctx->d_spacing_pts.as<T>((size_t)sp->n_bnd * D);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(b, sp->bnd_pts, (size_t)sp->n_bnd * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        bvh_build<T>(ctx, ctx->bvh, b, sp->n_bnd, D);
+    }
+    const SpacingP<T> spp{sp->kind, (T)sp->a, (T)sp->b, (T)sp->c};
+    spacing_eval<T>(ctx, spp, ctx->bvh, d_pts, N, D, *d_spacing);
+    knn_device_self<T>(ctx, d_pts, N, D, k, *d_idx, *d_dist);
+}
+
+template <class T>
+static int32_t spacing_metrics_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, wtp_spacing_metrics_t* out) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(pts && sp && out && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(k >= 2 && (int64_t)k <= N, WTP_ERR_K_TOO_LARGE, "spacing_metrics needs 2 <= k <= N");
+    int64_t* d_idx; T* d_dist; T* d_s;
+    spacing_metrics_front<T>(ctx, pts, N, D, k, sp, &d_idx, &d_dist, &d_s);
+    T* d_err = ctx->d_nn.as<T>((size_t)N);
+    spacing_error_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_dist, N, k, d_s, d_err);
+    LAUNCH_CHECK(ctx);
+    const StatPartial a = stat_reduce<T>(ctx, d_err, N, 0.0, 1);
+    const double mu = a.sum / (double)N;
+    const StatPartial b = stat_reduce<T>(ctx, d_err, N, mu, 2);
+    out->max_error = a.mx; out->mean_error = mu;
+    out->std_error = N > 1 ? std::sqrt(b.sum / (double)(N - 1)) : std::nan("");
+    API_END(ctx)
+}
+
+template <class T>
+static int32_t spacing_fidelity_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_t k, double coord_radius, const wtp_spacing* sp,
+                                     wtp_spacing_fidelity_t* out) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(pts && sp && out && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    k = (int32_t)std::min<int64_t>(k, N);                                                    // src/metrics.jl:93
+    WTP_REQUIRE(k >= 1 && k <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K");
+    int64_t* d_idx; T* d_dist; T* d_s;
+    spacing_metrics_front<T>(ctx, pts, N, D, k, sp, &d_idx, &d_dist, &d_s);
+    T* d_u = ctx->d_nn.as<T>((size_t)N);
+    float* d_c = ctx->d_counts.as<float>((size_t)N);
+    fidelity_kernel<T><<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(d_idx, d_dist, N, k, d_s, (T)coord_radius, d_u, d_c);
+    LAUNCH_CHECK(ctx);
+    const StatPartial a = stat_reduce<T>(ctx, d_u, N, 0.0, 1);
+    const double mu = a.sum / (double)N;
+    const StatPartial b = stat_reduce<T>(ctx, d_u, N, mu, 2);
+    const StatPartial c = stat_reduce<float>(ctx, d_c, N, 0.0, 1);
+    const double p[3] = {0.05, 0.5, 0.95};
+    double q[3];
+    quantiles<T>(ctx, d_u, N, p, 3, q);
+    out->mean_dnn_h = mu;
+    out->cv = (N > 1 ? std::sqrt(b.sum / (double)(N - 1)) : std::nan("")) / mu;
+    out->p05 = q[0]; out->p50 = q[1]; out->p95 = q[2];
+    out->coordination = c.sum / (double)N;
+    API_END(ctx)
+}
+
+}  // namespace wtp
+
+extern "C" {
+int32_t wtp_spacing_metrics_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, wtp_spacing_metrics_t* out) { return spacing_metrics_host<float>(c, p, N, D, k, sp, out); }
+int32_t wtp_spacing_metrics_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, wtp_spacing_metrics_t* out) { return spacing_metrics_host<double>(c, p, N, D, k, sp, out); }
+int32_t wtp_spacing_fidelity_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, wtp_spacing_fidelity_t* out) { return spacing_fidelity_host<float>(c, p, N, D, k, cr, sp, out); }
+int32_t wtp_spacing_fidelity_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, wtp_spacing_fidelity_t* out) { return spacing_fidelity_host<double>(c, p, N, D, k, cr, sp, out); }
+}
+
 extern "C" {
 int32_t wtp_metrics_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<float>(c, p, N, D, k, out); }
 int32_t wtp_metrics_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<double>(c, p, N, D, k, out); }
