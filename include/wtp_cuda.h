@@ -304,6 +304,14 @@ int32_t wtp_metrics_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_
 int32_t wtp_metrics_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k,
                         wtp_cloud_metrics* out);
 
+/* _near_duplicate_keep_mask(pts, spacings, ratio) (src/repel.jl:565-580), the cull of repel(...; cull_ratio):
+ * greedy, order-preserving: a point is dropped when a kept, lower-indexed... more precisely, walking the points in
+ * index order, every kept point i drops each still-kept j != i with |p_j - p_i| < ratio * spacings[i]. The ball search
+ * at radius ratio * max(spacings) runs on the device (radius CSR); the index-ordered sweep is serial by design and runs
+ * on the host over that CSR. keep: N flags (1 = kept). HOST pointers. */
+int32_t wtp_cull_mask_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, const float* spacings, double ratio, uint8_t* keep);
+int32_t wtp_cull_mask_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, const double* spacings, double ratio, uint8_t* keep);
+
 /* spacing_metrics(cloud, spacing; k) (src/metrics.jl:56-71): error_i = |mean distance to the k-1 nearest
  * others - s(x_i)| / s(x_i); max, mean and (sample) standard deviation over the points. */
 typedef struct { double max_error, mean_error, std_error; } wtp_spacing_metrics_t;

@@ -260,6 +260,17 @@ def metrics(pts, k=20, *, threads=0):
     return {n: getattr(out, n) for n, _ in CloudMetrics._fields_}
 
 
+def cull_mask(pts, spacings, ratio):
+    """_near_duplicate_keep_mask(pts, spacings, ratio) (src/repel.jl:565-580) -> bool keep mask."""
+    pts = _pts(pts)
+    sp = np.ascontiguousarray(spacings, dtype=pts.dtype)
+    keep = np.ones(pts.shape[0], dtype=np.uint8)
+    rc = getattr(lib(), "wtpo_cull_mask_" + _sfx(pts.dtype))(pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]),
+                                                             sp.ctypes.data_as(C.c_void_p), C.c_double(ratio), keep.ctypes.data_as(C.c_void_p))
+    assert rc == 0, rc
+    return keep.astype(bool)
+
+
 class SpacingMetrics(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("max_error", "mean_error", "std_error")]
 

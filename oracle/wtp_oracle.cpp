@@ -545,6 +545,30 @@ int32_t metrics_impl(const T* pts, int64_t N, int k, int threads, wtp_cloud_metr
     return WTP_OK;
 }
 
+// _near_duplicate_keep_mask (src/repel.jl:565-580): ball search at ratio * max spacing, greedy sweep in index order
+template <class T, int D>
+int32_t cull_mask_impl(const T* pts, int64_t N, const T* spacings, double ratio, uint8_t* keep) {
+    std::fill(keep, keep + N, uint8_t(1));
+    if (!(ratio > 0) || N < 2) return WTP_OK;
+    KDTree<T, D> tree;
+    tree.build(pts, N);
+    const T r = T(ratio) * *std::max_element(spacings, spacings + N);
+    std::vector<int64_t> hits;
+    for (int64_t i = 0; i < N; ++i) {
+        if (!keep[i]) continue;
+        const T thr = T(ratio) * spacings[i];
+        hits.clear();
+        if (tree.n > 0) tree.inrange_rec(0, &pts[size_t(i) * D], r * r, [&](int64_t j) { hits.push_back(j); });
+        for (int64_t j : hits) {
+            if (j == i || !keep[j]) continue;
+            T d2 = T(0);
+            for (int d = 0; d < D; ++d) { const T v = pts[size_t(j) * D + d] - pts[size_t(i) * D + d]; d2 = d2 + v * v; }
+            if (std::sqrt(d2) < thr) keep[j] = 0;
+        }
+    }
+    return WTP_OK;
+}
+
 // spacing_metrics (src/metrics.jl:56-71) and spacing_fidelity_metrics (:88-129)
 template <class T, int D>
 int32_t spacing_metrics_impl(const T* pts, int64_t N, int k, const wtp_spacing* sp_in, int threads, wtp_spacing_metrics_t* out) {
@@ -766,6 +790,12 @@ int32_t wtpo_metrics_f64(const double* pts, int64_t N, int32_t D, int32_t k, int
     return DISPATCH_D(double, D, (metrics_impl<double, 2>(pts, N, k, threads, out)), (metrics_impl<double, 3>(pts, N, k, threads, out)));
 }
 
+int32_t wtpo_cull_mask_f32(const float* pts, int64_t N, int32_t D, const float* s, double ratio, uint8_t* keep) {
+    return DISPATCH_D(float, D, (cull_mask_impl<float, 2>(pts, N, s, ratio, keep)), (cull_mask_impl<float, 3>(pts, N, s, ratio, keep)));
+}
+int32_t wtpo_cull_mask_f64(const double* pts, int64_t N, int32_t D, const double* s, double ratio, uint8_t* keep) {
+    return DISPATCH_D(double, D, (cull_mask_impl<double, 2>(pts, N, s, ratio, keep)), (cull_mask_impl<double, 3>(pts, N, s, ratio, keep)));
+}
 int32_t wtpo_spacing_metrics_f32(const float* pts, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, int32_t threads, wtp_spacing_metrics_t* out) {
     threads = default_threads(threads);
     return DISPATCH_D(float, D, (spacing_metrics_impl<float, 2>(pts, N, k, sp, threads, out)), (spacing_metrics_impl<float, 3>(pts, N, k, sp, threads, out)));

@@ -426,6 +426,30 @@ def test_spacing_metrics_match_oracle(ctx, oracle, pkg, dt, D):
     assert set(api) == {"max_error", "mean_error", "std_error", "k"} and api["max_error"] >= api["mean_error"] >= 0
 
 
+# ------------------------------------------------------------------- cull
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_cull_mask(ctx, oracle, pkg, dt):
+    pts = np.array([[0.0, 0, 0], [1, 0, 0], [2, 0, 0], [2.01, 0, 0], [3, 0, 0]], dtype=dt)      # test/repel.jl:301-325
+    keep = ctx.cull_mask(pts, np.ones(5, dtype=dt), 0.5)
+    assert keep.tolist() == [True, True, True, False, True]
+    assert ctx.cull_mask(pts, np.ones(5, dtype=dt), 0.0).all()
+    cpts = np.concatenate([pts, np.array([[10.0 + 1.0e-3 * i, 0, 0] for i in range(1, 13)], dtype=dt)])
+    ck = ctx.cull_mask(cpts, np.ones(len(cpts), dtype=dt), 0.5)
+    assert ck[5:].sum() == 1 and ck[5]
+    rng = np.random.default_rng(50)
+    for D in (2, 3):
+        p = rng.random((40000, D)).astype(dt)
+        s = (0.5 + rng.random(len(p))).astype(dt) * len(p) ** (-1.0 / D)                       # variable spacings
+        a, b = ctx.cull_mask(p, s, 0.6), oracle.cull_mask(p, s, 0.6)
+        assert np.array_equal(a, b) and 0 < (~a).sum() < len(p) // 2
+    cloud = pkg.PointCloud(rng.random((200, 3)).astype(dt), rng.random((5000, 3)).astype(dt))
+    h = 5000 ** (-1 / 3)
+    out = pkg.repel(cloud, pkg.ConstantSpacing(dt(h)), max_iters=2, stall_after=0, tol=0.0, cull_ratio=0.6, ctx=ctx)
+    assert len(out.volume) < 5000                                                               # test/repel.jl:375-397: separation guarantee
+    m = ctx.metrics(out.volume.points, 2)
+    assert m["separation"] >= 0.6 * h * (1 - 1e-6)
+
+
 # ------------------------------------------------------- BASELINE sizes
 def _brute_rows(pts, qi, k):
     """Canonical (d2, index) brute force for a few queries in the input precision (no FMA in numpy)."""

@@ -350,6 +350,15 @@ class Context:
         self._check(getattr(self._lib, "wtp_mesh_project_" + _sfx(pts.dtype))(self._h, C.byref(w), _vp(pts), C.c_int64(pts.shape[0]), _vp(out), _vp(tri)))
         return out, tri
 
+    def cull_mask(self, pts, spacings, ratio: float) -> np.ndarray:
+        """_near_duplicate_keep_mask(pts, spacings, ratio) (src/repel.jl:565-580) -> bool keep mask."""
+        pts = _as_points(pts)
+        sp = np.ascontiguousarray(spacings, dtype=pts.dtype)
+        keep = np.ones(pts.shape[0], dtype=np.uint8)
+        fn = getattr(self._lib, "wtp_cull_mask_" + _sfx(pts.dtype))
+        self._check(fn(self._h, _vp(pts), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]), _vp(sp), C.c_double(ratio), _vp(keep)))
+        return keep.astype(bool)
+
     def spacing_metrics(self, pts, sp: Spacing, k=20) -> dict:
         """spacing_metrics(cloud, spacing; k) (src/metrics.jl:56-71)."""
         pts = _as_points(pts)

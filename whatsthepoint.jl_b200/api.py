@@ -420,7 +420,7 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
     filter `filter(x -> isinside(x, cloud), p)` (:90) runs on the device too when `isinside=True`
     (Green's function over the boundary elements in 3-D, which needs their normals and areas;
     winding number in 2-D) or with a caller's predicate on an N x D array; by default every
-    moved point is kept. The optional cull (:91-93) is a row "next" of the scope table.
+    moved point is kept. `cull_ratio > 0` applies the near-duplicate cull (:91-93, :549-580).
     """
     if rebuild_every < 1:
         raise WtpArgumentError(1, "rebuild_every must be ≥ 1")                     # src/repel.jl:74
@@ -430,8 +430,6 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         raise WtpArgumentError(1, "deposit_ratio must be ≥ 0")                     # src/repel.jl:143
     if deposit_ratio > 0:
         raise WtpError(3, "deposit_ratio > 0 (_deposit_escaped!, src/repel.jl:483-514, serial by design) is not provided by this build")
-    if cull_ratio > 0:
-        raise WtpError(3, "cull_ratio > 0 (_cull, src/repel.jl:549-580) is not provided by this build")
     if not isinstance(spacing, AbstractSpacing):
         raise WtpError(3, "only ConstantSpacing, LogLike and BoundaryLayerSpacing can cross the C ABI (no CPU fallback)")
     ctx = ctx or default_context()
@@ -471,7 +469,8 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
     elif max_iters > 0:
         log.warning("Node repel reached maximum iterations")
     if octree is not None:
-        out = _reconstruct_cloud(cloud, new_snap, ctx.last_wall["tri_indices"], is_bnd, n_bnd, octree)
+        keep_mask = _cull(new_snap, spacing, cull_ratio, ctx) if cull_ratio > 0 else None   # :179
+        out = _reconstruct_cloud(cloud, new_snap, ctx.last_wall["tri_indices"], is_bnd, n_bnd, octree, keep_mask)
         out.repel_result = res
         out.escaped = ctx.last_wall["escaped"].astype(bool)
         return out
@@ -480,20 +479,37 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         keep_mask = isinside(p) if callable(isinside) else (globals()["isinside"](p, cloud, ctx=ctx) if isinside else None)
         if keep_mask is not None:
             p = p[np.asarray(keep_mask, dtype=bool)]
+    if cull_ratio > 0 and len(p) > 0:                                              # :91-93
+        p = p[_cull(p, spacing, cull_ratio, ctx)]
     out = PointCloud(cloud.boundary, PointVolume(p), NoTopology())                 # :94
     out.repel_result = res
     return out
 
 
-def _reconstruct_cloud(cloud: PointCloud, p: np.ndarray, tri_indices: np.ndarray, is_bnd: np.ndarray, n_boundary: int, octree) -> PointCloud:
+def _cull(pts: np.ndarray, spacing: AbstractSpacing, ratio, ctx) -> np.ndarray:
+    """_cull(pts, spacing, ratio) (src/repel.jl:549-556): near-duplicate keep mask plus the defect warning."""
+    sp, keep = spacing._abi(pts.dtype)
+    s = ctx.spacing_eval(sp, pts)
+    del keep
+    mask = ctx.cull_mask(pts, s, float(ratio))
+    n_culled = int((~mask).sum())
+    if n_culled > 0:
+        log.warning("Cull removed %d near-duplicate point(s) — repel left defects behind (cull_ratio = %s)", n_culled, ratio)
+    return mask
+
+
+def _reconstruct_cloud(cloud: PointCloud, p: np.ndarray, tri_indices: np.ndarray, is_bnd: np.ndarray, n_boundary: int, octree,
+                       keep: np.ndarray | None = None) -> PointCloud:
     """src/repel.jl:590-629: kept points are split by is_bnd into one `boundary` surface and the
     volume; projected boundary points take the landing triangle's normal, imported ones keep
     their area."""
+    if keep is None:
+        keep = np.ones(len(p), dtype=bool)
     normals = [s.normals for s in cloud.boundary.surfaces.values()]
     areas = [s.areas for s in cloud.boundary.surfaces.values()]
     orig_normals = np.concatenate(normals, axis=0) if all(x is not None for x in normals) and normals else None
     orig_areas = np.concatenate(areas, axis=0) if all(x is not None for x in areas) and areas else None
-    b = np.flatnonzero(is_bnd)
+    b = np.flatnonzero(is_bnd & keep)
     tri = tri_indices[b]
     face = octree.astype(p.dtype).face
     new_normals = face[np.maximum(tri, 1) - 1].copy()
@@ -502,7 +518,7 @@ def _reconstruct_cloud(cloud: PointCloud, p: np.ndarray, tri_indices: np.ndarray
         new_normals[keep_orig] = orig_normals[b[keep_orig]]
     new_areas = orig_areas[b] if orig_areas is not None else None
     surf = PointSurface(p[b], new_normals, new_areas)
-    return PointCloud(PointBoundary({"boundary": surf}), PointVolume(p[~is_bnd]), NoTopology())
+    return PointCloud(PointBoundary({"boundary": surf}), PointVolume(p[~is_bnd & keep]), NoTopology())
 
 
 def _boundary_elements(domain):

@@ -455,6 +455,55 @@ static int32_t metrics_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, in
 }
 }  // namespace wtp
 
+// ------------------------------------------------------------------ cull
+namespace wtp {
+template <class T>
+static int32_t cull_mask_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, const T* spacings, double ratio, uint8_t* keep) {
+    API_BEGIN(ctx)
+    WTP_REQUIRE(pts && spacings && keep && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
+    WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
+    WTP_REQUIRE(ctx->world == 1, WTP_ERR_UNSUPPORTED, "the cull runs on a single-GPU context");
+    memset(keep, 1, (size_t)N);
+    if (!(ratio > 0) || N < 2) return WTP_OK;                                        // src/repel.jl:568
+    T smax = spacings[0];
+    for (int64_t i = 1; i < N; ++i) smax = std::max(smax, spacings[i]);
+    const T r = (T)ratio * smax;                                                     // MetricBall(ratio * maximum(spacings)), :570
+    // ball search on the device: CSR rows sorted by index, self removed
+    ctx->timer.reset(ctx->stream);
+    T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    int64_t* d_off = ctx->d_offsets.as<int64_t>((size_t)N + 1);
+    radius_count_device<T>(ctx, d_pts, N, D, r, d_off);
+    const int64_t nnz = ctx->radius.nnz;
+    ctx->radius.pending = false;
+    std::vector<int64_t> off((size_t)N + 1), ind((size_t)std::max<int64_t>(nnz, 1));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(off.data(), d_off, (size_t)(N + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nnz > 0) {
+        int64_t* d_ind = ctx->d_indices.as<int64_t>((size_t)nnz);
+        radius_fill_device<T>(ctx, d_off, d_ind);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(ind.data(), d_ind, (size_t)nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    // the greedy sweep in index order (:571-578): earlier decisions must be visible to later points
+    for (int64_t i = 0; i < N; ++i) {
+        if (!keep[i]) continue;
+        const T thr = (T)ratio * spacings[i];
+        for (int64_t e = off[(size_t)i]; e < off[(size_t)i + 1]; ++e) {
+            const int64_t j = ind[(size_t)e] - 1;
+            if (!keep[j]) continue;
+            T d2 = (T)0;
+            for (int d = 0; d < D; ++d) { const T v = pts[j * D + d] - pts[i * D + d]; d2 = d2 + v * v; }
+            if (std::sqrt(d2) < thr) keep[j] = 0;
+        }
+    }
+    API_END(ctx)
+}
+}  // namespace wtp
+extern "C" {
+int32_t wtp_cull_mask_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, const float* s, double ratio, uint8_t* keep) { return cull_mask_host<float>(c, p, N, D, s, ratio, keep); }
+int32_t wtp_cull_mask_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, const double* s, double ratio, uint8_t* keep) { return cull_mask_host<double>(c, p, N, D, s, ratio, keep); }
+}
+
 // ------------------------------------------- spacing_metrics / spacing_fidelity_metrics
 namespace wtp {
 
