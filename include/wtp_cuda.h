@@ -220,12 +220,16 @@ typedef struct {
     int32_t max_iters;
     int32_t rebuild_every;         /* >= 1 (src/repel.jl:74)                              */
     int32_t stall_after;
-    int32_t kick_after;            /* must be 0: the kick draws randn (src/repel.jl:430)  */
+    int32_t kick_after;            /* > 0: _maybe_kick! (src/repel.jl:415-433) with the library's own
+                                      random stream (kick_seed): the reference draws from Julia's global
+                                      RNG, so trajectories after a kick are not reproducible across the two */
     int32_t wall;                  /* WTP_WALL_*                                          */
     int32_t want_trace;
     int32_t reserved;
     double alpha_lo, alpha_max;    /* ustrip(α_min), ustrip(α) (src/repel.jl:86)          */
     double tol, cv_target;
+    int64_t n_protected;           /* snapshot-global count of points a kick avoids: n_boundary (:85, :172) */
+    uint64_t kick_seed;
 } wtp_repel_params;
 
 enum { WTP_STOP_MAX_ITERS = 0, WTP_STOP_TOL = 1, WTP_STOP_CV_TARGET = 2, WTP_STOP_STALL = 3 };

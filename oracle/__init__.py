@@ -43,7 +43,8 @@ class RepelParams(C.Structure):
                 ("stall_after", C.c_int32), ("kick_after", C.c_int32), ("wall", C.c_int32),
                 ("want_trace", C.c_int32), ("reserved", C.c_int32),
                 ("alpha_lo", C.c_double), ("alpha_max", C.c_double),
-                ("tol", C.c_double), ("cv_target", C.c_double)]
+                ("tol", C.c_double), ("cv_target", C.c_double),
+                ("n_protected", C.c_int64), ("kick_seed", C.c_uint64)]
 
 
 class RepelResult(C.Structure):

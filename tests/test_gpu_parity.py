@@ -196,8 +196,8 @@ def test_repel_rejects_what_cannot_cross_the_abi(ctx, pkg):
     f = ctx.make_force("clipped", 0.2)
     with pytest.raises(pkg.WtpArgumentError):
         ctx.repel(snap, 50, sp, f, rebuild_every=0, alpha_lo=1e-4, alpha_max=1e-2)
-    with pytest.raises(pkg.WtpError):
-        ctx.repel(snap, 50, sp, f, kick_after=5, alpha_lo=1e-4, alpha_max=1e-2)           # randn on the device: unsupported
+    with pytest.raises(pkg.WtpArgumentError):
+        ctx.repel(snap, 50, sp, f, kick_after=-1, alpha_lo=1e-4, alpha_max=1e-2)
     bad = pkg._lib.Force(9, 0.2, 1.0, 3.0)
     with pytest.raises(pkg.WtpError):
         ctx.repel(snap, 50, sp, bad, alpha_lo=1e-4, alpha_max=1e-2)
@@ -424,6 +424,34 @@ def test_spacing_metrics_match_oracle(ctx, oracle, pkg, dt, D):
     assert set(api) == {"mean_dnn_h", "cv", "p05", "p50", "p95", "coordination", "k", "coord_radius"} and api["p05"] <= api["p50"] <= api["p95"]
     api = pkg.spacing_metrics(pkg.PointCloud(p[:100], p[100:]), pkg.ConstantSpacing(dt(h)), ctx=ctx)
     assert set(api) == {"max_error", "mean_error", "std_error", "k"} and api["max_error"] >= api["mean_error"] >= 0
+
+
+def test_repel_kick_after(ctx, pkg):
+    """_maybe_kick! (src/repel.jl:415-433; test/repel.jl:399-432): the frozen closest pair is kicked by s/10 in a random
+    direction. The random stream is the library's own, so only the semantics are checked: same seed -> same result,
+    kick_after = 1 kicks every iteration and moves exactly one point per iteration away from the no-kick trajectory."""
+    rng = np.random.default_rng(60)
+    for D in (2, 3):
+        snap = rng.random((3000, D))
+        h = 3000 ** (-1.0 / D)
+        sp, _ = ctx.make_spacing("constant", h)
+        f = ctx.make_force("clipped", 0.2)
+        kw = dict(max_iters=1, tol=0.0, stall_after=0, alpha_lo=h / 2000, alpha_max=h / 20)
+        base, _, _, _ = ctx.repel(snap, 300, sp, f, **kw)
+        a, conv, res, _ = ctx.repel(snap, 300, sp, f, kick_after=1, kick_seed=7, **kw)
+        b, _, _, _ = ctx.repel(snap, 300, sp, f, kick_after=1, kick_seed=7, **kw)
+        c, _, _, _ = ctx.repel(snap, 300, sp, f, kick_after=1, kick_seed=8, **kw)
+        assert np.array_equal(a, b) and not np.array_equal(a, c)
+        moved = np.flatnonzero((a != base).any(axis=1))
+        assert len(moved) == 1 and moved[0] >= 300                                  # one movable point, never the fixed wall
+        np.testing.assert_allclose(np.linalg.norm(a[moved[0]] - base[moved[0]]), h / 10, rtol=1e-9)
+        assert res["iters"] == 1 and np.isfinite(a).all()
+        long_run, conv, res, _ = ctx.repel(snap, 300, sp, f, kick_after=5, kick_seed=1, max_iters=30, tol=0.0, stall_after=0,
+                                           alpha_lo=h / 2000, alpha_max=h / 20)
+        assert res["iters"] == 30 and np.isfinite(long_run).all() and np.array_equal(long_run[:300], snap[:300])
+    cloud = pkg.PointCloud(snap[:300], snap[300:])
+    out = pkg.repel(cloud, pkg.ConstantSpacing(h), max_iters=3, kick_after=1, ctx=ctx)      # test/repel.jl:417-432
+    assert len(out) == len(cloud)
 
 
 # ------------------------------------------------------------------- cull

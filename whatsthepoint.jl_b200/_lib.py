@@ -45,7 +45,8 @@ class RepelParams(C.Structure):
                 ("stall_after", C.c_int32), ("kick_after", C.c_int32), ("wall", C.c_int32),
                 ("want_trace", C.c_int32), ("reserved", C.c_int32),
                 ("alpha_lo", C.c_double), ("alpha_max", C.c_double),
-                ("tol", C.c_double), ("cv_target", C.c_double)]
+                ("tol", C.c_double), ("cv_target", C.c_double),
+                ("n_protected", C.c_int64), ("kick_seed", C.c_uint64)]
 
 
 class RepelResult(C.Structure):
@@ -266,14 +267,16 @@ class Context:
         return Spacing(SPACING_KINDS[kind], float(a), float(b), float(c), bnd_ptr, n_bnd), None
 
     def repel(self, snap, n_fixed: int, sp: Spacing, force: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
-              stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, mesh=None, is_bnd=None):
+              stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, mesh=None, is_bnd=None,
+              n_protected=None, kick_seed=0):
         """_relax! on snap = [fixed head; movable tail] (host array, copied). Returns
         (new_snap, conv, result dict, trace list | None)."""
         snap = np.array(_as_points(snap), copy=True)
         n_all, d = snap.shape
         n_move = n_all - n_fixed
         prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0, 0,
-                          float(alpha_lo), float(alpha_max), float(tol), float(cv_target))
+                          float(alpha_lo), float(alpha_max), float(tol), float(cv_target),
+                          int(n_fixed if n_protected is None else n_protected), int(kick_seed))
         conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
         tr = (TraceEntry * max(max_iters, 1))() if trace else None
         res = RepelResult()

@@ -412,7 +412,7 @@ def compute_force(model: RepelForceModel, u, ctx=None):
 def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2, force_model: RepelForceModel | None = None,
           alpha=None, alpha_min=None, k=21, max_iters=1000, tol=1.0e-6, rebuild_every: int = 1, cull_ratio=0.0,
           kick_after: int = 0, stall_after: int = 50, cv_target=0.0, deposit_ratio=0.0, convergence: list | None = None,
-          trace: list | None = None, isinside: Callable | None = None, ctx=None) -> PointCloud:
+          trace: list | None = None, isinside: Callable | None = None, kick_seed: int = 0, ctx=None) -> PointCloud:
     """repel(cloud, spacing; kwargs...) (src/repel.jl:56-95): volume points move, boundary
     points are the fixed wall; returns a new cloud with NoTopology.
 
@@ -453,7 +453,7 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
     new_snap, conv, res, tr = ctx.repel(snap, 0 if octree is not None else n_bnd, sp, fm._abi(), k=k, max_iters=max_iters, tol=tol,
                                         rebuild_every=rebuild_every, stall_after=stall_after, cv_target=cv_target,
                                         alpha_lo=alpha_min, alpha_max=alpha, kick_after=kick_after, trace=trace is not None,
-                                        mesh=octree, is_bnd=is_bnd)
+                                        mesh=octree, is_bnd=is_bnd, n_protected=n_bnd, kick_seed=kick_seed)
     del keep
     if convergence is not None:
         convergence.extend(float(c) for c in conv)                                 # :88

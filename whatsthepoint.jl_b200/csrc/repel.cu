@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <limits>
+#include <random>
 
 #include "kernels.cuh"
 #include "knn_core.cuh"
@@ -371,7 +372,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     WTP_REQUIRE(n_fixed >= 0 && n_move >= 0 && n_fixed + n_move > 0, WTP_ERR_BAD_ARG, "empty snapshot");
     WTP_REQUIRE(prm->rebuild_every >= 1, WTP_ERR_BAD_ARG, "rebuild_every must be >= 1");          // src/repel.jl:74
     WTP_REQUIRE(prm->k >= 1 && prm->max_iters >= 0, WTP_ERR_BAD_ARG, "k must be >= 1 and max_iters >= 0");
-    WTP_REQUIRE(prm->kick_after == 0, WTP_ERR_UNSUPPORTED, "kick_after > 0 draws randn (src/repel.jl:430): not reproducible on the device");
+    WTP_REQUIRE(prm->kick_after >= 0, WTP_ERR_BAD_ARG, "kick_after must be >= 0");
     WTP_REQUIRE(prm->wall == WTP_WALL_IDENTITY || prm->wall == WTP_WALL_MESH, WTP_ERR_UNSUPPORTED, "user-defined constrain closure cannot cross the C ABI");
     WTP_REQUIRE((prm->wall == WTP_WALL_MESH) == (mesh != nullptr), WTP_ERR_BAD_ARG, "params.wall and the wall mesh argument disagree");
     WTP_REQUIRE(!mesh || D == 3, WTP_ERR_BAD_ARG, "the mesh wall rule is 3-D only (src/repel.jl:123)");
@@ -422,6 +423,13 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     RepelPartial<T>* h_tot = static_cast<RepelPartial<T>*>(ctx->h_pinned);
     WTP_REQUIRE(sizeof(RepelPartial<T>) * (size_t)(world + 1) + 64 <= 3072, WTP_ERR_BAD_ARG, "world size too large for the staging buffer");
     uint32_t* h_cnt = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 3072);
+
+    // _maybe_kick! state (pair, r/s, count) and the library's own random stream for the kick direction
+    int64_t kick_a = -1, kick_b = -1;
+    double kick_rs = 0.0;
+    int kick_count = 0;
+    std::mt19937_64 kick_rng(prm->kick_seed);
+    std::normal_distribution<double> kick_normal(0.0, 1.0);
 
     Grid<T> g{};
     int passes = 0;
@@ -510,7 +518,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         }
         for (int d = 0; d < 3; ++d) { mlo[d] = d < D ? (double)tot.lo[d] : 0.0; mhi[d] = d < D ? (double)tot.hi[d] : 0.0; }
         conv[n_conv++] = tot.max_force;                                                              // :293
-        if (trace) {                                                                                 // :294-296, 396-403
+        if (trace || prm->kick_after > 0) {                                                          // :294-304, 396-403
             const int64_t ig = (int64_t)tot.min_id + n_fixed + 1;
             const int64_t jg = tot.min_nn_idx == 0xffffffffu ? 0 : (int64_t)tot.min_nn_idx + 1;
             T sa_, sb_;
@@ -518,9 +526,37 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             WTP_CUDA_CHECK(cudaMemcpyAsync(&sb_, spacings + (jg > 0 ? jg - 1 : ig - 1), sizeof(T), cudaMemcpyDeviceToHost, st));
             WTP_CUDA_CHECK(cudaStreamSynchronize(st));
             const T s_pair = (sa_ + sb_) / (T)2;
-            wtp_trace_entry& te = trace[n_conv - 1];
-            te.r = (double)tot.min_nn; te.s = (double)s_pair; te.r_over_s = (double)(tot.min_nn / s_pair);
-            te.idx_a = std::min(ig, jg); te.idx_b = std::max(ig, jg);
+            const int64_t pa = std::min(ig, jg), pb = std::max(ig, jg);
+            const double rs = (double)(tot.min_nn / s_pair);
+            if (trace) {
+                wtp_trace_entry& te = trace[n_conv - 1];
+                te.r = (double)tot.min_nn; te.s = (double)s_pair; te.r_over_s = rs;
+                te.idx_a = pa; te.idx_b = pb;
+            }
+            if (prm->kick_after > 0) {                                                               // _maybe_kick!, :415-433
+                const bool frozen = pa == kick_a && pb == kick_b && std::fabs(rs - kick_rs) < 1.0e-8;
+                const int count = frozen ? kick_count + 1 : 1;
+                kick_a = pa; kick_b = pb; kick_rs = rs; kick_count = count;
+                if (count >= prm->kick_after) {
+                    // one point of the frozen pair (a volume point if there is one, always a movable one) moves by s/10
+                    // in a random direction; p is the configuration the sweep just produced (Pb)
+                    const int64_t target = pa > prm->n_protected ? pa : (pb > prm->n_protected ? pb : (pa > n_fixed ? pa : pb));
+                    if (target > n_fixed) {
+                        T s_t, x[3] = {(T)0, (T)0, (T)0};
+                        T* slot = Pb + (size_t)(target - 1 - n_fixed) * D;
+                        WTP_CUDA_CHECK(cudaMemcpyAsync(&s_t, spacings + (target - 1), sizeof(T), cudaMemcpyDeviceToHost, st));
+                        WTP_CUDA_CHECK(cudaMemcpyAsync(x, slot, (size_t)D * sizeof(T), cudaMemcpyDeviceToHost, st));
+                        WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+                        T dvec[3], nrm = (T)0;
+                        for (int d = 0; d < D; ++d) { dvec[d] = (T)kick_normal(kick_rng); nrm += dvec[d] * dvec[d]; }
+                        nrm = std::sqrt(nrm);
+                        for (int d = 0; d < D; ++d) x[d] = x[d] + (s_t / (T)10) * (dvec[d] / nrm);
+                        WTP_CUDA_CHECK(cudaMemcpyAsync(slot, x, (size_t)D * sizeof(T), cudaMemcpyHostToDevice, st));
+                        WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+                    }
+                    kick_count = 0;
+                }
+            }
         }
         bool stopped = false, keep_old = false;
         if (prm->stall_after > 0 || prm->cv_target > 0) {                                            // :305-327

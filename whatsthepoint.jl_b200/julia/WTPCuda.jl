@@ -87,6 +87,7 @@ struct CSpacing; kind::Int32; a::Float64; b::Float64; c::Float64; bnd::Ptr{Cvoid
 struct CParams
     k::Int32; max_iters::Int32; rebuild_every::Int32; stall_after::Int32; kick_after::Int32; wall::Int32
     want_trace::Int32; reserved::Int32; alpha_lo::Float64; alpha_max::Float64; tol::Float64; cv_target::Float64
+    n_protected::Int64; kick_seed::UInt64
 end
 struct CResult; iters::Int32; stop_reason::Int32; last_cv::Float64; end
 struct CTrace; r::Float64; s::Float64; r_over_s::Float64; idx_a::Int64; idx_b::Int64; end
@@ -167,7 +168,7 @@ function _relax!(
     sp, keep = cspacing(spacing, T)
     fm = cforce(force_model)
     prm = CParams(k, max_iters, rebuild_every, stall_after, kick_after, wall_mode ? MESH_WALL : IDENTITY_WALL, isnothing(trace) ? 0 : 1, 0,
-                  Float64(α_lo), Float64(α_max), Float64(tol), Float64(cv_target))
+                  Float64(α_lo), Float64(α_max), Float64(tol), Float64(cv_target), Int64(n_protected), rand(UInt64))
     conv = Vector{T}(undef, max(max_iters, 1))
     tr = isnothing(trace) ? CTrace[] : Vector{CTrace}(undef, max(max_iters, 1))
     res = Ref(CResult(0, 0, NaN))
