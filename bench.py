@@ -8,7 +8,8 @@ bounding box -> cell keys -> radix sort -> gather -> warp-per-query k-NN, N x 21
   value   : Mqueries/s with the points already resident in HBM (wtp_knn_dev_f32), CUDA
             events on the launching stream, max over ranks.
   e2e     : the same metric through the host C-ABI call a Julia user makes (wtp_knn_f32):
-            pinned host points in, pinned host N x 21 int64 out, copies inside the timed region.
+            pinned host points in, N x 21 int64 table in host memory out, copies inside the timed region
+            (the rows cross PCIe as 4-byte indices and are widened on the host by the library).
   roofline: the k-NN query kernel, 96 algorithmic bytes per query, timed by
             CUDA events inside the library on the same stream, against MEASURED_PEAKS.json.
   cpu_baseline: the CPU oracle (KD-tree port of the reference's path) on a bounded sample.
@@ -265,7 +266,7 @@ def main():
         hbm, how = peaks()
         achieved = ALGO_BYTES_PER_QUERY_F32 * nq / (q_ms_avg * 1e-3) / 1e9
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             import oracle
             sample = min(n, args.cpu_sample)
             threads = oracle.max_threads()
@@ -292,7 +293,9 @@ def main():
                        "sharding": f"queries split in {world} contiguous runs of the spatially sorted order, index replicated per GPU, no collective",
                        "l2": "working set (120 MB points + 160 MB sorted tiles + 1.68 GB output per step) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(pts_h.nbytes),
-                    "d2h_bytes_per_step": int(nq * K * 8), "api": "wtp_knn_f32 (host pointers, pinned)"},
+                    "d2h_bytes_per_step": int(nq * K * 4 + (nq * 8 if world > 1 else 0)),
+                    "api": "wtp_knn_f32: pinned host points in, N x 21 int64 table in host memory out; the rows cross PCIe as 4-byte "
+                           "indices and are widened to int64 by the library's host threads"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "knn_tile_kernel<float,3> (+ knn_kernel<float,3,1> for its leftovers)", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": ncu_traffic, "peak_source": how,

@@ -26,7 +26,17 @@ constexpr int TK_Q = 128;          // queries (= threads) per CTA
 constexpr int TK_WARPS = TK_Q / 32;
 constexpr int TK_LCAP = 48;        // hits kept per query
 constexpr int TK_LSTRIDE = 50;     // u16 slots per list: 25 words, odd, so the 32 lists of a warp start in 32 different banks
-template <class T> __host__ __device__ constexpr int tk_cap() { return sizeof(T) == 4 ? 1792 : 1664; }   // records per CTA tile
+#ifndef TK_CAP_F32
+#define TK_CAP_F32 1792
+#endif
+#ifndef TK_SWEEP_UNROLL
+#define TK_SWEEP_UNROLL 2
+#endif
+#ifndef TK_RADIUS_SIGMAS
+#define TK_RADIUS_SIGMAS 2.1f
+#endif
+constexpr int kSweepUnroll = TK_SWEEP_UNROLL;
+template <class T> __host__ __device__ constexpr int tk_cap() { return sizeof(T) == 4 ? TK_CAP_F32 : 1664; }   // records per CTA tile
 template <class T> __host__ __device__ constexpr size_t tk_smem() { return (size_t)tk_cap<T>() * sizeof(P4<T>) + (size_t)TK_LSTRIDE * TK_Q * sizeof(uint16_t); }
 
 // squared distance from the query to the shell of its 3^D block, conservative; +inf when the
@@ -51,7 +61,7 @@ __device__ __forceinline__ T block_shell2(const Grid<T>& g, T qx, T qy, T qz, in
 
 template <class T, int D>
 __device__ __forceinline__ T prefilter_radius2(const Grid<T>& g, uint32_t block_n, int K) {   // WarpKnn::set_prefilter_radius
-    const float target = (float)K + 2.5f * sqrtf((float)K) + 1.0f;
+    const float target = (float)K + TK_RADIUS_SIGMAS * sqrtf((float)K) + 1.0f;
     const float c = (float)g.c;
     float r2;
     if (D == 3) { const float r3 = target * 27.0f / (4.18879f * (float)block_n); r2 = c * c * cbrtf(r3 * r3); }
@@ -203,7 +213,7 @@ struct TileSearch {
         uint32_t addr = my_s;
 #pragma unroll
         for (int r = 0; r < NROWS; ++r) {
-#pragma unroll 4
+#pragma unroll kSweepUnroll
             for (uint32_t t = b[r]; t < e[r]; ++t) {
                 const P4<T> p = lds_p4(tile + t);
                 const T dx = q.x - p.x, dy = q.y - p.y;
