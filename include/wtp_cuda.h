@@ -79,9 +79,13 @@ int32_t wtp_host_unregister(wtp_ctx* ctx, void* ptr);
 int32_t wtp_set_cell_occupancy(wtp_ctx* ctx, double points_per_cell);
 
 /* Multi-GPU, one process per GPU. The NCCL unique id (128 bytes) is created on one
- * rank with wtp_comm_unique_id and distributed by the host program. After wtp_comm_init:
- *  - k-NN: every rank builds the (replicated) index and answers the contiguous run
- *    [wtp_shard_begin(N), wtp_shard_end(N)) of the SPATIALLY SORTED order, no collective.
+ * rank with wtp_comm_unique_id and distributed by the host program; a null id makes a shard-only
+ * context (rank and world set, no communicator): enough for k-NN and radius, refused by repel
+ * (WTP_ERR_STATE). After wtp_comm_init:
+ *  - k-NN: every rank answers the contiguous run [wtp_shard_begin(N), wtp_shard_end(N)) of the
+ *    SPATIALLY SORTED order, no collective. The rank indexes only the layers of the grid that run
+ *    needs (its own plus two on either side); if a search ever has to leave them (strongly graded
+ *    clouds) the call is repeated on the whole index and the context stops windowing.
  *    Host entry points write those rows into the caller's N x k table at their caller
  *    positions (other rows untouched); device entry points write a compact
  *    wtp_shard_owned_count() x k table. wtp_shard_owned gives the caller index of each row.
@@ -122,6 +126,9 @@ typedef struct {
     /* queries the tiled front end handed to the general kernel, by reason: block too sparse / too dense for
      * the tile / look-alike keys or exact ties (k-NN: last call; repel: last iteration) */
     int64_t n_leftover_sparse, n_leftover_dense, n_leftover_other;
+    /* sharded k-NN: points in the window of the grid this rank indexed (0: the whole set was indexed), and the
+     * queries whose search left the window (> 0: the call was repeated on the whole index) */
+    int64_t n_window_points, n_window_missed;
 } wtp_timing;
 
 /* enable != 0: record CUDA events around each phase of subsequent calls. */

@@ -79,6 +79,70 @@ def test_knn_cell_occupancy_invariance(ctx, oracle):
     ctx.set_cell_occupancy(0.0)
 
 
+# ----------------------------------------------------- sharded k-NN, one rank at a time
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("D", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_knn_shards_windowed_index(pkg, oracle, dt, D, world):
+    """Every rank of a sharded context (shard-only: no communicator is needed for k-NN) indexes only its window
+    of the grid; the rows it answers are the oracle's, and the ranks' runs tile the sorted order exactly."""
+    N = 60001
+    pts = np.random.default_rng(world * 10 + D).random((N, D)).astype(dt)
+    ref = oracle.knn(pts, 21)
+    seen = np.zeros(N, dtype=np.int32)
+    for rank in range(world):
+        c = pkg.Context(0)
+        c.comm_init(rank, world, None)
+        idx = np.zeros((N, 21), dtype=np.int64)
+        c.knn(pts, 21, out_idx=idx)
+        own = c.owned() - 1
+        b, e = c.shard(N)
+        t = c.timing()
+        assert len(own) == e - b and np.array_equal(idx[own], ref[own])
+        rest = np.ones(N, dtype=bool); rest[own] = False
+        assert (idx[rest] == 0).all()
+        assert 0 < t["n_window_points"] < N and t["n_window_missed"] == 0      # the window, not the whole set, was sorted
+        seen[own] += 1
+        c.close()
+    assert (seen == 1).all()
+
+
+def test_knn_shards_window_fallback(pkg, oracle):
+    """A strongly graded cloud: searches leave the window, the call is repeated on the whole index (same rows),
+    and the context stops windowing."""
+    rng = np.random.default_rng(3)
+    pts = (rng.random((40000, 3)) ** 4).astype(np.float32)
+    ref = oracle.knn(pts, 21)
+    seen = np.zeros(len(pts), dtype=np.int32)
+    missed = 0
+    for rank in range(4):
+        c = pkg.Context(0)
+        c.comm_init(rank, 4, None)
+        idx = np.zeros((len(pts), 21), dtype=np.int64)
+        c.knn(pts, 21, out_idx=idx)
+        own = c.owned() - 1
+        assert np.array_equal(idx[own], ref[own])
+        t = c.timing()
+        missed += t["n_window_missed"]
+        if t["n_window_missed"] > 0:                                    # second call: no window attempt any more
+            idx2 = np.zeros_like(idx)
+            c.knn(pts, 21, out_idx=idx2)
+            assert np.array_equal(idx2, idx) and c.timing()["n_window_points"] == 0
+        seen[own] += 1
+        c.close()
+    assert (seen == 1).all() and missed > 0
+
+
+def test_shard_only_context_refuses_repel(pkg):
+    c = pkg.Context(0)
+    c.comm_init(0, 2, None)
+    pts = np.random.default_rng(0).random((500, 3))
+    sp, _ = c.make_spacing("constant", a=0.1)
+    with pytest.raises(pkg.WtpError):
+        c.repel(pts, 50, sp, c.make_force("clipped", 0.2), max_iters=2, alpha_lo=1e-5, alpha_max=1e-3)
+    c.close()
+
+
 # ---------------------------------------------------------------- radius
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("D,r", [(2, 0.03), (3, 0.08), (2, 0.004), (3, 0.5)])

@@ -168,6 +168,8 @@ void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_
     ctx->last_timing.n_leftover_sparse = ctx->last_tile_sparse;
     ctx->last_timing.n_leftover_dense = ctx->last_tile_dense;
     ctx->last_timing.n_leftover_other = ctx->last_tile_other;
+    ctx->last_timing.n_window_points = ctx->last_window_points;
+    ctx->last_timing.n_window_missed = ctx->last_window_missed;
 }
 
 // ------------------------------------------------------------------- k-NN
@@ -191,19 +193,56 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     double lo[3], hi[3];
     compute_bbox<T>(ctx, ib, d_pts, N, D, lo, hi);
     Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy, 0.0, K1);
-    const int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
     const bool sharded = ctx->world > 1;
-    const int64_t sb = wtp_shard_begin(N, ctx->rank, ctx->world), se = wtp_shard_end(N, ctx->rank, ctx->world);
-    const int64_t nq = se - sb;
-    ctx->owned_begin = sb; ctx->owned_end = se; ctx->owned_f64 = sizeof(T) == 8;
-    const RowMap rows{0u, (uint32_t)sb, sharded ? 1 : 0};
-    unsigned long long* d_exp = ctx->d_reduce.as<unsigned long long>(1);
-    WTP_CUDA_CHECK(cudaMemsetAsync(d_exp, 0, sizeof(unsigned long long), ctx->stream));
     // CTA-tiled front end (knn_tile.cuh) whenever the list fits one register row, the general kernel alone otherwise
     const bool tiled = K1 <= 32 && std::getenv("WTP_NO_TILED") == nullptr;
-    auto compute = [&](void* d_idx, T* d_dist, bool out32) {
+    // the run of the sorted order this rank answers, in positions of the whole sorted set
+    const int64_t gsb = wtp_shard_begin(N, ctx->rank, ctx->world), gse = wtp_shard_end(N, ctx->rank, ctx->world);
+    const int64_t nq = gse - gsb;
+    // Sharded: index only the layers of the grid that the run needs (build_index_window); sb, se are then positions
+    // inside the window. A query whose search leaves the window is counted (d_exp[1]) and the call is repeated on
+    // the whole index; the context remembers that and builds the whole index at once from then on.
+    IndexWindow win;
+    int passes = 0;
+    bool windowed = sharded && tiled && !ctx->window_off && std::getenv("WTP_NO_WINDOW") == nullptr &&
+                    build_index_window<T>(ctx, ib, d_pts, N, D, g, gsb, gse, 2, &win, &passes);
+    if (!windowed) passes = build_index<T>(ctx, ib, d_pts, N, D, g);
+    int64_t sb = windowed ? gsb - win.P0 : gsb, se = windowed ? gse - win.P0 : gse;
+    ctx->owned_begin = sb; ctx->owned_end = se; ctx->owned_f64 = sizeof(T) == 8;
+    ctx->last_window_points = windowed ? win.M : 0; ctx->last_window_missed = 0;
+    RowMap rows{0u, (uint32_t)sb, sharded ? 1 : 0};
+    unsigned long long* d_exp = ctx->d_reduce.as<unsigned long long>(2);
+    WTP_CUDA_CHECK(cudaMemsetAsync(d_exp, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    auto compute_once = [&](void* d_idx, T* d_dist, bool out32) {
         if (tiled) knn_query_tiled<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, sb, se, rows, d_idx, d_dist, d_exp, out32);
         else knn_query<T>(ctx, ib, g, N, D, K1, drop_first ? 1 : 0, nullptr, nq, rows, d_idx, d_dist, d_exp, out32);
+    };
+    // h_pinned: [0] ring-expanded queries, [1] window misses, then the four counters of the tiled pass
+    unsigned long long* h_exp = static_cast<unsigned long long*>(ctx->h_pinned);
+    uint32_t* h_cnt = reinterpret_cast<uint32_t*>(h_exp + 2);
+    bool counters_read = false;
+    auto read_counters = [&] {
+        WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        if (tiled) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, ctx->d_fail.get<uint32_t>(), 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    };
+    auto compute = [&](void* d_idx, T* d_dist, bool out32) {
+        compute_once(d_idx, d_dist, out32);
+        if (!windowed) return;
+        read_counters();
+        counters_read = true;
+        if (h_exp[1] == 0) return;
+        ctx->last_window_missed = (int64_t)h_exp[1];
+        ctx->window_off = true;
+        windowed = false;
+        counters_read = false;
+        g.w_lo = 0; g.w_hi = g.n[D - 1] - 1;
+        passes = build_index<T>(ctx, ib, d_pts, N, D, g);
+        sb = gsb; se = gse;
+        ctx->owned_begin = sb; ctx->owned_end = se;
+        rows.pos_base = (uint32_t)sb;
+        WTP_CUDA_CHECK(cudaMemsetAsync(d_exp, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        compute_once(d_idx, d_dist, out32);
     };
     int n_chunks = 1;
     if (!h_out_idx) {
@@ -287,11 +326,10 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
         WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
     }
-    unsigned long long* h_exp = static_cast<unsigned long long*>(ctx->h_pinned);
-    uint32_t* h_cnt = reinterpret_cast<uint32_t*>(h_exp + 1);
-    WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-    if (tiled) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, ctx->d_fail.get<uint32_t>(), 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (!counters_read || h_out_idx) {
+        if (!counters_read) read_counters();
+        else WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->last_tile_sparse = tiled ? h_cnt[1] : 0; ctx->last_tile_dense = tiled ? h_cnt[2] : 0; ctx->last_tile_other = tiled ? h_cnt[3] : 0;
     finish_timing(ctx, passes, n_chunks, g.ncells, (int64_t)*h_exp);
 }

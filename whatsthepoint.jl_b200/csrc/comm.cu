@@ -122,7 +122,11 @@ int32_t wtp_comm_init(wtp_ctx* ctx, int32_t rank, int32_t world, const void* uni
         WTP_CUDA_CHECK(cudaSetDevice(ctx->device));
         wtp_comm_destroy_internal(ctx);
         if (world == 1) return WTP_OK;
-        WTP_REQUIRE(unique_id128, WTP_ERR_BAD_ARG, "null NCCL unique id");
+        if (!unique_id128) {   // shard-only context: k-NN and radius shards need no collective (repel refuses it)
+            ctx->rank = rank;
+            ctx->world = world;
+            return WTP_OK;
+        }
         NcclApi* api = load_nccl();
         nccl_unique_id id;
         memcpy(&id, unique_id128, sizeof(id));

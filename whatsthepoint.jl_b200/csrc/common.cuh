@@ -73,6 +73,10 @@ struct Grid {
     T slack;     // absolute safety margin for pruning bounds (few ulps of the extent)
     int n[3];    // cells per dimension (n[2] = 1 in 2-D)
     uint32_t ncells;
+    // Layers of the slowest axis (z in 3-D, y in 2-D) that the index holds, inclusive. The whole grid, except for
+    // the windowed index of a sharded k-NN call (grid.cu, build_index_window): a search that needs a layer outside
+    // the window must say so instead of reading it.
+    int w_lo, w_hi;
 };
 
 template <class T>
@@ -180,6 +184,17 @@ struct IndexBuffers {
     DevBuf cell_start;                      // u32[ncells + 1]
     DevBuf bbox_partial;                    // per-block min/max
     DevBuf bbox;                            // 6 x T
+    DevBuf unit_hist;                       // windowed build: points per layer of the slowest axis + the picked window
+    int64_t cs_rebase = 0;                  // windowed build: cell_start[0] belongs to this cell id (0: whole grid)
+    const uint32_t* cells() const { return cell_start.get<uint32_t>() - cs_rebase; }   // indexable by global cell id
+};
+
+// The part of the sorted order a windowed index holds: the points of the cell ids [key_lo, key_hi), which are the
+// sorted positions [P0, P0 + M) of the whole set.
+struct IndexWindow {
+    int64_t P0 = 0, M = 0;
+    uint32_t key_lo = 0, key_hi = 0;
+    int w_lo = 0, w_hi = 0;
 };
 
 // Implicit BVH over the Morton-sorted boundary set of a variable spacing (bvh.cu).
@@ -261,6 +276,8 @@ struct wtp_ctx {
     } radius;
     unsigned char grid_storage[2][128];  // last Grid<T> per index (host copy)
     int64_t owned_begin = 0, owned_end = 0; bool owned_f64 = false;   // sorted range answered by the last sharded k-NN call
+    bool window_off = false;     // a windowed k-NN call had to fall back (graded cloud): later calls build the whole index at once
+    int64_t last_window_points = 0, last_window_missed = 0;   // statistics of the last sharded k-NN call
     int64_t last_tile_sparse = 0, last_tile_dense = 0, last_tile_other = 0;   // leftovers of the last tiled sweep, by kind
     // multi-GPU
     int rank = 0, world = 1;

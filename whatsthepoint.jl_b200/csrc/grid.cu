@@ -144,6 +144,8 @@ Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], doub
     // cell boundaries lo + i*c and the (v-lo)*inv_c rounding are each off by a few ulps of
     // the coordinate magnitude; 16 ulps of slack keeps every pruning bound conservative.
     g.slack = (T)(16.0 * eps * std::max(maxabs, maxext) + 4.0 * eps * c);
+    g.w_lo = 0;
+    g.w_hi = g.n[D - 1] - 1;
     return g;
 }
 template Grid<float> make_grid<float>(int64_t, int, const double*, const double*, double, double, int);
@@ -442,6 +444,7 @@ int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D
     uint32_t* vals_a = ib.vals_a.as<uint32_t>((size_t)N);
     P4<T>* sorted = ib.sorted.as<P4<T>>((size_t)N);
     uint32_t* cell_start = ib.cell_start.as<uint32_t>((size_t)g.ncells + 1);
+    ib.cs_rebase = 0;
     const unsigned nb256 = (unsigned)((N + 255) / 256);
     {
         ScopedPhase ph(ctx->timer, PH_CELLKEY);
@@ -464,5 +467,202 @@ int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D
 }
 template int build_index<float>(wtp_ctx*, IndexBuffers&, const float*, int64_t, int, const Grid<float>&);
 template int build_index<double>(wtp_ctx*, IndexBuffers&, const double*, int64_t, int, const Grid<double>&);
+
+// =========================================================== windowed index
+// A sharded k-NN rank answers the sorted positions [sb, se) only. Its queries live in a run of x-rows of cells, so
+// their neighbourhoods live in a few layers of the slowest axis: instead of sorting all N points, the rank
+//   1. computes every cell key and counts the points of every layer of the slowest axis;
+//   2. scans the counts, finds the layers of positions sb and se-1, adds `halo` layers on either side (the
+//      window), and learns how many points lie below and inside it (one small D2H);
+//   3. compacts the (key, id) pairs of the window in input order (stable), sorts them, and gathers the records.
+// The sorted records of the window are exactly the run [P0, P0 + M) of the whole sorted order (same stable sort on
+// the same keys), so rows, their order and wtp_shard_owned are identical to the replicated build.
+constexpr int WC_THREADS = 256;
+constexpr int WC_ITEMS = 16;
+constexpr int WC_TILE = WC_THREADS * WC_ITEMS;
+
+constexpr int WH_MAX_LAYERS = 8192;     // layer histogram in shared memory (32 KB)
+constexpr int WH_THREADS = 256;
+
+// every cell key + the number of points per layer of the slowest axis: per-CTA histogram in shared memory,
+// flushed with one global atomic per non-empty bin
+template <class T, int D>
+__global__ void __launch_bounds__(WH_THREADS) cellkey_hist_kernel(const T* __restrict__ pts, int64_t N, Grid<T> g, uint32_t* __restrict__ keys,
+                                                                  uint32_t* __restrict__ layer_hist) {
+    extern __shared__ uint32_t s_hist[];
+    const int n_layers = g.n[D - 1];
+    for (int i = threadIdx.x; i < n_layers; i += WH_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * WH_THREADS + threadIdx.x; i < N; i += (int64_t)gridDim.x * WH_THREADS) {
+        const int cx = cell_coord(g, pts[i * D + 0], 0);
+        const int cy = cell_coord(g, pts[i * D + 1], 1);
+        const int cz = D == 3 ? cell_coord(g, pts[i * D + (D - 1)], 2) : 0;
+        keys[i] = ((uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy) * (uint32_t)g.n[0] + (uint32_t)cx;
+        atomicAdd(&s_hist[D == 3 ? cz : cy], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_layers; i += WH_THREADS) {
+        const uint32_t c = s_hist[i];
+        if (c) atomicAdd(layer_hist + i, c);
+    }
+}
+
+// One CTA: exclusive scan of the layer counts in shared memory, the layers of the sorted positions sb and se-1,
+// the window. out: {P0, M, w_lo, w_hi}
+__global__ void __launch_bounds__(1024) window_pick_kernel(const uint32_t* __restrict__ layer_hist, uint32_t n_layers, uint32_t sb, uint32_t se,
+                                                           uint32_t halo, uint32_t* __restrict__ out) {
+    __shared__ uint32_t s_pre[WH_MAX_LAYERS + 1];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry, s_first, s_last;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t c0 = 0; c0 < n_layers; c0 += 1024) {
+        const uint32_t i = c0 + threadIdx.x;
+        const uint32_t v = i < n_layers ? layer_hist[i] : 0u;
+        uint32_t incl = v;
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_warp[w] = incl;
+        __syncthreads();
+        uint32_t base = s_carry;
+        for (int k = 0; k < w; ++k) base += s_warp[k];
+        if (i < n_layers) s_pre[i] = base + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = base + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) s_pre[n_layers] = s_carry;
+    __syncthreads();
+    // the layer of position p: the one with pre[l] <= p < pre[l + 1] (never an empty layer)
+    for (uint32_t l = threadIdx.x; l < n_layers; l += 1024) {
+        if (s_pre[l] <= sb && sb < s_pre[l + 1]) s_first = l;
+        if (s_pre[l] <= se - 1 && se - 1 < s_pre[l + 1]) s_last = l;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t w_lo = s_first > halo ? s_first - halo : 0u;
+        const uint32_t w_hi = s_last + halo < n_layers - 1 ? s_last + halo : n_layers - 1;
+        out[0] = s_pre[w_lo];
+        out[1] = s_pre[w_hi + 1] - s_pre[w_lo];
+        out[2] = w_lo;
+        out[3] = w_hi;
+    }
+}
+
+__global__ void __launch_bounds__(WC_THREADS) window_count_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t key_lo, uint32_t key_hi,
+                                                                  uint32_t* __restrict__ block_counts) {
+    const uint32_t base = blockIdx.x * WC_TILE;
+    uint32_t c = 0;
+    for (uint32_t i = base + threadIdx.x; i < min(n, base + WC_TILE); i += WC_THREADS) {
+        const uint32_t k = keys[i];
+        c += (k >= key_lo && k < key_hi) ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    __shared__ uint32_t s[WC_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < WC_THREADS / 32; ++i) t += s[i];
+        block_counts[blockIdx.x] = t;
+    }
+}
+
+// stable: thread t of a CTA takes the WC_ITEMS consecutive keys [t * WC_ITEMS, ...) of the CTA's tile
+__global__ void __launch_bounds__(WC_THREADS) window_compact_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t key_lo, uint32_t key_hi,
+                                                                    const uint32_t* __restrict__ block_offsets,
+                                                                    uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out) {
+    __shared__ uint32_t s_warp[WC_THREADS / 32];
+    const uint32_t first = blockIdx.x * WC_TILE + threadIdx.x * WC_ITEMS;
+    uint32_t k[WC_ITEMS];
+    uint32_t c = 0;
+    if (first + WC_ITEMS <= n) {
+        const uint4* k4 = reinterpret_cast<const uint4*>(keys + first);
+#pragma unroll
+        for (int r = 0; r < WC_ITEMS / 4; ++r) { const uint4 v = k4[r]; k[4 * r] = v.x; k[4 * r + 1] = v.y; k[4 * r + 2] = v.z; k[4 * r + 3] = v.w; }
+    } else {
+#pragma unroll
+        for (int r = 0; r < WC_ITEMS; ++r) k[r] = first + r < n ? keys[first + r] : 0xffffffffu;   // key_hi <= ncells < 2^32 - 1
+    }
+#pragma unroll
+    for (int r = 0; r < WC_ITEMS; ++r) c += (k[r] >= key_lo && k[r] < key_hi) ? 1u : 0u;
+    uint32_t out = block_exclusive_scan<uint32_t>(c, s_warp, nullptr) + block_offsets[blockIdx.x];
+#pragma unroll
+    for (int r = 0; r < WC_ITEMS; ++r) {
+        if (k[r] >= key_lo && k[r] < key_hi) {
+            keys_out[out] = k[r] - key_lo;
+            vals_out[out] = first + r;
+            ++out;
+        }
+    }
+}
+
+template <class T>
+bool build_index_window(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, Grid<T>& g, int64_t sb, int64_t se, int halo,
+                        IndexWindow* win, int* passes_out) {
+    WTP_REQUIRE(N > 0 && N < (int64_t)0xfffffff0u, WTP_ERR_BAD_ARG, "point count must be in [1, 2^32)");
+    const uint32_t rows_per_layer = D == 3 ? (uint32_t)g.n[1] : 1u;
+    const uint32_t n_layers = (uint32_t)g.n[D - 1];
+    if (se <= sb || n_layers > (uint32_t)WH_MAX_LAYERS || (int64_t)n_layers <= 2 * halo + 1) return false;   // nothing to gain: build the whole index
+    cudaStream_t st = ctx->stream;
+    uint32_t* keys_all = ib.keys_b.as<uint32_t>((size_t)N);
+    uint32_t* hist = ib.unit_hist.as<uint32_t>((size_t)n_layers + 8);
+    uint32_t* pick = hist + n_layers;
+    {
+        ScopedPhase ph(ctx->timer, PH_CELLKEY);
+        WTP_CUDA_CHECK(cudaMemsetAsync(hist, 0, ((size_t)n_layers + 8) * sizeof(uint32_t), st));
+        const unsigned nbh = (unsigned)std::min<int64_t>((N + WH_THREADS - 1) / WH_THREADS, (int64_t)kNumSMs * 8);
+        const size_t smem = (size_t)n_layers * sizeof(uint32_t);
+        if (D == 2) cellkey_hist_kernel<T, 2><<<nbh, WH_THREADS, smem, st>>>(d_pts, N, g, keys_all, hist);
+        else cellkey_hist_kernel<T, 3><<<nbh, WH_THREADS, smem, st>>>(d_pts, N, g, keys_all, hist);
+        LAUNCH_CHECK(ctx);
+        window_pick_kernel<<<1, 1024, 0, st>>>(hist, n_layers, (uint32_t)sb, (uint32_t)se, (uint32_t)halo, pick);
+        LAUNCH_CHECK(ctx);
+        uint32_t* h = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 2048);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(h, pick, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+        win->P0 = h[0]; win->M = h[1]; win->w_lo = (int)h[2]; win->w_hi = (int)h[3];
+    }
+    win->key_lo = (uint32_t)win->w_lo * rows_per_layer * (uint32_t)g.n[0];
+    win->key_hi = ((uint32_t)win->w_hi + 1u) * rows_per_layer * (uint32_t)g.n[0];
+    const int64_t M = win->M;
+    WTP_REQUIRE(M > 0 && win->P0 <= sb && se <= win->P0 + M, WTP_ERR_CUDA, "windowed index: the window does not hold the owned run");
+    uint32_t* keys_a = ib.keys_a.as<uint32_t>((size_t)N);
+    uint32_t* vals_a = ib.vals_a.as<uint32_t>((size_t)N);
+    {
+        ScopedPhase ph(ctx->timer, PH_CELLKEY);
+        const int64_t nb = (N + WC_TILE - 1) / WC_TILE;
+        uint32_t* counts = ib.block_hist.as<uint32_t>((size_t)nb + 1);
+        window_count_kernel<<<(unsigned)nb, WC_THREADS, 0, st>>>(keys_all, (uint32_t)N, win->key_lo, win->key_hi, counts);
+        LAUNCH_CHECK(ctx);
+        exclusive_scan_u32(ctx, ib.scan_tmp, counts, counts, nb);
+        window_compact_kernel<<<(unsigned)nb, WC_THREADS, 0, st>>>(keys_all, (uint32_t)N, win->key_lo, win->key_hi, counts, keys_a, vals_a);
+        LAUNCH_CHECK(ctx);
+    }
+    const uint32_t ncells_w = win->key_hi - win->key_lo;
+    int bits = 0;
+    while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)ncells_w) ++bits;
+    const int passes = radix_sort_pairs(ctx, ib, M, bits);
+    keys_a = ib.keys_a.get<uint32_t>();
+    vals_a = ib.vals_a.get<uint32_t>();
+    P4<T>* sorted = ib.sorted.as<P4<T>>((size_t)M);
+    uint32_t* cell_start = ib.cell_start.as<uint32_t>((size_t)ncells_w + 1);
+    ib.cs_rebase = (int64_t)win->key_lo;
+    {
+        ScopedPhase ph(ctx->timer, PH_REORDER);
+        const unsigned nbm = (unsigned)((M + 255) / 256);
+        if (D == 2) reorder_kernel<T, 2><<<nbm, 256, 0, st>>>(d_pts, keys_a, vals_a, (uint32_t)M, ncells_w, sorted, cell_start);
+        else reorder_kernel<T, 3><<<nbm, 256, 0, st>>>(d_pts, keys_a, vals_a, (uint32_t)M, ncells_w, sorted, cell_start);
+        LAUNCH_CHECK(ctx);
+    }
+    g.w_lo = win->w_lo;
+    g.w_hi = win->w_hi;
+    if (passes_out) *passes_out = passes;
+    return true;
+}
+template bool build_index_window<float>(wtp_ctx*, IndexBuffers&, const float*, int64_t, int, Grid<float>&, int64_t, int64_t, int, IndexWindow*, int*);
+template bool build_index_window<double>(wtp_ctx*, IndexBuffers&, const double*, int64_t, int, Grid<double>&, int64_t, int64_t, int, IndexWindow*, int*);
 
 }  // namespace wtp

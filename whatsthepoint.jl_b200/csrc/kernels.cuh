@@ -18,6 +18,13 @@ Grid<T> make_grid(int64_t N, int D, const double lo[3], const double hi[3], doub
 template <class T>
 int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, const Grid<T>& g);
 
+// The same for the part of the grid a sharded k-NN rank needs: the layers of the sorted positions [sb, se) plus `halo`
+// layers on either side (see grid.cu). On success g.w_lo / g.w_hi and ib.cs_rebase describe the window and the
+// sorted records are the run [win->P0, win->P0 + win->M) of the whole sorted order. False: not worthwhile, nothing built.
+template <class T>
+bool build_index_window(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, Grid<T>& g, int64_t sb, int64_t se, int halo,
+                        IndexWindow* win, int* passes_out);
+
 // Stable LSD radix sort (8-bit digits) of the pairs in ib.keys_a / ib.vals_a on the low `bits` key bits.
 int radix_sort_pairs(wtp_ctx* ctx, IndexBuffers& ib, int64_t N, int bits);
 
@@ -33,7 +40,7 @@ void exclusive_scan_u32_to_i64(wtp_ctx* ctx, DevBuf& tmp, const uint32_t* d_in, 
 template <class T>
 void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
                const uint32_t* d_qlist, int64_t n_queries, const RowMap& rows, void* d_out_idx, T* d_out_dist,
-               unsigned long long* d_expanded_counter, bool out32 = false);   // out32: uint32 rows instead of int64
+               unsigned long long* d_expanded_counter, bool out32 = false);   // out32: uint32 rows instead of int64; counter[1]: window misses
 
 // CTA-tiled front end + general kernel for the leftovers, over the sorted positions [s_begin, s_end)
 // (K1 <= 32). Rows are written at (orig - q_begin) * (K1 - drop_first) like knn_query. Fully asynchronous.

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
         const P4<T> q = load_p4<T>(sorted + j);
         const int rings = s.run(q.x, q.y, q.z, K1);
         if (rings > 1 && lane == 0 && expanded) atomicAdd(expanded, 1ULL);
+        if (s.missed && lane == 0 && expanded) atomicAdd(expanded + 1, 1ULL);   // windowed index: the caller repeats the call on the whole index
         const int64_t row = rows.row(j, idx_of(q)) * k_out;
 #pragma unroll
         for (int e = 0; e < KPL; ++e) {
@@ -89,7 +90,7 @@ static void launch_knn(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, i
     // a device-side count (the tiled pass's leftovers): a fixed grid strides over however many entries there are
     const unsigned nblocks = (unsigned)std::min<int64_t>((nq + KNN_QPB - 1) / KNN_QPB, d_nq ? (int64_t)kNumSMs * 4 : (int64_t)0x7fffffff);
     const P4<T>* sorted = ib.sorted.get<P4<T>>();
-    const uint32_t* cs = ib.cell_start.get<uint32_t>();
+    const uint32_t* cs = ib.cells();
     if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
     else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
     else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
@@ -132,7 +133,7 @@ static void run_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, in
     }
     const TileFails f = tile_fails(ctx, s_end - s_begin);
     const unsigned nblocks = (unsigned)((s_end - s_begin + TK_Q - 1) / TK_Q);
-    knn_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cell_start.get<uint32_t>(), (uint32_t)s_begin,
+    knn_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cells(), (uint32_t)s_begin,
                                                                (uint32_t)s_end, rows, K1, drop, d_out_idx, out32, d_out_dist, f);
     LAUNCH_CHECK(ctx);
     launch_knn<T, D>(ctx, ib, g, K1, drop, f.list, s_end - s_begin, f.counters, rows, d_out_idx, out32, d_out_dist, d_exp);

@@ -239,6 +239,7 @@ struct WarpKnn {
     T qx, qy, qz;
     int cx, cy, cz;
     bool seeded;
+    bool missed;        // a ring reached a layer outside the index window (Grid::w_lo, w_hi): the list may be incomplete
     WarpList<T, KPL> list;
 
     static constexpr int PF_CAP = 64;
@@ -415,6 +416,8 @@ struct WarpKnn {
     __device__ __forceinline__ void ring_row(int R, int dy, int dz) {
         const int ry = cy + dy, rz = cz + dz;
         if (ry < 0 || ry >= g.n[1] || rz < 0 || rz >= g.n[2]) return;
+        const int layer = D == 3 ? rz : ry;
+        if (layer < g.w_lo || layer > g.w_hi) { missed = true; return; }   // not indexed here (windowed index): reported, never read
         const T gy = gap(1, qy, cy, dy), gz = D == 3 ? gap(2, qz, cz, dz) : (T)0;
         const int ady = dy < 0 ? -dy : dy, adz = dz < 0 ? -dz : dz;
         const bool outer = (ady > adz ? ady : adz) == R;
@@ -454,6 +457,7 @@ struct WarpKnn {
         cy = cell_coord(g, qy, 1);
         cz = D == 3 ? cell_coord(g, qz, 2) : 0;
         seeded = false;
+        missed = false;
         list.init(K);
         bool staged = false;
         if (TILE_CAP > 0) {

@@ -378,6 +378,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     WTP_REQUIRE(!mesh || D == 3, WTP_ERR_BAD_ARG, "the mesh wall rule is 3-D only (src/repel.jl:123)");
     WTP_REQUIRE(fm->kind >= WTP_FORCE_INVERSE && fm->kind <= WTP_FORCE_STRONG, WTP_ERR_UNSUPPORTED, "user-defined RepelForceModel cannot cross the C ABI");
     WTP_REQUIRE(sp_in->kind >= WTP_SPACING_CONSTANT && sp_in->kind <= WTP_SPACING_BOUNDARY_LAYER, WTP_ERR_UNSUPPORTED, "user-defined spacing callable cannot cross the C ABI");
+    WTP_REQUIRE(ctx->world == 1 || ctx->nccl_comm, WTP_ERR_STATE, "repel on a sharded context needs the NCCL communicator (wtp_comm_init with a unique id)");
     const int64_t n_all = n_fixed + n_move;
     WTP_REQUIRE(n_all < (int64_t)0xfffffff0u, WTP_ERR_BAD_ARG, "snapshot too large");
     const int kk = (int)std::min<int64_t>(prm->k, n_all);                                           // :208
