@@ -68,17 +68,18 @@ struct RepelPartial {
     uint32_t min_id;            // movable id of the pair's first point
     uint32_t min_nn_idx;        // snapshot-global 0-based index of its nearest neighbour
     T lo[3], hi[3];             // bounding box of the new positions
+    unsigned long long missed;  // searches that had to leave the window of a windowed index (the iteration is redone)
 };
 
 template <class T>
 __device__ __forceinline__ void partial_init(RepelPartial<T>& p) {
-    p.s1 = 0; p.s2 = 0; p.n = 0; p.max_force = (T)0; p.min_nn = t_inf<T>(); p.min_id = 0xffffffffu; p.min_nn_idx = 0xffffffffu;
+    p.s1 = 0; p.s2 = 0; p.n = 0; p.missed = 0; p.max_force = (T)0; p.min_nn = t_inf<T>(); p.min_id = 0xffffffffu; p.min_nn_idx = 0xffffffffu;
     for (int d = 0; d < 3; ++d) { p.lo[d] = t_inf<T>(); p.hi[d] = -t_inf<T>(); }
 }
 // fold b into a; b covers later points than a (sum order = point order within a CTA)
 template <class T>
 __host__ __device__ inline void partial_merge(RepelPartial<T>& a, const RepelPartial<T>& b) {
-    a.s1 += b.s1; a.s2 += b.s2; a.n += b.n;
+    a.s1 += b.s1; a.s2 += b.s2; a.n += b.n; a.missed += b.missed;
     a.max_force = b.max_force > a.max_force ? b.max_force : a.max_force;
     if (b.min_nn < a.min_nn || (b.min_nn == a.min_nn && b.min_id < a.min_id)) { a.min_nn = b.min_nn; a.min_id = b.min_id; a.min_nn_idx = b.min_nn_idx; }
     for (int d = 0; d < 3; ++d) { a.lo[d] = b.lo[d] < a.lo[d] ? b.lo[d] : a.lo[d]; a.hi[d] = b.hi[d] > a.hi[d] ? b.hi[d] : a.hi[d]; }
@@ -100,6 +101,10 @@ struct SweepArgs {
     uint32_t nq;
     const uint32_t* nq_dev; // device-side length of qlist (the tiled sweep's leftovers), or null
     int kk, rebuild;
+    // Sharded by runs of the sorted order: this rank sweeps the sorted positions [s_begin, s_end) and writes the new
+    // position of position j, with the point's caller index, to C[j - s_begin] (C null: P_new by caller index).
+    uint32_t s_begin, s_end;
+    P4<T>* C;
     T a_lo, a_max;
     ForceP<T> force;
     RepelPartial<T>* partials;
@@ -184,10 +189,16 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
         if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
         const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;                       // :291 (identity wall)
         if (lane == 0) {
-            a.P_new[(size_t)id * D + 0] = p0;
-            a.P_new[(size_t)id * D + 1] = p1;
-            if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
+            if (a.C) {
+                P4<T> rec; rec.x = p0; rec.y = p1; rec.z = p2; rec.w = idx_bits((T)0, self);
+                a.C[j - a.s_begin] = rec;
+            } else {
+                a.P_new[(size_t)id * D + 0] = p0;
+                a.P_new[(size_t)id * D + 1] = p1;
+                if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
+            }
         }
+        if (knn.missed) acc.missed += 1;
         const T nn = found ? sqrt(nn_d2) : t_max<T>();
         const T s_mon = a.spacings[self];   // spacing as of the last rebuild (:251, :379)
         const T u = nn / s_mon;
@@ -220,6 +231,7 @@ __device__ __forceinline__ void partial_warp_reduce(RepelPartial<T>& p) {
     for (int o = 16; o > 0; o >>= 1) {
         RepelPartial<T> b;
         b.s1 = __shfl_down_sync(FULL, p.s1, o); b.s2 = __shfl_down_sync(FULL, p.s2, o); b.n = __shfl_down_sync(FULL, p.n, o);
+        b.missed = __shfl_down_sync(FULL, p.missed, o);
         b.max_force = __shfl_down_sync(FULL, p.max_force, o); b.min_nn = __shfl_down_sync(FULL, p.min_nn, o);
         b.min_id = __shfl_down_sync(FULL, p.min_id, o); b.min_nn_idx = __shfl_down_sync(FULL, p.min_nn_idx, o);
 #pragma unroll
@@ -235,8 +247,9 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
     __shared__ typename TileSearch<T, D>::Shared sh;
     __shared__ RepelPartial<T> s_part[TK_WARPS];
     TileSearch<T, D> ts(a.g, a.sorted, a.cell_start, smem_raw, sh);
-    const uint32_t j = blockIdx.x * TK_Q + threadIdx.x;
-    ts.init(j, j < a.n_all, a.n_fixed + a.id_lo, a.n_fixed + a.id_hi);   // fixed wall / other rank's points are not swept
+    const uint32_t j = a.s_begin + blockIdx.x * TK_Q + threadIdx.x;
+    ts.init(j, j < a.s_end, a.n_fixed + a.id_lo, a.n_fixed + a.id_hi);   // fixed wall / other rank's points are not swept
+    if (a.C && ts.active && !ts.query) a.C[j - a.s_begin] = ts.q;         // a fixed point of this rank's run: the record as it is
     RepelPartial<T> acc;
     partial_init(acc);
     while (ts.next_group()) {
@@ -280,13 +293,18 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
                 const T dn = sqrt(dn2);
                 if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
                 const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;          // :291 (the wall rule follows in its own kernel)
-                a.P_new[(size_t)id * D + 0] = p0;
-                a.P_new[(size_t)id * D + 1] = p1;
-                if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
+                if (a.C) {
+                    P4<T> rec; rec.x = p0; rec.y = p1; rec.z = p2; rec.w = idx_bits((T)0, self);
+                    a.C[ts.j - a.s_begin] = rec;
+                } else {
+                    a.P_new[(size_t)id * D + 0] = p0;
+                    a.P_new[(size_t)id * D + 1] = p1;
+                    if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
+                }
                 const T nn = nn_idx != 0xffffffffu ? sqrt(nn_d2) : t_max<T>();
                 const T u = nn / a.spacings[self];                            // spacing as of the last rebuild (:251, :379)
                 RepelPartial<T> one;
-                one.s1 = (double)u; one.s2 = (double)(u * u); one.n = 1; one.max_force = fs;
+                one.s1 = (double)u; one.s2 = (double)(u * u); one.n = 1; one.missed = 0; one.max_force = fs;
                 one.min_nn = nn; one.min_id = id; one.min_nn_idx = nn_idx;
                 one.lo[0] = one.hi[0] = p0; one.lo[1] = one.hi[1] = p1;
                 one.lo[2] = D == 3 ? p2 : t_inf<T>(); one.hi[2] = D == 3 ? p2 : -t_inf<T>();
@@ -331,6 +349,24 @@ template <class T>
 __global__ void __launch_bounds__(256) fill_kernel(T* __restrict__ out, int64_t n, T v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = v;
+}
+
+// After the all-gather of the ranks' runs (slot records per rank, rank r's first cnt_r are live): every movable
+// point's new position goes to its caller slot of P_new.
+template <class T, int D>
+__global__ void __launch_bounds__(256) scatter_runs_kernel(const P4<T>* __restrict__ C_all, uint32_t slot, uint32_t n_all, uint32_t world,
+                                                           uint32_t n_fixed, T* __restrict__ P_new) {
+    const uint32_t r = blockIdx.y;
+    const uint32_t begin = (uint32_t)(((uint64_t)n_all * r) / world), end = (uint32_t)(((uint64_t)n_all * (r + 1)) / world);
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= end - begin) return;
+    const P4<T> rec = load_p4<T>(C_all + (size_t)r * slot + t);
+    const uint32_t self = idx_of(rec);
+    if (self < n_fixed) return;
+    const size_t id = self - n_fixed;
+    P_new[id * D + 0] = rec.x;
+    P_new[id * D + 1] = rec.y;
+    if (D == 3) P_new[id * D + (D - 1)] = rec.z;
 }
 
 template <class T, int D, int KPL>
@@ -391,6 +427,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     }
     cudaStream_t st = ctx->stream;
     IndexBuffers& ib = ctx->index[0];
+    ctx->last_window_points = 0; ctx->last_window_missed = 0;
     const SpacingP<T> sp{sp_in->kind, (T)sp_in->a, (T)sp_in->b, (T)sp_in->c};
     const ForceP<T> force{fm->kind, (T)fm->beta, (T)fm->u0, (T)fm->gamma};
     const bool variable = sp.kind != WTP_SPACING_CONSTANT;
@@ -411,11 +448,20 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     compute_bbox<T>(ctx, ib, S_tail, n_move, D, mlo, mhi);
 
     const int32_t rank = ctx->rank, world = ctx->world;
-    const int64_t id_lo = wtp_shard_begin(n_move, rank, world), id_hi = wtp_shard_end(n_move, rank, world);
+    // Sharding. By runs (the default whenever the tiled sweep applies): rank r sweeps the run [gsb, gse) of the
+    // spatially sorted order of each iteration's snapshot — the same tiled kernel as on one GPU — writes (position,
+    // caller index) records, the runs are all-gathered and scattered into caller order on every rank. By caller
+    // range (mesh wall, rebuild_every > 1, k > 32): rank r sweeps the movable ids [id_lo, id_hi) with the general kernel.
+    const bool by_runs = world > 1 && kk <= 32 && prm->rebuild_every == 1 && !mesh && std::getenv("WTP_NO_TILED") == nullptr &&
+                         std::getenv("WTP_REPEL_BY_RANGE") == nullptr;
+    const int64_t id_lo = by_runs ? 0 : wtp_shard_begin(n_move, rank, world), id_hi = by_runs ? n_move : wtp_shard_end(n_move, rank, world);
+    const int64_t gsb = by_runs ? wtp_shard_begin(n_all, rank, world) : 0, gse = by_runs ? wtp_shard_end(n_all, rank, world) : n_all;
+    const int64_t run_slot = (n_all + world - 1) / world;        // records per rank in the all-gather buffer
     const int nblocks = (int)std::min<int64_t>((n_all + SW_WARPS * SW_RUN - 1) / (SW_WARPS * SW_RUN), (int64_t)kNumSMs * 8);
-    // tiled sweep (one thread per point) whenever the list fits one register row and this rank sweeps every point
-    const bool tiled_ok = kk <= 32 && world == 1 && std::getenv("WTP_NO_TILED") == nullptr;
-    const int n_tiled_blocks = tiled_ok ? (int)((n_all + TK_Q - 1) / TK_Q) : 0;
+    // tiled sweep (one thread per point) whenever the list fits one register row and this rank sweeps whole runs
+    const bool tiled_ok = kk <= 32 && (world == 1 || by_runs) && std::getenv("WTP_NO_TILED") == nullptr;
+    const int n_tiled_blocks = tiled_ok ? (int)((gse - gsb + TK_Q - 1) / TK_Q) : 0;
+    P4<T>* C_all = by_runs ? ctx->d_misc2.as<P4<T>>((size_t)run_slot * world) : nullptr;
     // per-CTA partials of the sweep launches of an iteration (general sweep | tiled sweep), folded together
     RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + (size_t)n_tiled_blocks + 256 + 1 + world);
     RepelPartial<T>* d_fold = partials + (size_t)nblocks + (size_t)n_tiled_blocks;   // first stage of a two-stage fold
@@ -434,6 +480,8 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 
     Grid<T> g{};
     int passes = 0;
+    IndexWindow win;
+    bool windowed = false;
     T best_cv_T = t_max<T>();
     int64_t last_impr = 0;
     int it = 1, n_conv = 0;
@@ -456,15 +504,21 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
                 hi[d] = n_fixed > 0 ? std::max(fhi[d], mhi[d]) : mhi[d];
             }
             g = make_grid<T>(n_all, D, lo, hi, ctx->cell_occupancy, 0.0, kk);
-            passes = build_index<T>(ctx, ib, d_snap, n_all, D, g);                                   // :252
-            if (world > 1) {
+            // by runs, constant spacing: only the window of the grid around this rank's run is indexed (grid.cu); the
+            // variable spacings visit the points in the order of the whole sorted set, so they keep the whole index
+            windowed = by_runs && !variable && !ctx->window_off && std::getenv("WTP_NO_WINDOW") == nullptr &&
+                       build_index_window<T>(ctx, ib, d_snap, n_all, D, g, gsb, gse, 2, &win, &passes);
+            if (!windowed) passes = build_index<T>(ctx, ib, d_snap, n_all, D, g);                    // :252
+            if (world > 1 && !by_runs) {
                 build_query_list(ctx, ib, n_all, n_fixed + id_lo, n_fixed + id_hi, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
                 qlist = ctx->d_qlist.get<uint32_t>();
                 nq = (uint32_t)(id_hi - id_lo);
             }
         }
+        const int64_t sb = windowed ? gsb - win.P0 : gsb, se = windowed ? gse - win.P0 : gse;   // this rank's run in positions of the index
         SweepArgs<T> a;
-        a.g = g; a.sorted = ib.sorted.get<P4<T>>(); a.cell_start = ib.cell_start.get<uint32_t>();
+        a.g = g; a.sorted = ib.sorted.get<P4<T>>(); a.cell_start = ib.cells();
+        a.s_begin = (uint32_t)sb; a.s_end = (uint32_t)se; a.C = by_runs ? C_all + (size_t)rank * run_slot : nullptr;
         a.S = d_snap; a.P_old = Pa; a.P_new = Pb; a.s_cur = s_cur; a.spacings = spacings; a.s_const = sp.a;
         a.n_fixed = (uint32_t)n_fixed; a.n_all = (uint32_t)n_all; a.id_lo = (uint32_t)id_lo; a.id_hi = (uint32_t)id_hi;
         a.qlist = qlist; a.nq = nq; a.kk = kk; a.rebuild = rebuild ? 1 : 0;
@@ -477,11 +531,11 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             ScopedPhase ph(ctx->timer, PH_QUERY);
             if (tiled_now) {
                 // tiled sweep over every sorted position, then the general sweep over what it handed back
-                fails = tile_fails(ctx, n_all);
+                fails = tile_fails(ctx, se - sb);
                 SweepArgs<T> at = a;
-                at.qlist = nullptr; at.nq = (uint32_t)n_all; at.partials = partials + nblocks;
-                if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, fails); else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, fails);
-                a.qlist = fails.list; a.nq = (uint32_t)n_all; a.nq_dev = fails.counters;
+                at.qlist = nullptr; at.nq = (uint32_t)(se - sb); at.partials = partials + nblocks;
+                if (n_tiled_blocks > 0) { if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, fails); else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, fails); }
+                a.qlist = fails.list; a.nq = (uint32_t)(se - sb); a.nq_dev = fails.counters;
                 n_partials = nblocks + n_tiled_blocks;
             }
             if (D == 2) launch_sweep<T, 2>(ctx, a, nblocks); else launch_sweep<T, 3>(ctx, a, nblocks);
@@ -504,12 +558,27 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         RepelPartial<T> tot;
         if (world > 1) {
             ScopedPhase ph(ctx->timer, PH_COMM);
-            comm_allgather_rows(ctx, Pb, n_move, (size_t)D * sizeof(T));                            // moved positions of every rank
+            if (by_runs) {   // every rank's run of (position, caller index) records, then into caller order
+                comm_allgather_fixed(ctx, C_all + (size_t)rank * run_slot, C_all, (size_t)run_slot * sizeof(P4<T>));
+                const dim3 grid((unsigned)((run_slot + 255) / 256), (unsigned)world);
+                if (D == 2) scatter_runs_kernel<T, 2><<<grid, 256, 0, st>>>(C_all, (uint32_t)run_slot, (uint32_t)n_all, (uint32_t)world, (uint32_t)n_fixed, Pb);
+                else scatter_runs_kernel<T, 3><<<grid, 256, 0, st>>>(C_all, (uint32_t)run_slot, (uint32_t)n_all, (uint32_t)world, (uint32_t)n_fixed, Pb);
+                LAUNCH_CHECK(ctx);
+            } else {
+                comm_allgather_rows(ctx, Pb, n_move, (size_t)D * sizeof(T));                        // moved positions of every rank
+            }
             comm_allgather_fixed(ctx, d_tot, d_all, sizeof(RepelPartial<T>));
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_all, sizeof(RepelPartial<T>) * world, cudaMemcpyDeviceToHost, st));
             WTP_CUDA_CHECK(cudaStreamSynchronize(st));
             tot = h_tot[0];
             for (int r = 1; r < world; ++r) partial_merge(tot, h_tot[r]);
+            if (tot.missed > 0 && !ctx->window_off) {
+                // some rank's search left its window: every rank sees the same merged count, drops the windows for
+                // good and repeats this iteration on the whole index (nothing of it has been committed yet)
+                ctx->window_off = true;
+                ctx->last_window_missed += (int64_t)tot.missed;
+                continue;
+            }
         } else {
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_tot, sizeof(RepelPartial<T>), cudaMemcpyDeviceToHost, st));
             if (tiled_now) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, fails.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -592,6 +661,8 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     ctx->last_timing.n_leftover_sparse = ctx->last_tile_sparse;
     ctx->last_timing.n_leftover_dense = ctx->last_tile_dense;
     ctx->last_timing.n_leftover_other = ctx->last_tile_other;
+    ctx->last_timing.n_window_points = windowed ? win.M : 0;
+    ctx->last_timing.n_window_missed = ctx->last_window_missed;
 }
 
 template void relax_device<float>(wtp_ctx*, float*, int64_t, int64_t, int, const wtp_spacing*, const float*, const wtp_force*,
