@@ -154,6 +154,30 @@ def test_radius_csr_bit_exact(ctx, oracle, dt, D, r):
     assert np.array_equal(off, roff) and np.array_equal(ind, rind)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("D", [2, 3])
+def test_radius_tiled_and_leftover_rows(ctx, oracle, dt, D):
+    """Rows around the capacity of the tiled fill's per-thread lists (about 100 hits): short rows are merged in the
+    tiled pass, longer ones go to the general kernel; graded density mixes both in one call. Lattice points give
+    exact distance ties at the radius (inclusive) and rows whose runs interleave."""
+    rng = np.random.default_rng(11 + D)
+    n = 40000
+    graded = (rng.random((n, D)) ** 2).astype(dt)                        # density varies ~100x across the domain
+    r = (60.0 / n) ** (1.0 / D) * (0.55 if D == 2 else 0.6)
+    off, ind = ctx.radius(graded, r)
+    roff, rind = oracle.radius(graded, r)
+    assert np.array_equal(off, roff) and np.array_equal(ind, rind)
+    rows = np.diff(off)
+    assert rows.max() > 130 and np.median(rows) < 100                    # both sides of the list capacity
+    m = 60 if D == 2 else 16
+    axes = [np.arange(m, dtype=np.float64) / 8.0] * D                    # spacing 0.125: exactly representable
+    lattice = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, D)
+    lattice = lattice[rng.permutation(len(lattice))].astype(dt)
+    off, ind = ctx.radius(lattice, 0.25)                                 # neighbours at exactly r are hits (d2 <= r2)
+    roff, rind = oracle.radius(lattice, 0.25)
+    assert np.array_equal(off, roff) and np.array_equal(ind, rind)
+
+
 def test_radius_known_answer_and_edges(ctx, oracle, known):
     g = known["radius_grid5x5"]                                      # test/topology.jl:46-52
     for dt in (np.float64, np.float32):

@@ -44,8 +44,9 @@ static void radius_count_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, 
     IndexBuffers& ib = ctx->index[0];
     double lo[3], hi[3];
     compute_bbox<T>(ctx, ib, d_pts, N, D, lo, hi);
-    // cell size >= r (with margin) so the 3^D block around a query contains every hit
-    Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy, (double)r * 1.001, 0);
+    // cell size >= r (with margin) so the 3^D block around a query contains every hit; as close to r as possible
+    // (fewer candidates per hit), never below two points per cell on average (tiny radii)
+    Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy > 0 ? ctx->cell_occupancy : 2.0, (double)r * 1.001, 0);
     int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
     const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
     const uint32_t* qlist = nullptr;

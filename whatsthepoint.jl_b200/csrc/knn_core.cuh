@@ -214,6 +214,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
+// shared-memory accesses that must keep their program order among themselves (volatile asm): per-thread lists that
+// are written and read back through differently typed views
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return (uint32_t)v;
+}
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v)); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v)); }
+
 // row offsets of the 3^D block, centre row first, then face rows, then corner rows
 __device__ __forceinline__ int row_dy(int t) { return (int)((0x22161u >> (2 * t)) & 3u) - 1; }   // 0,-1,+1,0,0,-1,+1,-1,+1
 __device__ __forceinline__ int row_dz(int t) { return (int)((0x28215u >> (2 * t)) & 3u) - 1; }   // 0,0,0,-1,+1,-1,-1,+1,+1

@@ -86,10 +86,10 @@ __device__ __forceinline__ void append_if_le(uint32_t& addr, uint32_t t, double 
 //       ... read ts.tile[ts.my[r]], r < K, check the order with ts.verify() ...
 //       ts.report(fail, ...);
 //   }
-template <class T, int D>
+template <class T, int D, int CAP_ = tk_cap<T>()>
 struct TileSearch {
     static constexpr int NROWS = D == 3 ? 9 : 3;
-    static constexpr int CAP = tk_cap<T>();
+    static constexpr int CAP = CAP_;                // records of the staged slab
     struct Shared {
         uint64_t bar;
         uint32_t rowid[TK_Q];
@@ -286,27 +286,54 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
     const int k_out = K1 - drop;
     int64_t* __restrict__ out_idx = static_cast<int64_t*>(out_idx_v);
     uint32_t* __restrict__ out_idx32 = static_cast<uint32_t*>(out_idx_v);
+    // Rows leave the CTA a row at a time: each thread parks the caller indices of its K best in its own list (as
+    // 32-bit words over the 16-bit slots it has consumed), then the lanes of the warp write one row per store
+    // instruction, k contiguous entries. A thread storing its own row entry by entry would touch 32 scattered rows
+    // (32 sectors, 32 pages) per store instruction instead of one. Rows with distances (searchdists) and lists longer
+    // than the slot area keep the per-thread stores.
+    const uint32_t my_s = smem_u32(ts.my);                                              // this thread's list, as 16-bit slots and as K1 words
+    const uint32_t warp_s = my_s - (uint32_t)ts.lane * (uint32_t)(TK_LSTRIDE * 2);
+    const bool coop = K1 <= TK_LSTRIDE / 2 && out_dist == nullptr;                       // the row fits the list as words
     while (ts.next_group()) {
         int status = ts.select(K1);
+        int64_t row = 0;
         if (status == TK_OK) {
-            // re-read the K best in order, check strict canonical order (the images of two keys collide only when
-            // their d2 agree to ~17 bits, or on exact ties) and write the row
-            const int64_t row = rows.row(ts.j, idx_of(ts.q)) * k_out;
-            Key<T> prev = Key<T>::make((T)0, 0u);
+            // re-read the K best from the last to the first, check strict canonical order (the images of two keys
+            // collide only when their d2 agree to ~17 bits, or on exact ties) and park the indices: word r overwrites
+            // slots 2r and 2r+1, both already consumed on the way down
+            row = rows.row(ts.j, idx_of(ts.q)) * k_out;
+            asm volatile("" ::: "memory");                                                // select()'s plain stores to the list come first
+            Key<T> next = Key<T>::make((T)0, 0u), kth = next;
             bool ok = true;
 #pragma unroll 2
-            for (int r = 0; r < K1; ++r) {
-                const P4<T> p = lds_p4(ts.tile + ts.my[r]);
+            for (int r = K1 - 1; r >= 0; --r) {
+                const P4<T> p = lds_p4(ts.tile + lds_u16(my_s + 2u * (uint32_t)r));
                 const Key<T> key = Key<T>::make(dist2_rn<T, D>(ts.q.x, ts.q.y, ts.q.z, p.x, p.y, p.z), idx_of(p));
-                if (r > 0) ok = ok && prev.less(key);
-                prev = key;
-                if (r >= drop) {
+                if (r == K1 - 1) kth = key; else ok = ok && key.less(next);
+                next = key;
+                if (coop) sts_u32(my_s + 4u * (uint32_t)r, key.idx());
+                else if (r >= drop) {
                     if (out32) out_idx32[row + r - drop] = key.idx() + 1u;
                     else out_idx[row + r - drop] = (int64_t)key.idx() + 1;
                     if (out_dist) out_dist[row + r - drop] = sqrt(key.d2());
                 }
             }
-            status = ts.accept(ok, prev);
+            status = ts.accept(ok, kth);
+        }
+        if (coop) {
+            __syncwarp();
+            unsigned todo = __ballot_sync(FULL, status == TK_OK);
+            while (todo) {
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int64_t row_s = __shfl_sync(FULL, row, src);
+                if (ts.lane < k_out) {
+                    const uint32_t v = lds_u32(warp_s + (uint32_t)src * (uint32_t)(TK_LSTRIDE * 2) + 4u * (uint32_t)(ts.lane + drop)) + 1u;
+                    if (out32) out_idx32[row_s + ts.lane] = v;
+                    else out_idx[row_s + ts.lane] = (int64_t)v;
+                }
+            }
+            __syncwarp();                                                                 // the lists are free for the next group
         }
         ts.report(status, fails);
     }
