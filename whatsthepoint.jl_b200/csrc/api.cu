@@ -172,6 +172,45 @@ void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_
     ctx->last_timing.n_window_missed = ctx->last_window_missed;
 }
 
+// A device array of 4-byte indices -> the caller's int64 host array: chunk by chunk into a pinned staging ring on the
+// copy stream, widened on the host pool while the next chunks are on the wire (4 B per entry cross PCIe instead of 8,
+// and the caller's array does not have to be pinned). The data must be complete on ctx->stream when this is called.
+void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst) {
+    if (n == 0) return;
+    constexpr int S = 3;                                     // staging slots
+    constexpr size_t SLOT = (size_t)32 << 20;                // bytes per slot
+    if (!ctx->h_stage) {
+        WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, S * SLOT));
+        ctx->h_stage_slot_bytes = SLOT;
+    }
+    if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());
+    WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0));
+    const size_t per = SLOT / sizeof(uint32_t);
+    const size_t n_chunks = (n + per - 1) / per;
+    auto enqueue_copy = [&](size_t c) {
+        const size_t cb = c * per, ce = std::min(n, cb + per);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(ctx->h_stage) + (c % S) * SLOT, d_src + cb, (ce - cb) * sizeof(uint32_t),
+                                       cudaMemcpyDeviceToHost, ctx->copy_stream));
+        WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[c % 4], ctx->copy_stream));
+    };
+    for (size_t c = 0; c < std::min<size_t>(2, n_chunks); ++c) enqueue_copy(c);   // two copies ahead of the chunk being widened
+    for (size_t c = 0; c < n_chunks; ++c) {
+        if (c + 2 < n_chunks) enqueue_copy(c + 2);                                // slots c, c+1, c+2 are distinct
+        WTP_CUDA_CHECK(cudaEventSynchronize(ctx->ev_copied[c % 4]));
+        const size_t cb = c * per, ce = std::min(n, cb + per);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<char*>(ctx->h_stage) + (c % S) * SLOT);
+        int64_t* dst = h_dst + cb;
+        const size_t total = ce - cb;
+        ctx->pool->run([&](int part, int parts) {
+            const size_t a = (total * part / parts) & ~(size_t)3, b = part + 1 == parts ? total : ((total * (part + 1) / parts) & ~(size_t)3);
+            widen_u32_to_i64(src + a, dst + a, b - a);
+        });
+    }
+    WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
+    WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
+}
+
 // ------------------------------------------------------------------- k-NN
 // Index build + queries. Single context: every point is a query and rows go by caller index. Sharded context
 // (wtp_comm_init): this rank answers the contiguous run [sb, se) of the spatially sorted order (the sorted set is

@@ -36,6 +36,17 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 
 namespace wtp {
 
+void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst);   // api.cu
+
+__global__ void __launch_bounds__(256) narrow_indices_kernel(const int64_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (uint32_t)in[i];
+}
+static void narrow_indices(wtp_ctx* ctx, const int64_t* d_in, size_t n, uint32_t* d_out) {
+    const unsigned nb = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 16);
+    narrow_indices_kernel<<<nb, 256, 0, ctx->stream>>>(d_in, n, d_out);
+    LAUNCH_CHECK(ctx);
+}
+
 // ----------------------------------------------------------------- radius
 template <class T>
 static void radius_count_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, T r, int64_t* d_offsets) {
@@ -149,7 +160,14 @@ int32_t wtp_radius_fill(wtp_ctx* ctx, int64_t* indices) {
         else radius_fill_device<float>(ctx, ctx->d_offsets.get<int64_t>(), d_ind);
         {
             ScopedPhase ph(ctx->timer, PH_D2H);
-            WTP_CUDA_CHECK(cudaMemcpyAsync(indices, d_ind, (size_t)st.nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            if (st.nnz < ((int64_t)4 << 20)) {
+                WTP_CUDA_CHECK(cudaMemcpyAsync(indices, d_ind, (size_t)st.nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            } else {
+                // large result: 4 bytes per entry cross PCIe, widened into the caller's array by the host pool (api.cu)
+                uint32_t* d_ind32 = ctx->d_out_idx.as<uint32_t>((size_t)st.nnz);
+                narrow_indices(ctx, d_ind, (size_t)st.nnz, d_ind32);
+                d2h_widen_u32(ctx, d_ind32, (size_t)st.nnz, indices);
+            }
         }
         ctx->timer.end_total();
         WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -70,13 +70,20 @@ __device__ __forceinline__ T prefilter_radius2(const Grid<T>& g, uint32_t block_
 }
 
 // predicated append used by the filter: if (d <= r) { *(u16*)addr = t; addr += 2; }
+// TK_APPEND_NOCLOBBER: the asm does not claim to touch memory, so the tile reads of later candidates may be scheduled
+// across it (they never alias the lists); the caller then fences once after the sweep, before the lists are read.
+#ifdef TK_APPEND_NOCLOBBER
+#define TK_APPEND_CLOBBER
+#else
+#define TK_APPEND_CLOBBER : "memory"
+#endif
 __device__ __forceinline__ void append_if_le(uint32_t& addr, uint32_t t, float d, float r) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %2, %3;\n\t@p st.shared.u16 [%0], %1;\n\t@p add.u32 %0, %0, 2;\n\t}"
-                 : "+r"(addr) : "h"((uint16_t)t), "f"(d), "f"(r) : "memory");
+                 : "+r"(addr) : "h"((uint16_t)t), "f"(d), "f"(r) TK_APPEND_CLOBBER);
 }
 __device__ __forceinline__ void append_if_le(uint32_t& addr, uint32_t t, double d, double r) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %2, %3;\n\t@p st.shared.u16 [%0], %1;\n\t@p add.u32 %0, %0, 2;\n\t}"
-                 : "+r"(addr) : "h"((uint16_t)t), "d"(d), "d"(r) : "memory");
+                 : "+r"(addr) : "h"((uint16_t)t), "d"(d), "d"(r) TK_APPEND_CLOBBER);
 }
 
 // The search state of one thread (= one query) of a tiled CTA. Usage (all threads of the CTA together):
@@ -223,6 +230,7 @@ struct TileSearch {
                 addr = min(addr, lim);                     // slots LCAP, LCAP+1 absorb an overflowing list
             }
         }
+        asm volatile("" ::: "memory");                     // the appends are done before the lists are read
         const uint32_t cnt = (addr - my_s) >> 1;
         if (cnt < (uint32_t)K) return TK_SPARSE;
         if (cnt > (uint32_t)TK_LCAP) return TK_DENSE;

@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
         }
         if (knn.missed) acc.missed += 1;
         const T nn = found ? sqrt(nn_d2) : t_max<T>();
-        const T s_mon = a.spacings[self];   // spacing as of the last rebuild (:251, :379)
+        const T s_mon = a.s_cur ? a.spacings[self] : a.s_const;   // spacing as of the last rebuild (:251, :379); a constant spacing needs no gather
         const T u = nn / s_mon;
         acc.s1 += (double)u; acc.s2 += (double)(u * u); acc.n += 1;
         acc.max_force = fs > acc.max_force ? fs : acc.max_force;
@@ -302,7 +302,7 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
                     if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
                 }
                 const T nn = nn_idx != 0xffffffffu ? sqrt(nn_d2) : t_max<T>();
-                const T u = nn / a.spacings[self];                            // spacing as of the last rebuild (:251, :379)
+                const T u = nn / (a.s_cur ? a.spacings[self] : a.s_const);     // spacing as of the last rebuild (:251, :379); a constant spacing needs no gather
                 RepelPartial<T> one;
                 one.s1 = (double)u; one.s2 = (double)(u * u); one.n = 1; one.missed = 0; one.max_force = fs;
                 one.min_nn = nn; one.min_id = id; one.min_nn_idx = nn_idx;
