@@ -47,7 +47,7 @@ typedef enum {
     WTP_OK = 0,
     WTP_ERR_BAD_ARG = 1,       /* null pointer, D not in {2,3}, negative size ...       -> ArgumentError */
     WTP_ERR_K_TOO_LARGE = 2,   /* k+1 > N (upstream knn throws), or k above WTP_MAX_K   -> ArgumentError */
-    WTP_ERR_UNSUPPORTED = 3,   /* user force model / spacing callable / kick / deposit   -> ErrorException */
+    WTP_ERR_UNSUPPORTED = 3,   /* user force model / spacing callable / constrain closure -> ErrorException */
     WTP_ERR_CUDA = 4,          /* CUDA runtime failure (message has the CUDA error)     */
     WTP_ERR_NCCL = 5,
     WTP_ERR_OOM = 6,
@@ -217,7 +217,7 @@ typedef struct {
     int64_t n_tri;
     double bbox_min[3], bbox_max[3]; /* index.bbox_min / bbox_max (domain_bounds)                 */
     double offset_dist;            /* 1e-6 * |bbox_max - bbox_min|  (src/repel.jl:150)            */
-    const uint8_t* is_bnd;         /* n_move flags (src/repel.jl:155)                             */
+    const uint8_t* is_bnd;         /* n_move flags (src/repel.jl:155); rewritten when deposit_ratio > 0 */
     int64_t* tri_indices;          /* out, n_move, 1-based landing triangle (0 = untouched)       */
     uint8_t* escaped;              /* out, n_move                                                 */
 } wtp_wall_mesh;
@@ -237,6 +237,13 @@ typedef struct {
     double tol, cv_target;
     int64_t n_protected;           /* snapshot-global count of points a kick avoids: n_boundary (:85, :172) */
     uint64_t kick_seed;
+    double deposit_ratio;          /* > 0 (mesh wall, n_fixed = 0, one GPU): _deposit_escaped! after every sweep
+                                      (src/repel.jl:161-168, 328, 483-514): escaped volume points are projected onto
+                                      their nearest triangle and become boundary points unless a boundary point
+                                      already sits within deposit_ratio * spacing of the landing site. Projection,
+                                      spacing and the snapshot k-NN of the landing sites run on the device, batched;
+                                      the occupancy sweep is serial by design and runs on the host in index order.
+                                      wall->is_bnd is then an in/out array. */
 } wtp_repel_params;
 
 enum { WTP_STOP_MAX_ITERS = 0, WTP_STOP_TOL = 1, WTP_STOP_CV_TARGET = 2, WTP_STOP_STALL = 3 };

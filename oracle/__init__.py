@@ -44,7 +44,7 @@ class RepelParams(C.Structure):
                 ("want_trace", C.c_int32), ("reserved", C.c_int32),
                 ("alpha_lo", C.c_double), ("alpha_max", C.c_double),
                 ("tol", C.c_double), ("cv_target", C.c_double),
-                ("n_protected", C.c_int64), ("kick_seed", C.c_uint64)]
+                ("n_protected", C.c_int64), ("kick_seed", C.c_uint64), ("deposit_ratio", C.c_double)]
 
 
 class RepelResult(C.Structure):
@@ -218,13 +218,14 @@ def spacing_eval(sp: Spacing, pts):
 
 
 def repel(snap, n_fixed, sp: Spacing, f: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
-          stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, threads=0, mesh=None, is_bnd=None):
+          stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, threads=0, mesh=None, is_bnd=None,
+          deposit_ratio=0.0):
     """_relax! on snap = [fixed head; movable tail]. Returns (new_snap, conv, result dict, trace)."""
     snap = np.array(_pts(snap), copy=True)
     n_all, d = snap.shape
     n_move = n_all - n_fixed
     prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0, 0,
-                      float(alpha_lo), float(alpha_max), float(tol), float(cv_target))
+                      float(alpha_lo), float(alpha_max), float(tol), float(cv_target), 0, 0, float(deposit_ratio))
     conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
     tr = (TraceEntry * max(max_iters, 1))() if trace else None
     res = RepelResult()
@@ -235,7 +236,7 @@ def repel(snap, n_fixed, sp: Spacing, f: Force, *, k=21, max_iters=1000, tol=1e-
         tri_idx, esc = np.zeros(n_move, dtype=np.int64), np.zeros(n_move, dtype=np.uint8)
         w, keep = wall_from(mesh, snap.dtype, flags, tri_idx, esc)
         wall = C.byref(w)
-        repel.last_wall = dict(tri_indices=tri_idx, escaped=esc)
+        repel.last_wall = dict(tri_indices=tri_idx, escaped=esc, is_bnd=flags)
     rc = getattr(lib(), "wtpo_repel_" + _sfx(snap.dtype))(
         snap.ctypes.data_as(C.c_void_p), C.c_int64(n_fixed), C.c_int64(n_move), C.c_int32(d),
         C.byref(sp), C.byref(f), C.byref(prm), wall, conv.ctypes.data_as(C.c_void_p),

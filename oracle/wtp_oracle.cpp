@@ -327,6 +327,7 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
     if (prm->kick_after > 0) return WTP_ERR_UNSUPPORTED;                     // randn, :430
     if ((prm->wall == WTP_WALL_MESH) != (wall != nullptr)) return WTP_ERR_BAD_ARG;
     if (wall && D != 3) return WTP_ERR_BAD_ARG;
+    if (prm->deposit_ratio < 0 || (prm->deposit_ratio > 0 && (!wall || n_fixed != 0))) return WTP_ERR_BAD_ARG;   // :143, :172
     const int kk = int(std::min<int64_t>(prm->k, n_all));                   // :208
     Spacing<T, D> spacing;
     spacing.init(sp_in);
@@ -436,6 +437,33 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
             }
         }
         if (stopped) break;
+        if (wall && D == 3 && prm->deposit_ratio > 0) {                        // deposit!(p, tree, i) :328 -> _deposit_escaped! :483-514
+            uint8_t* is_bnd = const_cast<uint8_t*>(wall->is_bnd);
+            const int kq = int(std::min<int64_t>(prm->k, n_move));            // min(k, length(p_cur)) :163
+            std::vector<Cand<T>> near(size_t(kq) > 0 ? size_t(kq) : 1);
+            for (int64_t id = 0; id < n_move; ++id) {                          // serial on purpose
+                if (!wall->escaped[id]) continue;
+                wall->escaped[id] = 0;
+                if (is_bnd[id]) continue;
+                T here[3] = {p[size_t(id) * D], p[size_t(id) * D + 1], p[size_t(id) * D + (D - 1)]}, site[3];
+                const int64_t tri = mesh_project<T>(wall, here, site);        // :495
+                if (tri == 0) continue;
+                const double thr = prm->deposit_ratio * double(spacing(site));   // :501 (Float64 ratio times T spacing)
+                tree.knn(site, kq, near.data());                              // the sweep's snapshot tree :502
+                bool occupied = false;
+                for (int j = 0; j < kq && !occupied; ++j) {                   // :503-506 (n_fixed = 0: snapshot index = movable id)
+                    const int64_t jj = near[size_t(j)].idx;
+                    if (jj == id || !is_bnd[jj]) continue;
+                    const T* pj = &p[size_t(jj) * D];
+                    const T dx = pj[0] - site[0], dy = pj[1] - site[1], dz = pj[D - 1] - site[2];
+                    occupied = double(std::sqrt((dx * dx + dy * dy) + dz * dz)) < thr;
+                }
+                if (occupied) continue;
+                for (int d = 0; d < 3; ++d) p[size_t(id) * D + d] = site[d];  // :508-510
+                is_bnd[id] = 1;
+                wall->tri_indices[id] = tri;
+            }
+        }
         if (double(conv[n_conv - 1]) < prm->tol) { stop = WTP_STOP_TOL; break; }   // :329-332
         ++it;
     }

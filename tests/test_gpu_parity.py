@@ -417,6 +417,32 @@ def test_repel_mesh_wall_10_iterations(ctx, oracle, pkg, dt, skind):
     assert oracle.mesh_isinside(sph, out[~is_bnd]).all()                                   # test/repel.jl:31-37
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_repel_deposit_matches_oracle(ctx, oracle, pkg, dt):
+    """deposit_ratio > 0 (src/repel.jl:161-168, 328, 483-514): same conversions, landing triangles and positions as the
+    serial CPU restatement; cv_target stop before any deposit; deposition needs the mesh-wall method."""
+    from test_oracle_golden import _deposit_problem
+    sph, snap, is_bnd = _deposit_problem(pkg, np.random.default_rng(9), dt)
+    nb = int(is_bnd.sum())
+    h = 0.13
+    sp, _ = ctx.make_spacing("constant", h)
+    osp, _ = oracle.make_spacing("constant", h)
+    kw = dict(max_iters=12, tol=0.0, stall_after=0, alpha_lo=h / 2000, alpha_max=h / 2, mesh=sph, is_bnd=is_bnd, deposit_ratio=0.5)
+    out, conv, res, _ = ctx.repel(snap, 0, sp, ctx.make_force("clipped", dt(0.2)), **kw)
+    wall = ctx.last_wall
+    oout, oconv, ores, _ = oracle.repel(snap, 0, osp, oracle.make_force("clipped", dt(0.2)), **kw)
+    owall = oracle.repel.last_wall
+    assert wall["is_bnd"].sum() > nb                                                          # the boundary grew (test/repel.jl:349)
+    assert np.array_equal(wall["is_bnd"], owall["is_bnd"]) and np.array_equal(wall["escaped"], owall["escaped"])
+    assert (wall["tri_indices"] == owall["tri_indices"]).mean() > 0.999
+    assert np.abs(out.astype(np.float64) - oout).max() <= TOL[dt] * h
+    np.testing.assert_allclose(conv, oconv, rtol=1e-4 if dt == np.float32 else 1e-9)
+    stopped, _, sres, _ = ctx.repel(snap, 0, sp, ctx.make_force("clipped", dt(0.2)), cv_target=10.0, **kw)
+    assert sres["stop_reason"] == "cv_target" and np.array_equal(stopped, snap) and ctx.last_wall["is_bnd"].sum() == nb
+    with pytest.raises(pkg.WtpArgumentError):                                                 # not the mesh-wall method
+        ctx.repel(snap, nb, sp, ctx.make_force("clipped", dt(0.2)), max_iters=2, alpha_lo=h / 2000, alpha_max=h / 20, deposit_ratio=0.5)
+
+
 def test_repel_octree_api(ctx, pkg, oracle):
     sph, snap, is_bnd = _wall_problem(pkg, np.random.default_rng(22), np.float64, n_vol=2500, sub=2)
     nb = int(is_bnd.sum())
@@ -430,8 +456,12 @@ def test_repel_octree_api(ctx, pkg, oracle):
     assert pkg.isinside(out.volume.points, sph, ctx=ctx).all()                              # :35-37
     n = out.boundary.surfaces["boundary"].normals
     np.testing.assert_allclose(np.linalg.norm(n, axis=1), 1.0, atol=1e-12)
-    with pytest.raises(pkg.WtpError):
-        pkg.repel(cloud, pkg.ConstantSpacing(0.11), sph, deposit_ratio=0.5, ctx=ctx)
+    dep = pkg.repel(cloud, pkg.ConstantSpacing(0.11), sph, max_iters=6, stall_after=0, tol=0.0, deposit_ratio=0.5, alpha=0.05, ctx=ctx)
+    assert len(dep) == len(cloud) and len(dep.boundary) >= nb                              # conversions conserve the total (test/repel.jl:348)
+    a = dep.boundary.surfaces["boundary"].areas
+    assert np.allclose(a[:nb], 0.01) and np.allclose(a[nb:], 0.11 ** 2)                    # deposited points get spacing^2 (:617)
+    with pytest.raises(TypeError):
+        pkg.repel(cloud, pkg.ConstantSpacing(0.11), deposit_ratio=0.5, ctx=ctx)             # keyword of the octree method only
     with pytest.raises(TypeError):
         pkg.repel(pkg.PointCloud(snap[:50, :2], snap[50:200, :2]), pkg.ConstantSpacing(0.1), sph, ctx=ctx)
 

@@ -46,7 +46,7 @@ class RepelParams(C.Structure):
                 ("want_trace", C.c_int32), ("reserved", C.c_int32),
                 ("alpha_lo", C.c_double), ("alpha_max", C.c_double),
                 ("tol", C.c_double), ("cv_target", C.c_double),
-                ("n_protected", C.c_int64), ("kick_seed", C.c_uint64)]
+                ("n_protected", C.c_int64), ("kick_seed", C.c_uint64), ("deposit_ratio", C.c_double)]
 
 
 class RepelResult(C.Structure):
@@ -268,7 +268,7 @@ class Context:
 
     def repel(self, snap, n_fixed: int, sp: Spacing, force: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
               stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, mesh=None, is_bnd=None,
-              n_protected=None, kick_seed=0):
+              n_protected=None, kick_seed=0, deposit_ratio=0.0):
         """_relax! on snap = [fixed head; movable tail] (host array, copied). Returns
         (new_snap, conv, result dict, trace list | None)."""
         snap = np.array(_as_points(snap), copy=True)
@@ -276,7 +276,7 @@ class Context:
         n_move = n_all - n_fixed
         prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0, 0,
                           float(alpha_lo), float(alpha_max), float(tol), float(cv_target),
-                          int(n_fixed if n_protected is None else n_protected), int(kick_seed))
+                          int(n_fixed if n_protected is None else n_protected), int(kick_seed), float(deposit_ratio))
         conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
         tr = (TraceEntry * max(max_iters, 1))() if trace else None
         res = RepelResult()
@@ -287,7 +287,7 @@ class Context:
             tri_idx, esc = np.zeros(n_move, dtype=np.int64), np.zeros(n_move, dtype=np.uint8)
             w, keep = mesh.astype(snap.dtype).wall(flags, tri_idx, esc)
             wall = C.byref(w)
-            self.last_wall = dict(tri_indices=tri_idx, escaped=esc)
+            self.last_wall = dict(tri_indices=tri_idx, escaped=esc, is_bnd=flags)   # is_bnd: rewritten by deposition
         fn = getattr(self._lib, "wtp_repel_" + _sfx(snap.dtype))
         self._check(fn(self._h, _vp(snap), C.c_int64(n_fixed), C.c_int64(n_move), C.c_int32(d), C.byref(sp), C.byref(force),
                        C.byref(prm), wall, _vp(conv), tr, C.byref(res)))

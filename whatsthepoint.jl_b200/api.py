@@ -428,8 +428,8 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         raise WtpError(3, "repel(cloud, spacing, octree): octree must be a TriangleOctree (only its TriangleIndex arrays cross the C ABI)")
     if deposit_ratio < 0:
         raise WtpArgumentError(1, "deposit_ratio must be ≥ 0")                     # src/repel.jl:143
-    if deposit_ratio > 0:
-        raise WtpError(3, "deposit_ratio > 0 (_deposit_escaped!, src/repel.jl:483-514, serial by design) is not provided by this build")
+    if deposit_ratio > 0 and octree is None:
+        raise TypeError("deposit_ratio belongs to repel(cloud, spacing, octree)")      # keyword of the 3-argument method only, :138
     if not isinstance(spacing, AbstractSpacing):
         raise WtpError(3, "only ConstantSpacing, LogLike and BoundaryLayerSpacing can cross the C ABI (no CPU fallback)")
     ctx = ctx or default_context()
@@ -453,7 +453,8 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
     new_snap, conv, res, tr = ctx.repel(snap, 0 if octree is not None else n_bnd, sp, fm._abi(), k=k, max_iters=max_iters, tol=tol,
                                         rebuild_every=rebuild_every, stall_after=stall_after, cv_target=cv_target,
                                         alpha_lo=alpha_min, alpha_max=alpha, kick_after=kick_after, trace=trace is not None,
-                                        mesh=octree, is_bnd=is_bnd, n_protected=n_bnd, kick_seed=kick_seed)
+                                        mesh=octree, is_bnd=is_bnd, n_protected=n_bnd, kick_seed=kick_seed,
+                                        deposit_ratio=deposit_ratio if octree is not None else 0.0)
     del keep
     if convergence is not None:
         convergence.extend(float(c) for c in conv)                                 # :88
@@ -470,7 +471,8 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         log.warning("Node repel reached maximum iterations")
     if octree is not None:
         keep_mask = _cull(new_snap, spacing, cull_ratio, ctx) if cull_ratio > 0 else None   # :179
-        out = _reconstruct_cloud(cloud, new_snap, ctx.last_wall["tri_indices"], is_bnd, n_bnd, octree, keep_mask)
+        is_bnd = ctx.last_wall["is_bnd"].astype(bool)                              # deposition converts volume points (:152-155, :509)
+        out = _reconstruct_cloud(cloud, new_snap, ctx.last_wall["tri_indices"], is_bnd, n_bnd, octree, keep_mask, spacing, ctx)
         out.repel_result = res
         out.escaped = ctx.last_wall["escaped"].astype(bool)
         return out
@@ -499,10 +501,10 @@ def _cull(pts: np.ndarray, spacing: AbstractSpacing, ratio, ctx) -> np.ndarray:
 
 
 def _reconstruct_cloud(cloud: PointCloud, p: np.ndarray, tri_indices: np.ndarray, is_bnd: np.ndarray, n_boundary: int, octree,
-                       keep: np.ndarray | None = None) -> PointCloud:
+                       keep: np.ndarray | None = None, spacing=None, ctx=None) -> PointCloud:
     """src/repel.jl:590-629: kept points are split by is_bnd into one `boundary` surface and the
     volume; projected boundary points take the landing triangle's normal, imported ones keep
-    their area."""
+    their area, deposited ones (id > n_boundary) get spacing²."""
     if keep is None:
         keep = np.ones(len(p), dtype=bool)
     normals = [s.normals for s in cloud.boundary.surfaces.values()]
@@ -516,7 +518,15 @@ def _reconstruct_cloud(cloud: PointCloud, p: np.ndarray, tri_indices: np.ndarray
     if orig_normals is not None:
         keep_orig = (tri == 0) & (b < n_boundary)
         new_normals[keep_orig] = orig_normals[b[keep_orig]]
-    new_areas = orig_areas[b] if orig_areas is not None else None
+    new_areas = None
+    if orig_areas is not None:
+        new_areas = np.empty(len(b), dtype=orig_areas.dtype)
+        imported = b < n_boundary
+        new_areas[imported] = orig_areas[b[imported]]
+        if (~imported).any():                                                      # deposited points: spacing(p[id])^2 (:617)
+            sp, keepalive = spacing._abi(p.dtype)
+            new_areas[~imported] = (ctx or default_context()).spacing_eval(sp, p[b[~imported]]) ** 2
+            del keepalive
     surf = PointSurface(p[b], new_normals, new_areas)
     return PointCloud(PointBoundary({"boundary": surf}), PointVolume(p[~is_bnd & keep]), NoTopology())
 

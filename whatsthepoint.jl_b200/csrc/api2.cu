@@ -241,6 +241,8 @@ static int32_t repel_host(wtp_ctx* ctx, T* snap, int64_t n_fixed, int64_t n_move
                                        cudaMemcpyDeviceToHost, ctx->stream));
         if (mesh && wall->tri_indices) WTP_CUDA_CHECK(cudaMemcpyAsync(wall->tri_indices, mesh->tri_idx.get<int64_t>(), (size_t)n_move * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (mesh && wall->escaped) WTP_CUDA_CHECK(cudaMemcpyAsync(wall->escaped, mesh->escaped.get<uint8_t>(), (size_t)n_move, cudaMemcpyDeviceToHost, ctx->stream));
+        if (mesh && prm->deposit_ratio > 0)   // deposition converts volume points into boundary points (src/repel.jl:509)
+            WTP_CUDA_CHECK(cudaMemcpyAsync(const_cast<uint8_t*>(wall->is_bnd), mesh->is_bnd.get<uint8_t>(), (size_t)n_move, cudaMemcpyDeviceToHost, ctx->stream));
     }
     ctx->timer.end_total();
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

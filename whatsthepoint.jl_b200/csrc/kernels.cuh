@@ -48,6 +48,9 @@ template <class T>
 void knn_query_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int D, int K1, int drop_first,
                      int64_t s_begin, int64_t s_end, const RowMap& rows, void* d_out_idx, T* d_out_dist,
                      unsigned long long* d_expanded_counter, bool out32 = false);
+// K nearest index points (1-based caller indices, uint32 rows of K, ascending (d2, index)) of n_q arbitrary query points
+template <class T>
+void knn_points(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int D, int K, const T* d_q, int64_t n_q, uint32_t* d_out_idx32);
 // caller indices (1-based) of the sorted positions [s_begin, s_end)
 void owned_ids(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, int64_t* d_ids);
 

@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
                                                           const uint32_t* __restrict__ cell_start,
                                                           const uint32_t* __restrict__ qlist, uint32_t nq, const uint32_t* __restrict__ nq_dev,
                                                           const RowMap rows, int K1, int drop, void* __restrict__ out_idx_v, int out32,
-                                                          T* __restrict__ out_dist, unsigned long long* __restrict__ expanded) {
+                                                          T* __restrict__ out_dist, unsigned long long* __restrict__ expanded,
+                                                          const T* __restrict__ ext_q) {
     constexpr int CAP = knn_tile_cap<T, KPL>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t s_bar[KNN_WARPS];
@@ -43,11 +44,14 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
     int64_t* __restrict__ out_idx = static_cast<int64_t*>(out_idx_v);     // ABI layout: int64, 1-based
     uint32_t* __restrict__ out_idx32 = static_cast<uint32_t*>(out_idx_v); // staging layout of the host entry points (widened on the host)
     auto answer = [&](uint32_t j) {
-        const P4<T> q = load_p4<T>(sorted + j);
+        // the query: record j of the index, or (ext_q) point j of a separate array, whose row is row j
+        P4<T> q;
+        if (ext_q) { q.x = ext_q[(size_t)j * D]; q.y = ext_q[(size_t)j * D + 1]; q.z = D == 3 ? ext_q[(size_t)j * D + (D - 1)] : (T)0; q.w = idx_bits((T)0, j); }
+        else q = load_p4<T>(sorted + j);
         const int rings = s.run(q.x, q.y, q.z, K1);
         if (rings > 1 && lane == 0 && expanded) atomicAdd(expanded, 1ULL);
         if (s.missed && lane == 0 && expanded) atomicAdd(expanded + 1, 1ULL);   // windowed index: the caller repeats the call on the whole index
-        const int64_t row = rows.row(j, idx_of(q)) * k_out;
+        const int64_t row = (ext_q ? (int64_t)j : rows.row(j, idx_of(q))) * k_out;
 #pragma unroll
         for (int e = 0; e < KPL; ++e) {
             const int r = e * 32 + lane;
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
 template <class T, int D, int KPL>
 static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, const P4<T>* sorted, const uint32_t* cs,
                            const uint32_t* d_qlist, int64_t nq, const uint32_t* d_nq, const RowMap& rows, int K1, int drop,
-                           void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
+                           void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp, const T* d_ext_q = nullptr) {
     constexpr size_t smem = (size_t)knn_tile_cap<T, KPL>() * sizeof(P4<T>) * KNN_WARPS;
     static bool configured = false;
     if (!configured && smem > 48 * 1024) {
@@ -80,20 +84,20 @@ static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, con
         configured = true;
     }
     knn_kernel<T, D, KPL><<<nblocks, KNN_THREADS, smem, ctx->stream>>>(g, sorted, cs, d_qlist, (uint32_t)nq, d_nq, rows,
-                                                                       K1, drop, d_out_idx, out32, d_out_dist, d_exp);
+                                                                       K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
 }
 
 template <class T, int D>
 static void launch_knn(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int K1, int drop, const uint32_t* d_qlist,
                        int64_t nq, const uint32_t* d_nq, const RowMap& rows, void* d_out_idx, int out32, T* d_out_dist,
-                       unsigned long long* d_exp) {
+                       unsigned long long* d_exp, const T* d_ext_q = nullptr) {
     // a device-side count (the tiled pass's leftovers): a fixed grid strides over however many entries there are
     const unsigned nblocks = (unsigned)std::min<int64_t>((nq + KNN_QPB - 1) / KNN_QPB, d_nq ? (int64_t)kNumSMs * 4 : (int64_t)0x7fffffff);
     const P4<T>* sorted = ib.sorted.get<P4<T>>();
     const uint32_t* cs = ib.cells();
-    if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
-    else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
-    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp);
+    if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
+    else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
+    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
     LAUNCH_CHECK(ctx);
 }
 
@@ -113,6 +117,19 @@ template void knn_query<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&
                                const RowMap&, void*, float*, unsigned long long*, bool);
 template void knn_query<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int64_t, int, int, int, const uint32_t*, int64_t,
                                 const RowMap&, void*, double*, unsigned long long*, bool);
+
+// The K nearest index points of arbitrary query points (n_q x D, device): 0-based caller indices + 1 as uint32 rows,
+// ascending (d2, index). Used by the deposition pass of repel (knn(tree, site, kq), src/repel.jl:502).
+template <class T>
+void knn_points(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int D, int K, const T* d_q, int64_t n_q, uint32_t* d_out_idx32) {
+    WTP_REQUIRE(K >= 1 && K <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K (128 list entries)");
+    if (n_q <= 0) return;
+    const RowMap rows{0u, 0u, 1};
+    if (D == 2) launch_knn<T, 2>(ctx, ib, g, K, 0, nullptr, n_q, nullptr, rows, d_out_idx32, 1, nullptr, nullptr, d_q);
+    else launch_knn<T, 3>(ctx, ib, g, K, 0, nullptr, n_q, nullptr, rows, d_out_idx32, 1, nullptr, nullptr, d_q);
+}
+template void knn_points<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int, int, const float*, int64_t, uint32_t*);
+template void knn_points<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int, int, const double*, int64_t, uint32_t*);
 
 TileFails tile_fails(wtp_ctx* ctx, int64_t n) {
     uint32_t* base = ctx->d_fail.as<uint32_t>(16 + (size_t)n);

@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <limits>
 #include <random>
+#include <algorithm>
+#include <vector>
 
 #include "kernels.cuh"
 #include "knn_core.cuh"
@@ -399,6 +401,137 @@ static void launch_sweep_tiled(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks,
     LAUNCH_CHECK(ctx);
 }
 
+// ------------------------------------------------------------ deposition
+// _deposit_escaped! (src/repel.jl:483-514) after a sweep of the mesh-wall method. What does not depend on earlier
+// deposits of the pass runs on the device, batched over the escaped volume points: their projection onto the mesh,
+// the spacing at the landing sites, the k nearest snapshot points of the sites and those neighbours' current
+// positions and flags. The occupancy sweep is serial by design (an earlier deposit must be visible to a later
+// candidate) and runs on the host in index order over those small arrays; the deposits are then applied on the device.
+__global__ void __launch_bounds__(256) deposit_flag_kernel(uint8_t* __restrict__ escaped, const uint8_t* __restrict__ is_bnd, uint32_t n,
+                                                           uint32_t* __restrict__ flags) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n) return;
+    const bool e = escaped[id] != 0;
+    if (e) escaped[id] = 0;                                                       // :493
+    flags[id] = (e && !is_bnd[id]) ? 1u : 0u;                                     // :494
+}
+template <class T>
+__global__ void __launch_bounds__(256) deposit_gather_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ pos, uint32_t n,
+                                                             const T* __restrict__ P, uint32_t* __restrict__ ids, T* __restrict__ pts) {
+    const uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= n || !flags[id]) return;
+    const uint32_t e = pos[id];
+    ids[e] = id;
+    for (int d = 0; d < 3; ++d) pts[(size_t)e * 3 + d] = P[(size_t)id * 3 + d];
+}
+template <class T>
+__global__ void __launch_bounds__(256) deposit_neighbours_kernel(const uint32_t* __restrict__ nbr, uint32_t n, const T* __restrict__ P,
+                                                                 const uint8_t* __restrict__ is_bnd, T* __restrict__ npos, uint8_t* __restrict__ nflag) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t j = nbr[t] - 1u;
+    for (int d = 0; d < 3; ++d) npos[(size_t)t * 3 + d] = P[(size_t)j * 3 + d];
+    nflag[t] = is_bnd[j];
+}
+template <class T>
+__global__ void __launch_bounds__(256) deposit_apply_kernel(const uint32_t* __restrict__ ids, const T* __restrict__ sites, const int64_t* __restrict__ tris,
+                                                            uint32_t n, T* __restrict__ P, uint8_t* __restrict__ is_bnd, int64_t* __restrict__ tri_idx) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t id = ids[t];
+    for (int d = 0; d < 3; ++d) P[(size_t)id * 3 + d] = sites[(size_t)t * 3 + d];  // :508
+    is_bnd[id] = 1;                                                               // :509
+    tri_idx[id] = tris[t];                                                        // :510
+}
+
+// returns the number of points deposited. P: the movable points after the sweep (n_fixed = 0: movable id = snapshot index).
+template <class T>
+static int64_t deposit_pass(wtp_ctx* ctx, MeshBuffers& mb, const IndexBuffers& ib, const Grid<T>& g, T* P, int64_t n_move, int kq,
+                            const SpacingP<T>& sp, double ratio) {
+    cudaStream_t st = ctx->stream;
+    const unsigned nb = (unsigned)((n_move + 255) / 256);
+    uint32_t* flags = ctx->d_misc.as<uint32_t>((size_t)n_move);
+    uint32_t* pos = ctx->d_qlist.as<uint32_t>((size_t)n_move + 1);
+    deposit_flag_kernel<<<nb, 256, 0, st>>>(mb.escaped.get<uint8_t>(), mb.is_bnd.get<uint8_t>(), (uint32_t)n_move, flags);
+    LAUNCH_CHECK(ctx);
+    exclusive_scan_u32(ctx, const_cast<IndexBuffers&>(ib).scan_tmp, flags, pos, n_move);
+    uint32_t* h_n = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 2048);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(h_n, pos + n_move, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+    const size_t nE = *h_n;
+    if (nE == 0) return 0;
+    // device scratch: ids | candidate points | sites | landing triangles | spacing at the sites | neighbours | their positions, flags
+    const size_t nN = nE * (size_t)kq;
+    char* base = static_cast<char*>(ctx->d_misc2.reserve(nE * (4 + 3 * sizeof(T) * 2 + 8 + sizeof(T)) + nN * (4 + 3 * sizeof(T) + 1) + 256));
+    auto take = [&](size_t bytes) { char* p = base; base += (bytes + 15) & ~(size_t)15; return p; };
+    int64_t* d_tri = reinterpret_cast<int64_t*>(take(nE * 8));
+    T* d_pts = reinterpret_cast<T*>(take(nE * 3 * sizeof(T)));
+    T* d_site = reinterpret_cast<T*>(take(nE * 3 * sizeof(T)));
+    T* d_s = reinterpret_cast<T*>(take(nE * sizeof(T)));
+    T* d_npos = reinterpret_cast<T*>(take(nN * 3 * sizeof(T)));
+    uint32_t* d_ids = reinterpret_cast<uint32_t*>(take(nE * 4));
+    uint32_t* d_nbr = reinterpret_cast<uint32_t*>(take(nN * 4));
+    uint8_t* d_nflag = reinterpret_cast<uint8_t*>(take(nN));
+    deposit_gather_kernel<T><<<nb, 256, 0, st>>>(flags, pos, (uint32_t)n_move, P, d_ids, d_pts);
+    LAUNCH_CHECK(ctx);
+    mesh_project<T>(ctx, mb, d_pts, (int64_t)nE, d_site, d_tri);                                    // :495
+    spacing_eval<T>(ctx, sp, ctx->bvh, d_site, (int64_t)nE, 3, d_s);                                // spacing(site_pt) :501
+    knn_points<T>(ctx, ib, g, 3, kq, d_site, (int64_t)nE, d_nbr);                                   // knn(tree, site, kq) :502
+    deposit_neighbours_kernel<T><<<(unsigned)((nN + 255) / 256), 256, 0, st>>>(d_nbr, (uint32_t)nN, P, mb.is_bnd.get<uint8_t>(), d_npos, d_nflag);
+    LAUNCH_CHECK(ctx);
+    std::vector<uint32_t> ids(nE), nbr(nN);
+    std::vector<int64_t> tri(nE);
+    std::vector<T> site(nE * 3), s_at(nE), npos(nN * 3);
+    std::vector<uint8_t> nflag(nN);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(ids.data(), d_ids, nE * 4, cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(tri.data(), d_tri, nE * 8, cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(site.data(), d_site, nE * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(s_at.data(), d_s, nE * sizeof(T), cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(nbr.data(), d_nbr, nN * 4, cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(npos.data(), d_npos, nN * 3 * sizeof(T), cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(nflag.data(), d_nflag, nN, cudaMemcpyDeviceToHost, st));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+    // the serial sweep, in index order (ids ascend): a neighbour deposited earlier in this pass sits at its site and is a boundary point
+    std::vector<uint32_t> dep_of(nE);      // for the candidates deposited so far: slot -> slot in the deposit list
+    std::vector<uint32_t> dep_ids; std::vector<T> dep_sites; std::vector<int64_t> dep_tris;
+    std::vector<uint8_t> deposited(nE, 0);
+    for (size_t e = 0; e < nE; ++e) {
+        if (tri[e] == 0) continue;                                                                  // :498
+        const double thr = ratio * (double)s_at[e];                                                 // :501
+        const T* sx = &site[e * 3];
+        bool occupied = false;
+        for (int r = 0; r < kq && !occupied; ++r) {                                                 // :503-506
+            const uint32_t j = nbr[e * kq + r] - 1u;
+            if (j == ids[e]) continue;
+            const T* pj = &npos[(e * kq + r) * 3];
+            bool bnd = nflag[e * kq + r] != 0;
+            // j among this pass's earlier candidates? (ids is sorted)
+            const auto it = std::lower_bound(ids.begin(), ids.begin() + (ptrdiff_t)e, j);
+            if (it != ids.begin() + (ptrdiff_t)e && *it == j) {
+                const size_t ej = (size_t)(it - ids.begin());
+                if (deposited[ej]) { bnd = true; pj = &site[ej * 3]; }
+            }
+            if (!bnd) continue;
+            const T dx = pj[0] - sx[0], dy = pj[1] - sx[1], dz = pj[2] - sx[2];
+            occupied = (double)std::sqrt((dx * dx + dy * dy) + dz * dz) < thr;
+        }
+        if (occupied) continue;
+        deposited[e] = 1;
+        dep_ids.push_back(ids[e]);
+        dep_sites.insert(dep_sites.end(), sx, sx + 3);
+        dep_tris.push_back(tri[e]);
+    }
+    const size_t nD = dep_ids.size();
+    if (nD == 0) return 0;
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_ids, dep_ids.data(), nD * 4, cudaMemcpyHostToDevice, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_site, dep_sites.data(), nD * 3 * sizeof(T), cudaMemcpyHostToDevice, st));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_tri, dep_tris.data(), nD * 8, cudaMemcpyHostToDevice, st));
+    deposit_apply_kernel<T><<<(unsigned)((nD + 255) / 256), 256, 0, st>>>(d_ids, d_site, d_tri, (uint32_t)nD, P, mb.is_bnd.get<uint8_t>(), mb.tri_idx.get<int64_t>());
+    LAUNCH_CHECK(ctx);
+    WTP_CUDA_CHECK(cudaStreamSynchronize(st));                                                      // the host vectors go out of scope
+    return (int64_t)nD;
+}
+
 // ------------------------------------------------------------- host driver
 template <class T>
 void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int D, const wtp_spacing* sp_in, const T* d_bnd,
@@ -412,6 +545,9 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     WTP_REQUIRE(prm->wall == WTP_WALL_IDENTITY || prm->wall == WTP_WALL_MESH, WTP_ERR_UNSUPPORTED, "user-defined constrain closure cannot cross the C ABI");
     WTP_REQUIRE((prm->wall == WTP_WALL_MESH) == (mesh != nullptr), WTP_ERR_BAD_ARG, "params.wall and the wall mesh argument disagree");
     WTP_REQUIRE(!mesh || D == 3, WTP_ERR_BAD_ARG, "the mesh wall rule is 3-D only (src/repel.jl:123)");
+    WTP_REQUIRE(prm->deposit_ratio >= 0, WTP_ERR_BAD_ARG, "deposit_ratio must be >= 0");            // src/repel.jl:143
+    WTP_REQUIRE(!(prm->deposit_ratio > 0) || (mesh && n_fixed == 0), WTP_ERR_BAD_ARG, "deposit_ratio belongs to the mesh-wall method (every point movable, src/repel.jl:161-172)");
+    WTP_REQUIRE(!(prm->deposit_ratio > 0) || ctx->world == 1, WTP_ERR_UNSUPPORTED, "deposition runs on an unsharded context");
     WTP_REQUIRE(fm->kind >= WTP_FORCE_INVERSE && fm->kind <= WTP_FORCE_STRONG, WTP_ERR_UNSUPPORTED, "user-defined RepelForceModel cannot cross the C ABI");
     WTP_REQUIRE(sp_in->kind >= WTP_SPACING_CONSTANT && sp_in->kind <= WTP_SPACING_BOUNDARY_LAYER, WTP_ERR_UNSUPPORTED, "user-defined spacing callable cannot cross the C ABI");
     WTP_REQUIRE(ctx->world == 1 || ctx->nccl_comm, WTP_ERR_STATE, "repel on a sharded context needs the NCCL communicator (wtp_comm_init with a unique id)");
@@ -482,6 +618,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     int passes = 0;
     IndexWindow win;
     bool windowed = false;
+    int64_t n_deposited = 0;
     T best_cv_T = t_max<T>();
     int64_t last_impr = 0;
     int it = 1, n_conv = 0;
@@ -644,6 +781,8 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         }
         if (!keep_old) std::swap(Pa, Pb);  // Pa = p after the sweep
         if (stopped) break;
+        if (mesh && prm->deposit_ratio > 0)                                                          // deposit!(p, tree, i), :328
+            n_deposited += deposit_pass<T>(ctx, *mesh, ib, g, Pa, n_move, (int)std::min<int64_t>(prm->k, n_move), sp, prm->deposit_ratio);
         if ((double)conv[n_conv - 1] < prm->tol) { res->stop_reason = WTP_STOP_TOL; break; }          // :329-332
         ++it;
     }
@@ -653,6 +792,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         comm_allgather_rows(ctx, mesh->escaped.get<uint8_t>(), n_move, sizeof(uint8_t));
     }
     WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+    (void)n_deposited;
     res->iters = n_conv;
     ctx->last_timing = wtp_timing{};
     ctx->last_timing.sort_passes = passes;

@@ -87,7 +87,7 @@ struct CSpacing; kind::Int32; a::Float64; b::Float64; c::Float64; bnd::Ptr{Cvoid
 struct CParams
     k::Int32; max_iters::Int32; rebuild_every::Int32; stall_after::Int32; kick_after::Int32; wall::Int32
     want_trace::Int32; reserved::Int32; alpha_lo::Float64; alpha_max::Float64; tol::Float64; cv_target::Float64
-    n_protected::Int64; kick_seed::UInt64
+    n_protected::Int64; kick_seed::UInt64; deposit_ratio::Float64
 end
 struct CResult; iters::Int32; stop_reason::Int32; last_cv::Float64; end
 struct CTrace; r::Float64; s::Float64; r_over_s::Float64; idx_a::Int64; idx_b::Int64; end
@@ -145,7 +145,9 @@ function _relax!(
         n_fixed, n_protected, α_lo, α_max, k, max_iters, tol, rebuild_every,
         kick_after, trace, stall_after = 0, cv_target = 0.0, (deposit!) = nothing,
     )
-    isnothing(deposit!) || error("libwtp_cuda: deposit! (_deposit_escaped!, serial by design) is not available on the device path")
+    # deposit! is the closure of src/repel.jl:161-168 over (escaped, is_bnd, tri_indices, octree, spacing, deposit_ratio, ...):
+    # only its ratio crosses the ABI, the library runs _deposit_escaped! itself after every sweep
+    deposit_ratio = isnothing(deposit!) ? 0.0 : Float64(deposit!.deposit_ratio)
     T, D = machine_type(snap), dimension(snap)
     n_move = length(p)
     # repel(cloud, spacing, octree) calls with n_fixed = 0, n_protected = n_boundary (src/repel.jl:172) and a
@@ -168,7 +170,7 @@ function _relax!(
     sp, keep = cspacing(spacing, T)
     fm = cforce(force_model)
     prm = CParams(k, max_iters, rebuild_every, stall_after, kick_after, wall_mode ? MESH_WALL : IDENTITY_WALL, isnothing(trace) ? 0 : 1, 0,
-                  Float64(α_lo), Float64(α_max), Float64(tol), Float64(cv_target), Int64(n_protected), rand(UInt64))
+                  Float64(α_lo), Float64(α_max), Float64(tol), Float64(cv_target), Int64(n_protected), rand(UInt64), deposit_ratio)
     conv = Vector{T}(undef, max(max_iters, 1))
     tr = isnothing(trace) ? CTrace[] : Vector{CTrace}(undef, max(max_iters, 1))
     res = Ref(CResult(0, 0, NaN))
@@ -182,7 +184,12 @@ function _relax!(
     end
     if wall_mode                                        # side arrays written from inside the sweep (src/repel.jl:462,467)
         constrain.tri_indices .= tri_idx
-        constrain.escaped .|= (esc .!= 0)
+        if deposit_ratio > 0                            # deposition clears the flags it has seen and converts volume points (:493, :509)
+            constrain.escaped .= (esc .!= 0)
+            constrain.is_bnd .= (is_bnd .!= 0)
+        else
+            constrain.escaped .|= (esc .!= 0)
+        end
     end
     @views p .= snap[(n_fixed + 1):end]                 # final positions (pre-sweep ones on a cv_target stop)
     r = res[]
