@@ -59,25 +59,36 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks and throttle reasons through NVML every 20 ms during the timed region."""
+    """Samples SM clocks and throttle reasons through NVML every 5 ms during the timed region. NVML is initialised
+    when the sampler is made (outside the timed region), so that the first sample is taken as the region opens."""
 
     def __init__(self, index: int):
         self.index, self.samples, self.stop = index, [], threading.Event()
         self.t = threading.Thread(target=self._run, daemon=True)
-        self.max_mhz = None
-
-    def _run(self):
+        self.max_mhz, self.nv, self.h, self.error = None, None, None, None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-            while not self.stop.is_set():
-                self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
-                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
-                                     else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
-                self.stop.wait(0.02)
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
         except Exception as e:  # pragma: no cover - NVML missing
+            self.error = repr(e)
+
+    def _sample(self):
+        nv, h = self.nv, self.h
+        reasons = (nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
+                   else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(reasons)))
+
+    def _run(self):
+        if self.nv is None:
+            return
+        try:
+            while not self.stop.is_set():
+                self._sample()
+                self.stop.wait(0.005)
+            self._sample()
+        except Exception as e:  # pragma: no cover
             self.error = repr(e)
 
     def __enter__(self):
@@ -196,7 +207,8 @@ def main():
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     q_ms, phases = [], []
-    with ClockSampler(local) as clocks:
+    sampler = ClockSampler(local)
+    with sampler as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
             step_dev()
