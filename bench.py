@@ -212,11 +212,13 @@ def main():
         ev0.record(stream)
         for _ in range(args.steps):
             step_dev()
-            t = ctx.timing()
-            q_ms.append(t["ms_query"])
-            phases.append(t)
         ev1.record(stream)
         barrier()
+    # per-phase CUDA-event times of the last timed step (the library records them on the launching stream during the
+    # call; reading them after every step would put a host round trip between the steps)
+    t = ctx.timing()
+    q_ms.append(t["ms_query"])
+    phases.append(t)
     launches = ctx.launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
@@ -274,6 +276,8 @@ def main():
         hbm, _ = peaks()
         repel = {"metric": "repel_iters_per_s", "value": 1e3 / rms, "unit": "iters/s", "points": nr, "dtype": "f32",
                  "iters": res["iters"], "ms_per_iter": rms, "sweep_ms_per_iter": sweep_ms, "comm_ms_per_iter": rt["ms_comm"] / max(res["iters"], 1),
+                 "exchange": ("sweep kernels store their runs into every rank's buffer over NVLink peer memory" if rt["n_peer_ranks"] > 0
+                              else ("ncclAllGather of the runs after the sweep" if world > 1 else None)),
                  "conv_last": float(conv[-1]),
                  "roofline": {"bound": "hbm", "achieved": ALGO_BYTES_REPEL_F32 * nr / world / (rms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                               "frac": ALGO_BYTES_REPEL_F32 * nr / world / (rms * 1e-3) / 1e9 / hbm, "traffic": None}}
@@ -318,6 +322,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "knn_tile_kernel<float,3> (+ knn_kernel<float,3,1> for its leftovers)", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": ncu_traffic, "peak_source": how,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_QUERY_F32 * nq, "kernel_ms": q_ms_avg,
+                         "kernel_ms_source": "CUDA events around the query launches of the last timed step, recorded by the library on the launching stream",
                          "kernel_share_of_step": q_ms_avg / ms_step,
                          "note": "k-NN is bound by instruction issue and the shared-memory pipe, not by DRAM: 96 B/query is compulsory traffic only (SURVEY.md §8d); kernel_ms = tiled pass + leftover pass"},
             "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("ms_bbox", "ms_cellkey", "ms_sort", "ms_reorder", "ms_query")},

@@ -129,6 +129,9 @@ typedef struct {
     /* sharded k-NN: points in the window of the grid this rank indexed (0: the whole set was indexed), and the
      * queries whose search left the window (> 0: the call was repeated on the whole index) */
     int64_t n_window_points, n_window_missed;
+    /* sharded repel: ranks whose run buffers the sweep kernels wrote directly over NVLink peer memory (0: the runs
+     * were exchanged with an NCCL all-gather after the sweep) */
+    int64_t n_peer_ranks;
 } wtp_timing;
 
 /* enable != 0: record CUDA events around each phase of subsequent calls. */

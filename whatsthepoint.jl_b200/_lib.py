@@ -81,7 +81,8 @@ class Timing(C.Structure):
                                          "ms_scan", "ms_reduce", "ms_comm", "ms_d2h", "ms_total")] + \
                [("sort_passes", C.c_int32), ("query_launches", C.c_int32), ("n_cells", C.c_int64),
                 ("n_ring_expanded", C.c_int64), ("n_leftover_sparse", C.c_int64), ("n_leftover_dense", C.c_int64),
-                ("n_leftover_other", C.c_int64), ("n_window_points", C.c_int64), ("n_window_missed", C.c_int64)]
+                ("n_leftover_other", C.c_int64), ("n_window_points", C.c_int64), ("n_window_missed", C.c_int64),
+                ("n_peer_ranks", C.c_int64)]
 
 
 _lib = None

@@ -9,6 +9,8 @@
 //                   stop-test partials (a few dozen bytes)
 #include <dlfcn.h>
 
+#include <vector>
+
 #include "kernels.cuh"
 
 namespace wtp {
@@ -86,6 +88,72 @@ void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t by
     NCCL_CHECK(api, api->AllGather(d_in, d_out, bytes_per_rank, NCCL_INT8, ctx->nccl_comm, ctx->stream));
 }
 
+// Peer buffers of the run-sharded repel: every rank allocates 2 x bytes_each, the CUDA IPC handles go round with one
+// small ncclAllGather, and every rank maps the others' buffers (NVLink peer access). Returns false — and the caller
+// keeps the NCCL all-gather — when the ranks are not all peers of each other or IPC is not available (decided
+// collectively, so every rank takes the same path). Collective: every rank must call it with the same size.
+static void peers_unmap(wtp_ctx* ctx) {
+    for (int r = 0; r < WTP_MAX_PEERS; ++r) {
+        if (ctx->peers.base[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peers.base[r]);
+        ctx->peers.base[r] = nullptr;
+    }
+    ctx->peers.mapped = false;
+}
+
+bool comm_peer_buffers(wtp_ctx* ctx, size_t bytes_each) {
+    auto& pb = ctx->peers;
+    if (ctx->world <= 1 || ctx->world > WTP_MAX_PEERS || !ctx->nccl_comm || pb.unavailable || getenv("WTP_NO_P2P")) return false;
+    if (pb.mapped && pb.bytes_each >= bytes_each) return true;
+    NcclApi* api = ctx->nccl;
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    peers_unmap(ctx);
+    if (pb.own.p) { cudaFree(pb.own.p); pb.own.p = nullptr; pb.own.cap = 0; }     // a fresh allocation: the handle names the whole allocation
+    const size_t each = (bytes_each + bytes_each / 8 + 4095) & ~(size_t)4095;
+    void* mine = nullptr;
+    cudaIpcMemHandle_t handle;
+    int ok = cudaMalloc(&mine, 2 * each) == cudaSuccess && cudaIpcGetMemHandle(&handle, mine) == cudaSuccess ? 1 : 0;
+    (void)cudaGetLastError();
+    // all-gather {ok, handle} (72 bytes per rank)
+    struct Msg { int64_t ok; cudaIpcMemHandle_t h; };
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    Msg m{ok, {}};
+    if (ok) m.h = handle;
+    Msg* d_msg = ctx->d_misc.as<Msg>((size_t)ctx->world + 1);
+    std::vector<Msg> all((size_t)ctx->world);
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_msg + ctx->world, &m, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(api, api->AllGather(d_msg + ctx->world, d_msg, sizeof(Msg), NCCL_INT8, ctx->nccl_comm, ctx->stream));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_msg, sizeof(Msg) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    int all_ok = 1;
+    for (int r = 0; r < ctx->world; ++r) all_ok &= all[(size_t)r].ok ? 1 : 0;
+    if (all_ok) {
+        for (int r = 0; r < ctx->world && all_ok; ++r) {
+            if (r == ctx->rank) { pb.base[r] = mine; continue; }
+            void* p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); all_ok = 0; }
+            else pb.base[r] = p;
+        }
+    }
+    // second round: did every rank map every peer?
+    m.ok = all_ok;
+    WTP_CUDA_CHECK(cudaMemcpyAsync(d_msg + ctx->world, &m, sizeof(Msg), cudaMemcpyHostToDevice, ctx->stream));
+    NCCL_CHECK(api, api->AllGather(d_msg + ctx->world, d_msg, sizeof(Msg), NCCL_INT8, ctx->nccl_comm, ctx->stream));
+    WTP_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_msg, sizeof(Msg) * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int r = 0; r < ctx->world; ++r) all_ok &= all[(size_t)r].ok ? 1 : 0;
+    if (!all_ok) {
+        pb.base[ctx->rank] = nullptr;
+        peers_unmap(ctx);
+        pb.own.p = mine; pb.own.cap = mine ? 2 * each : 0;   // freed with the context, when no peer can still have it mapped
+        pb.unavailable = true;
+        return false;
+    }
+    pb.own.p = mine; pb.own.cap = 2 * each;
+    pb.bytes_each = each;
+    pb.mapped = true;
+    return true;
+}
+
 int32_t fail(wtp_ctx* ctx, const Error& e);
 
 }  // namespace wtp
@@ -95,6 +163,7 @@ using namespace wtp;
 extern "C" {
 
 void wtp_comm_destroy_internal(wtp_ctx* ctx) {
+    wtp::peers_unmap(ctx);
     if (ctx->nccl_comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     ctx->rank = 0;

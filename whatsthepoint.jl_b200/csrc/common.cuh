@@ -15,6 +15,9 @@ namespace wtp {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
 constexpr int kWarp = 32;
+}
+constexpr int WTP_MAX_PEERS = 8;  // ranks of one NVSwitch domain whose buffers a context can map
+namespace wtp {
 
 // ------------------------------------------------------------------ errors
 struct Error {
@@ -283,6 +286,15 @@ struct wtp_ctx {
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
     wtp::NcclApi* nccl = nullptr;
+    // peer-memory exchange of the run-sharded repel (comm.cu, comm_peer_buffers): every rank's two run buffers, mapped
+    // into this process with CUDA IPC, so that the sweep kernels store their records straight into all ranks' buffers
+    // over NVLink instead of an all-gather afterwards
+    struct {
+        wtp::DevBuf own;                 // this rank's buffers (2 x bytes_each)
+        size_t bytes_each = 0;
+        void* base[WTP_MAX_PEERS] = {};  // base[r]: rank r's buffers in this process's address space (own for r == rank)
+        bool mapped = false, unavailable = false;
+    } peers;
     // host k-NN pipeline: 4-byte index staging (pinned ring) and the widening threads
     void* h_stage = nullptr;
     size_t h_stage_slot_bytes = 0;

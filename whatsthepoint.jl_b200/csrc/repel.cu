@@ -26,6 +26,7 @@ namespace wtp {
     } while (0)
 
 // comm.cu
+bool comm_peer_buffers(wtp_ctx* ctx, size_t bytes_each);
 void comm_allgather_rows(wtp_ctx* ctx, void* d_buf, int64_t n_rows, size_t row_bytes);
 void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t bytes_per_rank);
 
@@ -104,9 +105,12 @@ struct SweepArgs {
     const uint32_t* nq_dev; // device-side length of qlist (the tiled sweep's leftovers), or null
     int kk, rebuild;
     // Sharded by runs of the sorted order: this rank sweeps the sorted positions [s_begin, s_end) and writes the new
-    // position of position j, with the point's caller index, to C[j - s_begin] (C null: P_new by caller index).
+    // position of position j, with the point's caller index, to Cp[r][j - s_begin] for r < n_peers: its slot in the run
+    // buffer of every rank (peer memory over NVLink), or just its own (n_peers = 1: an all-gather follows).
+    // n_peers = 0: P_new by caller index.
     uint32_t s_begin, s_end;
-    P4<T>* C;
+    int n_peers;
+    P4<T>* Cp[WTP_MAX_PEERS];
     T a_lo, a_max;
     ForceP<T> force;
     RepelPartial<T>* partials;
@@ -191,9 +195,9 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
         if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
         const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;                       // :291 (identity wall)
         if (lane == 0) {
-            if (a.C) {
+            if (a.n_peers > 0) {
                 P4<T> rec; rec.x = p0; rec.y = p1; rec.z = p2; rec.w = idx_bits((T)0, self);
-                a.C[j - a.s_begin] = rec;
+                for (int r = 0; r < a.n_peers; ++r) a.Cp[r][j - a.s_begin] = rec;
             } else {
                 a.P_new[(size_t)id * D + 0] = p0;
                 a.P_new[(size_t)id * D + 1] = p1;
@@ -217,6 +221,21 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
         RepelPartial<T> tot = s_part[0];
         for (int w = 1; w < SW_WARPS; ++w) partial_merge(tot, s_part[w]);
         a.partials[blockIdx.x] = tot;
+    }
+}
+
+// Rows of D coordinates to scattered caller slots, written by the warp together: the 32 x D words are dealt to the lanes
+// so that the D words of a row sit in adjacent lanes and leave as one memory transaction, instead of D stores per lane
+// that each touch 32 different rows. Every lane of the warp must call it (valid = false: nothing to store).
+template <class T, int D>
+__device__ __forceinline__ void warp_store_rows(bool valid, size_t id, T x, T y, T z, T* __restrict__ P, int lane) {
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        const int flat = lane + 32 * i, src = flat / D, comp = flat % D;
+        const T sx = __shfl_sync(FULL, x, src), sy = __shfl_sync(FULL, y, src), sz = D == 3 ? __shfl_sync(FULL, z, src) : (T)0;
+        const unsigned long long sid = __shfl_sync(FULL, (unsigned long long)id, src);
+        const bool sv = __shfl_sync(FULL, valid ? 1 : 0, src) != 0;
+        if (sv) P[(size_t)sid * D + comp] = comp == 0 ? sx : (comp == 1 ? sy : sz);
     }
 }
 
@@ -251,11 +270,15 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
     TileSearch<T, D> ts(a.g, a.sorted, a.cell_start, smem_raw, sh);
     const uint32_t j = a.s_begin + blockIdx.x * TK_Q + threadIdx.x;
     ts.init(j, j < a.s_end, a.n_fixed + a.id_lo, a.n_fixed + a.id_hi);   // fixed wall / other rank's points are not swept
-    if (a.C && ts.active && !ts.query) a.C[j - a.s_begin] = ts.q;         // a fixed point of this rank's run: the record as it is
+    if (a.n_peers > 0 && ts.active && !ts.query)                          // a fixed point of this rank's run: the record as it is
+        for (int r = 0; r < a.n_peers; ++r) a.Cp[r][j - a.s_begin] = ts.q;
     RepelPartial<T> acc;
     partial_init(acc);
     while (ts.next_group()) {
         int status = ts.select(a.kk);                                         // :259
+        bool moved = false;                                                   // this thread has a new position for P_new
+        size_t moved_id = 0;
+        T m0 = (T)0, m1 = (T)0, m2 = (T)0;
         if (status == TK_OK) {
             bool ok = true;
             const uint32_t self = idx_of(ts.q), id = self - a.n_fixed;
@@ -295,13 +318,11 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
                 const T dn = sqrt(dn2);
                 if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
                 const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;          // :291 (the wall rule follows in its own kernel)
-                if (a.C) {
+                if (a.n_peers > 0) {
                     P4<T> rec; rec.x = p0; rec.y = p1; rec.z = p2; rec.w = idx_bits((T)0, self);
-                    a.C[ts.j - a.s_begin] = rec;
+                    for (int r = 0; r < a.n_peers; ++r) a.Cp[r][ts.j - a.s_begin] = rec;
                 } else {
-                    a.P_new[(size_t)id * D + 0] = p0;
-                    a.P_new[(size_t)id * D + 1] = p1;
-                    if (D == 3) a.P_new[(size_t)id * D + (D - 1)] = p2;
+                    moved = true; moved_id = id; m0 = p0; m1 = p1; m2 = p2;
                 }
                 const T nn = nn_idx != 0xffffffffu ? sqrt(nn_d2) : t_max<T>();
                 const T u = nn / (a.s_cur ? a.spacings[self] : a.s_const);     // spacing as of the last rebuild (:251, :379); a constant spacing needs no gather
@@ -313,6 +334,7 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
                 partial_merge(acc, one);
             }
         }
+        if (a.n_peers == 0) warp_store_rows<T, D>(moved, moved_id, m0, m1, m2, a.P_new, ts.lane);
         ts.report(status, fails);
     }
     partial_warp_reduce(acc);
@@ -361,14 +383,12 @@ __global__ void __launch_bounds__(256) scatter_runs_kernel(const P4<T>* __restri
     const uint32_t r = blockIdx.y;
     const uint32_t begin = (uint32_t)(((uint64_t)n_all * r) / world), end = (uint32_t)(((uint64_t)n_all * (r + 1)) / world);
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= end - begin) return;
-    const P4<T> rec = load_p4<T>(C_all + (size_t)r * slot + t);
+    P4<T> rec; rec.x = rec.y = rec.z = (T)0; rec.w = idx_bits((T)0, 0u);
+    const bool live = t < end - begin;
+    if (live) rec = load_p4<T>(C_all + (size_t)r * slot + t);
     const uint32_t self = idx_of(rec);
-    if (self < n_fixed) return;
-    const size_t id = self - n_fixed;
-    P_new[id * D + 0] = rec.x;
-    P_new[id * D + 1] = rec.y;
-    if (D == 3) P_new[id * D + (D - 1)] = rec.z;
+    const bool movable = live && self >= n_fixed;
+    warp_store_rows<T, D>(movable, movable ? (size_t)(self - n_fixed) : 0, rec.x, rec.y, rec.z, P_new, threadIdx.x & 31);
 }
 
 template <class T, int D, int KPL>
@@ -597,7 +617,13 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     // tiled sweep (one thread per point) whenever the list fits one register row and this rank sweeps whole runs
     const bool tiled_ok = kk <= 32 && (world == 1 || by_runs) && std::getenv("WTP_NO_TILED") == nullptr;
     const int n_tiled_blocks = tiled_ok ? (int)((gse - gsb + TK_Q - 1) / TK_Q) : 0;
-    P4<T>* C_all = by_runs ? ctx->d_misc2.as<P4<T>>((size_t)run_slot * world) : nullptr;
+    // the ranks' runs meet in one buffer per rank: through peer memory (every sweep stores its records into all ranks'
+    // buffers, two buffers alternate so that a rank may run ahead of its peers' scatter) or, when the ranks cannot map
+    // each other's memory, through an all-gather after the sweep
+    const size_t run_bytes = (size_t)run_slot * world * sizeof(P4<T>);
+    const bool p2p = by_runs && comm_peer_buffers(ctx, run_bytes);
+    P4<T>* C_local = by_runs && !p2p ? ctx->d_misc2.as<P4<T>>((size_t)run_slot * world) : nullptr;
+    uint64_t n_sweeps = 0;
     // per-CTA partials of the sweep launches of an iteration (general sweep | tiled sweep), folded together
     RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + (size_t)n_tiled_blocks + 256 + 1 + world);
     RepelPartial<T>* d_fold = partials + (size_t)nblocks + (size_t)n_tiled_blocks;   // first stage of a two-stage fold
@@ -655,7 +681,19 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         const int64_t sb = windowed ? gsb - win.P0 : gsb, se = windowed ? gse - win.P0 : gse;   // this rank's run in positions of the index
         SweepArgs<T> a;
         a.g = g; a.sorted = ib.sorted.get<P4<T>>(); a.cell_start = ib.cells();
-        a.s_begin = (uint32_t)sb; a.s_end = (uint32_t)se; a.C = by_runs ? C_all + (size_t)rank * run_slot : nullptr;
+        a.s_begin = (uint32_t)sb; a.s_end = (uint32_t)se;
+        a.n_peers = 0;
+        P4<T>* C_all = C_local;                      // where this rank finds every rank's run after the exchange
+        if (p2p) {
+            const size_t parity = (size_t)(n_sweeps++ & 1u);
+            a.n_peers = world;
+            for (int r = 0; r < world; ++r)
+                a.Cp[r] = reinterpret_cast<P4<T>*>(static_cast<char*>(ctx->peers.base[r]) + parity * ctx->peers.bytes_each) + (size_t)rank * run_slot;
+            C_all = reinterpret_cast<P4<T>*>(static_cast<char*>(ctx->peers.base[rank]) + parity * ctx->peers.bytes_each);
+        } else if (by_runs) {
+            a.n_peers = 1;
+            a.Cp[0] = C_local + (size_t)rank * run_slot;
+        }
         a.S = d_snap; a.P_old = Pa; a.P_new = Pb; a.s_cur = s_cur; a.spacings = spacings; a.s_const = sp.a;
         a.n_fixed = (uint32_t)n_fixed; a.n_all = (uint32_t)n_all; a.id_lo = (uint32_t)id_lo; a.id_hi = (uint32_t)id_hi;
         a.qlist = qlist; a.nq = nq; a.kk = kk; a.rebuild = rebuild ? 1 : 0;
@@ -696,7 +734,8 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         if (world > 1) {
             ScopedPhase ph(ctx->timer, PH_COMM);
             if (by_runs) {   // every rank's run of (position, caller index) records, then into caller order
-                comm_allgather_fixed(ctx, C_all + (size_t)rank * run_slot, C_all, (size_t)run_slot * sizeof(P4<T>));
+                if (p2p) comm_allgather_fixed(ctx, d_tot, d_all, sizeof(RepelPartial<T>));   // also the barrier: every rank's sweep has stored its records here
+                else comm_allgather_fixed(ctx, C_all + (size_t)rank * run_slot, C_all, (size_t)run_slot * sizeof(P4<T>));
                 const dim3 grid((unsigned)((run_slot + 255) / 256), (unsigned)world);
                 if (D == 2) scatter_runs_kernel<T, 2><<<grid, 256, 0, st>>>(C_all, (uint32_t)run_slot, (uint32_t)n_all, (uint32_t)world, (uint32_t)n_fixed, Pb);
                 else scatter_runs_kernel<T, 3><<<grid, 256, 0, st>>>(C_all, (uint32_t)run_slot, (uint32_t)n_all, (uint32_t)world, (uint32_t)n_fixed, Pb);
@@ -704,7 +743,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             } else {
                 comm_allgather_rows(ctx, Pb, n_move, (size_t)D * sizeof(T));                        // moved positions of every rank
             }
-            comm_allgather_fixed(ctx, d_tot, d_all, sizeof(RepelPartial<T>));
+            if (!p2p) comm_allgather_fixed(ctx, d_tot, d_all, sizeof(RepelPartial<T>));
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_all, sizeof(RepelPartial<T>) * world, cudaMemcpyDeviceToHost, st));
             WTP_CUDA_CHECK(cudaStreamSynchronize(st));
             tot = h_tot[0];
@@ -803,6 +842,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     ctx->last_timing.n_leftover_other = ctx->last_tile_other;
     ctx->last_timing.n_window_points = windowed ? win.M : 0;
     ctx->last_timing.n_window_missed = ctx->last_window_missed;
+    ctx->last_timing.n_peer_ranks = p2p ? world : 0;
 }
 
 template void relax_device<float>(wtp_ctx*, float*, int64_t, int64_t, int, const wtp_spacing*, const float*, const wtp_force*,
