@@ -20,8 +20,9 @@ with all host threads on a bounded sample per step.
 
 Multi-GPU (torchrun, one rank per GPU): the point set is replicated, every rank indexes the
 window of the grid around its contiguous 1/N run of the sorted order and answers that run (no
-data-path collective); repel sweeps the same kind of run and all-gathers the moved points
-over NCCL every iteration. Total work is fixed: "strong".
+data-path collective); repel sweeps the same kind of run and its kernels store the moved points
+into every rank's buffer over NVLink peer memory (NCCL all-gather as the fallback). Total work
+is fixed: "strong".
 """
 from __future__ import annotations
 

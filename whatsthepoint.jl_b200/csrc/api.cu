@@ -183,7 +183,7 @@ void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst
         WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, S * SLOT));
         ctx->h_stage_slot_bytes = SLOT;
     }
-    if (!ctx->pool) ctx->pool = new HostPool(std::max(2, HostPool::default_threads() / std::max(1, ctx->world)));   // the ranks of a node share its cores
+    if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());   // also per rank on a shared node: measured, more threads in flight hide the latency of the scattered row writes
     WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
     WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0));
     const size_t per = SLOT / sizeof(uint32_t);
@@ -301,7 +301,7 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
             WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, S * SLOT));
             ctx->h_stage_slot_bytes = SLOT;
         }
-        if (!ctx->pool) ctx->pool = new HostPool(std::max(2, HostPool::default_threads() / std::max(1, ctx->world)));   // the ranks of a node share its cores
+        if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());   // also per rank on a shared node: measured, more threads in flight hide the latency of the scattered row writes
         uint32_t* d_idx32 = ctx->d_out_idx.as<uint32_t>((size_t)nq * k);
         T* d_dist = h_out_dist ? ctx->d_out_dist.as<T>((size_t)nq * k) : nullptr;
         compute(d_idx32, d_dist, true);

@@ -4,9 +4,10 @@
 // the host program already loaded (torch's bundled copy under torchrun) and needs no
 // link-time dependency for single-GPU use. Collectives on the data path:
 //   k-NN / radius : none (queries shard by contiguous range, index replicated)
-//   repel         : per iteration one all-gather of the moved positions (grouped in-place
-//                   broadcasts, uneven shards allowed) + one all-gather of the per-rank
-//                   stop-test partials (a few dozen bytes)
+//   repel         : per iteration the ranks' runs of moved points meet in every rank's buffer — stored there by the
+//                   sweep kernels themselves through peer memory (comm_peer_buffers: CUDA IPC over NVLink), or by one
+//                   all-gather after the sweep when the ranks cannot map each other — + one all-gather of the per-rank
+//                   stop-test partials (about a hundred bytes), which is also the barrier of the peer-memory path
 #include <dlfcn.h>
 
 #include <vector>
