@@ -88,17 +88,20 @@ def test_knn_shards_windowed_index(pkg, oracle, dt, D, world):
     of the grid; the rows it answers are the oracle's, and the ranks' runs tile the sorted order exactly."""
     N = 60001
     pts = np.random.default_rng(world * 10 + D).random((N, D)).astype(dt)
-    ref = oracle.knn(pts, 21)
+    ref, ref_d = oracle.knn(pts, 21, dists=True)
     seen = np.zeros(N, dtype=np.int32)
     for rank in range(world):
         c = pkg.Context(0)
         c.comm_init(rank, world, None)
         idx = np.zeros((N, 21), dtype=np.int64)
-        c.knn(pts, 21, out_idx=idx)
+        dist = np.zeros((N, 21), dtype=dt) if world == 3 else None          # searchdists through the sharded host path too
+        c.knn(pts, 21, out_idx=idx, out_dist=dist)
         own = c.owned() - 1
         b, e = c.shard(N)
         t = c.timing()
         assert len(own) == e - b and np.array_equal(idx[own], ref[own])
+        if dist is not None:
+            assert np.array_equal(dist[own], ref_d[own]) and (dist[np.setdiff1d(np.arange(N), own)] == 0).all()
         rest = np.ones(N, dtype=bool); rest[own] = False
         assert (idx[rest] == 0).all()
         assert 0 < t["n_window_points"] < N and t["n_window_missed"] == 0      # the window, not the whole set, was sorted

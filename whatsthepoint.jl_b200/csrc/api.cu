@@ -85,6 +85,7 @@ void wtp_destroy(wtp_ctx* ctx) {
     delete ctx->pool;
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto e : ctx->ev_copied) if (e) cudaEventDestroy(e);
+    if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
     if (ctx->ev_copy_done) cudaEventDestroy(ctx->ev_copy_done);
@@ -305,14 +306,26 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         uint32_t* d_idx32 = ctx->d_out_idx.as<uint32_t>((size_t)nq * k);
         T* d_dist = h_out_dist ? ctx->d_out_dist.as<T>((size_t)nq * k) : nullptr;
         compute(d_idx32, d_dist, true);
-        // sharded: row t belongs to caller index ids[t]
-        std::vector<int64_t> ids;
+        // sharded: row t belongs to caller index ids[t] (1-based; 4-byte values in a pinned buffer of the context)
+        const uint32_t* ids = nullptr;
         std::vector<T> dist_tmp;
         if (sharded) {
-            int64_t* d_ids = ctx->d_misc.as<int64_t>((size_t)std::max<int64_t>(nq, 1));
-            owned_ids(ctx, ib, sizeof(T) == 8, sb, se, d_ids);
-            ids.resize((size_t)nq);
-            WTP_CUDA_CHECK(cudaMemcpyAsync(ids.data(), d_ids, (size_t)nq * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+            const size_t need = (size_t)std::max<int64_t>(nq, 1) * sizeof(uint32_t);
+            if (need > ctx->h_ids_bytes) {
+                if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
+                ctx->h_ids = nullptr; ctx->h_ids_bytes = 0;
+                WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_ids, need + need / 8));
+                ctx->h_ids_bytes = need + need / 8;
+            }
+            // the rows in ascending caller index: the host then writes forward through the caller's table
+            uint32_t* d_ids = ctx->d_misc.as<uint32_t>((size_t)std::max<int64_t>(nq, 1));
+            uint32_t* d_rows2 = ctx->d_indices.as<uint32_t>((size_t)nq * k);
+            T* d_dist2 = h_out_dist ? ctx->d_misc2.as<T>((size_t)nq * k) : nullptr;
+            rows_by_caller_index<T>(ctx, ib, N, sb, nq, k, d_idx32, d_dist, d_rows2, d_dist2, d_ids);
+            d_idx32 = d_rows2;
+            if (h_out_dist) d_dist = d_dist2;
+            WTP_CUDA_CHECK(cudaMemcpyAsync(ctx->h_ids, d_ids, (size_t)nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+            ids = static_cast<const uint32_t*>(ctx->h_ids);
             if (h_out_dist) {
                 dist_tmp.resize((size_t)nq * k);
                 WTP_CUDA_CHECK(cudaMemcpyAsync(dist_tmp.data(), d_dist, (size_t)nq * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
@@ -352,11 +365,13 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
             } else {
                 const int64_t nrow = ce - cb;
                 ctx->pool->run([&](int part, int parts) {
-                    for (int64_t t = nrow * part / parts; t < nrow * (part + 1) / parts; ++t) {
-                        int64_t* dst = h_out_idx + (ids[(size_t)(cb + t)] - 1) * k;
-                        for (int r = 0; r < k; ++r) dst[r] = (int64_t)src[t * k + r];
-                        if (h_out_dist) memcpy(h_out_dist + (ids[(size_t)(cb + t)] - 1) * k, dist_tmp.data() + (size_t)(cb + t) * k, (size_t)k * sizeof(T));
+                    const int64_t t_end = nrow * (part + 1) / parts;
+                    for (int64_t t = nrow * part / parts; t < t_end; ++t) {
+                        int64_t* dst = h_out_idx + ((int64_t)ids[(size_t)(cb + t)] - 1) * k;
+                        for (int r = 0; r < k; ++r) _mm_stream_si64(reinterpret_cast<long long*>(dst + r), (long long)src[t * k + r]);   // no read-for-ownership of the caller's table
+                        if (h_out_dist) memcpy(h_out_dist + ((int64_t)ids[(size_t)(cb + t)] - 1) * k, dist_tmp.data() + (size_t)(cb + t) * k, (size_t)k * sizeof(T));
                     }
+                    _mm_sfence();
                 });
             }
             if (dbg) { t_wait += t1 - t0; t_widen += now() - t1; }

@@ -107,7 +107,14 @@ bool comm_peer_buffers(wtp_ctx* ctx, size_t bytes_each) {
     if (pb.mapped && pb.bytes_each >= bytes_each) return true;
     NcclApi* api = ctx->nccl;
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    peers_unmap(ctx);
+    if (pb.mapped) {
+        // growing: every rank closes its mappings first, and only after all have done so (a tiny all-gather as the
+        // barrier) does anybody free the buffer the others had mapped
+        peers_unmap(ctx);
+        int64_t* d_flag = ctx->d_misc.as<int64_t>((size_t)ctx->world + 1);
+        NCCL_CHECK(api, api->AllGather(d_flag + ctx->world, d_flag, sizeof(int64_t), NCCL_INT8, ctx->nccl_comm, ctx->stream));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     if (pb.own.p) { cudaFree(pb.own.p); pb.own.p = nullptr; pb.own.cap = 0; }     // a fresh allocation: the handle names the whole allocation
     const size_t each = (bytes_each + bytes_each / 8 + 4095) & ~(size_t)4095;
     void* mine = nullptr;

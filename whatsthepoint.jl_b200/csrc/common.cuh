@@ -300,6 +300,8 @@ struct wtp_ctx {
     size_t h_stage_slot_bytes = 0;
     cudaEvent_t ev_copied[4] = {};
     wtp::HostPool* pool = nullptr;
+    void* h_ids = nullptr;            // pinned, grow-only: caller indices of a sharded host call's rows (4 bytes each)
+    size_t h_ids_bytes = 0;
     // pinned staging for scalar read-backs
     void* h_pinned = nullptr;
     size_t h_pinned_bytes = 0;

@@ -53,6 +53,12 @@ template <class T>
 void knn_points(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int D, int K, const T* d_q, int64_t n_q, uint32_t* d_out_idx32);
 // caller indices (1-based) of the sorted positions [s_begin, s_end)
 void owned_ids(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, int64_t* d_ids);
+// the n rows (uint32, k wide; optionally their distances) of the run starting at sorted position s_begin, reordered by
+// ascending caller index (uses the index's radix sort scratch); d_ids_out: the caller indices + 1 in that order
+template <class T>
+void rows_by_caller_index(wtp_ctx* ctx, IndexBuffers& ib, int64_t N, int64_t s_begin, int64_t n, int k, const uint32_t* d_rows, const T* d_dist,
+                          uint32_t* d_rows_out, T* d_dist_out, uint32_t* d_ids_out);
+void owned_ids32(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, uint32_t* d_ids);   // the same as 4-byte values
 
 // Sinks of a tiled pass inside ctx->d_fail: 16 counters (zeroed here), then the list of up to n sorted positions.
 TileFails tile_fails(wtp_ctx* ctx, int64_t n);

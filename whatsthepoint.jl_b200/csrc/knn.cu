@@ -177,6 +177,66 @@ __global__ void __launch_bounds__(256) owned_ids_kernel(const P4<T>* __restrict_
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (s_begin + t < s_end) ids[t] = (int64_t)idx_of(sorted[s_begin + t]) + 1;
 }
+template <class T>
+__global__ void __launch_bounds__(256) owned_ids32_kernel(const P4<T>* __restrict__ sorted, uint32_t s_begin, uint32_t s_end, uint32_t* __restrict__ ids) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s_begin + t < s_end) ids[t] = idx_of(sorted[s_begin + t]) + 1u;
+}
+void owned_ids32(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, uint32_t* d_ids) {
+    if (s_end <= s_begin) return;
+    const unsigned nb = (unsigned)((s_end - s_begin + 255) / 256);
+    if (f64) owned_ids32_kernel<double><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<double>>(), (uint32_t)s_begin, (uint32_t)s_end, d_ids);
+    else owned_ids32_kernel<float><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<float>>(), (uint32_t)s_begin, (uint32_t)s_end, d_ids);
+    LAUNCH_CHECK(ctx);
+}
+// Rows of a sharded host call in ascending caller index (the host then writes forward through the caller's table
+// instead of at random rows): sort (caller index, row) pairs with the index's own radix sort scratch — dead once the
+// index is built — and gather the rows in that order. d_rows_out / d_dist_out: n x k; d_ids_out: caller indices + 1.
+template <class T>
+__global__ void __launch_bounds__(256) row_keys_kernel(const P4<T>* __restrict__ sorted, uint32_t s_begin, uint32_t n, uint32_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ vals) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) { keys[t] = idx_of(sorted[s_begin + t]); vals[t] = t; }
+}
+template <class U>
+__global__ void __launch_bounds__(256) row_gather_kernel(const U* __restrict__ in, const uint32_t* __restrict__ perm, uint64_t n_elems, uint32_t k,
+                                                         U* __restrict__ out) {
+    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_elems) return;
+    const uint64_t r = e / k;
+    out[e] = in[(uint64_t)perm[r] * k + (e - r * k)];
+}
+__global__ void __launch_bounds__(256) ids_plus_one_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ ids) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) ids[t] = keys[t] + 1u;
+}
+template <class T>
+void rows_by_caller_index(wtp_ctx* ctx, IndexBuffers& ib, int64_t N, int64_t s_begin, int64_t n, int k, const uint32_t* d_rows, const T* d_dist,
+                          uint32_t* d_rows_out, T* d_dist_out, uint32_t* d_ids_out) {
+    if (n <= 0) return;
+    uint32_t* keys = ib.keys_a.as<uint32_t>((size_t)n);
+    uint32_t* vals = ib.vals_a.as<uint32_t>((size_t)n);
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    row_keys_kernel<T><<<nb, 256, 0, ctx->stream>>>(ib.sorted.get<P4<T>>(), (uint32_t)s_begin, (uint32_t)n, keys, vals);
+    LAUNCH_CHECK(ctx);
+    int bits = 1;
+    while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)N) ++bits;
+    radix_sort_pairs(ctx, ib, n, bits);
+    keys = ib.keys_a.get<uint32_t>();
+    vals = ib.vals_a.get<uint32_t>();
+    const uint64_t ne = (uint64_t)n * (uint64_t)k;
+    row_gather_kernel<uint32_t><<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(d_rows, vals, ne, (uint32_t)k, d_rows_out);
+    LAUNCH_CHECK(ctx);
+    if (d_dist) {
+        row_gather_kernel<T><<<(unsigned)((ne + 255) / 256), 256, 0, ctx->stream>>>(d_dist, vals, ne, (uint32_t)k, d_dist_out);
+        LAUNCH_CHECK(ctx);
+    }
+    ids_plus_one_kernel<<<nb, 256, 0, ctx->stream>>>(keys, (uint32_t)n, d_ids_out);
+    LAUNCH_CHECK(ctx);
+}
+template void rows_by_caller_index<float>(wtp_ctx*, IndexBuffers&, int64_t, int64_t, int64_t, int, const uint32_t*, const float*, uint32_t*, float*, uint32_t*);
+template void rows_by_caller_index<double>(wtp_ctx*, IndexBuffers&, int64_t, int64_t, int64_t, int, const uint32_t*, const double*, uint32_t*, double*, uint32_t*);
+
 void owned_ids(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, int64_t* d_ids) {
     if (s_end <= s_begin) return;
     const unsigned nb = (unsigned)((s_end - s_begin + 255) / 256);
