@@ -297,7 +297,18 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
                 if (nn_idx == 0xffffffffu) { nn_idx = key.idx(); nn_d2 = key.d2(); }   // :272-275
                 const T rr = sqrt(key.d2());
                 if (rr > (T)0) {                                              // _safe_direction (:358-364)
+#ifndef WTP_NO_INLINE_CLIPPED
+                    // the default law in line (the same operations as force_fn's case): no call out of the hot loop
+                    T f;
+                    const T u = rr / s;
+                    if (a.force.kind == WTP_FORCE_CLIPPED) {
+                        const T u2 = u * u, t = u2 + a.force.beta;
+                        const T Fc = (a.force.u0 * a.force.u0 - u2) / (t * t);
+                        f = Fc > (T)0 ? Fc : (T)0;
+                    } else f = force_fn<T>(a.force, u);
+#else
                     const T f = force_fn<T>(a.force, rr / s);
+#endif
                     F0 = F0 + f * ((xi0 - p.x) / rr);
                     F1 = F1 + f * ((xi1 - p.y) / rr);
                     if (D == 3) F2 = F2 + f * ((xi2 - p.z) / rr);
