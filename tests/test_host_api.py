@@ -60,3 +60,16 @@ def test_spacing_constructors_validate(pkg):
         pkg.BoundaryLayerSpacing(np.random.rand(5, 3), at_wall=0.1, bulk=1.0, layer_thickness=0.0)
     f = pkg.ClippedSpacingForce(0.5)
     assert f.u0 == 1.0 and pkg.StrongSpacingForce(0.5).gamma == 3.0 and pkg.InverseDistanceForce().beta == 0.2   # test/repel.jl:142-170
+
+
+def test_sorting_networks_are_the_generators_output():
+    """The register sorting networks compiled into the tiled kernels (csrc/sortnet*.inc) are exactly what
+    scripts/gen_sortnet.py emits (the generator checks each network with the 0-1 principle and random permutations
+    before it prints it)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gen = os.path.join(root, "scripts", "gen_sortnet.py")
+    csrc = os.path.join(root, "whatsthepoint.jl_b200", "csrc")
+    for name, args in (("sortnet48.inc", ("48", "33")), ("sortnet32.inc", ("32", "32")), ("sortnet48full.inc", ("48", "48"))):
+        out = subprocess.run([sys.executable, gen, *args], capture_output=True, text=True, check=True).stdout
+        assert out.strip() == open(os.path.join(csrc, name)).read().strip(), name
