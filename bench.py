@@ -316,7 +316,7 @@ def main():
                                    f"the window of the grid around its run (the whole grid at 1 GPU); no collective",
                        "l2": "working set (120 MB points + 160 MB sorted tiles + 1.68 GB output per step) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(pts_h.nbytes),
-                    "d2h_bytes_per_step": int(nq * K * 4 + (nq * 8 if world > 1 else 0)),
+                    "d2h_bytes_per_step": int(nq * K * 4 + (nq * 4 if world > 1 else 0)),   # rows as 4-byte indices (+ their 4-byte caller indices when sharded)
                     "api": "wtp_knn_f32: pinned host points in, N x 21 int64 table in host memory out; the rows cross PCIe as 4-byte "
                            "indices and are widened to int64 by the library's host threads"},
             "gpu_launches": int(launches),
