@@ -3,20 +3,27 @@
 
 Workload (BASELINE.json `metric`): KNNTopology k=21 on a synthetic uniform 3-D cloud of
 10 M float32 points ("U3(10M)"). One step = one full set_topology pass:
-bounding box -> cell keys -> radix sort -> gather -> warp-per-query k-NN, N x 21 int64 out.
+bounding box -> cell keys -> radix sort -> gather -> tiled k-NN, N x 21 int64 out.
 
   value   : Mqueries/s with the points already resident in HBM (wtp_knn_dev_f32), CUDA
             events on the launching stream, max over ranks.
   e2e     : the same metric through the host C-ABI call a Julia user makes (wtp_knn_f32):
             pinned host points in, N x 21 int64 table in host memory out, copies inside the timed region
             (the rows cross PCIe as 4-byte indices and are widened on the host by the library).
-  roofline: the k-NN query kernel, 96 algorithmic bytes per query, timed by
+  roofline: the k-NN query kernels, 96 algorithmic bytes per query, timed by
             CUDA events inside the library on the same stream, against MEASURED_PEAKS.json.
-  cpu_baseline: the CPU oracle (KD-tree port of the reference's path) on a bounded sample.
+            `traffic` is the ncu dram__bytes of the same launch at the same N when a capture of
+            this round is committed (profiles/r02_knn_traffic_n<N>.json), else null.
+  cpu_baseline: the CPU oracle (KD-tree port of the reference's path) on the same cloud.
   repel   : extra object — iterations/s of the fused repel sweep on the same cloud size.
+  extras  : the other BASELINE configurations, each with its own roofline object: k-NN on the
+            10 M cloud in Float64, config #3 (repel on the 2 M graded cube, Float32 and Float64),
+            config #4 (radius CSR on the 10 M quadtree-graded square).
+  parity_check (world > 1): outside the timed regions every rank brute-forces 256 of the rows it
+            answered and 64 positions of one sharded repel sweep in numpy.
 
-`--impl reference` times the CPU port (the reference itself is Julia and cannot run here)
-with all host threads on a bounded sample per step.
+`--impl reference` times the CPU port (the reference itself is Julia and cannot run here) on
+the SAME cloud (all 10 M points per step) with every core of the process's affinity mask.
 
 Multi-GPU (torchrun, one rank per GPU): the point set is replicated, every rank indexes the
 window of the grid around its contiguous 1/N run of the sorted order and answers that run (no
@@ -37,18 +44,22 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
 K = 21
-ALGO_BYTES_PER_QUERY_F32 = 96.0       # read 12 B coords + write 21 x 4 B indices
-ALGO_BYTES_REPEL_F32 = 136.0          # per point per iteration incl. index rebuild
+ALGO_BYTES_PER_QUERY = {"f32": 96.0, "f64": 108.0}    # read D*T coords + write 21 x 4 B indices
+ALGO_BYTES_REPEL = {"f32": 136.0, "f64": 196.0}       # per point per iteration incl. index rebuild
 
 
 def synth_uniform(n: int, seed: int = 0x57545031) -> np.ndarray:
-    """U3(N): iid uniform in [0,1)^3, float64 draw rounded once to float32; exact duplicate
-    rows are redrawn (none in practice)."""
+    """U3(N): iid uniform in [0,1)^3, float64 draw rounded once to float32 (scripts/synth.uniform_cube, stream 0)."""
     rng = np.random.Generator(np.random.Philox(key=seed))
-    pts = rng.random((n, 3)).astype(np.float32)
-    return pts
+    return rng.random((n, 3)).astype(np.float32)
+
+
+def workload_config(n: int) -> dict:
+    """The `config` object of BOTH arms (the driver compares them): the workload only, nothing about how it is run."""
+    return {"workload": f"U3({n}) uniform 3-D unit cube, KNNTopology k=21, float32, N x 21 int64 out", "points": n, "k": K}
 
 
 def peaks():
@@ -57,6 +68,29 @@ def peaks():
         with open(p) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(name: str, world: int):
+    """dram__bytes_read + dram__bytes_write per launch of the kernel from an ncu --set full capture of THIS round at
+    THIS GPU count (profiles/r02_<name>_traffic_n<world>.json, written from the .ncu-rep by scripts/ncu_traffic.py), or
+    None: a number from another configuration is not evidence for this line."""
+    p = os.path.join(ROOT, "profiles", f"r02_{name}_traffic_n{world}.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
+def roofline(kernel, algo_bytes, kernel_ms, traffic=None, note=None, **more):
+    hbm, how = peaks()
+    achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms and kernel_ms > 0 else None
+    r = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+         "frac": achieved / hbm if achieved else None, "traffic": traffic, "peak_source": how,
+         "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": kernel_ms}
+    if note:
+        r["note"] = note
+    r.update(more)
+    return r
 
 
 class ClockSampler:
@@ -108,29 +142,112 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+# ------------------------------------------------------------------ numpy checkers (parity_check, tests)
+def _slab_order(pts):
+    """Sort once by x so that the candidates of a sample are a contiguous slice (brute force inside the slab only)."""
+    order = np.argsort(pts[:, 0], kind="stable")
+    return order, np.ascontiguousarray(pts[order, 0])
+
+
+def _candidates(pts, order, xs, x, half):
+    lo, hi = np.searchsorted(xs, x - half), np.searchsorted(xs, x + half, side="right")
+    return order[lo:hi]
+
+
+def sample_rows_brute_force(pts: np.ndarray, qi, k: int, half: float | None = None) -> np.ndarray:
+    """Canonical (d2, index) k nearest OTHER points of the sampled queries, in the input precision without FMA (numpy
+    evaluates ((dx*dx + dy*dy) + dz*dz) operation by operation), 1-based. Candidates come from an x-slab of half-width
+    `half` (default: wide enough for ~40 k points per unit density); the result is checked to lie inside it."""
+    n, d = pts.shape
+    if half is None:
+        half = min(1.0, 1.3 * (float(k + 1) / n) ** (1.0 / d)) * float(np.ptp(pts[:, 0]) or 1.0)   # ~2x the k-th neighbour distance of a uniform cloud
+    order, xs = _slab_order(pts)
+    out = np.empty((len(qi), k), dtype=np.int64)
+    for a, i in enumerate(qi):
+        while True:
+            cand = _candidates(pts, order, xs, pts[i, 0], pts.dtype.type(half))
+            diff = pts[cand] - pts[i]
+            d2 = diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]
+            if d == 3:
+                d2 = d2 + diff[:, 2] * diff[:, 2]
+            if len(cand) > k:
+                sel = np.lexsort((cand, d2))[:k + 1]
+                if float(d2[sel[-1]]) < float(half) ** 2 or len(cand) == n:
+                    break
+            half *= 2.0
+        out[a] = cand[sel[1:]] + 1        # position 0 is the query itself (d2 = 0, or a lower-indexed twin: n[2:end] drops it either way)
+    return out
+
+
+def sample_repel_sweep(snap: np.ndarray, n_fixed: int, ids, s: float, beta: float, alpha_lo: float, alpha_max: float, k: int = K):
+    """One Jacobi sweep of _relax! (src/repel.jl:256-292) for the sampled movable ids, constant spacing s, clipped force
+    (u0 = 1), identity wall — in float64 numpy on the given coordinates. Returns the new positions of those points."""
+    pts = snap.astype(np.float64)
+    n, d = pts.shape
+    half = min(1.0, 1.3 * (float(k) / n) ** (1.0 / d)) * float(np.ptp(pts[:, 0]) or 1.0)
+    order, xs = _slab_order(pts)
+    out = np.empty((len(ids), d))
+    for a, mid in enumerate(ids):
+        i = int(mid) + n_fixed
+        h = half
+        while True:
+            cand = _candidates(pts, order, xs, pts[i, 0], h)
+            diff = pts[i] - pts[cand]
+            d2 = (diff * diff).sum(1)
+            sel = np.lexsort((cand, d2))[:k]
+            if len(cand) >= k and (d2[sel[-1]] < h * h or len(cand) == n):
+                break
+            h *= 2.0
+        F = np.zeros(d)
+        for j in sel:
+            if cand[j] == i:
+                continue
+            r = np.sqrt(d2[j])
+            u = r / s
+            f = max((1.0 - u * u) / (u * u + beta) ** 2, 0.0)
+            if r > 0:
+                F += f * diff[j] / r
+        fn = np.linalg.norm(F)
+        ai = min(max(1.0 / (fn + 1e-30), alpha_lo), alpha_max)
+        disp = s * ai * F
+        dn = np.linalg.norm(disp)
+        if dn > s:
+            disp *= s / dn
+        out[a] = pts[i] + disp
+    return out
+
+
+# ------------------------------------------------------------------------------ the CPU arm
 def run_reference(args, n_points):
-    """CPU arm: the oracle's KD-tree k-NN (port of the reference's NearestNeighbors path)."""
+    """CPU arm: the oracle's KD-tree k-NN (port of the reference's NearestNeighbors path) on the same cloud, every
+    step the whole problem (tree build + N queries), with all the cores of this process's affinity mask."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
-    sample = min(n_points, args.cpu_sample)
-    pts = synth_uniform(n_points)[:sample]
-    threads = oracle.max_threads()
+    pts = synth_uniform(n_points)
+    threads = oracle.host_threads()                      # not OpenMP's env: torchrun exports OMP_NUM_THREADS=1
     for _ in range(args.warmup):
-        oracle.knn(pts[: max(sample // 10, 1000)], K, threads=threads)
+        oracle.knn(pts[: max(n_points // 10, 1000)], K, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         oracle.knn(pts, K, threads=threads)
     dt = (time.perf_counter() - t0) / args.steps
-    val = sample / dt / 1e6
+    val = n_points / dt / 1e6
+    s1 = max(n_points // 80, 1000)
+    t0 = time.perf_counter()
+    oracle.knn(pts[:s1], K, threads=1)
+    one = s1 / (time.perf_counter() - t0) / 1e6
     line = {
         "impl": "reference", "metric": "knn_k21_Mqueries_per_s", "value": val, "unit": "Mqueries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"U3({n_points}) uniform 3-D unit cube, KNNTopology k=21, float32", "points": n_points, "k": K},
+        "config": workload_config(n_points),
         "cpu_baseline": {"value": val, "unit": "Mqueries/s", "cores": threads, "kind": "port",
-                         "sample": f"first {sample} points of the cloud as their own set_topology problem (KD-tree build + {sample} queries) per step"},
+                         "sample": f"the whole cloud per step: KD-tree build + {n_points} queries, {threads} threads (sched_getaffinity); warm-up steps "
+                                   f"on a tenth of it; reference-faithful single thread (set_topology is serial, src/topology.jl:81) on {s1} points: "
+                                   f"{one:.3f} Mqueries/s",
+                         "single_thread_value": one},
         "e2e": {"value": val, "unit": "Mqueries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is 100% Julia (not runnable in this image); this arm is oracle/wtp_oracle.cpp, the CPU port of its path, "
                 "on all host threads (the reference's own set_topology is single-threaded, src/topology.jl:81)",
@@ -145,11 +262,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=10_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=1_000_000)
     ap.add_argument("--repel-points", type=int, default=10_000_000)
     ap.add_argument("--repel-iters", type=int, default=20)
     ap.add_argument("--no-repel", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations (f64 k-NN, config #3, config #4)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the numpy self-check of the sharded paths (world > 1)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (very large clouds: N x 21 int64 pinned per rank)")
     args = ap.parse_args()
     n = args.points
@@ -191,6 +309,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks_ok(flag: bool) -> bool:
+        if world == 1:
+            return flag
+        t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed_dev(step, steps, warmup):
+        """W untimed + K timed calls of `step`, CUDA events on the launching stream, max over ranks -> ms per call."""
+        for _ in range(warmup):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
     pts_h = synth_uniform(n)
     qb, qe = ctx.shard(n)
     nq = qe - qb
@@ -207,7 +345,6 @@ def main():
     barrier()
     launches0 = ctx.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    q_ms, phases = [], []
     sampler = ClockSampler(local)
     with sampler as clocks:
         ev0.record(stream)
@@ -218,22 +355,29 @@ def main():
     # per-phase CUDA-event times of the last timed step (the library records them on the launching stream during the
     # call; reading them after every step would put a host round trip between the steps)
     t = ctx.timing()
-    q_ms.append(t["ms_query"])
-    phases.append(t)
     launches = ctx.launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_step = ms_total / args.steps
     value = n / (ms_step * 1e-3) / 1e6
-    q_ms_avg = float(np.mean(q_ms))
-    expanded = int(phases[-1]["n_ring_expanded"])
+    q_ms = float(t["ms_query"])
     # quick self-check of the measured output (self excluded). Sharded: row t of the compact table belongs to owned()[t].
     chk = d_idx[:1000].cpu().numpy()
-    own = ctx.owned()[:1000] if world > 1 else np.arange(1, 1001)
+    own_all = ctx.owned() if world > 1 else None
+    own = own_all[:1000] if world > 1 else np.arange(1, 1001)
     assert (chk >= 1).all() and (chk <= n).all() and not (chk == own[:, None]).any()
+
+    # ---------------------------------------------------------------- parity of the sharded rows (world > 1)
+    parity = None
+    if world > 1 and not args.no_parity:
+        rng = np.random.default_rng(1000 + rank)
+        rows_t = np.sort(rng.choice(nq, size=min(256, nq), replace=False))
+        got = d_idx[torch.from_numpy(rows_t).to(dev)].cpu().numpy()
+        want = sample_rows_brute_force(pts_h, own_all[rows_t] - 1, K)
+        parity = {"knn_rows_checked_per_rank": int(len(rows_t)), "knn_ok": all_ranks_ok(bool(np.array_equal(got, want)))}
 
     # ------------------------------------------------------------------ end-to-end arm
     ctx.set_timing(False)
-    e2e_ms, e2e_val = None, None
+    e2e_ms, e2e_val, e2e_phases = None, None, None
     if not args.no_e2e:
         h_pts = torch.from_numpy(pts_h).pin_memory()
         h_idx = torch.empty((n, K), dtype=torch.int64).pin_memory()
@@ -252,6 +396,16 @@ def main():
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
         e2e_val = n / (e2e_ms * 1e-3) / 1e6
         assert np.array_equal(h_idx_np[own - 1], chk), "host and device entry points disagree"
+        # where the time of one host call goes (one more, untimed call with the library's phase events on)
+        ctx.set_timing(True)
+        t0 = time.perf_counter()
+        step_e2e()
+        wall = (time.perf_counter() - t0) * 1e3
+        te = ctx.timing()
+        ctx.set_timing(False)
+        dev_ms = te["ms_bbox"] + te["ms_cellkey"] + te["ms_sort"] + te["ms_reorder"] + te["ms_query"]
+        e2e_phases = {"ms_h2d": float(te["ms_h2d"]), "ms_device_compute": float(dev_ms),
+                      "ms_d2h_and_widen": float(max(wall - te["ms_h2d"] - dev_ms, 0.0)), "ms_wall_this_call": float(wall)}
         del h_pts, h_idx
 
     # --------------------------------------------------------------------- repel extra
@@ -259,11 +413,24 @@ def main():
     if not args.no_repel:
         nr = args.repel_points
         ctx.set_timing(True)
-        snap = torch.from_numpy(synth_uniform(nr, seed=0x57545032)).to(dev)
+        snap_h = synth_uniform(nr, seed=0x57545032)
+        snap = torch.from_numpy(snap_h).to(dev)
         h = nr ** (-1.0 / 3.0)
         sp, _ = ctx.make_spacing("constant", a=h)
         fm = ctx.make_force("clipped", 0.2)
         kw = dict(k=K, tol=0.0, stall_after=0, alpha_lo=h / 2000, alpha_max=h / 20)
+        if world > 1 and not args.no_parity:
+            # one sharded sweep from the known snapshot, every rank checks 64 points anywhere in the cloud (so also
+            # points another rank swept and sent over NVLink) against the numpy restatement of the sweep
+            one = snap.clone()
+            ctx.repel_dev(one.data_ptr(), 0, nr, 3, np.float32, sp, fm, max_iters=1, **kw)
+            ids = np.sort(np.random.default_rng(2000 + rank).choice(nr, size=64, replace=False))
+            got = one[torch.from_numpy(ids).to(dev)].cpu().numpy().astype(np.float64)
+            want = sample_repel_sweep(snap_h, 0, ids, h, 0.2, h / 2000, h / 20)
+            err = float(np.abs(got - want).max() / h)
+            parity.update({"repel_points_checked_per_rank": 64, "repel_max_err_over_spacing": max_over_ranks(err),
+                           "repel_ok": all_ranks_ok(err <= 1e-3)})
+            del one
         ctx.repel_dev(snap.data_ptr(), 0, nr, 3, np.float32, sp, fm, max_iters=3, **kw)
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -272,66 +439,132 @@ def main():
         r1.record(stream)
         barrier()
         rt = ctx.timing()
-        rms = max_over_ranks(r0.elapsed_time(r1)) / max(res["iters"], 1)
-        sweep_ms = rt["ms_query"] / max(res["iters"], 1)
-        hbm, _ = peaks()
+        it = max(res["iters"], 1)
+        rms = max_over_ranks(r0.elapsed_time(r1)) / it
         repel = {"metric": "repel_iters_per_s", "value": 1e3 / rms, "unit": "iters/s", "points": nr, "dtype": "f32",
-                 "iters": res["iters"], "ms_per_iter": rms, "sweep_ms_per_iter": sweep_ms, "comm_ms_per_iter": rt["ms_comm"] / max(res["iters"], 1),
+                 "iters": res["iters"], "ms_per_iter": rms, "sweep_ms_per_iter": rt["ms_query"] / it, "comm_ms_per_iter": rt["ms_comm"] / it,
                  "exchange": ("sweep kernels store their runs into every rank's buffer over NVLink peer memory" if rt["n_peer_ranks"] > 0
                               else ("ncclAllGather of the runs after the sweep" if world > 1 else None)),
                  "conv_last": float(conv[-1]),
-                 "roofline": {"bound": "hbm", "achieved": ALGO_BYTES_REPEL_F32 * nr / world / (rms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                              "frac": ALGO_BYTES_REPEL_F32 * nr / world / (rms * 1e-3) / 1e9 / hbm, "traffic": None}}
+                 "roofline": roofline("repel_tile_kernel<float,3,clipped> + index rebuild (whole iteration)", ALGO_BYTES_REPEL["f32"] * nr / world, rms,
+                                      traffic=measured_traffic("repel", world))}
         del snap
 
+    # ------------------------------------------------------------------ the other BASELINE configurations
+    extras = None
+    if not args.no_extras:
+        import synth
+        extras = {}
+        ctx.set_timing(True)
+        steps_x, warm_x = max(3, min(args.steps, 5)), 3
+        # k-NN on the same cloud in Float64 (Julia's default coordinate type)
+        d64 = d_pts.double()
+        d_idx.zero_()
+        ms = timed_dev(lambda: ctx.knn_dev(d64.data_ptr(), n, 3, K, np.float64, d_idx.data_ptr()), steps_x, warm_x)
+        tq = ctx.timing()
+        extras["knn_f64_10M"] = {"metric": "knn_k21_Mqueries_per_s", "value": n / (ms * 1e-3) / 1e6, "unit": "Mqueries/s", "dtype": "f64", "ms_per_step": ms,
+                                 "config": {"workload": f"U3({n}) uniform 3-D, KNNTopology k=21, float64", "points": n},
+                                 "roofline": roofline("knn_tile_kernel<double,3> (+ leftovers)", ALGO_BYTES_PER_QUERY["f64"] * nq, float(tq["ms_query"]),
+                                                      traffic=measured_traffic("knn_f64", world))}
+        del d64
+        # config #3: repel on the 2 M graded cube, BoundaryLayerSpacing, Float32 and Float64
+        for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
+            gp, nw, hw = synth.graded_cube(2_000_000, dt)
+            d_g = torch.from_numpy(gp).to(dev)
+            d_b = d_g[:nw].clone()
+            spg, _ = ctx.make_spacing("boundary_layer", hw, 4 * hw, 0.2, bnd_ptr=d_b.data_ptr(), n_bnd=nw)
+            kwg = dict(k=K, tol=0.0, stall_after=0, alpha_lo=hw / 2000, alpha_max=hw / 20)
+            ctx.repel_dev(d_g.data_ptr(), nw, len(gp) - nw, 3, dt, spg, ctx.make_force("clipped", 0.2), max_iters=3, **kwg)
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            convg, resg = ctx.repel_dev(d_g.data_ptr(), nw, len(gp) - nw, 3, dt, spg, ctx.make_force("clipped", 0.2), max_iters=args.repel_iters, **kwg)
+            g1.record(stream)
+            barrier()
+            tg = ctx.timing()
+            itg = max(resg["iters"], 1)
+            msg = max_over_ranks(g0.elapsed_time(g1)) / itg
+            extras[f"repel_config3_graded_2M_{tag}"] = {
+                "metric": "repel_iters_per_s", "value": 1e3 / msg, "unit": "iters/s", "dtype": tag, "ms_per_iter": msg, "iters": resg["iters"],
+                "sweep_ms_per_iter": tg["ms_query"] / itg, "spacing_ms_per_iter": tg["ms_scan"] / itg,
+                "leftovers_last_iter": {k2: int(tg[k2]) for k2 in ("n_leftover_sparse", "n_leftover_dense", "n_leftover_other")},
+                "config": {"workload": f"G3({len(gp)}) graded unit cube (wall lattice {nw} fixed points, h_bulk/h_wall = 4, delta = 0.2), repel beta=0.2 "
+                                       f"k=21 BoundaryLayerSpacing, {tag}", "points": int(len(gp)), "seconds_per_1000_iters": msg},
+                "roofline": roofline(f"repel_tile_kernel<{'float' if tag == 'f32' else 'double'},3,clipped> + spacing evaluation + index rebuild (whole iteration)",
+                                     ALGO_BYTES_REPEL[tag] * len(gp) / world, msg, traffic=measured_traffic(f"repel_config3_{tag}", world))}
+            del d_g, d_b
+        # config #4: radius CSR on the 10 M quadtree-graded square (2-D, Float64), r = 2.5 h_mid
+        q2, hm = synth.graded_square(10_000_000, np.float64)
+        d_q = torch.from_numpy(q2).to(dev)
+        b4, e4 = ctx.shard(len(q2))
+        d_off = torch.empty(e4 - b4 + 1, dtype=torch.int64, device=dev)
+        nnz = ctx.radius_dev(d_q.data_ptr(), len(q2), 2, 2.5 * hm, np.float64, d_off.data_ptr())
+        d_ind = torch.empty(max(nnz, 1), dtype=torch.int64, device=dev)
+        ctx.radius_fill_dev(d_ind.data_ptr())
+
+        def step_radius():
+            ctx.radius_dev(d_q.data_ptr(), len(q2), 2, 2.5 * hm, np.float64, d_off.data_ptr())
+            ctx.radius_fill_dev(d_ind.data_ptr())
+
+        msr = timed_dev(step_radius, steps_x, warm_x)
+        nnz_all = nnz
+        if world > 1:
+            tt = torch.tensor([nnz], dtype=torch.int64, device=dev)
+            dist.all_reduce(tt)
+            nnz_all = int(tt.item())
+        extras["radius_config4_graded2d_10M_f64"] = {
+            "metric": "radius_Mpoints_per_s", "value": len(q2) / (msr * 1e-3) / 1e6, "unit": "Mpoints/s", "dtype": "f64", "ms_per_step": msr, "nnz": int(nnz_all),
+            "config": {"workload": f"Q2({len(q2)}) quadtree-graded unit square (h, h/2, h/4), RadiusTopology r = 2.5 h_mid = {2.5 * hm:.3e}, CSR int64 out, float64",
+                       "points": int(len(q2))},
+            "roofline": roofline("radius_tile_count_kernel + scan + radius_tile_fill_kernel (whole step incl. index build)",
+                                 (40.0 * (e4 - b4) + 4.0 * nnz), msr, traffic=measured_traffic("radius_config4", world),
+                                 note="algorithmic bytes = 2*D*T read + 4 count + 4 offset per point + 4 per entry (SURVEY.md §8d; the device writes int64 entries)")}
+        del d_q, d_off, d_ind
+
     if rank == 0:
-        hbm, how = peaks()
-        achieved = ALGO_BYTES_PER_QUERY_F32 * nq / (q_ms_avg * 1e-3) / 1e9
         cpu = None
         if not args.no_cpu and world == 1:
             import oracle
-            sample = min(n, args.cpu_sample)
-            threads = oracle.max_threads()
+            threads = oracle.host_threads()
             t0 = time.perf_counter()
-            oracle.knn(pts_h[:sample], K, threads=threads)
+            oracle.knn(pts_h, K, threads=threads)
             dt_all = time.perf_counter() - t0
-            s1 = max(sample // 8, 1000)
+            s1 = max(n // 80, 1000)
             t0 = time.perf_counter()
             oracle.knn(pts_h[:s1], K, threads=1)
             dt_one = time.perf_counter() - t0
-            cpu = {"value": sample / dt_all / 1e6, "unit": "Mqueries/s", "cores": threads, "kind": "port",
-                   "sample": f"first {sample} points as their own set_topology problem (KD-tree build + queries), all threads; "
-                             f"reference-faithful single thread on {s1} points: {s1 / dt_one / 1e6:.3f} Mqueries/s"}
-        ncu_traffic = None
-        tp = os.path.join(ROOT, "profiles", "knn_kernel_traffic.json")
-        if os.path.exists(tp):
-            with open(tp) as f:
-                ncu_traffic = json.load(f).get("dram_bytes_per_launch")
+            cpu = {"value": n / dt_all / 1e6, "unit": "Mqueries/s", "cores": threads, "kind": "port",
+                   "sample": f"the whole cloud once: KD-tree build + {n} queries, {threads} threads (sched_getaffinity); reference-faithful single thread "
+                             f"(set_topology is serial, src/topology.jl:81) on {s1} points: {s1 / dt_one / 1e6:.3f} Mqueries/s",
+                   "single_thread_value": s1 / dt_one / 1e6}
         line = {
             "metric": "knn_k21_Mqueries_per_s", "value": value, "unit": "Mqueries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"U3({n}) uniform 3-D unit cube, KNNTopology k=21, float32, N x 21 int64 out", "points": n, "k": K,
-                       "sharding": f"queries split in {world} contiguous runs of the spatially sorted order; every GPU holds the point set and indexes "
-                                   f"the window of the grid around its run (the whole grid at 1 GPU); no collective",
-                       "l2": "working set (120 MB points + 160 MB sorted tiles + 1.68 GB output per step) exceeds the 126 MB L2; no explicit flush"},
+            "config": workload_config(n),
+            "run": {"sharding": f"queries split in {world} contiguous runs of the spatially sorted order; every GPU holds the point set and indexes "
+                                f"the window of the grid around its run (the whole grid at 1 GPU); no collective",
+                    "l2": "working set (120 MB points + 160 MB sorted tiles + 1.68 GB output per step) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(pts_h.nbytes),
                     "d2h_bytes_per_step": int(nq * K * 4 + (nq * 4 if world > 1 else 0)),   # rows as 4-byte indices (+ their 4-byte caller indices when sharded)
+                    "phases_ms": e2e_phases,
                     "api": "wtp_knn_f32: pinned host points in, N x 21 int64 table in host memory out; the rows cross PCIe as 4-byte "
                            "indices and are widened to int64 by the library's host threads"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "knn_tile_kernel<float,3> (+ knn_kernel<float,3,1> for its leftovers)", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                         "frac": achieved / hbm, "traffic": ncu_traffic, "peak_source": how,
-                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_QUERY_F32 * nq, "kernel_ms": q_ms_avg,
-                         "kernel_ms_source": "CUDA events around the query launches of the last timed step, recorded by the library on the launching stream",
-                         "kernel_share_of_step": q_ms_avg / ms_step,
-                         "note": "k-NN is bound by instruction issue and the shared-memory pipe, not by DRAM: 96 B/query is compulsory traffic only (SURVEY.md §8d); kernel_ms = tiled pass + leftover pass"},
-            "phases_ms": {k: float(np.mean([p[k] for p in phases])) for k in ("ms_bbox", "ms_cellkey", "ms_sort", "ms_reorder", "ms_query")},
-            "ring_expanded_queries": expanded,
-            "tiled_pass_leftovers": {k: int(phases[-1][k]) for k in ("n_leftover_sparse", "n_leftover_dense", "n_leftover_other")},
-            "index_window": {"points_indexed_rank0": int(phases[-1]["n_window_points"]) or n, "missed": int(phases[-1]["n_window_missed"])},
+            "roofline": roofline("knn_tile_kernel<float,3> (+ knn_kernel<float,3,1> for its leftovers)", ALGO_BYTES_PER_QUERY["f32"] * nq, q_ms,
+                                 traffic=measured_traffic("knn", world),
+                                 note="k-NN is bound by instruction issue and the shared-memory pipe, not by DRAM: 96 B/query is compulsory traffic only "
+                                      "(SURVEY.md §8d); kernel_ms = tiled pass + leftover pass",
+                                 kernel_ms_source="CUDA events around the query launches of the last timed step, recorded by the library on the launching stream",
+                                 kernel_share_of_step=q_ms / ms_step),
+            "phases_ms": {k2: float(t[k2]) for k2 in ("ms_bbox", "ms_cellkey", "ms_sort", "ms_reorder", "ms_query")},
+            "ring_expanded_queries": int(t["n_ring_expanded"]),
+            "tiled_pass_leftovers": {k2: int(t[k2]) for k2 in ("n_leftover_sparse", "n_leftover_dense", "n_leftover_other")},
+            "index_window": {"points_indexed_rank0": int(t["n_window_points"]) or n, "missed": int(t["n_window_missed"])},
             "cpu_baseline": cpu,
             "repel": repel,
+            "extras": extras,
+            "parity_check": (dict(parity, ok=bool(parity.get("knn_ok", True) and parity.get("repel_ok", True))) if parity is not None else None),
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

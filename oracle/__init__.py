@@ -149,7 +149,17 @@ def _pts(pts):
 
 
 def max_threads() -> int:
+    """Threads the oracle uses by default (OpenMP's view: OMP_NUM_THREADS, which torchrun sets to 1)."""
     return int(lib().wtpo_max_threads())
+
+
+def host_threads() -> int:
+    """The cores this process may run on (sched_getaffinity): what bench.py passes as `threads=` so that the CPU arm
+    uses the same number of threads whatever launcher exported OMP_NUM_THREADS."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
 
 
 def knn(pts, k, *, drop_first=True, algo="kdtree", threads=0, dists=False):
@@ -219,13 +229,13 @@ def spacing_eval(sp: Spacing, pts):
 
 def repel(snap, n_fixed, sp: Spacing, f: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
           stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, threads=0, mesh=None, is_bnd=None,
-          deposit_ratio=0.0):
+          deposit_ratio=0.0, kick_seed=0):
     """_relax! on snap = [fixed head; movable tail]. Returns (new_snap, conv, result dict, trace)."""
     snap = np.array(_pts(snap), copy=True)
     n_all, d = snap.shape
     n_move = n_all - n_fixed
     prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0, 0,
-                      float(alpha_lo), float(alpha_max), float(tol), float(cv_target), 0, 0, float(deposit_ratio))
+                      float(alpha_lo), float(alpha_max), float(tol), float(cv_target), 0, int(kick_seed), float(deposit_ratio))
     conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
     tr = (TraceEntry * max(max_iters, 1))() if trace else None
     res = RepelResult()

@@ -317,6 +317,36 @@ inline int64_t mesh_project(const wtp_wall_mesh* m, const T* p, T* out) {
     return nb.tri + 1;
 }
 
+// ------------------------------------------------- the random direction of coincident pairs
+// _safe_direction (src/repel.jl:358-364) returns randn(...)/norm for r == 0, drawn from Julia's global RNG: a stream no
+// other implementation can reproduce. The library defines its own counter-based stream (include/wtp_cuda.h, "random
+// directions"); this is its restatement: the first point of a hashed sequence in [-1, 1)^D inside the unit ball and at
+// least 2^-5 from the origin, normalised. Exactly rounded operations only, so the bits agree with the device.
+inline uint64_t mix64(uint64_t z) {
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+inline uint64_t sweep_key(uint64_t seed, uint64_t iteration) { return mix64(seed ^ mix64(iteration)); }
+template <class T, int D>
+inline void random_unit(uint64_t key, uint32_t i, uint32_t j, T* out) {
+    const uint64_t h1 = mix64(key ^ ((uint64_t(i) << 32) | uint64_t(j)));
+    for (uint64_t c = 0;; ++c) {
+        const uint64_t h = mix64(h1 + c);
+        const T scale = T(1.0 / 1048576.0);
+        T v[3] = {T(int(h & 0x1fffffu) - 1048576) * scale, T(int((h >> 21) & 0x1fffffu) - 1048576) * scale,
+                  D == 3 ? T(int((h >> 42) & 0x1fffffu) - 1048576) * scale : T(0)};
+        T n2 = v[0] * v[0] + v[1] * v[1];
+        if (D == 3) n2 = n2 + v[2] * v[2];
+        if (n2 <= T(1) && n2 >= T(1.0 / 1024.0)) {
+            const T n = std::sqrt(n2);
+            for (int d = 0; d < D; ++d) out[d] = v[d] / n;
+            return;
+        }
+    }
+}
+
 // ------------------------------------------------------------------- relax
 template <class T, int D>
 int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in, const wtp_force* fm,
@@ -333,6 +363,7 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
     spacing.init(sp_in);
     const T beta = T(fm->beta), u0 = T(fm->u0), gamma = T(fm->gamma);
     std::vector<T> spacings(size_t(n_all) > 0 ? size_t(n_all) : 1);
+#pragma omp parallel for num_threads(threads) schedule(static)
     for (int64_t i = 0; i < n_all; ++i) spacings[i] = spacing(&snap[size_t(i) * D]);   // :209
     std::vector<T> p(snap + size_t(n_fixed) * D, snap + size_t(n_all) * D);  // movable, current
     std::vector<T> p_old(p);
@@ -352,6 +383,8 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
         p_old = p;                                                            // :244
         if ((it - 1) % prm->rebuild_every == 0) {                             // :245-253
             std::copy(p.begin(), p.end(), coords.begin() + size_t(n_fixed) * D);
+            // (serial in the reference, :251; elementwise, so the threads change nothing but the time)
+#pragma omp parallel for num_threads(threads) schedule(static)
             for (int64_t i = 0; i < n_move; ++i) spacings[size_t(n_fixed + i)] = spacing(&p[size_t(i) * D]);
             tree.build(coords.data(), n_all);
         }
@@ -372,10 +405,13 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
                     if (nid == 0) { nid = buf[j].idx + 1; nd = r; }
                     const T* xj = &coords[size_t(buf[j].idx) * D];
                     const T f = force_eval<T>(fm->kind, beta, u0, gamma, r / s);
-                    // _safe_direction :358-364 (r == 0 draws randn: parity inputs avoid it;
-                    // here the term is dropped deterministically).
-                    if (r > T(0))
+                    if (r > T(0)) {                                           // _safe_direction :358-364
                         for (int d = 0; d < D; ++d) F[d] = F[d] + f * ((xi[d] - xj[d]) / r);
+                    } else {                                                  // coincident: the library's random stream
+                        T dir[3];
+                        random_unit<T, D>(sweep_key(prm->kick_seed, uint64_t(it)), uint32_t(self), uint32_t(buf[j].idx), dir);
+                        for (int d = 0; d < D; ++d) F[d] = F[d] + f * dir[d];
+                    }
                 }
                 T n2 = T(0); for (int d = 0; d < D; ++d) n2 = n2 + F[d] * F[d];
                 const T Fn = std::sqrt(n2);                                   // :282

@@ -1,8 +1,12 @@
 """CPU, world_size 2, gloo: the N>1 host logic. k-NN queries shard by contiguous runs of a spatial
 (cell-sorted) order with the point set replicated (no collective), every rank returning the rows of
 the points it owns plus their caller indices; a Jacobi repel sweep shards the movable points by
-contiguous caller-order range and all-gathers the moved positions each iteration. The per-rank compute here is the CPU
-oracle standing in for the device kernels: what is tested is the sharding/gather logic."""
+contiguous caller-order range and all-gathers the moved positions each iteration. No GPU here, so the per-rank compute
+is the CPU oracle standing in for the device kernels; what belongs to the PRODUCT and is exercised through the C ABI of
+libwtp_cuda.so in every rank is the partition itself (wtp_shard_begin / wtp_shard_end: the ranges must tile [0, n)
+exactly for every n and world, and agree with the host mirror's shard_range) and bench.py's parity sampler
+(`sample_rows_brute_force`, the self-check every rank runs under world > 1). The device side of the same paths is
+tests/test_gpu_multi.py (2 and 4 GPUs)."""
 import os
 import sys
 
@@ -57,7 +61,20 @@ def _worker(rank, world, port, ret):
         convs.append(conv[0])
     ref, rconv, _, _ = oracle.repel(pts, n_fixed, sp, f, max_iters=iters, **kw)
     ok_repel = np.array_equal(snap, ref)
-    ret[rank] = (ok_knn, ok_repel)
+    # --- the product's partition through the C ABI (no GPU needed): every rank reports its own range, together they tile [0, n)
+    lib = pkg._lib.load()
+    ok_part = True
+    for n in (0, 1, 7, 4001, 10_000_000, (1 << 32) - 17):
+        mine = (int(lib.wtp_shard_begin(n, rank, world)), int(lib.wtp_shard_end(n, rank, world)))
+        ranges = [None] * world
+        dist.all_gather_object(ranges, mine)
+        ok_part = ok_part and mine == pkg.shard_range(n, rank, world) and ranges[0][0] == 0 and ranges[-1][1] == n \
+            and all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1)) and all(a <= b for a, b in ranges)
+    # --- bench.py's parity sampler on this rank's rows (brute force in numpy against the table the ranks assembled)
+    import bench
+    qi = own[:: max(len(own) // 16, 1)][:16]
+    ok_sampler = np.array_equal(bench.sample_rows_brute_force(pts, qi, 9), full[qi])
+    ret[rank] = (ok_knn, ok_repel, ok_part, ok_sampler)
     dist.destroy_process_group()
 
 
@@ -65,4 +82,4 @@ def test_sharded_knn_and_repel_world2():
     world = 2
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, 29611, ret), nprocs=world, join=True)
-    assert all(ret[r] == (True, True) for r in range(world)), dict(ret)
+    assert all(ret[r] == (True, True, True, True) for r in range(world)), dict(ret)

@@ -412,15 +412,16 @@ def compute_force(model: RepelForceModel, u, ctx=None):
 def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2, force_model: RepelForceModel | None = None,
           alpha=None, alpha_min=None, k=21, max_iters=1000, tol=1.0e-6, rebuild_every: int = 1, cull_ratio=0.0,
           kick_after: int = 0, stall_after: int = 50, cv_target=0.0, deposit_ratio=0.0, convergence: list | None = None,
-          trace: list | None = None, isinside: Callable | None = None, kick_seed: int = 0, ctx=None) -> PointCloud:
+          trace: list | None = None, isinside: Callable | bool | None = None, kick_seed: int = 0, ctx=None) -> PointCloud:
     """repel(cloud, spacing; kwargs...) (src/repel.jl:56-95): volume points move, boundary
     points are the fixed wall; returns a new cloud with NoTopology.
 
-    The relaxation (_relax!, src/repel.jl:202-339) runs in libwtp_cuda.so. The survivor
-    filter `filter(x -> isinside(x, cloud), p)` (:90) runs on the device too when `isinside=True`
-    (Green's function over the boundary elements in 3-D, which needs their normals and areas;
-    winding number in 2-D) or with a caller's predicate on an N x D array; by default every
-    moved point is kept. `cull_ratio > 0` applies the near-duplicate cull (:91-93, :549-580).
+    The relaxation (_relax!, src/repel.jl:202-339) runs in libwtp_cuda.so, and so does the survivor
+    filter `filter(x -> isinside(x, cloud), p)` (:90), which the reference always applies: Green's
+    function over the boundary elements in 3-D (it needs their normals and areas, which every
+    reference PointSurface carries), winding number in 2-D. `isinside=False` opts out (a mirror-only
+    convenience for clouds built from bare coordinates); a callable is used as the predicate on the
+    N x D array of moved points. `cull_ratio > 0` applies the near-duplicate cull (:91-93, :549-580).
     """
     if rebuild_every < 1:
         raise WtpArgumentError(1, "rebuild_every must be ≥ 1")                     # src/repel.jl:74
@@ -477,10 +478,9 @@ def repel(cloud: PointCloud, spacing: AbstractSpacing, octree=None, *, beta=0.2,
         out.escaped = ctx.last_wall["escaped"].astype(bool)
         return out
     p = new_snap[n_bnd:]
-    if isinside is not None:                                                       # :90  filter(x -> isinside(x, cloud), p)
-        keep_mask = isinside(p) if callable(isinside) else (globals()["isinside"](p, cloud, ctx=ctx) if isinside else None)
-        if keep_mask is not None:
-            p = p[np.asarray(keep_mask, dtype=bool)]
+    if isinside is not False and len(p) > 0:                                       # :90  filter(x -> isinside(x, cloud), p)
+        keep_mask = isinside(p) if callable(isinside) else globals()["isinside"](p, cloud, ctx=ctx)
+        p = p[np.asarray(keep_mask, dtype=bool)]
     if cull_ratio > 0 and len(p) > 0:                                              # :91-93
         p = p[_cull(p, spacing, cull_ratio, ctx)]
     out = PointCloud(cloud.boundary, PointVolume(p), NoTopology())                 # :94
@@ -540,7 +540,9 @@ def _boundary_elements(domain):
     if pts.shape[1] == 2:
         return pts, None, None
     if any(s.normals is None or s.areas is None for s in surfaces):
-        raise WtpArgumentError(1, "the 3-D isinside needs the normal and area of every boundary element")
+        raise WtpArgumentError(1, "the 3-D isinside (Green's function, src/isinside.jl:86-106) needs the normal and area of every "
+                                  "boundary element; repel(cloud, spacing) applies it to the moved points (src/repel.jl:90) — "
+                                  "build the surfaces with normals and areas, or pass isinside=False")
     return pts, np.concatenate([s.normals for s in surfaces], axis=0), np.concatenate([s.areas for s in surfaces], axis=0)
 
 

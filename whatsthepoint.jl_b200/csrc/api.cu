@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <new>
 
+#include "d2h_pipeline.h"
 #include "host_pool.h"
 #include "kernels.cuh"
 
@@ -85,6 +86,7 @@ void wtp_destroy(wtp_ctx* ctx) {
     delete ctx->pool;
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     for (auto e : ctx->ev_copied) if (e) cudaEventDestroy(e);
+    for (auto e : ctx->ev_ring) if (e) cudaEventDestroy(e);
     if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
@@ -173,43 +175,38 @@ void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_
     ctx->last_timing.n_window_missed = ctx->last_window_missed;
 }
 
-// A device array of 4-byte indices -> the caller's int64 host array: chunk by chunk into a pinned staging ring on the
-// copy stream, widened on the host pool while the next chunks are on the wire (4 B per entry cross PCIe instead of 8,
+// The pinned staging ring of the host entry points (d2h_pipeline.h): R slots of WTP_STAGE_MB MiB (default 4, R = 8).
+// Small slots keep the freshly DMA-written data in the last-level cache until the widening threads read it; the ring is
+// deep enough to keep the link busy while they do. (Re)allocated when the geometry changes.
+static size_t ensure_stage(wtp_ctx* ctx) {
+    size_t mb = 4;
+    if (const char* e = std::getenv("WTP_STAGE_MB")) { const long v = std::atol(e); if (v >= 1 && v <= 256) mb = (size_t)v; }
+    int ring = (int)std::max<size_t>(3, std::min<size_t>(16, 32 / mb));
+    if (const char* e = std::getenv("WTP_STAGE_SLOTS")) { const long v = std::atol(e); if (v >= 2 && v <= 64) ring = (int)v; }
+    const size_t slot = mb << 20;
+    if (!ctx->h_stage || ctx->h_stage_slot_bytes != slot || ctx->h_stage_ring != ring) {
+        if (ctx->h_stage) { cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; }
+        WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, (size_t)ring * slot));
+        ctx->h_stage_slot_bytes = slot;
+        ctx->h_stage_ring = ring;
+    }
+    if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads(ctx->world));
+    return slot;
+}
+
+// A device array of 4-byte indices -> the caller's int64 host array: chunk by chunk through the staging ring on the
+// copy stream, widened by the host pool while the next chunks are on the wire (4 B per entry cross PCIe instead of 8,
 // and the caller's array does not have to be pinned). The data must be complete on ctx->stream when this is called.
 void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst) {
     if (n == 0) return;
-    constexpr int S = 3;                                     // staging slots
-    constexpr size_t SLOT = (size_t)32 << 20;                // bytes per slot
-    if (!ctx->h_stage) {
-        WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, S * SLOT));
-        ctx->h_stage_slot_bytes = SLOT;
-    }
-    if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());   // also per rank on a shared node: measured, more threads in flight hide the latency of the scattered row writes
-    WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
-    WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0));
-    const size_t per = SLOT / sizeof(uint32_t);
-    const size_t n_chunks = (n + per - 1) / per;
-    auto enqueue_copy = [&](size_t c) {
-        const size_t cb = c * per, ce = std::min(n, cb + per);
-        WTP_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(ctx->h_stage) + (c % S) * SLOT, d_src + cb, (ce - cb) * sizeof(uint32_t),
-                                       cudaMemcpyDeviceToHost, ctx->copy_stream));
-        WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[c % 4], ctx->copy_stream));
-    };
-    for (size_t c = 0; c < std::min<size_t>(2, n_chunks); ++c) enqueue_copy(c);   // two copies ahead of the chunk being widened
-    for (size_t c = 0; c < n_chunks; ++c) {
-        if (c + 2 < n_chunks) enqueue_copy(c + 2);                                // slots c, c+1, c+2 are distinct
-        WTP_CUDA_CHECK(cudaEventSynchronize(ctx->ev_copied[c % 4]));
-        const size_t cb = c * per, ce = std::min(n, cb + per);
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<char*>(ctx->h_stage) + (c % S) * SLOT);
-        int64_t* dst = h_dst + cb;
-        const size_t total = ce - cb;
-        ctx->pool->run([&](int part, int parts) {
-            const size_t a = (total * part / parts) & ~(size_t)3, b = part + 1 == parts ? total : ((total * (part + 1) / parts) & ~(size_t)3);
-            widen_u32_to_i64(src + a, dst + a, b - a);
-        });
-    }
-    WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
-    WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
+    const size_t slot = ensure_stage(ctx);
+    d2h_pipeline(ctx, d_src, n * sizeof(uint32_t), slot, slot, ctx->h_stage_ring,
+                 [&](int64_t, const char* staged, size_t off, size_t len, int w, int workers) {
+                     const size_t total = len / sizeof(uint32_t), first = off / sizeof(uint32_t);
+                     const size_t a = (total * (size_t)w / (size_t)workers) & ~(size_t)3;
+                     const size_t b = w + 1 == workers ? total : ((total * (size_t)(w + 1) / (size_t)workers) & ~(size_t)3);
+                     widen_u32_to_i64(reinterpret_cast<const uint32_t*>(staged) + a, h_dst + first + a, b - a);
+                 });
 }
 
 // ------------------------------------------------------------------- k-NN
@@ -296,13 +293,7 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_idx, d_idx, (size_t)nq * k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         if (h_out_dist) WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist, d_dist, (size_t)nq * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     } else {
-        constexpr int S = 3;                                     // staging slots
-        constexpr size_t SLOT = (size_t)32 << 20;                // bytes per slot
-        if (!ctx->h_stage) {
-            WTP_CUDA_CHECK(cudaMallocHost(&ctx->h_stage, S * SLOT));
-            ctx->h_stage_slot_bytes = SLOT;
-        }
-        if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads());   // also per rank on a shared node: measured, more threads in flight hide the latency of the scattered row writes
+        const size_t SLOT = ensure_stage(ctx);
         uint32_t* d_idx32 = ctx->d_out_idx.as<uint32_t>((size_t)nq * k);
         T* d_dist = h_out_dist ? ctx->d_out_dist.as<T>((size_t)nq * k) : nullptr;
         compute(d_idx32, d_dist, true);
@@ -330,55 +321,36 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
                 dist_tmp.resize((size_t)nq * k);
                 WTP_CUDA_CHECK(cudaMemcpyAsync(dist_tmp.data(), d_dist, (size_t)nq * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
             }
+            WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));               // ids (and distances) are on the host
         } else if (h_out_dist) {
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_out_dist, d_dist, (size_t)nq * k * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
         }
-        WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_chunk[0], ctx->stream));
-        WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_chunk[0], 0));
-        const int64_t rows_per = std::max<int64_t>(1, (int64_t)(SLOT / ((size_t)k * sizeof(uint32_t))));
-        n_chunks = (int)((nq + rows_per - 1) / rows_per);
-        auto enqueue_copy = [&](int c) {
-            const int64_t cb = (int64_t)c * rows_per, ce = std::min<int64_t>(nq, cb + rows_per);
-            WTP_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT, d_idx32 + cb * k,
-                                           (size_t)(ce - cb) * k * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
-            WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[c % 4], ctx->copy_stream));
-        };
-        for (int c = 0; c < std::min(2, n_chunks); ++c) enqueue_copy(c);   // two copies ahead of the chunk being widened
-        const bool dbg = std::getenv("WTP_PIPE_DEBUG") != nullptr;
-        double t_wait = 0, t_widen = 0;
-        auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-        if (sharded) WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));       // ids (and distances) are on the host
-        for (int c = 0; c < n_chunks; ++c) {
-            if (c + 2 < n_chunks) enqueue_copy(c + 2);                         // slots c, c+1, c+2 are distinct
-            const double t0 = dbg ? now() : 0;
-            WTP_CUDA_CHECK(cudaEventSynchronize(ctx->ev_copied[c % 4]));
-            const double t1 = dbg ? now() : 0;
-            const int64_t cb = (int64_t)c * rows_per, ce = std::min<int64_t>(nq, cb + rows_per);
-            const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<char*>(ctx->h_stage) + (size_t)(c % S) * SLOT);
-            if (!sharded) {
-                int64_t* dst = h_out_idx + cb * k;
-                const size_t total = (size_t)(ce - cb) * k;
-                ctx->pool->run([&](int part, int parts) {
-                    const size_t a = (total * part / parts) & ~(size_t)3, b = part + 1 == parts ? total : ((total * (part + 1) / parts) & ~(size_t)3);
-                    widen_u32_to_i64(src + a, dst + a, b - a);
-                });
-            } else {
-                const int64_t nrow = ce - cb;
-                ctx->pool->run([&](int part, int parts) {
-                    const int64_t t_end = nrow * (part + 1) / parts;
-                    for (int64_t t = nrow * part / parts; t < t_end; ++t) {
-                        int64_t* dst = h_out_idx + ((int64_t)ids[(size_t)(cb + t)] - 1) * k;
-                        for (int r = 0; r < k; ++r) _mm_stream_si64(reinterpret_cast<long long*>(dst + r), (long long)src[t * k + r]);   // no read-for-ownership of the caller's table
-                        if (h_out_dist) memcpy(h_out_dist + ((int64_t)ids[(size_t)(cb + t)] - 1) * k, dist_tmp.data() + (size_t)(cb + t) * k, (size_t)k * sizeof(T));
-                    }
-                    _mm_sfence();
-                });
-            }
-            if (dbg) { t_wait += t1 - t0; t_widen += now() - t1; }
-        }
-        if (dbg) fprintf(stderr, "[wtp pipe] chunks=%d threads=%d wait_copy=%.2f ms widen=%.2f ms\n", n_chunks, ctx->pool->size(), t_wait, t_widen);
-        WTP_CUDA_CHECK(cudaEventRecord(ctx->ev_copy_done, ctx->copy_stream));
-        WTP_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy_done, 0));
+        const size_t row_bytes = (size_t)k * sizeof(uint32_t);
+        const size_t chunk_bytes = std::max<size_t>(1, SLOT / row_bytes) * row_bytes;   // whole rows per chunk
+        n_chunks = (int)(((size_t)nq * row_bytes + chunk_bytes - 1) / chunk_bytes);
+        const auto t_pipe = std::chrono::steady_clock::now();
+        d2h_pipeline(ctx, d_idx32, (size_t)nq * row_bytes, chunk_bytes, SLOT, ctx->h_stage_ring,
+                     [&](int64_t, const char* staged, size_t off, size_t len, int w, int workers) {
+                         const uint32_t* src = reinterpret_cast<const uint32_t*>(staged);
+                         if (!sharded) {
+                             const size_t total = len / sizeof(uint32_t), first = off / sizeof(uint32_t);
+                             const size_t a = (total * (size_t)w / (size_t)workers) & ~(size_t)3;
+                             const size_t b = w + 1 == workers ? total : ((total * (size_t)(w + 1) / (size_t)workers) & ~(size_t)3);
+                             widen_u32_to_i64(src + a, h_out_idx + first + a, b - a);
+                         } else {
+                             const int64_t nrow = (int64_t)(len / row_bytes), cb = (int64_t)(off / row_bytes);
+                             const int64_t t_end = nrow * (w + 1) / workers;
+                             for (int64_t t = nrow * w / workers; t < t_end; ++t) {
+                                 int64_t* dst = h_out_idx + ((int64_t)ids[(size_t)(cb + t)] - 1) * k;
+                                 for (int r = 0; r < k; ++r) _mm_stream_si64(reinterpret_cast<long long*>(dst + r), (long long)src[t * k + r]);   // no read-for-ownership of the caller's table
+                                 if (h_out_dist) memcpy(h_out_dist + ((int64_t)ids[(size_t)(cb + t)] - 1) * k, dist_tmp.data() + (size_t)(cb + t) * k, (size_t)k * sizeof(T));
+                             }
+                             _mm_sfence();
+                         }
+                     });
+        if (std::getenv("WTP_PIPE_DEBUG"))
+            fprintf(stderr, "[wtp pipe] chunks=%d slot=%zu MiB ring=%d threads=%d d2h+widen=%.2f ms\n", n_chunks, SLOT >> 20, ctx->h_stage_ring, ctx->pool->size(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pipe).count());
     }
     if (!counters_read || h_out_idx) {
         if (!counters_read) read_counters();

@@ -257,4 +257,32 @@ void spacing_eval(wtp_ctx* ctx, const SpacingP<T>& sp, const BvhBuffers& bv, con
 template void spacing_eval<float>(wtp_ctx*, const SpacingP<float>&, const BvhBuffers&, const float*, int64_t, int, float*, uint32_t*, bool);
 template void spacing_eval<double>(wtp_ctx*, const SpacingP<double>&, const BvhBuffers&, const double*, int64_t, int, double*, uint32_t*, bool);
 
+// ------------------------------------------------------------------ forces
+// compute_force(model, u) elementwise (src/repel_forces.jl:37, 57-60, 96-100, 124-127), the operations of the
+// reference in its order, not contracted (this translation unit is compiled with -fmad=false). The repel sweeps
+// (repel.cu) evaluate the same laws from u^2 with fused arithmetic.
+template <class T>
+__device__ __forceinline__ T force_fn(const ForceP<T> f, T u) {
+    const T u2 = u * u;
+    switch (f.kind) {
+        case WTP_FORCE_INVERSE: { const T t = u2 + f.beta; return (T)1 / (t * t); }
+        case WTP_FORCE_EQUILIBRIUM: { const T t = u2 + f.beta; return ((T)1 - u2) / (t * t); }
+        case WTP_FORCE_CLIPPED: { const T t = u2 + f.beta; const T F = (f.u0 * f.u0 - u2) / (t * t); return F > (T)0 ? F : (T)0; }
+        default: return ((T)1 - u2) / pow(u2 + f.beta, f.gamma);
+    }
+}
+template <class T>
+__global__ void __launch_bounds__(256) force_eval_kernel(const ForceP<T> f, const T* __restrict__ u, int64_t n, T* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = force_fn<T>(f, u[i]);
+}
+template <class T>
+void force_eval(wtp_ctx* ctx, const ForceP<T>& f, const T* d_u, int64_t n, T* d_out) {
+    if (n <= 0) return;
+    force_eval_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(f, d_u, n, d_out);
+    LAUNCH_CHECK(ctx);
+}
+template void force_eval<float>(wtp_ctx*, const ForceP<float>&, const float*, int64_t, float*);
+template void force_eval<double>(wtp_ctx*, const ForceP<double>&, const double*, int64_t, double*);
+
 }  // namespace wtp

@@ -111,6 +111,22 @@ __device__ __forceinline__ uint32_t spread2(uint32_t v) {  // 16 bits -> every s
     return v;
 }
 
+// ------------------------------------------------- the library's random stream
+// _safe_direction (src/repel.jl:358-364) draws a random unit vector for a coincident neighbour from Julia's global
+// RNG; that stream cannot be reproduced outside Julia, so the library defines its own, counter-based one (documented
+// in include/wtp_cuda.h, restated in the oracle): the direction for (sweep key, point i, neighbour j) is the first
+// point of a hashed sequence in the cube [-1, 1)^D that falls inside the unit ball (and not within 2^-5 of the
+// origin), normalised — uniform on the circle / sphere like randn/norm. Only exactly rounded operations (integer
+// hash, int -> T conversion, multiply, add, sqrt, divide, none fused), so every implementation gives the same bits.
+__host__ __device__ inline uint64_t mix64(uint64_t z) {   // splitmix64 finaliser
+    z += 0x9e3779b97f4a7c15ULL;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    return z ^ (z >> 31);
+}
+// key of one sweep: the seed of the call and the 1-based iteration number
+__host__ __device__ inline uint64_t sweep_key(uint64_t seed, uint64_t iteration) { return mix64(seed ^ mix64(iteration)); }
+
 // ------------------------------------------------------------ device memory
 struct DevBuf {
     void* p = nullptr;
@@ -299,6 +315,8 @@ struct wtp_ctx {
     void* h_stage = nullptr;
     size_t h_stage_slot_bytes = 0;
     cudaEvent_t ev_copied[4] = {};
+    std::vector<cudaEvent_t> ev_ring;     // one event per slot of the staging ring (d2h_pipeline.h)
+    int h_stage_ring = 0;                  // slots in the ring
     wtp::HostPool* pool = nullptr;
     void* h_ids = nullptr;            // pinned, grow-only: caller indices of a sharded host call's rows (4 bytes each)
     size_t h_ids_bytes = 0;

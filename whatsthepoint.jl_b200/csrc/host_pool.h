@@ -48,10 +48,13 @@ class HostPool {
         cv_done_.wait(lk, [this] { return pending_ == 0; });
         job_ = nullptr;
     }
-    static int default_threads() {
+    // WTP_HOST_THREADS, else the host's hardware threads (at most 16: more do not widen faster, the stores saturate the
+    // memory system) divided among the ranks that share the host (one process per GPU: `ranks` = the context's world)
+    static int default_threads(int ranks = 1) {
         if (const char* e = std::getenv("WTP_HOST_THREADS")) { int v = std::atoi(e); if (v > 0) return v > 64 ? 64 : v; }
         unsigned h = std::thread::hardware_concurrency();
         if (h == 0) h = 4;
+        if (ranks > 1) h = h / (unsigned)ranks > 2 ? h / (unsigned)ranks : 2;
         return (int)(h > 16 ? 16 : h);
     }
 

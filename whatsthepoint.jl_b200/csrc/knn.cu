@@ -78,11 +78,8 @@ static void launch_knn_kpl(wtp_ctx* ctx, unsigned nblocks, const Grid<T>& g, con
                            const uint32_t* d_qlist, int64_t nq, const uint32_t* d_nq, const RowMap& rows, int K1, int drop,
                            void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp, const T* d_ext_q = nullptr) {
     constexpr size_t smem = (size_t)knn_tile_cap<T, KPL>() * sizeof(P4<T>) * KNN_WARPS;
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        WTP_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<T, D, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // the attribute belongs to the (function, device) pair: set per launch, a context may sit on any device
+    if (smem > 48 * 1024) WTP_CUDA_CHECK(cudaFuncSetAttribute(knn_kernel<T, D, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_kernel<T, D, KPL><<<nblocks, KNN_THREADS, smem, ctx->stream>>>(g, sorted, cs, d_qlist, (uint32_t)nq, d_nq, rows,
                                                                        K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
 }
@@ -143,11 +140,7 @@ template <class T, int D>
 static void run_tiled(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N, int K1, int drop, int64_t s_begin, int64_t s_end,
                       const RowMap& rows, void* d_out_idx, int out32, T* d_out_dist, unsigned long long* d_exp) {
     constexpr size_t smem = tk_smem<T>();
-    static bool configured = false;
-    if (!configured) {
-        WTP_CUDA_CHECK(cudaFuncSetAttribute(knn_tile_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    WTP_CUDA_CHECK(cudaFuncSetAttribute(knn_tile_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set per launch
     const TileFails f = tile_fails(ctx, s_end - s_begin);
     const unsigned nblocks = (unsigned)((s_end - s_begin + TK_Q - 1) / TK_Q);
     knn_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cells(), (uint32_t)s_begin,

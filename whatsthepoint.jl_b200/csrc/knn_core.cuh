@@ -41,6 +41,32 @@ __device__ __forceinline__ T dist2_rn(T qx, T qy, T qz, T px, T py, T pz) {
     return s;
 }
 
+__device__ __forceinline__ float sqrt_rn(float a) { return __fsqrt_rn(a); }
+__device__ __forceinline__ double sqrt_rn(double a) { return __dsqrt_rn(a); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// The library's random unit vector for the pair (i, j) of one sweep (common.cuh: mix64, sweep_key): the stand-in for
+// _safe_direction's randn(...)/norm (src/repel.jl:358-364). Cold path, kept out of line.
+template <class T, int D>
+__device__ __noinline__ void random_unit(uint64_t key, uint32_t i, uint32_t j, T* out /*[3]*/) {
+    const uint64_t h1 = mix64(key ^ (((uint64_t)i << 32) | (uint64_t)j));
+    for (uint64_t c = 0;; ++c) {
+        const uint64_t h = mix64(h1 + c);
+        const T scale = (T)(1.0 / 1048576.0);
+        const T v0 = mul_rn((T)((int)(h & 0x1fffffu) - 1048576), scale);
+        const T v1 = mul_rn((T)((int)((h >> 21) & 0x1fffffu) - 1048576), scale);
+        const T v2 = D == 3 ? mul_rn((T)((int)((h >> 42) & 0x1fffffu) - 1048576), scale) : (T)0;
+        T n2 = add_rn(mul_rn(v0, v0), mul_rn(v1, v1));
+        if (D == 3) n2 = add_rn(n2, mul_rn(v2, v2));
+        if (n2 <= (T)1 && n2 >= (T)(1.0 / 1024.0)) {
+            const T n = sqrt_rn(n2);
+            out[0] = div_rn(v0, n); out[1] = div_rn(v1, n); out[2] = D == 3 ? div_rn(v2, n) : (T)0;
+            return;
+        }
+    }
+}
+
 template <class T>
 __device__ __forceinline__ P4<T> load_p4(const P4<T>* p);
 template <>

@@ -25,7 +25,12 @@ namespace wtp {
 constexpr int TK_Q = 128;          // queries (= threads) per CTA
 constexpr int TK_WARPS = TK_Q / 32;
 constexpr int TK_LCAP = 48;        // hits kept per query
-constexpr int TK_LSTRIDE = 50;     // u16 slots per list: 25 words, odd, so the 32 lists of a warp start in 32 different banks
+#ifndef TK_FILTER_WIDE
+#define TK_FILTER_WIDE 4           // candidates per trip of the filter loop: their tile reads are issued together (1: one at a time)
+#endif
+// u16 slots per list: an odd number of words, so the 32 lists of a warp start in 32 different banks; LCAP slots + the
+// ones an overflowing list can still reach between two clamps of the write position (one clamp per trip)
+constexpr int TK_LSTRIDE = TK_FILTER_WIDE > 1 ? 54 : 50;
 #ifndef TK_CAP_F32
 #define TK_CAP_F32 1792
 #endif
@@ -218,6 +223,32 @@ struct TileSearch {
         const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));
         const uint32_t my_s = smem_u32(my), lim = my_s + (uint32_t)(TK_LCAP + 1) * 2u;
         uint32_t addr = my_s;
+#if TK_FILTER_WIDE > 1
+        // TK_FILTER_WIDE candidates per trip: their tile reads are independent and issued back to back, so the latency of
+        // one shared-memory read is paid once per trip instead of once per candidate. Reads past the end of the run stay
+        // inside the CTA's shared memory (the lists follow the tile) and are masked by position.
+        const T t_far = t_inf<T>();
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) {
+#pragma unroll 1
+            for (uint32_t t = b[r]; t < e[r]; t += TK_FILTER_WIDE) {
+                T d[TK_FILTER_WIDE];
+#pragma unroll
+                for (int w = 0; w < TK_FILTER_WIDE; ++w) {
+                    const P4<T> p = lds_p4(tile + t + w);
+                    const T dx = q.x - p.x, dy = q.y - p.y;
+                    d[w] = fma(dy, dy, dx * dx);
+                    if (D == 3) { const T dz = q.z - p.z; d[w] = fma(dz, dz, d[w]); }
+                }
+#pragma unroll
+                for (int w = 0; w < TK_FILTER_WIDE; ++w) {
+                    if (w > 0) d[w] = t + w < e[r] ? d[w] : t_far;
+                    append_if_le(addr, t + w, d[w], r0pad);
+                }
+                addr = min(addr, lim);                     // slots LCAP .. LCAP + WIDE absorb an overflowing list
+            }
+        }
+#else
 #pragma unroll
         for (int r = 0; r < NROWS; ++r) {
 #pragma unroll kSweepUnroll
@@ -230,6 +261,7 @@ struct TileSearch {
                 addr = min(addr, lim);                     // slots LCAP, LCAP+1 absorb an overflowing list
             }
         }
+#endif
         asm volatile("" ::: "memory");                     // the appends are done before the lists are read
         const uint32_t cnt = (addr - my_s) >> 1;
         if (cnt < (uint32_t)K) return TK_SPARSE;

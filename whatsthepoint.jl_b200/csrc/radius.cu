@@ -339,11 +339,7 @@ template <class T, int D>
 static void launch_radius_tile_count(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t n, int64_t q_begin, T r2, uint32_t* d_counts,
                                      const TileFails& f) {
     constexpr size_t smem = RadTile<T, D>::SMEM_COUNT;
-    static bool configured = false;
-    if (!configured) {
-        WTP_CUDA_CHECK(cudaFuncSetAttribute(radius_tile_count_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    WTP_CUDA_CHECK(cudaFuncSetAttribute(radius_tile_count_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set per launch
     radius_tile_count_kernel<T, D><<<(unsigned)((n + TK_Q - 1) / TK_Q), TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cells(), 0u, (uint32_t)n,
                                                                                                    (uint32_t)q_begin, r2, d_counts, f);
     LAUNCH_CHECK(ctx);
@@ -352,11 +348,7 @@ template <class T, int D>
 static void launch_radius_tile_fill(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t n, int64_t q_begin, T r2, const int64_t* d_offsets,
                                     int64_t* d_indices, const TileFails& f) {
     constexpr size_t smem = RadTile<T, D>::SMEM_FILL;
-    static bool configured = false;
-    if (!configured) {
-        WTP_CUDA_CHECK(cudaFuncSetAttribute(radius_tile_fill_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    WTP_CUDA_CHECK(cudaFuncSetAttribute(radius_tile_fill_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set per launch
     radius_tile_fill_kernel<T, D><<<(unsigned)((n + TK_Q - 1) / TK_Q), TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cells(), 0u, (uint32_t)n,
                                                                                                   (uint32_t)q_begin, r2, d_offsets, d_indices, f);
     LAUNCH_CHECK(ctx);

@@ -31,31 +31,48 @@ void comm_allgather_rows(wtp_ctx* ctx, void* d_buf, int64_t n_rows, size_t row_b
 void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t bytes_per_rank);
 
 // ------------------------------------------------------------------ forces
-// src/repel_forces.jl:37, 57-60, 96-100, 124-127 (compiled with -fmad=false)
+// src/repel_forces.jl:37, 57-60, 96-100, 124-127. Every law depends on u = r/s through u^2 only, so the sweeps
+// evaluate F(u^2) with u^2 = d2 / s^2 and never need u itself; with the direction (xi - xj)/r the term of one
+// neighbour is F(u^2) * rsqrt(d2) * (xi - xj): one square root and one division per neighbour. This translation
+// unit is compiled with FMA contraction: the north star's contract for repel is a tolerance (1e-6 s in Float64,
+// 1e-3 s in Float32 after 10 iterations), not bit equality; what stays canonical is the neighbour SELECTION
+// (keys from dist2_rn, explicit round-to-nearest operations, ordered by (d2, index)).
+// FK: the law known at compile time (the default ClippedSpacingForce), or -1 = a switch on f.kind.
+template <class T> __device__ __forceinline__ T fast_div(T a, T b);
+template <> __device__ __forceinline__ float fast_div<float>(float a, float b) { return __fdividef(a, b); }   // MUFU.RCP + FMUL, 2 ulp
+template <> __device__ __forceinline__ double fast_div<double>(double a, double b) { return a / b; }
+template <class T> __device__ __forceinline__ T fast_sqrt(T a);
+template <> __device__ __forceinline__ float fast_sqrt<float>(float a) { return __fsqrt_rn(a); }
+template <> __device__ __forceinline__ double fast_sqrt<double>(double a) { return sqrt(a); }
+
 template <class T>
-__device__ __noinline__ T force_fn(const ForceP<T> f, T u) {
-    const T u2 = u * u;
+__device__ __noinline__ T force_u2_generic(const ForceP<T> f, T u2) {
     switch (f.kind) {
-        case WTP_FORCE_INVERSE: { const T t = u2 + f.beta; return (T)1 / (t * t); }
-        case WTP_FORCE_EQUILIBRIUM: { const T t = u2 + f.beta; return ((T)1 - u2) / (t * t); }
-        case WTP_FORCE_CLIPPED: { const T t = u2 + f.beta; const T F = (f.u0 * f.u0 - u2) / (t * t); return F > (T)0 ? F : (T)0; }
+        case WTP_FORCE_INVERSE: { const T t = u2 + f.beta; return fast_div<T>((T)1, t * t); }
+        case WTP_FORCE_EQUILIBRIUM: { const T t = u2 + f.beta; return fast_div<T>((T)1 - u2, t * t); }
+        case WTP_FORCE_CLIPPED: { const T t = u2 + f.beta; const T F = fast_div<T>(f.u0 * f.u0 - u2, t * t); return F > (T)0 ? F : (T)0; }
         default: return ((T)1 - u2) / pow(u2 + f.beta, f.gamma);
     }
 }
-
-template <class T>
-__global__ void __launch_bounds__(256) force_eval_kernel(const ForceP<T> f, const T* __restrict__ u, int64_t n, T* __restrict__ out) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = force_fn<T>(f, u[i]);
+// the term of one neighbour at squared distance d2 > 0, as the weight w of (xi - xj): F(d2 / s^2) / sqrt(d2).
+// Returns 0 when the law gives no force there (the clipped law beyond u0).
+template <class T, int FK>
+__device__ __forceinline__ T pair_weight(const ForceP<T>& f, T u0sq, T d2, T inv_s2) {
+    const T u2 = d2 * inv_s2;
+    if (FK == WTP_FORCE_CLIPPED) {
+        const T q = u0sq - u2;
+        if (!(q > (T)0)) return (T)0;
+        const T t = u2 + f.beta;
+        return fast_div<T>(q, t * t * fast_sqrt<T>(d2));
+    }
+    return fast_div<T>(force_u2_generic<T>(f, u2), fast_sqrt<T>(d2));
 }
-template <class T>
-void force_eval(wtp_ctx* ctx, const ForceP<T>& f, const T* d_u, int64_t n, T* d_out) {
-    if (n <= 0) return;
-    force_eval_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(f, d_u, n, d_out);
-    LAUNCH_CHECK(ctx);
+// F(0): the magnitude of the push between coincident points (_safe_direction, src/repel.jl:358-364)
+template <class T, int FK>
+__device__ __forceinline__ T force_at_zero(const ForceP<T>& f, T u0sq) {
+    if (FK == WTP_FORCE_CLIPPED) { const T F = fast_div<T>(u0sq, f.beta * f.beta); return F > (T)0 ? F : (T)0; }
+    return force_u2_generic<T>(f, (T)0);
 }
-template void force_eval<float>(wtp_ctx*, const ForceP<float>&, const float*, int64_t, float*);
-template void force_eval<double>(wtp_ctx*, const ForceP<double>&, const double*, int64_t, double*);
 
 // ------------------------------------------------------------------- sweep
 template <class T> __host__ __device__ inline T t_max();
@@ -113,6 +130,7 @@ struct SweepArgs {
     P4<T>* Cp[WTP_MAX_PEERS];
     T a_lo, a_max;
     ForceP<T> force;
+    uint64_t rng_key;      // sweep_key(kick_seed, iteration): the random directions of coincident pairs (common.cuh)
     RepelPartial<T>* partials;
 };
 
@@ -122,7 +140,24 @@ constexpr int SW_RUN = 8;                        // consecutive entries per warp
 template <class T, int KPL> __host__ __device__ constexpr int sw_tile_cap() { return KPL != 1 ? 0 : (sizeof(T) == 8 ? 224 : 288); }
 template <class T> __host__ __device__ constexpr int sw_min_blocks() { return sizeof(T) == 8 ? 3 : 4; }
 
-template <class T, int D, int KPL>
+// the adaptive step of one point (src/repel.jl:282-291): |F| s, alpha_i = clamp(1/(|F| + 1e-30), alpha_lo, alpha_max),
+// disp = s alpha_i F capped at one spacing. Returns |F| s; (F0, F1, F2) become the displacement.
+template <class T, int D>
+__device__ __forceinline__ T step_from_force(T s, T a_lo, T a_max, T& F0, T& F1, T& F2) {
+    T n2 = F0 * F0 + F1 * F1;
+    if (D == 3) n2 = n2 + F2 * F2;
+    const T Fn = fast_sqrt<T>(n2);                                                 // :282
+    T ai = fast_div<T>((T)1, Fn + (T)1.0e-30);                                     // :285
+    ai = ai > a_max ? a_max : (ai < a_lo ? a_lo : ai);
+    const T sa = s * ai;
+    F0 = sa * F0; F1 = sa * F1; F2 = D == 3 ? sa * F2 : (T)0;                      // :286
+    T dn2 = F0 * F0 + F1 * F1;
+    if (D == 3) dn2 = dn2 + F2 * F2;
+    if (dn2 > s * s) { const T sc = fast_div<T>(s, fast_sqrt<T>(dn2)); F0 = F0 * sc; F1 = F1 * sc; F2 = F2 * sc; }   // :288-290
+    return Fn * s;                                                                 // :283
+}
+
+template <class T, int D, int KPL, int FK>
 __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_kernel(const SweepArgs<T> a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int CAP = sw_tile_cap<T, KPL>();
@@ -135,6 +170,7 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
     WarpKnn<T, D, KPL, CAP> knn(a.g, a.sorted, a.cell_start, tile, reinterpret_cast<Key<T>*>(s_buf) + warp * 64, &s_bar[warp], lane);
     RepelPartial<T> acc;
     partial_init(acc);
+    const T u0sq = a.force.u0 * a.force.u0;
 
     // every warp takes runs of SW_RUN consecutive entries (sorted positions, or entries of qlist), dealt round-robin
     const uint32_t nq = a.nq_dev ? *a.nq_dev : a.nq;
@@ -148,6 +184,7 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
         const T xi2 = D == 3 ? a.P_old[(size_t)id * D + (D - 1)] : (T)0;
         knn.run(xi0, xi1, xi2, a.kk);                                             // :259
         const T s = a.s_cur ? a.s_cur[id] : a.s_const;                            // :260
+        const T inv_s = fast_div<T>((T)1, s), inv_s2 = inv_s * inv_s;
 
         bool found = false;
         T nn_d2 = (T)0; uint32_t nn_idx = 0xffffffffu;
@@ -158,12 +195,17 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
             const bool valid = r < a.kk && nj != 0xffffffffu && nj != self;       // skip self BY INDEX (:271)
             T t0 = (T)0, t1 = (T)0, t2 = (T)0;
             if (valid) {
-                const T rr = sqrt(knn.list.e[e].d2());
-                if (rr > (T)0) {                                                   // _safe_direction (:358-364)
-                    const T f = force_fn<T>(a.force, rr / s);
-                    t0 = f * ((xi0 - a.S[(size_t)nj * D + 0]) / rr);
-                    t1 = f * ((xi1 - a.S[(size_t)nj * D + 1]) / rr);
-                    if (D == 3) t2 = f * ((xi2 - a.S[(size_t)nj * D + (D - 1)]) / rr);
+                const T d2 = knn.list.e[e].d2();
+                if (d2 > (T)0) {
+                    const T w = pair_weight<T, FK>(a.force, u0sq, d2, inv_s2);
+                    t0 = w * (xi0 - a.S[(size_t)nj * D + 0]);
+                    t1 = w * (xi1 - a.S[(size_t)nj * D + 1]);
+                    if (D == 3) t2 = w * (xi2 - a.S[(size_t)nj * D + (D - 1)]);
+                } else {                                                           // _safe_direction's random branch (:358-364)
+                    T dir[3];
+                    random_unit<T, D>(a.rng_key, self, nj, dir);
+                    const T f0 = force_at_zero<T, FK>(a.force, u0sq);
+                    t0 = f0 * dir[0]; t1 = f0 * dir[1]; t2 = f0 * dir[2];
                 }
             }
             s_term[warp][r][0] = t0; s_term[warp][r][1] = t1; s_term[warp][r][2] = t2;
@@ -180,20 +222,9 @@ __global__ void __launch_bounds__(SW_THREADS, sw_min_blocks<T>()) repel_sweep_ke
         T Fc = (T)0;
         if (lane < D) for (int r = 0; r < a.kk; ++r) Fc = Fc + s_term[warp][r][lane];
         __syncwarp();
-        const T F0 = __shfl_sync(FULL, Fc, 0), F1 = __shfl_sync(FULL, Fc, 1), F2 = D == 3 ? __shfl_sync(FULL, Fc, 2) : (T)0;
-        T n2 = F0 * F0 + F1 * F1;
-        if (D == 3) n2 = n2 + F2 * F2;
-        const T Fn = sqrt(n2);                                                     // :282
-        const T fs = Fn * s;                                                       // :283
-        T ai = (T)1 / (Fn + (T)1.0e-30);                                           // :285
-        ai = ai > a.a_max ? a.a_max : (ai < a.a_lo ? a.a_lo : ai);
-        const T sa = s * ai;
-        T d0 = sa * F0, d1 = sa * F1, d2 = D == 3 ? sa * F2 : (T)0;                // :286
-        T dn2 = d0 * d0 + d1 * d1;
-        if (D == 3) dn2 = dn2 + d2 * d2;
-        const T dn = sqrt(dn2);
-        if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
-        const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;                       // :291 (identity wall)
+        T F0 = __shfl_sync(FULL, Fc, 0), F1 = __shfl_sync(FULL, Fc, 1), F2 = D == 3 ? __shfl_sync(FULL, Fc, 2) : (T)0;
+        const T fs = step_from_force<T, D>(s, a.a_lo, a.a_max, F0, F1, F2);
+        const T p0 = xi0 + F0, p1 = xi1 + F1, p2 = xi2 + F2;                       // :291 (identity wall)
         if (lane == 0) {
             if (a.n_peers > 0) {
                 P4<T> rec; rec.x = p0; rec.y = p1; rec.z = p2; rec.w = idx_bits((T)0, self);
@@ -261,7 +292,7 @@ __device__ __forceinline__ void partial_warp_reduce(RepelPartial<T>& p) {
     }
 }
 
-template <class T, int D>
+template <class T, int D, int FK>
 __global__ void __launch_bounds__(TK_Q, sizeof(T) == 4 ? 5 : 3)
 repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -274,6 +305,7 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
         for (int r = 0; r < a.n_peers; ++r) a.Cp[r][j - a.s_begin] = ts.q;
     RepelPartial<T> acc;
     partial_init(acc);
+    const T u0sq = a.force.u0 * a.force.u0;
     while (ts.next_group()) {
         int status = ts.select(a.kk);                                         // :259
         bool moved = false;                                                   // this thread has a new position for P_new
@@ -284,6 +316,7 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
             const uint32_t self = idx_of(ts.q), id = self - a.n_fixed;
             const T xi0 = ts.q.x, xi1 = ts.q.y, xi2 = ts.q.z;                 // == P_old[id] right after a rebuild (:246, :257)
             const T s = a.s_cur ? a.s_cur[id] : a.s_const;                    // :260
+            const T inv_s = fast_div<T>((T)1, s), inv_s2 = inv_s * inv_s;
             T F0 = (T)0, F1 = (T)0, F2 = (T)0, nn_d2 = (T)0;
             uint32_t nn_idx = 0xffffffffu;
             Key<T> prev = Key<T>::make((T)0, 0u);
@@ -295,40 +328,22 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
                 prev = key;
                 if (key.idx() == self) continue;                              // skip self BY INDEX (:271)
                 if (nn_idx == 0xffffffffu) { nn_idx = key.idx(); nn_d2 = key.d2(); }   // :272-275
-                const T rr = sqrt(key.d2());
-                if (rr > (T)0) {                                              // _safe_direction (:358-364)
-#ifndef WTP_NO_INLINE_CLIPPED
-                    // the default law in line (the same operations as force_fn's case): no call out of the hot loop
-                    T f;
-                    const T u = rr / s;
-                    if (a.force.kind == WTP_FORCE_CLIPPED) {
-                        const T u2 = u * u, t = u2 + a.force.beta;
-                        const T Fc = (a.force.u0 * a.force.u0 - u2) / (t * t);
-                        f = Fc > (T)0 ? Fc : (T)0;
-                    } else f = force_fn<T>(a.force, u);
-#else
-                    const T f = force_fn<T>(a.force, rr / s);
-#endif
-                    F0 = F0 + f * ((xi0 - p.x) / rr);
-                    F1 = F1 + f * ((xi1 - p.y) / rr);
-                    if (D == 3) F2 = F2 + f * ((xi2 - p.z) / rr);
+                if (key.d2() > (T)0) {
+                    const T w = pair_weight<T, FK>(a.force, u0sq, key.d2(), inv_s2);
+                    F0 = F0 + w * (xi0 - p.x);
+                    F1 = F1 + w * (xi1 - p.y);
+                    if (D == 3) F2 = F2 + w * (xi2 - p.z);
+                } else {                                                      // _safe_direction's random branch (:358-364)
+                    T dir[3];
+                    random_unit<T, D>(a.rng_key, self, key.idx(), dir);
+                    const T f0 = force_at_zero<T, FK>(a.force, u0sq);
+                    F0 = F0 + f0 * dir[0]; F1 = F1 + f0 * dir[1]; F2 = F2 + f0 * dir[2];
                 }
             }
             status = ts.accept(ok, prev);
             if (status == TK_OK) {
-                T n2 = F0 * F0 + F1 * F1;
-                if (D == 3) n2 = n2 + F2 * F2;
-                const T Fn = sqrt(n2);                                        // :282
-                const T fs = Fn * s;                                          // :283
-                T ai = (T)1 / (Fn + (T)1.0e-30);                              // :285
-                ai = ai > a.a_max ? a.a_max : (ai < a.a_lo ? a.a_lo : ai);
-                const T sa = s * ai;
-                T d0 = sa * F0, d1 = sa * F1, d2 = D == 3 ? sa * F2 : (T)0;   // :286
-                T dn2 = d0 * d0 + d1 * d1;
-                if (D == 3) dn2 = dn2 + d2 * d2;
-                const T dn = sqrt(dn2);
-                if (dn > s) { const T sc = s / dn; d0 = d0 * sc; d1 = d1 * sc; d2 = d2 * sc; }   // :288-290
-                const T p0 = xi0 + d0, p1 = xi1 + d1, p2 = xi2 + d2;          // :291 (the wall rule follows in its own kernel)
+                const T fs = step_from_force<T, D>(s, a.a_lo, a.a_max, F0, F1, F2);
+                const T p0 = xi0 + F0, p1 = xi1 + F1, p2 = xi2 + F2;          // :291 (the wall rule follows in its own kernel)
                 if (a.n_peers > 0) {
                     P4<T> rec; rec.x = p0; rec.y = p1; rec.z = p2; rec.w = idx_bits((T)0, self);
                     for (int r = 0; r < a.n_peers; ++r) a.Cp[r][ts.j - a.s_begin] = rec;
@@ -402,33 +417,33 @@ __global__ void __launch_bounds__(256) scatter_runs_kernel(const P4<T>* __restri
     warp_store_rows<T, D>(movable, movable ? (size_t)(self - n_fixed) : 0, rec.x, rec.y, rec.z, P_new, threadIdx.x & 31);
 }
 
-template <class T, int D, int KPL>
+template <class T, int D, int KPL, int FK>
 static void launch_sweep_kpl(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
     constexpr size_t smem = (size_t)sw_tile_cap<T, KPL>() * sizeof(P4<T>) * SW_WARPS;
-    static bool configured = false;
-    if (!configured && smem > 0) {
-        WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_sweep_kernel<T, D, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
-    repel_sweep_kernel<T, D, KPL><<<nblocks, SW_THREADS, smem, ctx->stream>>>(a);
+    // the attribute belongs to the (function, device) pair: set per launch, a context may sit on any device
+    if (smem > 0) WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_sweep_kernel<T, D, KPL, FK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    repel_sweep_kernel<T, D, KPL, FK><<<nblocks, SW_THREADS, smem, ctx->stream>>>(a);
 }
 template <class T, int D>
 static void launch_sweep(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks) {
-    if (a.kk <= 32) launch_sweep_kpl<T, D, 1>(ctx, a, nblocks);
-    else if (a.kk <= 64) launch_sweep_kpl<T, D, 2>(ctx, a, nblocks);
-    else launch_sweep_kpl<T, D, 4>(ctx, a, nblocks);
+    if (a.kk <= 32) {
+        if (a.force.kind == WTP_FORCE_CLIPPED) launch_sweep_kpl<T, D, 1, WTP_FORCE_CLIPPED>(ctx, a, nblocks);
+        else launch_sweep_kpl<T, D, 1, -1>(ctx, a, nblocks);
+    } else if (a.kk <= 64) launch_sweep_kpl<T, D, 2, -1>(ctx, a, nblocks);
+    else launch_sweep_kpl<T, D, 4, -1>(ctx, a, nblocks);
     LAUNCH_CHECK(ctx);
 }
 
 template <class T, int D>
 static void launch_sweep_tiled(wtp_ctx* ctx, const SweepArgs<T>& a, int nblocks, const TileFails& fails) {
     constexpr size_t smem = tk_smem<T>();
-    static bool configured = false;
-    if (!configured) {
-        WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_tile_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    if (a.force.kind == WTP_FORCE_CLIPPED) {
+        WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_tile_kernel<T, D, WTP_FORCE_CLIPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        repel_tile_kernel<T, D, WTP_FORCE_CLIPPED><<<nblocks, TK_Q, smem, ctx->stream>>>(a, fails);
+    } else {
+        WTP_CUDA_CHECK(cudaFuncSetAttribute(repel_tile_kernel<T, D, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        repel_tile_kernel<T, D, -1><<<nblocks, TK_Q, smem, ctx->stream>>>(a, fails);
     }
-    repel_tile_kernel<T, D><<<nblocks, TK_Q, smem, ctx->stream>>>(a, fails);
     LAUNCH_CHECK(ctx);
 }
 
@@ -655,6 +670,21 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     int passes = 0;
     IndexWindow win;
     bool windowed = false;
+    // Whether to window the index is decided once for all ranks: ctx->window_off is per-rank state (a sharded k-NN call
+    // on a graded cloud sets it on the ranks whose searches left their window), and ranks that disagreed would repeat
+    // different iterations below. Every rank adopts the OR of the ranks' flags; from here on the flag only changes on
+    // the merged partials, which are identical on every rank.
+    bool window_off = ctx->window_off;
+    if (by_runs) {
+        uint32_t* d_flag = reinterpret_cast<uint32_t*>(d_all);          // scratch, rewritten by the first sweep's all-gather
+        uint32_t* h_flag = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 3072);
+        h_flag[0] = window_off ? 1u : 0u;
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_flag + world, h_flag, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        comm_allgather_fixed(ctx, d_flag + world, d_flag, sizeof(uint32_t));
+        WTP_CUDA_CHECK(cudaMemcpyAsync(h_flag, d_flag, sizeof(uint32_t) * world, cudaMemcpyDeviceToHost, st));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (int r = 0; r < world; ++r) window_off = window_off || h_flag[r] != 0;
+    }
     int64_t n_deposited = 0;
     T best_cv_T = t_max<T>();
     int64_t last_impr = 0;
@@ -680,7 +710,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             g = make_grid<T>(n_all, D, lo, hi, ctx->cell_occupancy, 0.0, kk);
             // by runs, constant spacing: only the window of the grid around this rank's run is indexed (grid.cu); the
             // variable spacings visit the points in the order of the whole sorted set, so they keep the whole index
-            windowed = by_runs && !variable && !ctx->window_off && std::getenv("WTP_NO_WINDOW") == nullptr &&
+            windowed = by_runs && !variable && !window_off && std::getenv("WTP_NO_WINDOW") == nullptr &&
                        build_index_window<T>(ctx, ib, d_snap, n_all, D, g, gsb, gse, 2, &win, &passes);
             if (!windowed) passes = build_index<T>(ctx, ib, d_snap, n_all, D, g);                    // :252
             if (world > 1 && !by_runs) {
@@ -709,6 +739,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         a.n_fixed = (uint32_t)n_fixed; a.n_all = (uint32_t)n_all; a.id_lo = (uint32_t)id_lo; a.id_hi = (uint32_t)id_hi;
         a.qlist = qlist; a.nq = nq; a.kk = kk; a.rebuild = rebuild ? 1 : 0;
         a.a_lo = (T)prm->alpha_lo; a.a_max = (T)prm->alpha_max; a.force = force; a.partials = partials;
+        a.rng_key = sweep_key(prm->kick_seed, (uint64_t)it);
         a.nq_dev = nullptr;
         int n_partials = nblocks;
         const bool tiled_now = rebuild && tiled_ok;
@@ -759,9 +790,11 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             WTP_CUDA_CHECK(cudaStreamSynchronize(st));
             tot = h_tot[0];
             for (int r = 1; r < world; ++r) partial_merge(tot, h_tot[r]);
-            if (tot.missed > 0 && !ctx->window_off) {
-                // some rank's search left its window: every rank sees the same merged count, drops the windows for
-                // good and repeats this iteration on the whole index (nothing of it has been committed yet)
+            if (tot.missed > 0) {
+                // some rank's search left its window: every rank sees the same merged count (the only input of this
+                // decision), drops the windows for good and repeats this iteration on the whole index — a rank that
+                // was on the whole index already simply repeats it too (nothing of it has been committed yet)
+                window_off = true;
                 ctx->window_off = true;
                 ctx->last_window_missed += (int64_t)tot.missed;
                 continue;
