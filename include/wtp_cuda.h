@@ -182,6 +182,15 @@ int64_t wtp_radius_nnz(const wtp_ctx*);
 
 /* -------------------------------------------------------------------- repel */
 
+/* Random directions. _safe_direction (src/repel.jl:358-364) gives a coincident neighbour (r == 0) a random unit
+ * vector, randn(...)/norm, drawn from Julia's global RNG; no other implementation can reproduce that stream, so the
+ * library defines its own, counter-based and stateless: with
+ *     mix64(z): z += 0x9e3779b97f4a7c15; z = (z ^ z>>30) * 0xbf58476d1ce4e5b9; z = (z ^ z>>27) * 0x94d049bb133111eb; z ^ z>>31
+ *     key = mix64(kick_seed ^ mix64(iteration)),  h1 = mix64(key ^ (i << 32 | j))        (i, j: snapshot-global, 0-based)
+ * the direction of neighbour j seen from point i is the first v_c, c = 0, 1, ..., with 2^-10 <= |v_c|^2 <= 1, divided
+ * by |v_c|, where v_c[d] = (int(mix64(h1 + c) >> 21 d & 0x1fffff) - 2^20) * 2^-20 — uniform on the circle / sphere.
+ * Only exactly rounded operations: the oracle (oracle/wtp_oracle.cpp) produces the same bits. */
+
 /* Force laws F(u), u = r/s (src/repel_forces.jl). */
 enum { WTP_FORCE_INVERSE = 0,      /* 1/(u^2+beta)^2                      :37      */
        WTP_FORCE_EQUILIBRIUM = 1,  /* (1-u^2)/(u^2+beta)^2                :57-60   */
@@ -239,7 +248,8 @@ typedef struct {
     double alpha_lo, alpha_max;    /* ustrip(α_min), ustrip(α) (src/repel.jl:86)          */
     double tol, cv_target;
     int64_t n_protected;           /* snapshot-global count of points a kick avoids: n_boundary (:85, :172) */
-    uint64_t kick_seed;
+    uint64_t kick_seed;            /* seed of the library's random stream: the kick directions and the unit vectors of
+                                      coincident pairs ("random directions" below)                                */
     double deposit_ratio;          /* > 0 (mesh wall, n_fixed = 0, one GPU): _deposit_escaped! after every sweep
                                       (src/repel.jl:161-168, 328, 483-514): escaped volume points are projected onto
                                       their nearest triangle and become boundary points unless a boundary point
@@ -348,6 +358,25 @@ int32_t wtp_spacing_fidelity_f32(wtp_ctx*, const float* pts, int64_t N, int32_t 
                                  wtp_spacing_fidelity_t* out);
 int32_t wtp_spacing_fidelity_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k, double coord_radius, const wtp_spacing*,
                                  wtp_spacing_fidelity_t* out);
+
+/* ------------------------------------------- other consumers of the k-NN index */
+
+/* compute_normals(points; k) (src/normals.jl:9-44, _compute_normal :65-70): per point the unit eigenvector of the
+ * smallest eigenvalue of cov(its k nearest points, itself included) — the PCA normal of Hoppe (1992). k is clamped to
+ * N (:16). The sign is not defined by the reference (LAPACK's; orient_normals! fixes it afterwards): here the first
+ * nonzero component is positive. out: N x D of T. HOST pointers. */
+int32_t wtp_normals_f32(wtp_ctx*, const float* pts, int64_t N, int32_t D, int32_t k, float* out);
+int32_t wtp_normals_f64(wtp_ctx*, const double* pts, int64_t N, int32_t D, int32_t k, double* out);
+
+/* _gradient_limit_field(node_tree, leaves, h0_field, g; k, tol, max_sweeps) (src/discretization/algorithms/octree.jl:
+ * 677-717) on the leaf centres: the g-Lipschitz envelope of h0 by Jacobi min-plus sweeps over the k-NN graph of the
+ * centres, h[a] <- min(h[a], min_j h[j] + g * d_aj), until the largest relative change of a sweep is below tol (or
+ * max_sweeps). centers: n x D, h0 / out: n values (the caller maps them to and from its box-indexed field), sweeps
+ * (nullable): the number of sweeps run. k is clamped to n. HOST pointers. */
+int32_t wtp_gradient_limit_f32(wtp_ctx*, const float* centers, int64_t n, int32_t D, const float* h0, float g, int32_t k,
+                               double tol, int32_t max_sweeps, float* out, int32_t* sweeps);
+int32_t wtp_gradient_limit_f64(wtp_ctx*, const double* centers, int64_t n, int32_t D, const double* h0, double g, int32_t k,
+                               double tol, int32_t max_sweeps, double* out, int32_t* sweeps);
 
 #ifdef __cplusplus
 }

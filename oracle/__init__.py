@@ -229,12 +229,15 @@ def spacing_eval(sp: Spacing, pts):
 
 def repel(snap, n_fixed, sp: Spacing, f: Force, *, k=21, max_iters=1000, tol=1e-6, rebuild_every=1,
           stall_after=50, cv_target=0.0, alpha_lo, alpha_max, kick_after=0, trace=False, threads=0, mesh=None, is_bnd=None,
-          deposit_ratio=0.0, kick_seed=0):
+          deposit_ratio=0.0, kick_seed=0, cv_in_double=False):
     """_relax! on snap = [fixed head; movable tail]. Returns (new_snap, conv, result dict, trace)."""
     snap = np.array(_pts(snap), copy=True)
     n_all, d = snap.shape
     n_move = n_all - n_fixed
-    prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0, 0,
+    # cv_in_double: NOT the reference — accumulate the d_NN/s sums of the stop test in double like the device does (its
+    # documented deviation), to isolate what the accumulation precision does to a Float32 stall_after run
+    prm = RepelParams(k, max_iters, rebuild_every, stall_after, kick_after, 1 if mesh is not None else 0, 1 if trace else 0,
+                      1 if cv_in_double else 0,
                       float(alpha_lo), float(alpha_max), float(tol), float(cv_target), 0, int(kick_seed), float(deposit_ratio))
     conv = np.zeros(max(max_iters, 1), dtype=snap.dtype)
     tr = (TraceEntry * max(max_iters, 1))() if trace else None
@@ -309,6 +312,33 @@ def spacing_fidelity_metrics(pts, sp: Spacing, k=30, coord_radius=1.4, *, thread
     if rc != 0:
         raise ValueError(f"oracle spacing_fidelity_metrics failed with status {rc}")
     return {n: getattr(out, n) for n, _ in SpacingFidelity._fields_}
+
+
+def normals(pts, k=5, *, threads=0):
+    """compute_normals(points; k) (src/normals.jl:9-44): unit PCA normals, N x D, first nonzero component positive."""
+    pts = _pts(pts)
+    out = np.empty_like(pts)
+    rc = getattr(lib(), "wtpo_normals_" + _sfx(pts.dtype))(pts.ctypes.data_as(C.c_void_p), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]),
+                                                          C.c_int32(k), C.c_int32(threads), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError(f"oracle normals failed with status {rc}")
+    return out
+
+
+def gradient_limit(centers, h0, g, k=12, tol=1.0e-3, max_sweeps=2000, *, threads=0):
+    """_gradient_limit_field (src/discretization/algorithms/octree.jl:677-717) on the leaf centres -> (h, sweeps)."""
+    centers = _pts(centers)
+    h0 = np.ascontiguousarray(h0, dtype=centers.dtype)
+    out = np.empty_like(h0)
+    sweeps = C.c_int32(0)
+    sfx = _sfx(centers.dtype)
+    gg = C.c_float(g) if sfx == "f32" else C.c_double(g)
+    rc = getattr(lib(), "wtpo_gradient_limit_" + sfx)(centers.ctypes.data_as(C.c_void_p), C.c_int64(centers.shape[0]), C.c_int32(centers.shape[1]),
+                                                     h0.ctypes.data_as(C.c_void_p), gg, C.c_int32(k), C.c_double(tol), C.c_int32(max_sweeps),
+                                                     C.c_int32(threads), out.ctypes.data_as(C.c_void_p), C.byref(sweeps))
+    if rc != 0:
+        raise ValueError(f"oracle gradient_limit failed with status {rc}")
+    return out, int(sweeps.value)
 
 
 def closest_point_on_triangle(p, a, b, c):

@@ -24,6 +24,8 @@
 //                       stop logic :305-337)
 //   metrics             src/metrics.jl:19-41, spacing_metrics :56-71, spacing_fidelity_metrics :88-129
 //   isinside(p, cloud)  src/isinside.jl:18-35, 86-106 (winding number / Green's function over the boundary points)
+//   compute_normals     src/normals.jl:9-44, 65-70 (k-NN + smallest eigenvector of the covariance)
+//   _gradient_limit_field   src/discretization/algorithms/octree.jl:677-717 (min-plus sweeps over the k-NN graph)
 //   closest point / wall rule   src/octree/geometric_utils.jl:68-136, src/repel.jl:448-469,522-537,
 //                               src/octree/triangle_octree.jl:71-99,531-549,583-607 (brute force over triangles)
 //
@@ -456,6 +458,26 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
         bool stopped = false;
         if ((prm->stall_after > 0 || prm->cv_target > 0) && n_move > 0) {     // :305-327
             T s1 = T(0), s2 = T(0);                                           // _dnn_cv :374-386 (serial, in T)
+            if (prm->reserved & 1) {
+                // NOT the reference: the same terms accumulated in double, the device's documented deviation
+                // (DESIGN.md section 2). Test-only switch that isolates what the accumulation precision does to a
+                // Float32 stall_after run; the reference-faithful path is the else branch.
+                double a1 = 0, a2 = 0;
+                for (int64_t i = 0; i < n_move; ++i) {
+                    T u = nn_dist[size_t(i)] / spacings[size_t(i + n_fixed)];
+                    a1 += double(u); a2 += double(u * u);
+                }
+                s1 = T(a1); s2 = T(a2);
+                T mu = T(a1 / double(n_move));
+                T var = T(a2 / double(n_move)) - mu * mu;
+                T cv = std::sqrt(var > T(0) ? var : T(0)) / mu;
+                last_cv = double(cv);
+                if (prm->cv_target > 0 && double(cv) <= prm->cv_target) { p = p_old; stop = WTP_STOP_CV_TARGET; stopped = true; }
+                else if (prm->stall_after > 0) {
+                    if (double(cv) < double(best_cv) * (1 - 1.0e-3)) { best_cv = cv; last_impr = it; }
+                    else if (it - last_impr >= prm->stall_after) { stop = WTP_STOP_STALL; stopped = true; }
+                }
+            } else {
             for (int64_t i = 0; i < n_move; ++i) {
                 T u = nn_dist[size_t(i)] / spacings[size_t(i + n_fixed)];
                 s1 = s1 + u; s2 = s2 + u * u;
@@ -470,6 +492,7 @@ int32_t relax(T* snap, int64_t n_fixed, int64_t n_move, const wtp_spacing* sp_in
                 // :319 — Julia evaluates best_cv * (1 - 1.0e-3) with a Float64 literal.
                 if (double(cv) < double(best_cv) * (1 - 1.0e-3)) { best_cv = cv; last_impr = it; }
                 else if (it - last_impr >= prm->stall_after) { stop = WTP_STOP_STALL; stopped = true; }
+            }
             }
         }
         if (stopped) break;
@@ -712,6 +735,117 @@ int32_t spacing_fidelity_impl(const T* pts, int64_t N, int k, double coord_radiu
     return WTP_OK;
 }
 
+// ------------------------------------------------------------------ normals
+// compute_normals (src/normals.jl:9-44) + _compute_normal (:65-70): neighbors = search.(points, Ref(KNearestSearch(points, k)))
+// (self included), then per point eigen(Symmetric(cov(v))) of the gathered coordinates, Q[:, 1] = the eigenvector of the
+// smallest eigenvalue. cov in T (Statistics.cov: mean, centred second moments over k - 1); the symmetric eigenproblem by
+// cyclic Jacobi rotations in double (LAPACK in the reference: same eigenvector up to sign and rounding). The sign is
+// not defined by the reference; the first nonzero component is made positive.
+template <int D>
+inline void smallest_eigenvector(double C[3][3], double* out) {
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        double off = 0;
+        for (int p = 0; p < D; ++p) for (int q = p + 1; q < D; ++q) off += C[p][q] * C[p][q];
+        if (off == 0.0) break;
+        for (int p = 0; p < D; ++p)
+            for (int q = p + 1; q < D; ++q) {
+                if (C[p][q] == 0.0) continue;
+                const double theta = (C[q][q] - C[p][p]) / (2.0 * C[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+                for (int r = 0; r < D; ++r) { const double a = C[r][p], b = C[r][q]; C[r][p] = c * a - s * b; C[r][q] = s * a + c * b; }
+                for (int r = 0; r < D; ++r) { const double a = C[p][r], b = C[q][r]; C[p][r] = c * a - s * b; C[q][r] = s * a + c * b; }
+                for (int r = 0; r < D; ++r) { const double a = V[r][p], b = V[r][q]; V[r][p] = c * a - s * b; V[r][q] = s * a + c * b; }
+            }
+    }
+    int m = 0;
+    for (int d = 1; d < D; ++d) if (C[d][d] < C[m][m]) m = d;
+    double n2 = 0;
+    for (int d = 0; d < D; ++d) n2 += V[d][m] * V[d][m];
+    const double inv = 1.0 / std::sqrt(n2);
+    double sign = 1.0;
+    for (int d = 0; d < D; ++d) if (V[d][m] != 0.0) { sign = V[d][m] > 0 ? 1.0 : -1.0; break; }
+    for (int d = 0; d < D; ++d) out[d] = sign * V[d][m] * inv;
+}
+
+template <class T, int D>
+int32_t normals_impl(const T* pts, int64_t N, int k, int threads, T* out) {
+    if (k < 1 || N < 1) return WTP_ERR_BAD_ARG;
+    if (int64_t(k) > N) k = int(N);                                           // :16
+    KDTree<T, D> tree;
+    tree.build(pts, N);
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<Cand<T>> buf((size_t)k);
+#pragma omp for schedule(dynamic, 512)
+        for (int64_t i = 0; i < N; ++i) {
+            tree.knn(&pts[size_t(i) * D], k, buf.data());
+            T mean[3] = {T(0), T(0), T(0)};
+            for (int j = 0; j < k; ++j) for (int d = 0; d < D; ++d) mean[d] = mean[d] + pts[size_t(buf[j].idx) * D + d];
+            for (int d = 0; d < D; ++d) mean[d] = mean[d] / T(k);
+            T S[3][3] = {};
+            for (int j = 0; j < k; ++j) {
+                T c[3];
+                for (int d = 0; d < D; ++d) c[d] = pts[size_t(buf[j].idx) * D + d] - mean[d];
+                for (int a = 0; a < D; ++a) for (int b = a; b < D; ++b) S[a][b] = S[a][b] + c[a] * c[b];
+            }
+            double C[3][3] = {};
+            const T denom = T(k > 1 ? k - 1 : 1);
+            for (int a = 0; a < D; ++a) for (int b = a; b < D; ++b) { C[a][b] = double(S[a][b] / denom); C[b][a] = C[a][b]; }
+            double v[3];
+            smallest_eigenvector<D>(C, v);
+            for (int d = 0; d < D; ++d) out[size_t(i) * D + d] = T(v[d]);
+        }
+    }
+    return WTP_OK;
+}
+
+// --------------------------------------------------------- gradient-limit field
+// _gradient_limit_field (src/discretization/algorithms/octree.jl:677-717) on the leaf centres.
+template <class T, int D>
+int32_t gradient_limit_impl(const T* centers, int64_t n, const T* h0, T g, int k, double tol, int max_sweeps, int threads, T* out, int32_t* sweeps_out) {
+    if (n < 1 || k < 1) return WTP_ERR_BAD_ARG;
+    const int kk = int(std::min<int64_t>(k, n));                              // :684
+    KDTree<T, D> tree;
+    tree.build(centers, n);                                                   // :685
+    std::vector<int64_t> idx(size_t(n) * kk);
+    std::vector<T> dist(size_t(n) * kk);
+#pragma omp parallel num_threads(threads)
+    {
+        std::vector<Cand<T>> buf((size_t)kk);
+#pragma omp for schedule(dynamic, 512)
+        for (int64_t a = 0; a < n; ++a) {                                     // knn(tree, centers, kk, true) :686
+            tree.knn(&centers[size_t(a) * D], kk, buf.data());
+            for (int t = 0; t < kk; ++t) { idx[size_t(a) * kk + t] = buf[t].idx; dist[size_t(a) * kk + t] = std::sqrt(buf[t].d2); }
+        }
+    }
+    std::vector<T> h(h0, h0 + n), hnew((size_t)n);
+    int sweeps = 0;
+    for (int s = 0; s < max_sweeps; ++s) {                                    // :693
+#pragma omp parallel for num_threads(threads) schedule(static)
+        for (int64_t a = 0; a < n; ++a) {                                     // :694-702
+            T hi = h[size_t(a)];
+            for (int t = 0; t < kk; ++t) {
+                const T cand = h[size_t(idx[size_t(a) * kk + t])] + g * dist[size_t(a) * kk + t];
+                if (cand < hi) hi = cand;
+            }
+            hnew[size_t(a)] = hi;
+        }
+        T maxrel = T(0);                                                      // :703-707
+        for (int64_t a = 0; a < n; ++a) {
+            const T rel = std::fabs(hnew[size_t(a)] - h[size_t(a)]) / h[size_t(a)];
+            if (rel > maxrel) maxrel = rel;
+        }
+        h = hnew;                                                             // :708
+        ++sweeps;
+        if (sizeof(T) == 4 ? float(maxrel) < float(tol) : double(maxrel) < tol) break;   // :709
+    }
+    std::copy(h.begin(), h.end(), out);
+    if (sweeps_out) *sweeps_out = sweeps;
+    return WTP_OK;
+}
+
 int default_threads(int threads) {
 #ifdef _OPENMP
     return threads > 0 ? threads : omp_get_max_threads();
@@ -875,6 +1009,27 @@ int32_t wtpo_spacing_fidelity_f32(const float* pts, int64_t N, int32_t D, int32_
 int32_t wtpo_spacing_fidelity_f64(const double* pts, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, int32_t threads, wtp_spacing_fidelity_t* out) {
     threads = default_threads(threads);
     return DISPATCH_D(double, D, (spacing_fidelity_impl<double, 2>(pts, N, k, cr, sp, threads, out)), (spacing_fidelity_impl<double, 3>(pts, N, k, cr, sp, threads, out)));
+}
+
+int32_t wtpo_normals_f32(const float* pts, int64_t N, int32_t D, int32_t k, int32_t threads, float* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (normals_impl<float, 2>(pts, N, k, threads, out)), (normals_impl<float, 3>(pts, N, k, threads, out)));
+}
+int32_t wtpo_normals_f64(const double* pts, int64_t N, int32_t D, int32_t k, int32_t threads, double* out) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (normals_impl<double, 2>(pts, N, k, threads, out)), (normals_impl<double, 3>(pts, N, k, threads, out)));
+}
+int32_t wtpo_gradient_limit_f32(const float* c, int64_t n, int32_t D, const float* h0, float g, int32_t k, double tol, int32_t max_sweeps, int32_t threads,
+                                float* out, int32_t* sweeps) {
+    threads = default_threads(threads);
+    return DISPATCH_D(float, D, (gradient_limit_impl<float, 2>(c, n, h0, g, k, tol, max_sweeps, threads, out, sweeps)),
+                      (gradient_limit_impl<float, 3>(c, n, h0, g, k, tol, max_sweeps, threads, out, sweeps)));
+}
+int32_t wtpo_gradient_limit_f64(const double* c, int64_t n, int32_t D, const double* h0, double g, int32_t k, double tol, int32_t max_sweeps, int32_t threads,
+                                double* out, int32_t* sweeps) {
+    threads = default_threads(threads);
+    return DISPATCH_D(double, D, (gradient_limit_impl<double, 2>(c, n, h0, g, k, tol, max_sweeps, threads, out, sweeps)),
+                      (gradient_limit_impl<double, 3>(c, n, h0, g, k, tol, max_sweeps, threads, out, sweeps)));
 }
 
 int32_t wtpo_closest_point_on_triangle_f64(const double* p, const double* a, const double* b, const double* c, double* out) {

@@ -132,10 +132,12 @@ def test_repel_one_sweep_direction_known_answer(ctx, oracle):
 def test_repel_stop_logic_float32(ctx, oracle, kw):
     """stall_after / cv_target on a Float32 cloud. The reference (and the oracle) sum u and u^2 serially in Float32
     (_dnn_cv, src/repel.jl:374-386); the device accumulates the same Float32 terms in Float64 with a fixed reduction
-    tree, which is closer to the exact sums (documented deviation). The CV values agree to Float32
-    summation error, so a cv_target run stops at the same iteration unless a CV lands within ~1e-6 of the target; the
-    stall rule compares successive CVs against a 0.1 % improvement a hundred-odd iterations into a Float32 trajectory,
-    where a slip of an iteration or two is rounding, not logic."""
+    tree (documented deviation). A cv_target run stops at the same iteration (the CVs agree to
+    ~5e-5, the rounding noise of a 5300-term Float32 sum through var = E[u^2] - E[u]^2). The stall rule asks for a 0.1 %
+    improvement per iteration late in the run, where the improvements are of the size of that noise: the reference's
+    Float32 monitor stops when the noise first hides an improvement (iteration 160 here), the device's noise-free monitor
+    when the improvement really falls below 0.1 % (iteration ~354, with a lower CV). That this is the accumulation
+    precision and nothing else is shown by the oracle with its test-only `cv_in_double` switch: same stop as the device."""
     rng = np.random.default_rng(90)
     n, nf = 6000, 700
     snap = rng.random((n, 3)).astype(np.float32)
@@ -146,12 +148,17 @@ def test_repel_stop_logic_float32(ctx, oracle, kw):
     out, conv, res, _ = ctx.repel(snap, nf, sp, ctx.make_force("clipped", np.float32(0.2)), **a, **kw)
     oout, oconv, ores, _ = oracle.repel(snap, nf, osp, oracle.make_force("clipped", np.float32(0.2)), **a, **kw)
     stall = kw.get("stall_after", 0) > 0
-    _record("repel_stop_f32_" + ("stall" if stall else f"cv_target_{kw['cv_target']}"), iters=int(res["iters"]),
-            oracle_iters=int(ores["iters"]), reason=res["stop_reason"], cv=float(res["last_cv"]), oracle_cv=float(ores["last_cv"]))
+    rec = dict(iters=int(res["iters"]), oracle_iters=int(ores["iters"]), reason=res["stop_reason"], cv=float(res["last_cv"]), oracle_cv=float(ores["last_cv"]))
     assert res["stop_reason"] == ores["stop_reason"] == ("stall" if stall else "cv_target")
     if stall:
-        assert abs(res["iters"] - ores["iters"]) <= 2 and abs(res["last_cv"] - ores["last_cv"]) <= 2e-3 * ores["last_cv"]
+        dout, dconv, dres, _ = oracle.repel(snap, nf, osp, oracle.make_force("clipped", np.float32(0.2)), cv_in_double=True, **a, **kw)
+        rec.update(oracle_cv_in_double_iters=int(dres["iters"]), oracle_cv_in_double_cv=float(dres["last_cv"]))
+        _record("repel_stop_f32_stall", **rec)
+        assert dres["stop_reason"] == "stall" and abs(res["iters"] - dres["iters"]) <= 2
+        assert abs(res["last_cv"] - dres["last_cv"]) <= 1e-3 * dres["last_cv"]
+        assert res["iters"] >= ores["iters"] and res["last_cv"] <= ores["last_cv"] * (1 + 1e-3)   # never worse than the reference's stop
     else:
+        _record(f"repel_stop_f32_cv_target_{kw['cv_target']}", **rec)
         assert res["iters"] == ores["iters"]
         assert abs(res["last_cv"] - ores["last_cv"]) <= 2e-4 * ores["last_cv"]
         assert np.abs(out - oout).max() <= 1e-3 * h

@@ -380,6 +380,26 @@ class Context:
                        C.byref(sp), C.byref(out)))
         return {n: getattr(out, n) for n, _ in SpacingFidelity._fields_}
 
+    def normals(self, pts, k: int = 5) -> np.ndarray:
+        """compute_normals(points; k) (src/normals.jl:9-44): unit PCA normals, N x D (unoriented: first nonzero component positive)."""
+        pts = _as_points(pts)
+        out = np.empty_like(pts)
+        self._check(getattr(self._lib, "wtp_normals_" + _sfx(pts.dtype))(self._h, _vp(pts), C.c_int64(pts.shape[0]), C.c_int32(pts.shape[1]),
+                                                                       C.c_int32(k), _vp(out)))
+        return out
+
+    def gradient_limit(self, centers, h0, g: float, k: int = 12, tol: float = 1.0e-3, max_sweeps: int = 2000):
+        """_gradient_limit_field (src/discretization/algorithms/octree.jl:677-717) on the leaf centres -> (h, sweeps)."""
+        centers = _as_points(centers)
+        h0 = np.ascontiguousarray(h0, dtype=centers.dtype)
+        out = np.empty_like(h0)
+        sweeps = C.c_int32(0)
+        sfx = _sfx(centers.dtype)
+        gg = C.c_float(g) if sfx == "f32" else C.c_double(g)
+        self._check(getattr(self._lib, "wtp_gradient_limit_" + sfx)(self._h, _vp(centers), C.c_int64(centers.shape[0]), C.c_int32(centers.shape[1]),
+                                                                   _vp(h0), gg, C.c_int32(k), C.c_double(tol), C.c_int32(max_sweeps), _vp(out), C.byref(sweeps)))
+        return out, int(sweeps.value)
+
     def metrics(self, pts, k=20) -> dict:
         pts = _as_points(pts)
         out = CloudMetrics()

@@ -11,6 +11,8 @@ written in Python with the reference's names, argument meaning and error behavio
     repel(cloud, spacing, octree; ...)         src/repel.jl:122-181 (mesh wall rule, _reconstruct_cloud :590-629)
     isinside(points, octree)                   src/octree/triangle_octree.jl:97-115
     metrics(cloud; k)                          src/metrics.jl:19-41
+    compute_normals(points; k)                 src/normals.jl:9-44
+    _gradient_limit_field (gradient_limit_field)   src/discretization/algorithms/octree.jl:677-717
     ConstantSpacing / LogLike / BoundaryLayerSpacing   src/discretization/spacings.jl
     InverseDistanceForce / SpacingEquilibriumForce / ClippedSpacingForce / StrongSpacingForce
                                                src/repel_forces.jl
@@ -559,6 +561,23 @@ def isinside(pts, domain, ctx=None) -> np.ndarray:
         bx, bn, ba = _boundary_elements(domain)
         out = ctx.isinside(q.astype(bx.dtype, copy=False), bx, bn, ba)
     return bool(out[0]) if single else out
+
+
+# ------------------------------------------------------- other consumers of the index
+def compute_normals(x, k: int = 5, ctx=None) -> np.ndarray:
+    """compute_normals(surf | points; k) (src/normals.jl:9-44): unit PCA normals (Hoppe 1992) from the covariance of each
+    point's k nearest points, itself included; unoriented (orient_normals!, :75-117, is a serial graph walk on the host)."""
+    ctx = ctx or default_context()
+    pts = x._points() if hasattr(x, "_points") else _coords(x)
+    return ctx.normals(pts, int(k))
+
+
+def gradient_limit_field(centers, h0, g, k: int = 12, tol: float = 1.0e-3, max_sweeps: int = 2000, ctx=None) -> np.ndarray:
+    """_gradient_limit_field (src/discretization/algorithms/octree.jl:677-717) on the leaf centres: the g-Lipschitz
+    envelope of h0 by min-plus sweeps over the k-NN graph of the centres."""
+    ctx = ctx or default_context()
+    h, _ = ctx.gradient_limit(_coords(centers), h0, float(g), int(k), float(tol), int(max_sweeps))
+    return h
 
 
 # ------------------------------------------------------------------- metrics
