@@ -8,7 +8,7 @@ from ._lib import Context, WtpArgumentError, WtpError, default_context, shard_ra
 from .api import (AbstractSpacing, AbstractTopology, BoundaryLayerSpacing, ClippedSpacingForce, ConstantSpacing, CSRRows,
                   FlatRows, InverseDistanceForce, KNNTopology, LogLike, NoTopology, PointBoundary, PointCloud,
                   PointSurface, PointVolume, RadiusTopology, RepelForceModel, SpacingEquilibriumForce,
-                  StrongSpacingForce, compute_force, hastopology, isinside, metrics, neighbors, points, rebuild_topology_, repel,
+                  StrongSpacingForce, compute_force, compute_normals, gradient_limit_field, hastopology, isinside, metrics, neighbors, points, rebuild_topology_, repel,
                   search, searchdists, set_topology, spacing_fidelity_metrics, spacing_metrics, topology)
 from .mesh import TriangleOctree, cuboid_mesh, icosphere_mesh, read_binary_stl, torus_mesh, unit_cube_mesh
 
