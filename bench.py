@@ -377,7 +377,7 @@ def main():
 
     # ------------------------------------------------------------------ end-to-end arm
     ctx.set_timing(False)
-    e2e_ms, e2e_val, e2e_phases = None, None, None
+    e2e_ms, e2e_val, e2e_phases, e2e_direct, e2e_bytes, nq_e2e = None, None, None, False, (int(pts_h.nbytes), None), nq
     if not args.no_e2e:
         h_pts = torch.from_numpy(pts_h).pin_memory()
         h_idx = torch.empty((n, K), dtype=torch.int64).pin_memory()
@@ -395,7 +395,17 @@ def main():
         barrier()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
         e2e_val = n / (e2e_ms * 1e-3) / 1e6
-        assert np.array_equal(h_idx_np[own - 1], chk), "host and device entry points disagree"
+        if world == 1:
+            assert np.array_equal(h_idx_np[own - 1], chk), "host and device entry points disagree"
+        else:   # the host call fills the rows wtp_shard_owned reports (a contiguous caller range with the row exchange)
+            own_h = ctx.owned()
+            qs = own_h[:: max(len(own_h) // 64, 1)][:64] - 1
+            ok_rows = bool(np.array_equal(h_idx_np[qs], sample_rows_brute_force(pts_h, qs, K)))
+            if parity is not None:
+                parity["e2e_rows_checked_per_rank"] = int(len(qs))
+                parity["e2e_ok"] = all_ranks_ok(ok_rows)
+            else:
+                assert ok_rows, "host entry point rows disagree with brute force"
         # where the time of one host call goes (one more, untimed call with the library's phase events on)
         ctx.set_timing(True)
         t0 = time.perf_counter()
@@ -404,7 +414,9 @@ def main():
         te = ctx.timing()
         ctx.set_timing(False)
         dev_ms = te["ms_bbox"] + te["ms_cellkey"] + te["ms_sort"] + te["ms_reorder"] + te["ms_query"]
-        e2e_phases = {"ms_h2d": float(te["ms_h2d"]), "ms_device_compute": float(dev_ms),
+        e2e_direct = bool(te["bytes_d2h"] == nq_e2e * K * 8)
+        e2e_bytes = (int(te["bytes_h2d"]), int(te["bytes_d2h"]))
+        e2e_phases = {"ms_h2d": float(te["ms_h2d"]), "ms_device_compute": float(dev_ms), "ms_exchange_barrier": float(te["ms_comm"]),
                       "ms_d2h_and_widen": float(max(wall - te["ms_h2d"] - dev_ms, 0.0)), "ms_wall_this_call": float(wall)}
         del h_pts, h_idx
 
@@ -545,11 +557,12 @@ def main():
             "run": {"sharding": f"queries split in {world} contiguous runs of the spatially sorted order; every GPU holds the point set and indexes "
                                 f"the window of the grid around its run (the whole grid at 1 GPU); no collective",
                     "l2": "working set (120 MB points + 160 MB sorted tiles + 1.68 GB output per step) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(pts_h.nbytes),
-                    "d2h_bytes_per_step": int(nq * K * 4 + (nq * 4 if world > 1 else 0)),   # rows as 4-byte indices (+ their 4-byte caller indices when sharded)
+            "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1],   # per rank, as counted by the library
                     "phases_ms": e2e_phases,
-                    "api": "wtp_knn_f32: pinned host points in, N x 21 int64 table in host memory out; the rows cross PCIe as 4-byte "
-                           "indices and are widened to int64 by the library's host threads"},
+                    "api": "wtp_knn_f32: pinned host points in, N x 21 int64 table in host memory out. " +
+                           ("Sharded: the kernels hand every row to the rank owning its caller range over NVLink (peer stores); each rank's contiguous "
+                            "part of the table goes back as int64 written by the DMA engine (the table is pinned)" if e2e_direct else
+                            "The rows cross PCIe as 4-byte indices and are widened to int64 by the library's host threads")},
             "gpu_launches": int(launches),
             "roofline": roofline("knn_tile_kernel<float,3> (+ knn_kernel<float,3,1> for its leftovers)", ALGO_BYTES_PER_QUERY["f32"] * nq, q_ms,
                                  traffic=measured_traffic("knn", world),
@@ -564,7 +577,8 @@ def main():
             "cpu_baseline": cpu,
             "repel": repel,
             "extras": extras,
-            "parity_check": (dict(parity, ok=bool(parity.get("knn_ok", True) and parity.get("repel_ok", True))) if parity is not None else None),
+            "parity_check": (dict(parity, ok=bool(parity.get("knn_ok", True) and parity.get("repel_ok", True) and parity.get("e2e_ok", True)))
+                             if parity is not None else None),
             "clocks": clocks.summary(),
         }
         print(json.dumps(line), flush=True)

@@ -61,6 +61,17 @@ typedef enum {
 
 /* device: CUDA ordinal. Fails (no fallback) if the device is unusable. */
 int32_t wtp_create(wtp_ctx** out, int32_t device);
+/* One context over n_devices GPUs of the box, in ONE process (for a host program that is a single process, like a Julia
+ * session): the library runs one host thread and one stream per device, the devices are the ranks of one NCCL
+ * communicator with peer access between every pair. The HOST entry points that shard — wtp_knn_*, wtp_knn_self_*,
+ * wtp_radius_count_* / wtp_radius_fill, wtp_repel_* with the identity wall — are answered by all devices together and
+ * fill the caller's arrays completely, exactly as the same call on a single-device context would (k-NN: every device
+ * answers a run of the sorted order and the rows travel over NVLink to the device that owns their caller range; radius:
+ * contiguous caller ranges, one CSR; repel: runs of the sorted order, every device ends with the whole state). Everything
+ * else (metrics, isinside, mesh queries, normals, ..., the mesh-wall repel, point sets of fewer than 4096 per device)
+ * runs on the first device. Device-pointer entry points and wtp_set_stream are refused (WTP_ERR_UNSUPPORTED).
+ * wtp_comm_rank / wtp_comm_world of the handle are 0 / 1: it is one logical context. n_devices == 1 is wtp_create. */
+int32_t wtp_create_multi(wtp_ctx** out, const int32_t* devices, int32_t n_devices);
 void wtp_destroy(wtp_ctx* ctx);
 const char* wtp_last_error(const wtp_ctx* ctx);
 const char* wtp_status_string(int32_t status);
@@ -86,9 +97,13 @@ int32_t wtp_set_cell_occupancy(wtp_ctx* ctx, double points_per_cell);
  *    SPATIALLY SORTED order, no collective. The rank indexes only the layers of the grid that run
  *    needs (its own plus two on either side); if a search ever has to leave them (strongly graded
  *    clouds) the call is repeated on the whole index and the context stops windowing.
- *    Host entry points write those rows into the caller's N x k table at their caller
- *    positions (other rows untouched); device entry points write a compact
- *    wtp_shard_owned_count() x k table. wtp_shard_owned gives the caller index of each row.
+ *    Device entry points write a compact wtp_shard_owned_count() x k table; wtp_shard_owned gives
+ *    the caller index of each row. Host entry points fill rows of the caller's N x k table (the
+ *    others stay untouched) and wtp_shard_owned says which: with a communicator (non-null id) whose
+ *    ranks can map each other's memory, the kernels hand every row to the rank that owns its CALLER
+ *    range over NVLink, and each rank fills the contiguous rows [wtp_shard_begin(N), wtp_shard_end(N))
+ *    of the table (written as int64 by the DMA engine itself when the table is pinned); otherwise
+ *    (shard-only context, distances requested) the rows of the rank's sorted run, wherever they are.
  *  - radius: the contiguous range [wtp_shard_begin, wtp_shard_end) of the caller's order.
  *  - wtp_repel_*: the same kind of range of the movable points, all-gathering the moved
  *    positions over NCCL every iteration. */
@@ -130,8 +145,11 @@ typedef struct {
      * queries whose search left the window (> 0: the call was repeated on the whole index) */
     int64_t n_window_points, n_window_missed;
     /* sharded repel: ranks whose run buffers the sweep kernels wrote directly over NVLink peer memory (0: the runs
-     * were exchanged with an NCCL all-gather after the sweep) */
+     * were exchanged with an NCCL all-gather after the sweep); sharded host k-NN: ranks taking part in the row exchange */
     int64_t n_peer_ranks;
+    /* host k-NN entry points: bytes the call moved over PCIe (points in; rows out: 4 bytes per entry when they are widened
+     * on the host, 8 when the DMA engine writes the int64 table itself, plus the caller indices of a sharded scatter) */
+    int64_t bytes_h2d, bytes_d2h;
 } wtp_timing;
 
 /* enable != 0: record CUDA events around each phase of subsequent calls. */

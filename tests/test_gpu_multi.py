@@ -31,3 +31,15 @@ def test_sharded_paths_match_oracle(world):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0 and "MULTIGPU_CHECK OK" in r.stdout, tail
+
+
+@pytest.mark.parametrize("world", [2])
+def test_single_process_multi_device_context(world):
+    """wtp_create_multi: ONE process (a Julia session is one process), one context over several GPUs; set_topology /
+    repel calls on it are answered by all devices and fill the caller's arrays like a single-device context."""
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs on one box")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "multidevice_check.py"), str(world)], cwd=ROOT, capture_output=True,
+                       text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-4000:]
+    assert r.returncode == 0 and "MULTIDEVICE_CHECK OK" in r.stdout, tail

@@ -82,7 +82,7 @@ class Timing(C.Structure):
                [("sort_passes", C.c_int32), ("query_launches", C.c_int32), ("n_cells", C.c_int64),
                 ("n_ring_expanded", C.c_int64), ("n_leftover_sparse", C.c_int64), ("n_leftover_dense", C.c_int64),
                 ("n_leftover_other", C.c_int64), ("n_window_points", C.c_int64), ("n_window_missed", C.c_int64),
-                ("n_peer_ranks", C.c_int64)]
+                ("n_peer_ranks", C.c_int64), ("bytes_h2d", C.c_int64), ("bytes_d2h", C.c_int64)]
 
 
 _lib = None
@@ -141,13 +141,26 @@ def _vp(a):
 class Context:
     """One wtp_ctx: a CUDA device, a stream and the cached device buffers."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices=None):
+        """One device (wtp_create), or `devices=[0, 1, ...]`: one context over several GPUs of the box in this one process
+        (wtp_create_multi) — the host entry points that shard are then answered by all of them together."""
         self._lib = load()
         self._h = C.c_void_p()
-        rc = self._lib.wtp_create(C.byref(self._h), C.c_int32(device))
-        if rc != 0:
-            raise WtpError(rc, f"wtp_create(device={device}) failed: no usable sm_100 GPU (there is no CPU fallback)")
+        if devices is not None and len(devices) > 1:
+            arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            rc = self._lib.wtp_create_multi(C.byref(self._h), arr, C.c_int32(len(devices)))
+            if rc != 0:
+                raise WtpError(rc, f"wtp_create_multi(devices={list(devices)}) failed: the devices must be usable sm_100 GPUs that can "
+                                   "access each other's memory, with libnccl.so.2 loadable")
+            device = int(devices[0])
+        else:
+            if devices is not None:
+                device = int(devices[0])
+            rc = self._lib.wtp_create(C.byref(self._h), C.c_int32(device))
+            if rc != 0:
+                raise WtpError(rc, f"wtp_create(device={device}) failed: no usable sm_100 GPU (there is no CPU fallback)")
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
         self.rank, self.world = 0, 1
 
     def close(self):

@@ -8,12 +8,15 @@
 #include "d2h_pipeline.h"
 #include "host_pool.h"
 #include "kernels.cuh"
+#include "multi.h"
 
 using namespace wtp;
 
 namespace wtp {
+static std::atomic<uint64_t> g_error_stamp{0};
+uint64_t next_error_stamp() { return ++g_error_stamp; }
 int32_t fail(wtp_ctx* ctx, const Error& e) {
-    if (ctx) ctx->last_error = e.msg;
+    if (ctx) { ctx->last_error = e.msg; ctx->error_stamp = next_error_stamp(); }
     return e.status;
 }
 void finish_timing(wtp_ctx* ctx, int sort_passes, int query_launches, int64_t n_cells, int64_t n_expanded);
@@ -80,6 +83,13 @@ int32_t wtp_create(wtp_ctx** out, int32_t device) {
 
 void wtp_destroy(wtp_ctx* ctx) {
     if (!ctx) return;
+    if (!ctx->children.empty() || ctx->solo) {   // the parent of a multi-device context: no device state of its own
+        for (wtp_ctx* c : ctx->children) { c->group = nullptr; wtp_destroy(c); }
+        if (ctx->solo) wtp_destroy(ctx->solo);
+        delete ctx->group;
+        delete ctx;
+        return;
+    }
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     wtp_comm_destroy_internal(ctx);
@@ -96,21 +106,29 @@ void wtp_destroy(wtp_ctx* ctx) {
     delete ctx;
 }
 
-const char* wtp_last_error(const wtp_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+const char* wtp_last_error(const wtp_ctx* ctx) {
+    if (!ctx) return "null context";
+    const wtp_ctx* latest = ctx;                   // a multi-device context: the most recent failure of the parent or its single-device context
+    if (ctx->solo && ctx->solo->error_stamp > latest->error_stamp) latest = ctx->solo;
+    return latest->last_error.c_str();
+}
 
 int32_t wtp_set_stream(wtp_ctx* ctx, void* s) {
     if (!ctx) return WTP_ERR_BAD_ARG;
+    if (is_multi(ctx)) return fail(ctx, Error{WTP_ERR_UNSUPPORTED, "a multi-device context runs on its own streams (one per device)"});
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return WTP_OK;
 }
 
 int32_t wtp_host_register(wtp_ctx* ctx, void* ptr, int64_t bytes) {
+    ctx = solo_of(ctx);
     API_BEGIN(ctx)
     WTP_REQUIRE(ptr && bytes > 0, WTP_ERR_BAD_ARG, "wtp_host_register: null range");
-    WTP_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    WTP_CUDA_CHECK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));   // every device of the process may copy to / from it
     API_END(ctx)
 }
 int32_t wtp_host_unregister(wtp_ctx* ctx, void* ptr) {
+    ctx = solo_of(ctx);
     API_BEGIN(ctx)
     WTP_CUDA_CHECK(cudaHostUnregister(ptr));
     API_END(ctx)
@@ -118,17 +136,22 @@ int32_t wtp_host_unregister(wtp_ctx* ctx, void* ptr) {
 
 int32_t wtp_set_cell_occupancy(wtp_ctx* ctx, double m) {
     if (!ctx) return WTP_ERR_BAD_ARG;
+    for (wtp_ctx* c : ctx->children) c->cell_occupancy = m;
+    if (ctx->solo) ctx->solo->cell_occupancy = m;
     ctx->cell_occupancy = m;
     return WTP_OK;
 }
 
 int32_t wtp_set_timing(wtp_ctx* ctx, int32_t enable) {
     if (!ctx) return WTP_ERR_BAD_ARG;
+    for (wtp_ctx* c : ctx->children) c->timer.enabled = enable != 0;
+    if (ctx->solo) ctx->solo->timer.enabled = enable != 0;
     ctx->timer.enabled = enable != 0;
     return WTP_OK;
 }
 
 int32_t wtp_get_timing(wtp_ctx* ctx, wtp_timing* out) {
+    if (is_multi(ctx)) ctx = ctx->children[0];     // rank 0's view of the last sharded call
     API_BEGIN(ctx)
     WTP_REQUIRE(out, WTP_ERR_BAD_ARG, "null output");
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -147,7 +170,13 @@ int32_t wtp_get_timing(wtp_ctx* ctx, wtp_timing* out) {
     API_END(ctx)
 }
 
-int64_t wtp_launch_count(const wtp_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int64_t wtp_launch_count(const wtp_ctx* ctx) {
+    if (!ctx) return -1;
+    int64_t n = ctx->launches;
+    for (const wtp_ctx* c : ctx->children) n += c->launches;
+    if (ctx->solo) n += ctx->solo->launches;
+    return n;
+}
 
 int64_t wtp_shard_begin(int64_t n, int32_t rank, int32_t world) {
     if (world <= 1) return 0;
@@ -207,6 +236,20 @@ void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst
                      const size_t b = w + 1 == workers ? total : ((total * (size_t)(w + 1) / (size_t)workers) & ~(size_t)3);
                      widen_u32_to_i64(reinterpret_cast<const uint32_t*>(staged) + a, h_dst + first + a, b - a);
                  });
+}
+
+bool comm_peer_buffers(wtp_ctx* ctx, PeerSet& pb, size_t bytes_each);                                   // comm.cu
+void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t bytes_per_rank);
+
+__global__ void __launch_bounds__(256) widen_u32_kernel(const uint32_t* __restrict__ in, size_t n, int64_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (int64_t)in[i];
+}
+static void widen_on_device(wtp_ctx* ctx, const uint32_t* d_in, size_t n, int64_t* d_out) {
+    if (n == 0) return;
+    const unsigned nb = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)kNumSMs * 16);
+    widen_u32_kernel<<<nb, 256, 0, ctx->stream>>>(d_in, n, d_out);
+    ctx->launches++;
+    WTP_CUDA_CHECK(cudaPeekAtLastError());
 }
 
 // ------------------------------------------------------------------- k-NN
@@ -282,7 +325,51 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         compute_once(d_idx, d_dist, out32);
     };
     int n_chunks = 1;
-    if (!h_out_idx) {
+    ctx->owned_contiguous = false;
+    // Sharded host call on a communicator whose ranks can map each other's memory: the row exchange. The k-NN kernels store
+    // the row of caller index i straight into the buffer of the rank that owns the caller range of i (peer memory over
+    // NVLink, RowMap::elem), so that after one barrier every rank holds the rows of ONE CONTIGUOUS part of the caller's
+    // table: it goes back with one forward copy — as int64 written by the DMA engine itself when the caller's table is
+    // pinned (G links in parallel, no host thread touches the data), through the widening pipeline otherwise — instead
+    // of rows scattered all over the table by host threads.
+    const int64_t cb = wtp_shard_begin(N, ctx->rank, ctx->world), ce = wtp_shard_end(N, ctx->rank, ctx->world);   // caller range of this rank
+    const size_t rx_each = (size_t)((N + ctx->world - 1) / ctx->world) * (size_t)k * sizeof(uint32_t);
+    const bool exchange = sharded && h_out_idx && !h_out_dist && ctx->nccl_comm && std::getenv("WTP_NO_ROW_EXCHANGE") == nullptr &&
+                          comm_peer_buffers(ctx, ctx->row_peers, rx_each);
+    if (exchange) {
+        const size_t parity = (size_t)(ctx->row_exchanges++ & 1u);
+        auto rx = [&](int r) { return reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->row_peers.base[r]) + parity * ctx->row_peers.bytes_each); };
+        uint32_t* mine = rx(ctx->rank);
+        rows.n_owners = ctx->world;
+        for (int r = 0; r <= ctx->world; ++r) rows.owner_begin[r] = (uint32_t)wtp_shard_begin(N, r, ctx->world);
+        rows.owner_begin[ctx->world] = (uint32_t)N;
+        for (int r = 0; r < ctx->world; ++r)
+            rows.owner_delta[r] = (long long)(rx(r) - mine) - (long long)rows.owner_begin[r] * k;
+        compute(mine, nullptr, true);
+        {   // barrier: every rank's kernels have finished storing into this rank's buffer
+            ScopedPhase ph(ctx->timer, PH_COMM);
+            uint64_t* d_flag = ctx->d_misc.as<uint64_t>((size_t)ctx->world + 1);
+            comm_allgather_fixed(ctx, d_flag + ctx->world, d_flag, sizeof(uint64_t));
+        }
+        ScopedPhase ph(ctx->timer, PH_D2H);
+        const size_t n_elems = (size_t)(ce - cb) * k;
+        int64_t* h_dst = h_out_idx + cb * k;
+        cudaPointerAttributes attr{};
+        const bool pinned = n_elems > 0 && cudaPointerGetAttributes(&attr, h_dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        (void)cudaGetLastError();
+        const char* force = std::getenv("WTP_D2H_DIRECT");
+        const bool direct = force ? (force[0] == '1' && pinned) : pinned;
+        if (direct) {
+            int64_t* d_wide = ctx->d_indices.as<int64_t>(std::max<size_t>(n_elems, 1));
+            widen_on_device(ctx, mine, n_elems, d_wide);
+            WTP_CUDA_CHECK(cudaMemcpyAsync(h_dst, d_wide, n_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            d2h_widen_u32(ctx, mine, n_elems, h_dst);
+        }
+        ctx->owned_contiguous = true;
+        ctx->owned_begin = cb; ctx->owned_end = ce;
+        ctx->last_d2h_direct = direct;
+    } else if (!h_out_idx) {
         compute(d_out_idx, d_out_dist, false);
     } else if (!sharded && nq * (int64_t)k < ((int64_t)4 << 20)) {
         // small result: int64 rows straight from the device table
@@ -358,6 +445,12 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     }
     ctx->last_tile_sparse = tiled ? h_cnt[1] : 0; ctx->last_tile_dense = tiled ? h_cnt[2] : 0; ctx->last_tile_other = tiled ? h_cnt[3] : 0;
     finish_timing(ctx, passes, n_chunks, g.ncells, (int64_t)*h_exp);
+    ctx->last_timing.n_peer_ranks = exchange ? ctx->world : 0;
+    ctx->last_timing.bytes_d2h = !h_out_idx ? 0
+        : exchange ? (ce - cb) * (int64_t)k * (ctx->last_d2h_direct ? 8 : 4)
+        : (!sharded && nq * (int64_t)k < ((int64_t)4 << 20)) ? nq * (int64_t)k * 8
+        : nq * (int64_t)k * 4 + (sharded ? nq * 4 : 0);
+    if (h_out_idx && h_out_dist) ctx->last_timing.bytes_d2h += nq * (int64_t)k * (int64_t)sizeof(T);
 }
 
 template <class T>
@@ -381,6 +474,7 @@ static int32_t knn_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_
         WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     }
     knn_device<T>(ctx, d_pts, N, D, k, drop_first, nullptr, nullptr, out_idx, out_dist);
+    ctx->last_timing.bytes_h2d = N * (int64_t)D * (int64_t)sizeof(T);
     wtp_timing keep = ctx->last_timing;
     ctx->timer.end_total();
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -401,27 +495,52 @@ static int32_t knn_dev(wtp_ctx* ctx, const T* d_pts, int64_t N, int32_t D, int32
 
 }  // namespace wtp
 
+namespace wtp {
+// On a multi-device context every child answers its shard of the same call (one host thread per device): with the row
+// exchange each fills one contiguous part of the caller's table, together the whole table. Small point sets (fewer than
+// 4096 per device) are not worth sharding and run on the single-device context.
+template <class T>
+static int32_t knn_entry(wtp_ctx* c, const T* p, int64_t N, int32_t D, int32_t k, bool drop, int64_t* oi, T* od) {
+    if (is_multi(c) && N >= (int64_t)4096 * (int64_t)c->children.size())
+        return multi_run(c, [&](wtp_ctx* ch, int) { return knn_host<T>(ch, p, N, D, k, drop, oi, od); });
+    return knn_host<T>(solo_of(c), p, N, D, k, drop, oi, od);
+}
+static int32_t no_device_pointers(wtp_ctx* c) {
+    return fail(c, Error{WTP_ERR_UNSUPPORTED, "device-pointer entry points belong to one device: use a single-device context"});
+}
+}  // namespace wtp
+
 extern "C" {
 
-int32_t wtp_knn_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_host<float>(c, p, N, D, k, true, oi, od); }
-int32_t wtp_knn_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_host<double>(c, p, N, D, k, true, oi, od); }
-int32_t wtp_knn_self_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_host<float>(c, p, N, D, k, false, oi, od); }
-int32_t wtp_knn_self_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_host<double>(c, p, N, D, k, false, oi, od); }
-int32_t wtp_knn_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_dev<float>(c, p, N, D, k, oi, od); }
-int32_t wtp_knn_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_dev<double>(c, p, N, D, k, oi, od); }
+int32_t wtp_knn_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_entry<float>(c, p, N, D, k, true, oi, od); }
+int32_t wtp_knn_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_entry<double>(c, p, N, D, k, true, oi, od); }
+int32_t wtp_knn_self_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return knn_entry<float>(c, p, N, D, k, false, oi, od); }
+int32_t wtp_knn_self_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_entry<double>(c, p, N, D, k, false, oi, od); }
+int32_t wtp_knn_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return is_multi(c) ? no_device_pointers(c) : knn_dev<float>(c, p, N, D, k, oi, od); }
+int32_t wtp_knn_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return is_multi(c) ? no_device_pointers(c) : knn_dev<double>(c, p, N, D, k, oi, od); }
 
 int64_t wtp_shard_owned_count(const wtp_ctx* ctx) { return ctx ? ctx->owned_end - ctx->owned_begin : -1; }
 int32_t wtp_shard_owned_dev(wtp_ctx* ctx, int64_t* d_ids) {
+    if (is_multi(ctx)) return no_device_pointers(ctx);
     API_BEGIN(ctx)
     WTP_REQUIRE(d_ids || ctx->owned_end == ctx->owned_begin, WTP_ERR_BAD_ARG, "null output");
-    owned_ids(ctx, ctx->index[0], ctx->owned_f64, ctx->owned_begin, ctx->owned_end, d_ids);
+    if (ctx->owned_contiguous) {   // the row exchange: the caller range [owned_begin, owned_end) itself
+        std::vector<int64_t> ids((size_t)(ctx->owned_end - ctx->owned_begin));
+        for (size_t t = 0; t < ids.size(); ++t) ids[t] = ctx->owned_begin + (int64_t)t + 1;
+        WTP_CUDA_CHECK(cudaMemcpyAsync(d_ids, ids.data(), ids.size() * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        owned_ids(ctx, ctx->index[0], ctx->owned_f64, ctx->owned_begin, ctx->owned_end, d_ids);
+    }
     API_END(ctx)
 }
 int32_t wtp_shard_owned(wtp_ctx* ctx, int64_t* ids) {
     API_BEGIN(ctx)
     const int64_t n = ctx->owned_end - ctx->owned_begin;
     WTP_REQUIRE(ids || n == 0, WTP_ERR_BAD_ARG, "null output");
-    if (n > 0) {
+    if (ctx->owned_contiguous) {
+        for (int64_t t = 0; t < n; ++t) ids[t] = ctx->owned_begin + t + 1;
+    } else if (n > 0) {
         int64_t* d_ids = ctx->d_misc.as<int64_t>((size_t)n);
         owned_ids(ctx, ctx->index[0], ctx->owned_f64, ctx->owned_begin, ctx->owned_end, d_ids);
         WTP_CUDA_CHECK(cudaMemcpyAsync(ids, d_ids, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -5,6 +5,7 @@
 
 #include "kernels.cuh"
 #include "knn_core.cuh"
+#include "multi.h"
 
 using namespace wtp;
 
@@ -135,18 +136,64 @@ static int32_t radius_count_dev(wtp_ctx* ctx, const T* d_pts, int64_t N, int32_t
     API_END(ctx)
 }
 
+// The CSR of a multi-device context: every child counts the rows of its contiguous caller range into its own offsets
+// (0-based within the shard); the parent shifts them into one global prefix and remembers where each child's entries
+// start, so that wtp_radius_fill lets every child fill its part of the caller's indices array.
+template <class T>
+static int32_t radius_count_entry(wtp_ctx* c, const T* p, int64_t N, int32_t D, T r, int64_t* off) {
+    if (!is_multi(c) || N < (int64_t)4096 * (int64_t)c->children.size()) {
+        if (is_multi(c)) c->radius.pending = false;
+        return radius_count_host<T>(solo_of(c), p, N, D, r, off);
+    }
+    c->radius.pending = false;
+    if (!off) return fail(c, Error{WTP_ERR_BAD_ARG, "null offsets"});
+    const int G = (int)c->children.size();
+    std::vector<std::vector<int64_t>> local((size_t)G);
+    for (int g = 0; g < G; ++g) local[(size_t)g].resize((size_t)(wtp_shard_end(N, g, G) - wtp_shard_begin(N, g, G) + 1));
+    const int32_t rc = multi_run(c, [&](wtp_ctx* ch, int g) { return radius_count_host<T>(ch, p, N, D, r, local[(size_t)g].data()); });
+    if (rc != 0) return rc;
+    c->children_base.assign((size_t)G, 0);
+    int64_t base = 0;
+    for (int g = 0; g < G; ++g) {
+        const int64_t qb = wtp_shard_begin(N, g, G), nq = wtp_shard_end(N, g, G) - qb;
+        c->children_base[(size_t)g] = base;
+        for (int64_t t = 0; t < nq; ++t) off[qb + t] = base + local[(size_t)g][(size_t)t];
+        base += local[(size_t)g][(size_t)nq];
+    }
+    off[N] = base;
+    c->radius.pending = true;
+    c->radius.nnz = base;
+    return WTP_OK;
+}
+static int32_t no_device_pointers2(wtp_ctx* c) {
+    return fail(c, Error{WTP_ERR_UNSUPPORTED, "device-pointer entry points belong to one device: use a single-device context"});
+}
+
 }  // namespace wtp
 
 extern "C" {
 
-int32_t wtp_radius_count_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, float r, int64_t* off) { return radius_count_host<float>(c, p, N, D, r, off); }
-int32_t wtp_radius_count_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, double r, int64_t* off) { return radius_count_host<double>(c, p, N, D, r, off); }
-int32_t wtp_radius_count_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, float r, int64_t* off) { return radius_count_dev<float>(c, p, N, D, r, off); }
-int32_t wtp_radius_count_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, double r, int64_t* off) { return radius_count_dev<double>(c, p, N, D, r, off); }
+int32_t wtp_radius_count_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, float r, int64_t* off) { return radius_count_entry<float>(c, p, N, D, r, off); }
+int32_t wtp_radius_count_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, double r, int64_t* off) { return radius_count_entry<double>(c, p, N, D, r, off); }
+int32_t wtp_radius_count_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, float r, int64_t* off) { return is_multi(c) ? no_device_pointers2(c) : radius_count_dev<float>(c, p, N, D, r, off); }
+int32_t wtp_radius_count_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, double r, int64_t* off) { return is_multi(c) ? no_device_pointers2(c) : radius_count_dev<double>(c, p, N, D, r, off); }
 
-int64_t wtp_radius_nnz(const wtp_ctx* ctx) { return ctx && ctx->radius.pending ? ctx->radius.nnz : -1; }
+int64_t wtp_radius_nnz(const wtp_ctx* ctx) {
+    if (is_multi(ctx)) {
+        if (ctx->radius.pending) return ctx->radius.nnz;                 // the sharded count's total
+        ctx = ctx->solo;
+    }
+    return ctx && ctx->radius.pending ? ctx->radius.nnz : -1;
+}
 
 int32_t wtp_radius_fill(wtp_ctx* ctx, int64_t* indices) {
+    if (is_multi(ctx)) {
+        if (!ctx->radius.pending) return wtp_radius_fill(ctx->solo, indices);
+        ctx->radius.pending = false;
+        // every child fills its part of the CSR at the global offset the count pass gave it (kept in q_begin of the parent's
+        // state per child: see radius_count_entry)
+        return multi_run(ctx, [&](wtp_ctx* ch, int r) { return wtp_radius_fill(ch, indices ? indices + ctx->children_base[(size_t)r] : nullptr); });
+    }
     API_BEGIN(ctx)
     auto& st = ctx->radius;
     WTP_REQUIRE(st.pending && !st.dev_input, WTP_ERR_STATE, "wtp_radius_fill must directly follow wtp_radius_count_* on the same context");
@@ -176,6 +223,7 @@ int32_t wtp_radius_fill(wtp_ctx* ctx, int64_t* indices) {
 }
 
 int32_t wtp_radius_fill_dev(wtp_ctx* ctx, int64_t* d_indices) {
+    if (is_multi(ctx)) return no_device_pointers2(ctx);
     API_BEGIN(ctx)
     auto& st = ctx->radius;
     WTP_REQUIRE(st.pending && st.dev_input, WTP_ERR_STATE, "wtp_radius_fill_dev must directly follow wtp_radius_count_dev_* on the same context");
@@ -235,7 +283,7 @@ static int32_t repel_host(wtp_ctx* ctx, T* snap, int64_t n_fixed, int64_t n_move
     }
     relax_device<T>(ctx, d_snap, n_fixed, n_move, D, sp, d_bnd, fm, prm, mesh, conv, trace, res);
     wtp_timing keep = ctx->last_timing;
-    {
+    if (!ctx->quiet) {   // (a multi-device context: every child holds the same final state, rank 0 alone writes it back)
         ScopedPhase ph(ctx->timer, PH_D2H);
         WTP_CUDA_CHECK(cudaMemcpyAsync(snap + (size_t)n_fixed * D, d_snap + (size_t)n_fixed * D, (size_t)n_move * D * sizeof(T),
                                        cudaMemcpyDeviceToHost, ctx->stream));
@@ -297,6 +345,30 @@ static int32_t force_eval_host(wtp_ctx* ctx, const wtp_force* f, const T* u, int
     WTP_CUDA_CHECK(cudaMemcpyAsync(out, d_o, (size_t)n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     API_END(ctx)
+}
+
+// repel on a multi-device context: the children run the same call as the ranks of one communicator (sharded sweeps,
+// exchanged runs, identical stop decisions); every child ends with the whole final state, rank 0 writes it back. Small
+// problems, the mesh wall and deposition (whose host-side passes are per process) run on the single-device context.
+template <class T>
+static int32_t repel_entry(wtp_ctx* c, T* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
+                           const wtp_repel_params* prm, const wtp_wall_mesh* wall, T* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
+    if (!is_multi(c) || wall || !prm || nf + nm < (int64_t)4096 * (int64_t)c->children.size())
+        return repel_host<T>(solo_of(c), snap, nf, nm, D, sp, fm, prm, wall, conv, tr, res);
+    const int G = (int)c->children.size();
+    const size_t slots = (size_t)std::max(prm->max_iters, 1);
+    std::vector<std::vector<T>> conv_x((size_t)G);
+    std::vector<std::vector<wtp_trace_entry>> tr_x((size_t)G);
+    std::vector<wtp_repel_result> res_x((size_t)G);
+    for (int g = 1; g < G; ++g) { conv_x[(size_t)g].resize(slots); if (tr) tr_x[(size_t)g].resize(slots); }
+    return multi_run(c, [&](wtp_ctx* ch, int g) {
+        ch->quiet = g > 0;
+        const int32_t rc = g == 0 ? repel_host<T>(ch, snap, nf, nm, D, sp, fm, prm, nullptr, conv, tr, res)
+                                  : repel_host<T>(ch, snap, nf, nm, D, sp, fm, prm, nullptr, conv_x[(size_t)g].data(),
+                                                  tr ? tr_x[(size_t)g].data() : nullptr, &res_x[(size_t)g]);
+        ch->quiet = false;
+        return rc;
+    });
 }
 
 // ----------------------------------------------------------- mesh queries
@@ -408,36 +480,36 @@ extern "C" {
 
 int32_t wtp_repel_f32(wtp_ctx* c, float* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
                       const wtp_repel_params* prm, const wtp_wall_mesh* wall, float* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
-    return repel_host<float>(c, snap, nf, nm, D, sp, fm, prm, wall, conv, tr, res);
+    return repel_entry<float>(c, snap, nf, nm, D, sp, fm, prm, wall, conv, tr, res);
 }
 int32_t wtp_repel_f64(wtp_ctx* c, double* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
                       const wtp_repel_params* prm, const wtp_wall_mesh* wall, double* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
-    return repel_host<double>(c, snap, nf, nm, D, sp, fm, prm, wall, conv, tr, res);
+    return repel_entry<double>(c, snap, nf, nm, D, sp, fm, prm, wall, conv, tr, res);
 }
 int32_t wtp_repel_dev_f32(wtp_ctx* c, float* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
                           const wtp_repel_params* prm, float* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
-    return repel_dev<float>(c, snap, nf, nm, D, sp, fm, prm, conv, tr, res);
+    return is_multi(c) ? no_device_pointers2(c) : repel_dev<float>(c, snap, nf, nm, D, sp, fm, prm, conv, tr, res);
 }
 int32_t wtp_repel_dev_f64(wtp_ctx* c, double* snap, int64_t nf, int64_t nm, int32_t D, const wtp_spacing* sp, const wtp_force* fm,
                           const wtp_repel_params* prm, double* conv, wtp_trace_entry* tr, wtp_repel_result* res) {
-    return repel_dev<double>(c, snap, nf, nm, D, sp, fm, prm, conv, tr, res);
+    return is_multi(c) ? no_device_pointers2(c) : repel_dev<double>(c, snap, nf, nm, D, sp, fm, prm, conv, tr, res);
 }
 
-int32_t wtp_spacing_eval_f32(wtp_ctx* c, const wtp_spacing* sp, const float* p, int64_t N, int32_t D, float* out) { return spacing_eval_host<float>(c, sp, p, N, D, out); }
-int32_t wtp_spacing_eval_f64(wtp_ctx* c, const wtp_spacing* sp, const double* p, int64_t N, int32_t D, double* out) { return spacing_eval_host<double>(c, sp, p, N, D, out); }
-int32_t wtp_force_eval_f32(wtp_ctx* c, const wtp_force* f, const float* u, int64_t n, float* out) { return force_eval_host<float>(c, f, u, n, out); }
-int32_t wtp_force_eval_f64(wtp_ctx* c, const wtp_force* f, const double* u, int64_t n, double* out) { return force_eval_host<double>(c, f, u, n, out); }
+int32_t wtp_spacing_eval_f32(wtp_ctx* c, const wtp_spacing* sp, const float* p, int64_t N, int32_t D, float* out) { return spacing_eval_host<float>(solo_of(c), sp, p, N, D, out); }
+int32_t wtp_spacing_eval_f64(wtp_ctx* c, const wtp_spacing* sp, const double* p, int64_t N, int32_t D, double* out) { return spacing_eval_host<double>(solo_of(c), sp, p, N, D, out); }
+int32_t wtp_force_eval_f32(wtp_ctx* c, const wtp_force* f, const float* u, int64_t n, float* out) { return force_eval_host<float>(solo_of(c), f, u, n, out); }
+int32_t wtp_force_eval_f64(wtp_ctx* c, const wtp_force* f, const double* u, int64_t n, double* out) { return force_eval_host<double>(solo_of(c), f, u, n, out); }
 
 int32_t wtp_isinside_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, const float* bx, const float* bn, const float* ba, int64_t M, uint8_t* out, float* sums) {
-    return isinside_host<float>(c, p, N, D, bx, bn, ba, M, out, sums);
+    return isinside_host<float>(solo_of(c), p, N, D, bx, bn, ba, M, out, sums);
 }
 int32_t wtp_isinside_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, const double* bx, const double* bn, const double* ba, int64_t M, uint8_t* out, double* sums) {
-    return isinside_host<double>(c, p, N, D, bx, bn, ba, M, out, sums);
+    return isinside_host<double>(solo_of(c), p, N, D, bx, bn, ba, M, out, sums);
 }
-int32_t wtp_mesh_isinside_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, uint8_t* out) { return mesh_query_host<float>(c, m, p, N, out, nullptr, nullptr); }
-int32_t wtp_mesh_isinside_f64(wtp_ctx* c, const wtp_wall_mesh* m, const double* p, int64_t N, uint8_t* out) { return mesh_query_host<double>(c, m, p, N, out, nullptr, nullptr); }
-int32_t wtp_mesh_project_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, float* op, int64_t* ot) { return mesh_query_host<float>(c, m, p, N, nullptr, op, ot); }
-int32_t wtp_mesh_project_f64(wtp_ctx* c, const wtp_wall_mesh* m, const double* p, int64_t N, double* op, int64_t* ot) { return mesh_query_host<double>(c, m, p, N, nullptr, op, ot); }
+int32_t wtp_mesh_isinside_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, uint8_t* out) { return mesh_query_host<float>(solo_of(c), m, p, N, out, nullptr, nullptr); }
+int32_t wtp_mesh_isinside_f64(wtp_ctx* c, const wtp_wall_mesh* m, const double* p, int64_t N, uint8_t* out) { return mesh_query_host<double>(solo_of(c), m, p, N, out, nullptr, nullptr); }
+int32_t wtp_mesh_project_f32(wtp_ctx* c, const wtp_wall_mesh* m, const float* p, int64_t N, float* op, int64_t* ot) { return mesh_query_host<float>(solo_of(c), m, p, N, nullptr, op, ot); }
+int32_t wtp_mesh_project_f64(wtp_ctx* c, const wtp_wall_mesh* m, const double* p, int64_t N, double* op, int64_t* ot) { return mesh_query_host<double>(solo_of(c), m, p, N, nullptr, op, ot); }
 
 }  // extern "C"
 
@@ -521,8 +593,8 @@ static int32_t cull_mask_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, 
 }
 }  // namespace wtp
 extern "C" {
-int32_t wtp_cull_mask_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, const float* s, double ratio, uint8_t* keep) { return cull_mask_host<float>(c, p, N, D, s, ratio, keep); }
-int32_t wtp_cull_mask_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, const double* s, double ratio, uint8_t* keep) { return cull_mask_host<double>(c, p, N, D, s, ratio, keep); }
+int32_t wtp_cull_mask_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, const float* s, double ratio, uint8_t* keep) { return cull_mask_host<float>(solo_of(c), p, N, D, s, ratio, keep); }
+int32_t wtp_cull_mask_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, const double* s, double ratio, uint8_t* keep) { return cull_mask_host<double>(solo_of(c), p, N, D, s, ratio, keep); }
 }
 
 // ------------------------------------------- spacing_metrics / spacing_fidelity_metrics
@@ -720,13 +792,13 @@ static int32_t spacing_fidelity_host(wtp_ctx* ctx, const T* pts, int64_t N, int3
 }  // namespace wtp
 
 extern "C" {
-int32_t wtp_spacing_metrics_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, wtp_spacing_metrics_t* out) { return spacing_metrics_host<float>(c, p, N, D, k, sp, out); }
-int32_t wtp_spacing_metrics_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, wtp_spacing_metrics_t* out) { return spacing_metrics_host<double>(c, p, N, D, k, sp, out); }
-int32_t wtp_spacing_fidelity_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, wtp_spacing_fidelity_t* out) { return spacing_fidelity_host<float>(c, p, N, D, k, cr, sp, out); }
-int32_t wtp_spacing_fidelity_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, wtp_spacing_fidelity_t* out) { return spacing_fidelity_host<double>(c, p, N, D, k, cr, sp, out); }
+int32_t wtp_spacing_metrics_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, wtp_spacing_metrics_t* out) { return spacing_metrics_host<float>(solo_of(c), p, N, D, k, sp, out); }
+int32_t wtp_spacing_metrics_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, const wtp_spacing* sp, wtp_spacing_metrics_t* out) { return spacing_metrics_host<double>(solo_of(c), p, N, D, k, sp, out); }
+int32_t wtp_spacing_fidelity_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, wtp_spacing_fidelity_t* out) { return spacing_fidelity_host<float>(solo_of(c), p, N, D, k, cr, sp, out); }
+int32_t wtp_spacing_fidelity_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, double cr, const wtp_spacing* sp, wtp_spacing_fidelity_t* out) { return spacing_fidelity_host<double>(solo_of(c), p, N, D, k, cr, sp, out); }
 }
 
 extern "C" {
-int32_t wtp_metrics_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<float>(c, p, N, D, k, out); }
-int32_t wtp_metrics_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<double>(c, p, N, D, k, out); }
+int32_t wtp_metrics_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<float>(solo_of(c), p, N, D, k, out); }
+int32_t wtp_metrics_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, wtp_cloud_metrics* out) { return metrics_host<double>(solo_of(c), p, N, D, k, out); }
 }

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "multi.h"
 
 namespace wtp {
 
@@ -24,6 +25,7 @@ struct NcclApi {
     void* handle = nullptr;
     int (*GetUniqueId)(nccl_unique_id*) = nullptr;
     int (*CommInitRank)(nccl_comm_t*, int, nccl_unique_id, int) = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
@@ -49,6 +51,7 @@ static NcclApi* load_nccl() {
     if (!api.field) throw Error{WTP_ERR_NCCL, std::string("libnccl is missing symbol ") + sym};
     BIND(GetUniqueId, "ncclGetUniqueId")
     BIND(CommInitRank, "ncclCommInitRank")
+    BIND(CommInitAll, "ncclCommInitAll")
     BIND(CommDestroy, "ncclCommDestroy")
     BIND(AllGather, "ncclAllGather")
     BIND(Broadcast, "ncclBroadcast")
@@ -93,24 +96,49 @@ void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t by
 // small ncclAllGather, and every rank maps the others' buffers (NVLink peer access). Returns false — and the caller
 // keeps the NCCL all-gather — when the ranks are not all peers of each other or IPC is not available (decided
 // collectively, so every rank takes the same path). Collective: every rank must call it with the same size.
-static void peers_unmap(wtp_ctx* ctx) {
+static void peers_unmap(wtp_ctx* ctx, PeerSet& pb) {
     for (int r = 0; r < WTP_MAX_PEERS; ++r) {
-        if (ctx->peers.base[r] && r != ctx->rank) cudaIpcCloseMemHandle(ctx->peers.base[r]);
-        ctx->peers.base[r] = nullptr;
+        if (pb.base[r] && r != ctx->rank && !ctx->group) cudaIpcCloseMemHandle(pb.base[r]);   // in-process peers: plain pointers
+        pb.base[r] = nullptr;
     }
-    ctx->peers.mapped = false;
+    pb.mapped = false;
 }
 
-bool comm_peer_buffers(wtp_ctx* ctx, size_t bytes_each) {
-    auto& pb = ctx->peers;
+// The ranks of a single-process multi-device context reach each other's buffers directly (peer access was enabled when
+// the context was made): the pointers go round through the group's table, two in-process barriers instead of handles.
+static bool group_peer_buffers(wtp_ctx* ctx, PeerSet& pb, size_t bytes_each) {
+    LocalGroup* g = ctx->group;
+    const int which = &pb == &ctx->peers ? 0 : 1;
+    WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    g->barrier();                                           // nobody is still using the old buffers
+    if (pb.own.p) { cudaFree(pb.own.p); pb.own.p = nullptr; pb.own.cap = 0; }
+    const size_t each = (bytes_each + bytes_each / 8 + 4095) & ~(size_t)4095;
+    void* mine = nullptr;
+    const bool ok = cudaMalloc(&mine, 2 * each) == cudaSuccess;
+    (void)cudaGetLastError();
+    g->ptrs[which][ctx->rank] = ok ? mine : nullptr;
+    g->barrier();
+    bool all_ok = true;
+    for (int r = 0; r < ctx->world; ++r) all_ok = all_ok && g->ptrs[which][r] != nullptr;
+    for (int r = 0; r < ctx->world; ++r) pb.base[r] = all_ok ? g->ptrs[which][r] : nullptr;
+    g->barrier();                                           // everyone has read the table
+    pb.own.p = mine; pb.own.cap = mine ? 2 * each : 0;
+    pb.bytes_each = each;
+    pb.mapped = all_ok;
+    pb.unavailable = !all_ok;
+    return all_ok;
+}
+
+bool comm_peer_buffers(wtp_ctx* ctx, PeerSet& pb, size_t bytes_each) {
     if (ctx->world <= 1 || ctx->world > WTP_MAX_PEERS || !ctx->nccl_comm || pb.unavailable || getenv("WTP_NO_P2P")) return false;
     if (pb.mapped && pb.bytes_each >= bytes_each) return true;
+    if (ctx->group) return group_peer_buffers(ctx, pb, bytes_each);
     NcclApi* api = ctx->nccl;
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (pb.mapped) {
         // growing: every rank closes its mappings first, and only after all have done so (a tiny all-gather as the
         // barrier) does anybody free the buffer the others had mapped
-        peers_unmap(ctx);
+        peers_unmap(ctx, pb);
         int64_t* d_flag = ctx->d_misc.as<int64_t>((size_t)ctx->world + 1);
         NCCL_CHECK(api, api->AllGather(d_flag + ctx->world, d_flag, sizeof(int64_t), NCCL_INT8, ctx->nccl_comm, ctx->stream));
         WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -151,7 +179,7 @@ bool comm_peer_buffers(wtp_ctx* ctx, size_t bytes_each) {
     for (int r = 0; r < ctx->world; ++r) all_ok &= all[(size_t)r].ok ? 1 : 0;
     if (!all_ok) {
         pb.base[ctx->rank] = nullptr;
-        peers_unmap(ctx);
+        peers_unmap(ctx, pb);
         pb.own.p = mine; pb.own.cap = mine ? 2 * each : 0;   // freed with the context, when no peer can still have it mapped
         pb.unavailable = true;
         return false;
@@ -171,7 +199,8 @@ using namespace wtp;
 extern "C" {
 
 void wtp_comm_destroy_internal(wtp_ctx* ctx) {
-    wtp::peers_unmap(ctx);
+    wtp::peers_unmap(ctx, ctx->peers);
+    wtp::peers_unmap(ctx, ctx->row_peers);
     if (ctx->nccl_comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
     ctx->rank = 0;
@@ -221,5 +250,62 @@ int32_t wtp_comm_init(wtp_ctx* ctx, int32_t rank, int32_t world, const void* uni
 
 int32_t wtp_comm_rank(const wtp_ctx* ctx) { return ctx ? ctx->rank : -1; }
 int32_t wtp_comm_world(const wtp_ctx* ctx) { return ctx ? ctx->world : -1; }
+
+// One context over several GPUs of the box, in one process (wtp_create(ctx**, devices*, n)): the
+// parent handle owns a child context per device — the ranks of one NCCL communicator (ncclCommInitAll), with peer access
+// enabled between every pair so that the exchange kernels store straight into each other's memory — and a plain
+// single-device context for the entry points that do not shard. n_devices == 1 is wtp_create.
+int32_t wtp_create_multi(wtp_ctx** out, const int32_t* devices, int32_t n_devices) {
+    if (!out || !devices || n_devices < 1 || n_devices > WTP_MAX_PEERS) return WTP_ERR_BAD_ARG;
+    *out = nullptr;
+    if (n_devices == 1) return wtp_create(out, devices[0]);
+    for (int a = 0; a < n_devices; ++a)
+        for (int b = 0; b < a; ++b)
+            if (devices[a] == devices[b]) return WTP_ERR_BAD_ARG;
+    wtp_ctx* parent = new (std::nothrow) wtp_ctx();
+    if (!parent) return WTP_ERR_OOM;
+    parent->device = devices[0];
+    int32_t rc = WTP_OK;
+    try {
+        NcclApi* api = load_nccl();
+        for (int r = 0; r < n_devices && rc == WTP_OK; ++r) {
+            wtp_ctx* c = nullptr;
+            rc = wtp_create(&c, devices[r]);
+            if (rc == WTP_OK) parent->children.push_back(c);
+        }
+        if (rc == WTP_OK) rc = wtp_create(&parent->solo, devices[0]);
+        if (rc == WTP_OK) {
+            for (int a = 0; a < n_devices; ++a) {              // peer access between every pair (NVLink / NVSwitch)
+                WTP_CUDA_CHECK(cudaSetDevice(devices[a]));
+                for (int b = 0; b < n_devices; ++b) {
+                    if (a == b) continue;
+                    int can = 0;
+                    WTP_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
+                    WTP_REQUIRE(can, WTP_ERR_CUDA, "wtp_create_multi: the devices cannot access each other's memory");
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) WTP_CUDA_CHECK(e);
+                    (void)cudaGetLastError();
+                }
+            }
+            std::vector<nccl_comm_t> comms((size_t)n_devices, nullptr);
+            std::vector<int> devs(devices, devices + n_devices);
+            NCCL_CHECK(api, api->CommInitAll(comms.data(), n_devices, devs.data()));
+            LocalGroup* g = new LocalGroup();
+            g->world = n_devices;
+            parent->group = g;
+            for (int r = 0; r < n_devices; ++r) {
+                wtp_ctx* c = parent->children[(size_t)r];
+                c->nccl = api; c->nccl_comm = comms[(size_t)r]; c->rank = r; c->world = n_devices; c->group = g;
+            }
+        }
+    } catch (const Error& e) {
+        rc = e.status;
+    } catch (...) {
+        rc = WTP_ERR_CUDA;
+    }
+    if (rc != WTP_OK) { wtp_destroy(parent); return rc; }
+    *out = parent;
+    return WTP_OK;
+}
 
 }  // extern "C"

@@ -241,11 +241,27 @@ struct MeshBuffers {
 
 // Where the row of a query goes in the output table: at its caller index (minus q_begin), or, for the compact
 // table of a sharded host call, at its sorted position (minus pos_base).
+// Row exchange of a sharded host call (n_owners > 0): the row of caller index i belongs to the rank that owns the caller
+// range holding i and is stored straight into that rank's buffer (peer memory over NVLink), so that every rank ends up
+// with the rows of one contiguous caller range: the element address is out + owner_delta[r] + i * k_out (owner_delta in
+// table elements; the peers' buffers are mapped into this process's address space).
 struct RowMap {
     uint32_t q_begin, pos_base;
     int by_position;
+    int n_owners;
+    uint32_t owner_begin[WTP_MAX_PEERS + 1];
+    long long owner_delta[WTP_MAX_PEERS];
     __host__ __device__ int64_t row(uint32_t sorted_pos, uint32_t caller_idx) const {
         return by_position ? (int64_t)(sorted_pos - pos_base) : (int64_t)(caller_idx - q_begin);
+    }
+    // offset of the row's first element in the output table
+    __host__ __device__ int64_t elem(uint32_t sorted_pos, uint32_t caller_idx, int k_out) const {
+        if (n_owners > 0) {
+            int r = 0;
+            for (int t = 1; t < n_owners; ++t) r += caller_idx >= owner_begin[t] ? 1 : 0;
+            return (int64_t)owner_delta[r] + (int64_t)caller_idx * k_out;
+        }
+        return row(sorted_pos, caller_idx) * k_out;
     }
 };
 
@@ -260,8 +276,18 @@ struct TileFails {
     uint32_t* list;        // sorted positions
 };
 
+// Buffers that every rank of a communicator maps from every other rank (CUDA IPC over NVLink; comm.cu, comm_peer_buffers):
+// two per rank, alternating per use, so that a rank running ahead never writes into a buffer a peer is still reading.
+struct PeerSet {
+    DevBuf own;                      // this rank's buffers (2 x bytes_each)
+    size_t bytes_each = 0;
+    void* base[WTP_MAX_PEERS] = {};  // base[r]: rank r's buffers in this process's address space (own for r == rank)
+    bool mapped = false, unavailable = false;
+};
+
 struct NcclApi;  // comm.cu
 class HostPool;  // host_pool.h
+struct LocalGroup;  // comm.cu: the ranks of a single-process multi-device context (wtp_create_multi)
 
 }  // namespace wtp
 
@@ -302,15 +328,27 @@ struct wtp_ctx {
     int rank = 0, world = 1;
     void* nccl_comm = nullptr;
     wtp::NcclApi* nccl = nullptr;
+    // Single-process multi-device context (wtp_create_multi, comm.cu). The handle the caller holds is a PARENT: it owns
+    // one child context per device (ranks of one NCCL communicator made with ncclCommInitAll, sharing a LocalGroup for
+    // the in-process pointer exchange and barriers) and a plain single-device context (`solo`, on the first device) for
+    // the entry points that do not shard. A host entry point called on the parent runs on every child at once, one
+    // host thread per device; the children answer their shards exactly as one-process-per-GPU ranks would.
+    std::vector<wtp_ctx*> children;
+    std::vector<int64_t> children_base;  // parent, radius two-call state: where each child's entries start in the caller's CSR
+    wtp_ctx* solo = nullptr;
+    wtp::LocalGroup* group = nullptr;    // children: the group they belong to (owned by the parent)
+    bool quiet = false;                  // children of rank > 0 during a replicated call (repel): results are written back by rank 0 only
+    uint64_t error_stamp = 0;            // order of the last failure among the contexts of one parent
     // peer-memory exchange of the run-sharded repel (comm.cu, comm_peer_buffers): every rank's two run buffers, mapped
     // into this process with CUDA IPC, so that the sweep kernels store their records straight into all ranks' buffers
     // over NVLink instead of an all-gather afterwards
-    struct {
-        wtp::DevBuf own;                 // this rank's buffers (2 x bytes_each)
-        size_t bytes_each = 0;
-        void* base[WTP_MAX_PEERS] = {};  // base[r]: rank r's buffers in this process's address space (own for r == rank)
-        bool mapped = false, unavailable = false;
-    } peers;
+    wtp::PeerSet peers;                  // run buffers of the run-sharded repel
+    // row buffers of the sharded host k-NN: every rank's sweep stores the row of caller index i into the buffer of the rank
+    // that owns the caller range of i, so each rank brings back one contiguous part of the caller's table
+    wtp::PeerSet row_peers;
+    uint64_t row_exchanges = 0;          // calls that used the row exchange (buffer parity)
+    bool last_d2h_direct = false;         // ... and its rows went back as int64 written by the DMA engine (pinned caller table)
+    bool owned_contiguous = false;       // the last sharded k-NN call answered a contiguous caller range [owned_begin, owned_end)
     // host k-NN pipeline: 4-byte index staging (pinned ring) and the widening threads
     void* h_stage = nullptr;
     size_t h_stage_slot_bytes = 0;

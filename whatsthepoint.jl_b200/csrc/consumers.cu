@@ -15,6 +15,7 @@
 
 #include "kernels.cuh"
 #include "knn_core.cuh"
+#include "multi.h"
 
 using namespace wtp;
 
@@ -204,15 +205,15 @@ static int32_t gradient_limit_host(wtp_ctx* ctx, const T* centers, int64_t n, in
 
 extern "C" {
 
-int32_t wtp_normals_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, float* out) { return normals_host<float>(c, p, N, D, k, out); }
-int32_t wtp_normals_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, double* out) { return normals_host<double>(c, p, N, D, k, out); }
+int32_t wtp_normals_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, float* out) { return normals_host<float>(solo_of(c), p, N, D, k, out); }
+int32_t wtp_normals_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, double* out) { return normals_host<double>(solo_of(c), p, N, D, k, out); }
 int32_t wtp_gradient_limit_f32(wtp_ctx* c, const float* centers, int64_t n, int32_t D, const float* h0, float g, int32_t k, double tol, int32_t max_sweeps,
                                float* out, int32_t* sweeps) {
-    return gradient_limit_host<float>(c, centers, n, D, h0, g, k, tol, max_sweeps, out, sweeps);
+    return gradient_limit_host<float>(solo_of(c), centers, n, D, h0, g, k, tol, max_sweeps, out, sweeps);
 }
 int32_t wtp_gradient_limit_f64(wtp_ctx* c, const double* centers, int64_t n, int32_t D, const double* h0, double g, int32_t k, double tol, int32_t max_sweeps,
                                double* out, int32_t* sweeps) {
-    return gradient_limit_host<double>(c, centers, n, D, h0, g, k, tol, max_sweeps, out, sweeps);
+    return gradient_limit_host<double>(solo_of(c), centers, n, D, h0, g, k, tol, max_sweeps, out, sweeps);
 }
 
 }  // extern "C"

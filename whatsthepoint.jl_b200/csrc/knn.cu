@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(KNN_THREADS, knn_min_blocks<T>()) knn_kernel(c
         const int rings = s.run(q.x, q.y, q.z, K1);
         if (rings > 1 && lane == 0 && expanded) atomicAdd(expanded, 1ULL);
         if (s.missed && lane == 0 && expanded) atomicAdd(expanded + 1, 1ULL);   // windowed index: the caller repeats the call on the whole index
-        const int64_t row = (ext_q ? (int64_t)j : rows.row(j, idx_of(q))) * k_out;
+        const int64_t row = ext_q ? (int64_t)j * k_out : rows.elem(j, idx_of(q), k_out);
 #pragma unroll
         for (int e = 0; e < KPL; ++e) {
             const int r = e * 32 + lane;

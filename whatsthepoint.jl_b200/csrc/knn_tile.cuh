@@ -341,7 +341,7 @@ knn_tile_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_
             // re-read the K best from the last to the first, check strict canonical order (the images of two keys
             // collide only when their d2 agree to ~17 bits, or on exact ties) and park the indices: word r overwrites
             // slots 2r and 2r+1, both already consumed on the way down
-            row = rows.row(ts.j, idx_of(ts.q)) * k_out;
+            row = rows.elem(ts.j, idx_of(ts.q), k_out);
             asm volatile("" ::: "memory");                                                // select()'s plain stores to the list come first
             Key<T> next = Key<T>::make((T)0, 0u), kth = next;
             bool ok = true;

@@ -26,7 +26,7 @@ namespace wtp {
     } while (0)
 
 // comm.cu
-bool comm_peer_buffers(wtp_ctx* ctx, size_t bytes_each);
+bool comm_peer_buffers(wtp_ctx* ctx, PeerSet& pb, size_t bytes_each);
 void comm_allgather_rows(wtp_ctx* ctx, void* d_buf, int64_t n_rows, size_t row_bytes);
 void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t bytes_per_rank);
 
@@ -647,7 +647,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     // buffers, two buffers alternate so that a rank may run ahead of its peers' scatter) or, when the ranks cannot map
     // each other's memory, through an all-gather after the sweep
     const size_t run_bytes = (size_t)run_slot * world * sizeof(P4<T>);
-    const bool p2p = by_runs && comm_peer_buffers(ctx, run_bytes);
+    const bool p2p = by_runs && comm_peer_buffers(ctx, ctx->peers, run_bytes);
     P4<T>* C_local = by_runs && !p2p ? ctx->d_misc2.as<P4<T>>((size_t)run_slot * world) : nullptr;
     uint64_t n_sweeps = 0;
     // per-CTA partials of the sweep launches of an iteration (general sweep | tiled sweep), folded together
