@@ -21,7 +21,7 @@ sel = [r for r in rows[2:] if len(r) == len(h) and rx.search(r[kn])]
 tot = sum(to_bytes(r[rd], units[rd]) + to_bytes(r[wr], units[wr]) for r in sel)
 steps = max(len(sel) // per_step, 1)
 out = {"dram_bytes_per_launch": tot / steps, "launches_matched": len(sel), "launches_per_step": per_step,
-       "kernels": sorted({r[kn][:120] for r in sel}), "gpu_time_us_per_step": sum(float(r[du].replace(",", "")) for r in sel) / steps / (1e3 if units[du] == "ns" else 1),
+       "kernels": sorted({r[kn][:120] for r in sel}), "gpu_time_us_per_step": sum(float(r[du].replace(",", "")) for r in sel) / steps * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[du], 1.0),
        "source": f"ncu --set full --clock-control none, {os.path.basename(rep)}: dram__bytes_read.sum + dram__bytes_write.sum"}
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", f"r02_{name}_traffic_n{world}.json")
 json.dump(out, open(path, "w"), indent=1)
