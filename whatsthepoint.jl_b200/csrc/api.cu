@@ -223,12 +223,45 @@ static size_t ensure_stage(wtp_ctx* ctx) {
     return slot;
 }
 
-// A device array of 4-byte indices -> the caller's int64 host array: chunk by chunk through the staging ring on the
-// copy stream, widened by the host pool while the next chunks are on the wire (4 B per entry cross PCIe instead of 8,
-// and the caller's array does not have to be pinned). The data must be complete on ctx->stream when this is called.
-void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst) {
+// 4 indices below 2^24 -> 12 bytes (3 little-endian bytes each)
+__global__ void __launch_bounds__(256) pack24_kernel(const uint32_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
+    const size_t groups = (n + 3) / 4;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+        uint32_t v[4];
+        if (4 * g + 4 <= n) { const uint4 q = reinterpret_cast<const uint4*>(in)[g]; v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else for (int j = 0; j < 4; ++j) v[j] = 4 * g + j < n ? in[4 * g + j] : 0u;
+        out[3 * g + 0] = v[0] | (v[1] << 24);
+        out[3 * g + 1] = (v[1] >> 8) | (v[2] << 16);
+        out[3 * g + 2] = (v[2] >> 16) | (v[3] << 8);
+    }
+}
+
+// A device array of 4-byte indices (16-byte aligned) -> the caller's int64 host array: chunk by chunk through the
+// staging ring on the copy stream, widened by the host pool while the next chunks are on the wire, so the caller's array
+// does not have to be pinned and at most 4 bytes per entry cross PCIe instead of 8 — 3 when every value is below 2^24
+// (max_value; point sets of up to 16.7 M): the link, not the host, is what bounds this step, so the entries are packed
+// to 3 bytes on the device first (WTP_NO_PACK24 turns that off). The data must be complete on ctx->stream.
+void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst, uint64_t max_value) {
     if (n == 0) return;
     const size_t slot = ensure_stage(ctx);
+    if (max_value < ((uint64_t)1 << 24) && std::getenv("WTP_NO_PACK24") == nullptr) {
+        const size_t groups = (n + 3) / 4;
+        uint32_t* d_packed = ctx->d_pack.as<uint32_t>(3 * groups + 4);
+        const unsigned nb = (unsigned)std::min<size_t>((groups + 255) / 256, (size_t)kNumSMs * 16);
+        pack24_kernel<<<nb, 256, 0, ctx->stream>>>(d_src, n, d_packed);
+        ctx->launches++;
+        WTP_CUDA_CHECK(cudaPeekAtLastError());
+        const size_t chunk = ((slot - 16) / 12) * 12;                        // whole groups, 4 readable bytes behind the last one
+        d2h_pipeline(ctx, d_packed, 12 * groups, chunk, slot, ctx->h_stage_ring,
+                     [&](int64_t, const char* staged, size_t off, size_t len, int w, int workers) {
+                         const size_t first = off / 12 * 4, total = std::min(len / 12 * 4, n - first);
+                         const size_t a = (total * (size_t)w / (size_t)workers) & ~(size_t)3;
+                         const size_t b = w + 1 == workers ? total : ((total * (size_t)(w + 1) / (size_t)workers) & ~(size_t)3);
+                         widen_u24_to_i64(reinterpret_cast<const unsigned char*>(staged) + 3 * a, h_dst + first + a, b - a);
+                     });
+        ctx->last_d2h_bytes = 12 * groups;
+        return;
+    }
     d2h_pipeline(ctx, d_src, n * sizeof(uint32_t), slot, slot, ctx->h_stage_ring,
                  [&](int64_t, const char* staged, size_t off, size_t len, int w, int workers) {
                      const size_t total = len / sizeof(uint32_t), first = off / sizeof(uint32_t);
@@ -236,6 +269,7 @@ void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst
                      const size_t b = w + 1 == workers ? total : ((total * (size_t)(w + 1) / (size_t)workers) & ~(size_t)3);
                      widen_u32_to_i64(reinterpret_cast<const uint32_t*>(staged) + a, h_dst + first + a, b - a);
                  });
+    ctx->last_d2h_bytes = n * sizeof(uint32_t);
 }
 
 bool comm_peer_buffers(wtp_ctx* ctx, PeerSet& pb, size_t bytes_each);                                   // comm.cu
@@ -364,7 +398,7 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
             widen_on_device(ctx, mine, n_elems, d_wide);
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_dst, d_wide, n_elems * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
         } else {
-            d2h_widen_u32(ctx, mine, n_elems, h_dst);
+            d2h_widen_u32(ctx, mine, n_elems, h_dst, (uint64_t)N);
         }
         ctx->owned_contiguous = true;
         ctx->owned_begin = cb; ctx->owned_end = ce;
@@ -416,15 +450,12 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         const size_t chunk_bytes = std::max<size_t>(1, SLOT / row_bytes) * row_bytes;   // whole rows per chunk
         n_chunks = (int)(((size_t)nq * row_bytes + chunk_bytes - 1) / chunk_bytes);
         const auto t_pipe = std::chrono::steady_clock::now();
-        d2h_pipeline(ctx, d_idx32, (size_t)nq * row_bytes, chunk_bytes, SLOT, ctx->h_stage_ring,
-                     [&](int64_t, const char* staged, size_t off, size_t len, int w, int workers) {
-                         const uint32_t* src = reinterpret_cast<const uint32_t*>(staged);
-                         if (!sharded) {
-                             const size_t total = len / sizeof(uint32_t), first = off / sizeof(uint32_t);
-                             const size_t a = (total * (size_t)w / (size_t)workers) & ~(size_t)3;
-                             const size_t b = w + 1 == workers ? total : ((total * (size_t)(w + 1) / (size_t)workers) & ~(size_t)3);
-                             widen_u32_to_i64(src + a, h_out_idx + first + a, b - a);
-                         } else {
+        if (!sharded) {
+            d2h_widen_u32(ctx, d_idx32, (size_t)nq * k, h_out_idx, (uint64_t)N);
+        } else {
+            d2h_pipeline(ctx, d_idx32, (size_t)nq * row_bytes, chunk_bytes, SLOT, ctx->h_stage_ring,
+                         [&](int64_t, const char* staged, size_t off, size_t len, int w, int workers) {
+                             const uint32_t* src = reinterpret_cast<const uint32_t*>(staged);
                              const int64_t nrow = (int64_t)(len / row_bytes), cb = (int64_t)(off / row_bytes);
                              const int64_t t_end = nrow * (w + 1) / workers;
                              for (int64_t t = nrow * w / workers; t < t_end; ++t) {
@@ -433,8 +464,9 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
                                  if (h_out_dist) memcpy(h_out_dist + ((int64_t)ids[(size_t)(cb + t)] - 1) * k, dist_tmp.data() + (size_t)(cb + t) * k, (size_t)k * sizeof(T));
                              }
                              _mm_sfence();
-                         }
-                     });
+                         });
+            ctx->last_d2h_bytes = (size_t)nq * row_bytes + (size_t)nq * 4;
+        }
         if (std::getenv("WTP_PIPE_DEBUG"))
             fprintf(stderr, "[wtp pipe] chunks=%d slot=%zu MiB ring=%d threads=%d d2h+widen=%.2f ms\n", n_chunks, SLOT >> 20, ctx->h_stage_ring, ctx->pool->size(),
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pipe).count());
@@ -447,9 +479,9 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     finish_timing(ctx, passes, n_chunks, g.ncells, (int64_t)*h_exp);
     ctx->last_timing.n_peer_ranks = exchange ? ctx->world : 0;
     ctx->last_timing.bytes_d2h = !h_out_idx ? 0
-        : exchange ? (ce - cb) * (int64_t)k * (ctx->last_d2h_direct ? 8 : 4)
+        : exchange && ctx->last_d2h_direct ? (ce - cb) * (int64_t)k * 8
         : (!sharded && nq * (int64_t)k < ((int64_t)4 << 20)) ? nq * (int64_t)k * 8
-        : nq * (int64_t)k * 4 + (sharded ? nq * 4 : 0);
+        : (int64_t)ctx->last_d2h_bytes;
     if (h_out_idx && h_out_dist) ctx->last_timing.bytes_d2h += nq * (int64_t)k * (int64_t)sizeof(T);
 }
 

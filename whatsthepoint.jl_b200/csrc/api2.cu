@@ -1,6 +1,7 @@
 // api2.cu — C ABI entry points for radius topology, repel, spacing / force evaluation
 // and cloud metrics (include/wtp_cuda.h).
 #include <cmath>
+#include <cstdlib>
 #include <new>
 
 #include "kernels.cuh"
@@ -37,7 +38,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 
 namespace wtp {
 
-void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst);   // api.cu
+void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst, uint64_t max_value);   // api.cu
 
 __global__ void __launch_bounds__(256) narrow_indices_kernel(const int64_t* __restrict__ in, size_t n, uint32_t* __restrict__ out) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (uint32_t)in[i];
@@ -61,8 +62,9 @@ static void radius_count_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, 
     Grid<T> g = make_grid<T>(N, D, lo, hi, ctx->cell_occupancy > 0 ? ctx->cell_occupancy : 2.0, (double)r * 1.001, 0);
     int passes = build_index<T>(ctx, ib, d_pts, N, D, g);
     const int64_t qb = wtp_shard_begin(N, ctx->rank, ctx->world), qe = wtp_shard_end(N, ctx->rank, ctx->world);
+    // (sharded: the tiled passes take the caller range as a keep filter; only the general kernels on their own need a list)
     const uint32_t* qlist = nullptr;
-    if (ctx->world > 1) {
+    if (ctx->world > 1 && std::getenv("WTP_NO_TILED") != nullptr) {
         build_query_list(ctx, ib, N, qb, qe, sizeof(T) == 8, ctx->d_misc, ctx->d_misc2, ctx->d_qlist);
         qlist = ctx->d_qlist.get<uint32_t>();
     }
@@ -89,7 +91,7 @@ static void radius_fill_device(wtp_ctx* ctx, const int64_t* d_offsets, int64_t* 
     auto& st = ctx->radius;
     Grid<T> g;
     memcpy(&g, ctx->grid_storage[0], sizeof(g));
-    const uint32_t* qlist = ctx->world > 1 ? ctx->d_qlist.get<uint32_t>() : nullptr;
+    const uint32_t* qlist = ctx->world > 1 && std::getenv("WTP_NO_TILED") != nullptr ? ctx->d_qlist.get<uint32_t>() : nullptr;
     ctx->d_misc2.as<uint32_t>((size_t)std::max<int64_t>(st.nnz, 1));
     radius_fill<T>(ctx, ctx->index[0], g, st.N, st.D, (T)st.r, qlist, st.q_end - st.q_begin, st.q_begin, d_offsets, d_indices);
 }
@@ -213,7 +215,7 @@ int32_t wtp_radius_fill(wtp_ctx* ctx, int64_t* indices) {
                 // large result: 4 bytes per entry cross PCIe, widened into the caller's array by the host pool (api.cu)
                 uint32_t* d_ind32 = ctx->d_out_idx.as<uint32_t>((size_t)st.nnz);
                 narrow_indices(ctx, d_ind, (size_t)st.nnz, d_ind32);
-                d2h_widen_u32(ctx, d_ind32, (size_t)st.nnz, indices);
+                d2h_widen_u32(ctx, d_ind32, (size_t)st.nnz, indices, (uint64_t)st.N);
             }
         }
         ctx->timer.end_total();

@@ -311,7 +311,8 @@ struct wtp_ctx {
     // triangle mesh of the wall rule (3-argument repel) and of the batched mesh queries
     wtp::MeshBuffers mesh;
     wtp::DevBuf d_pts, d_out_idx, d_out_dist, d_offsets, d_counts, d_indices, d_misc, d_misc2;
-    wtp::DevBuf d_spacing_pts, d_spacings, d_p_new, d_reduce, d_qlist, d_nn, d_fail;
+    wtp::DevBuf d_spacing_pts, d_spacings, d_p_new, d_reduce, d_qlist, d_nn, d_fail, d_pack;
+    size_t last_d2h_bytes = 0;           // bytes the last widening copy moved over PCIe
     // radius two-call state
     struct {
         bool pending = false; bool f64 = false; bool dev_input = false;

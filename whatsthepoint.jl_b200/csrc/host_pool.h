@@ -7,6 +7,7 @@
 // computed on the CPU.
 #pragma once
 #include <emmintrin.h>
+#include <tmmintrin.h>
 #include <stdint.h>
 
 #include <condition_variable>
@@ -98,6 +99,24 @@ inline void widen_u32_to_i64(const uint32_t* src, int64_t* dst, size_t n) {
         _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 2), _mm_unpackhi_epi32(v, zero));
     }
     for (; i < n; ++i) dst[i] = (int64_t)src[i];
+    _mm_sfence();
+}
+
+// The same from 3-byte little-endian values (indices below 2^24 cross PCIe as 3 bytes each): 12 source bytes give 4
+// values. Reads 16 bytes per group: the caller keeps 4 readable bytes behind the last group. n is a multiple of 4 except
+// possibly in the last call of an array (scalar tail).
+__attribute__((target("ssse3"))) inline void widen_u24_to_i64(const unsigned char* src, int64_t* dst, size_t n) {
+    size_t i = 0;
+    const __m128i zero = _mm_setzero_si128();
+    const __m128i pick = _mm_setr_epi8(0, 1, 2, (char)0x80, 3, 4, 5, (char)0x80, 6, 7, 8, (char)0x80, 9, 10, 11, (char)0x80);
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (; i + 4 <= n; i += 4) {
+            const __m128i v = _mm_shuffle_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(src + 3 * i)), pick);
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i), _mm_unpacklo_epi32(v, zero));
+            _mm_stream_si128(reinterpret_cast<__m128i*>(dst + i + 2), _mm_unpackhi_epi32(v, zero));
+        }
+    }
+    for (; i < n; ++i) dst[i] = (int64_t)((uint32_t)src[3 * i] | ((uint32_t)src[3 * i + 1] << 8) | ((uint32_t)src[3 * i + 2] << 16));
     _mm_sfence();
 }
 

@@ -177,13 +177,13 @@ __device__ __forceinline__ void block_row_cells(const TS& ts, int r, uint32_t (&
 template <class T, int D>
 __global__ void __launch_bounds__(TK_Q, 4)
 radius_tile_count_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_t* __restrict__ cell_start, uint32_t s_begin, uint32_t s_end,
-                         uint32_t q_begin, T r2, uint32_t* __restrict__ counts, const TileFails fails) {
+                         uint32_t q_begin, uint32_t q_end, T r2, uint32_t* __restrict__ counts, const TileFails fails) {
     using R = RadTile<T, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ typename R::Search::Shared sh;
     typename R::Search ts(g, sorted, cell_start, smem_raw, sh);
     const uint32_t j = s_begin + blockIdx.x * TK_Q + threadIdx.x;
-    ts.init(j, j < s_end);
+    ts.init(j, j < s_end, q_begin, q_end);   // a sharded context answers the caller range [q_begin, q_end): the other records only shape the slab
     while (ts.next_group()) {
         int status = TK_OK;
         if (ts.in_group && ts.query) {
@@ -219,20 +219,20 @@ __device__ __forceinline__ void append_u16_if(uint32_t& addr, uint32_t t, bool p
 template <class T, int D>
 __global__ void __launch_bounds__(TK_Q, RadTile<T, D>::MIN_BLOCKS)
 radius_tile_fill_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const uint32_t* __restrict__ cell_start, uint32_t s_begin, uint32_t s_end,
-                        uint32_t q_begin, T r2, const int64_t* __restrict__ offsets, int64_t* __restrict__ indices, const TileFails fails) {
+                        uint32_t q_begin, uint32_t q_end, T r2, const int64_t* __restrict__ offsets, int64_t* __restrict__ indices, const TileFails fails) {
     using R = RadTile<T, D>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ typename R::Search::Shared sh;
     typename R::Search ts(g, sorted, cell_start, smem_raw, sh);
     const uint32_t j = s_begin + blockIdx.x * TK_Q + threadIdx.x;
-    ts.init(j, j < s_end);
+    ts.init(j, j < s_end, q_begin, q_end);
     const uint32_t list0 = smem_u32(smem_raw + R::SMEM_COUNT) + (uint32_t)threadIdx.x * (uint32_t)(R::LS * 2);
     const uint32_t lim = list0 + (uint32_t)(R::LS - 1) * 2u;   // a row can never be longer than its count: belt and braces
     // the row's place in the CSR arrays: two scattered loads, issued before the slab is staged
     const uint32_t self = idx_of(ts.q);
     int64_t off = 0;
     uint32_t cnt = 0;
-    if (ts.active) {
+    if (ts.active && ts.query) {
         off = __ldg(offsets + (self - q_begin));
         cnt = (uint32_t)(__ldg(offsets + (self - q_begin) + 1) - off);
     }
@@ -336,27 +336,30 @@ radius_tile_fill_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const
 }
 
 template <class T, int D>
-static void launch_radius_tile_count(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t n, int64_t q_begin, T r2, uint32_t* d_counts,
+static void launch_radius_tile_count(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t n, int64_t q_begin, int64_t q_end, T r2, uint32_t* d_counts,
                                      const TileFails& f) {
     constexpr size_t smem = RadTile<T, D>::SMEM_COUNT;
     WTP_CUDA_CHECK(cudaFuncSetAttribute(radius_tile_count_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set per launch
     radius_tile_count_kernel<T, D><<<(unsigned)((n + TK_Q - 1) / TK_Q), TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cells(), 0u, (uint32_t)n,
-                                                                                                   (uint32_t)q_begin, r2, d_counts, f);
+                                                                                                   (uint32_t)q_begin, (uint32_t)q_end, r2, d_counts, f);
     LAUNCH_CHECK(ctx);
 }
 template <class T, int D>
-static void launch_radius_tile_fill(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t n, int64_t q_begin, T r2, const int64_t* d_offsets,
+static void launch_radius_tile_fill(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t n, int64_t q_begin, int64_t q_end, T r2, const int64_t* d_offsets,
                                     int64_t* d_indices, const TileFails& f) {
     constexpr size_t smem = RadTile<T, D>::SMEM_FILL;
     WTP_CUDA_CHECK(cudaFuncSetAttribute(radius_tile_fill_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set per launch
     radius_tile_fill_kernel<T, D><<<(unsigned)((n + TK_Q - 1) / TK_Q), TK_Q, smem, ctx->stream>>>(g, ib.sorted.get<P4<T>>(), ib.cells(), 0u, (uint32_t)n,
-                                                                                                  (uint32_t)q_begin, r2, d_offsets, d_indices, f);
+                                                                                                  (uint32_t)q_begin, (uint32_t)q_end, r2, d_offsets, d_indices, f);
     LAUNCH_CHECK(ctx);
 }
 
-// tiled pass over every point (an unsharded context) + the general kernel over what it handed back
-static bool radius_tiled_enabled(const wtp_ctx* ctx, const uint32_t* d_qlist) {
-    return ctx->world == 1 && d_qlist == nullptr && std::getenv("WTP_NO_TILED") == nullptr;
+// Tiled pass over every sorted position + the general kernel over what it handed back. A sharded context answers a
+// caller range, whose points lie everywhere in the sorted order: it sweeps every tile with the queries of its range
+// switched on (TileSearch::init's keep range) — the staging is not shared out, but the pass is the fast one.
+static bool radius_tiled_enabled(const wtp_ctx* ctx) {
+    (void)ctx;
+    return std::getenv("WTP_NO_TILED") == nullptr;
 }
 
 template <class T>
@@ -367,10 +370,10 @@ void radius_count(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_
     const T r2 = r * r;
     const uint32_t* d_nq = nullptr;
     unsigned nb = (unsigned)((n_queries + RAD_WARPS - 1) / RAD_WARPS);
-    if (radius_tiled_enabled(ctx, d_qlist)) {
+    if (radius_tiled_enabled(ctx)) {
         const TileFails f = tile_fails(ctx, N);
-        if (D == 2) launch_radius_tile_count<T, 2>(ctx, ib, g, N, q_begin, r2, d_counts, f);
-        else launch_radius_tile_count<T, 3>(ctx, ib, g, N, q_begin, r2, d_counts, f);
+        if (D == 2) launch_radius_tile_count<T, 2>(ctx, ib, g, N, q_begin, q_begin + n_queries, r2, d_counts, f);
+        else launch_radius_tile_count<T, 3>(ctx, ib, g, N, q_begin, q_begin + n_queries, r2, d_counts, f);
         d_qlist = f.list; d_nq = f.counters;
         nb = std::min<unsigned>(nb, (unsigned)kNumSMs * 8u);
     }
@@ -388,10 +391,10 @@ void radius_fill(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t
     uint32_t* scratch = ctx->d_misc2.get<uint32_t>();
     const uint32_t* d_nq = nullptr;
     unsigned nb = (unsigned)((n_queries + RAD_WARPS - 1) / RAD_WARPS);
-    if (radius_tiled_enabled(ctx, d_qlist)) {
+    if (radius_tiled_enabled(ctx)) {
         const TileFails f = tile_fails(ctx, N);
-        if (D == 2) launch_radius_tile_fill<T, 2>(ctx, ib, g, N, q_begin, r2, d_offsets, d_indices, f);
-        else launch_radius_tile_fill<T, 3>(ctx, ib, g, N, q_begin, r2, d_offsets, d_indices, f);
+        if (D == 2) launch_radius_tile_fill<T, 2>(ctx, ib, g, N, q_begin, q_begin + n_queries, r2, d_offsets, d_indices, f);
+        else launch_radius_tile_fill<T, 3>(ctx, ib, g, N, q_begin, q_begin + n_queries, r2, d_offsets, d_indices, f);
         d_qlist = f.list; d_nq = f.counters;
         nb = std::min<unsigned>(nb, (unsigned)kNumSMs * 8u);
     }
