@@ -182,6 +182,27 @@ def test_radius_tiled_and_leftover_rows(ctx, oracle, dt, D):
     assert np.array_equal(off, roff) and np.array_equal(ind, rind)
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("D", [2, 3])
+def test_radius_shards_one_rank_at_a_time(pkg, oracle, dt, D):
+    """Sharded radius (shard-only contexts, one rank at a time on one GPU): rank r answers the caller range
+    [shard_begin, shard_end) with the tiled passes (the range is a keep filter on every tile) and returns that part of
+    the CSR, offsets 0-based within the shard; together the shards are the oracle's CSR."""
+    rng = np.random.default_rng(300 + D)
+    n = 50003
+    pts = (rng.random((n, D)) ** 1.5).astype(dt)                        # mildly graded: short and long rows
+    r = (40.0 / n) ** (1.0 / D) * 0.6
+    roff, rind = oracle.radius(pts, r)
+    world = 3
+    for rank in range(world):
+        c = pkg.Context(0)
+        c.comm_init(rank, world, None)
+        b, e = c.shard(n)
+        off, ind = c.radius(pts, r)
+        assert len(off) == e - b + 1 and np.array_equal(off, roff[b:e + 1] - roff[b]) and np.array_equal(ind, rind[roff[b]:roff[e]])
+        c.close()
+
+
 def test_radius_known_answer_and_edges(ctx, oracle, known):
     g = known["radius_grid5x5"]                                      # test/topology.jl:46-52
     for dt in (np.float64, np.float32):
