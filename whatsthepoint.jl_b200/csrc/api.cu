@@ -219,7 +219,9 @@ static size_t ensure_stage(wtp_ctx* ctx) {
         ctx->h_stage_slot_bytes = slot;
         ctx->h_stage_ring = ring;
     }
-    if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads(ctx->world));
+    // one of the pool's threads is the pipeline's producer and sleeps most of the time (d2h_pipeline.h): when the host is
+    // shared out among ranks it comes on top of the rank's share of the cores
+    if (!ctx->pool) ctx->pool = new HostPool(HostPool::default_threads(ctx->world) + (ctx->world > 1 ? 1 : 0));
     return slot;
 }
 
@@ -273,6 +275,7 @@ void d2h_widen_u32(wtp_ctx* ctx, const uint32_t* d_src, size_t n, int64_t* h_dst
 }
 
 bool comm_peer_buffers(wtp_ctx* ctx, PeerSet& pb, size_t bytes_each);                                   // comm.cu
+void comm_allgather_rows(wtp_ctx* ctx, void* d_buf, int64_t n_rows, size_t row_bytes);
 void comm_allgather_fixed(wtp_ctx* ctx, const void* d_in, void* d_out, size_t bytes_per_rank);
 
 __global__ void __launch_bounds__(256) widen_u32_kernel(const uint32_t* __restrict__ in, size_t n, int64_t* __restrict__ out) {
@@ -364,8 +367,8 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     // the row of caller index i straight into the buffer of the rank that owns the caller range of i (peer memory over
     // NVLink, RowMap::elem), so that after one barrier every rank holds the rows of ONE CONTIGUOUS part of the caller's
     // table: it goes back with one forward copy — as int64 written by the DMA engine itself when the caller's table is
-    // pinned (G links in parallel, no host thread touches the data), through the widening pipeline otherwise — instead
-    // of rows scattered all over the table by host threads.
+    // pinned and WTP_D2H_DIRECT=1, through the widening pipeline by default (see below) — instead of rows scattered all
+    // over the table by host threads.
     const int64_t cb = wtp_shard_begin(N, ctx->rank, ctx->world), ce = wtp_shard_end(N, ctx->rank, ctx->world);   // caller range of this rank
     const size_t rx_each = (size_t)((N + ctx->world - 1) / ctx->world) * (size_t)k * sizeof(uint32_t);
     const bool exchange = sharded && h_out_idx && !h_out_dist && ctx->nccl_comm && std::getenv("WTP_NO_ROW_EXCHANGE") == nullptr &&
@@ -391,8 +394,11 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         cudaPointerAttributes attr{};
         const bool pinned = n_elems > 0 && cudaPointerGetAttributes(&attr, h_dst) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         (void)cudaGetLastError();
+        // Opt-in (WTP_D2H_DIRECT=1): measured on the 8-GPU box, DMA writes into host memory are capped at ~92 GB/s for
+        // all GPUs together — two links' worth — so 8 bytes per entry written by the copy engines (18 ms for the 1.68 GB
+        // table, at 2 GPUs and at 8) lose to 3 or 4 bytes per entry through the staging ring with the host threads widening.
         const char* force = std::getenv("WTP_D2H_DIRECT");
-        const bool direct = force ? (force[0] == '1' && pinned) : pinned;
+        const bool direct = force && force[0] == '1' && pinned;
         if (direct) {
             int64_t* d_wide = ctx->d_indices.as<int64_t>(std::max<size_t>(n_elems, 1));
             widen_on_device(ctx, mine, n_elems, d_wide);
@@ -501,12 +507,24 @@ static int32_t knn_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_
     ctx->timer.reset(ctx->stream);
     ctx->timer.begin_total();
     T* d_pts = ctx->d_pts.as<T>((size_t)N * D);
+    // The ranks of a communicator share one host: uploading the whole point set on every rank moves it G times through
+    // the host's memory system (5.2 ms for 8 x 120 MB on the 8-GPU box against 2.2 ms for one copy). Every rank uploads
+    // the points of its own caller range instead and the ranges are all-gathered over NVLink.
+    const bool sliced = ctx->world > 1 && ctx->nccl_comm && N >= (int64_t)ctx->world * 4096 && std::getenv("WTP_NO_SLICED_H2D") == nullptr;
+    int64_t h2d_bytes = N * (int64_t)D * (int64_t)sizeof(T);
     {
         ScopedPhase ph(ctx->timer, PH_H2D);
-        WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        if (sliced) {
+            const int64_t b = wtp_shard_begin(N, ctx->rank, ctx->world), e = wtp_shard_end(N, ctx->rank, ctx->world);
+            h2d_bytes = (e - b) * (int64_t)D * (int64_t)sizeof(T);
+            WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts + b * D, pts + b * D, (size_t)h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            comm_allgather_rows(ctx, d_pts, N, (size_t)D * sizeof(T));
+        } else {
+            WTP_CUDA_CHECK(cudaMemcpyAsync(d_pts, pts, (size_t)N * D * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     knn_device<T>(ctx, d_pts, N, D, k, drop_first, nullptr, nullptr, out_idx, out_dist);
-    ctx->last_timing.bytes_h2d = N * (int64_t)D * (int64_t)sizeof(T);
+    ctx->last_timing.bytes_h2d = h2d_bytes;
     wtp_timing keep = ctx->last_timing;
     ctx->timer.end_total();
     WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -305,7 +305,7 @@ struct wtp_ctx {
     wtp::PhaseTimer timer;
     wtp_timing last_timing{};
     // spatial index of the queried point set / the repel snapshot
-    wtp::IndexBuffers index[1];
+    wtp::IndexBuffers index[3];          // [0]: every call; [1], [2]: the coarser density classes of a graded repel (repel.cu)
     // 1-NN structure of a variable spacing's boundary set
     wtp::BvhBuffers bvh;
     // triangle mesh of the wall rule (3-argument repel) and of the batched mesh queries

@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <functional>
 #include <memory>
 #include <vector>
@@ -61,6 +63,7 @@ inline void d2h_pipeline(wtp_ctx* ctx, const void* d_src, size_t total, size_t c
         PaddedCounter landed;
         std::atomic<int> failed{0};
         const int device = ctx->device;
+        const bool share_cores = ctx->world > 1;
         ctx->pool->run([&](int part, int) {
             if (part == 0) {   // producer
                 try {
@@ -77,7 +80,10 @@ inline void d2h_pipeline(wtp_ctx* ctx, const void* d_src, size_t total, size_t c
                             if (q == cudaSuccess) { landed.v.store(++next_land, std::memory_order_release); progressed = true; }
                             else if (q != cudaErrorNotReady) WTP_CUDA_CHECK(q);
                         }
-                        if (!progressed) _mm_pause();
+                        if (!progressed) {
+                            if (share_cores) std::this_thread::sleep_for(std::chrono::microseconds(15));   // leave the core to a worker
+                            else _mm_pause();
+                        }
                     }
                 } catch (...) {
                     failed.store(1);

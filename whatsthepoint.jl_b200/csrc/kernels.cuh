@@ -61,7 +61,8 @@ void rows_by_caller_index(wtp_ctx* ctx, IndexBuffers& ib, int64_t N, int64_t s_b
 void owned_ids32(wtp_ctx* ctx, const IndexBuffers& ib, bool f64, int64_t s_begin, int64_t s_end, uint32_t* d_ids);   // the same as 4-byte values
 
 // Sinks of a tiled pass inside ctx->d_fail: 16 counters (zeroed here), then the list of up to n sorted positions.
-TileFails tile_fails(wtp_ctx* ctx, int64_t n);
+// slot / slots: one of several sinks that are alive at the same time (the density classes of a graded repel).
+TileFails tile_fails(wtp_ctx* ctx, int64_t n, int slot = 0, int slots = 1);
 
 // Compact list of sorted positions whose original index is in [q_begin, q_end).
 void build_query_list(wtp_ctx* ctx, const IndexBuffers& ib, int64_t N, int64_t q_begin, int64_t q_end,

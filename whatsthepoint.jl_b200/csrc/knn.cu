@@ -128,8 +128,9 @@ void knn_points(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int D, i
 template void knn_points<float>(wtp_ctx*, const IndexBuffers&, const Grid<float>&, int, int, const float*, int64_t, uint32_t*);
 template void knn_points<double>(wtp_ctx*, const IndexBuffers&, const Grid<double>&, int, int, const double*, int64_t, uint32_t*);
 
-TileFails tile_fails(wtp_ctx* ctx, int64_t n) {
-    uint32_t* base = ctx->d_fail.as<uint32_t>(16 + (size_t)n);
+TileFails tile_fails(wtp_ctx* ctx, int64_t n, int slot, int slots) {
+    const size_t each = 16 + (size_t)n;
+    uint32_t* base = ctx->d_fail.as<uint32_t>(each * (size_t)slots) + each * (size_t)slot;
     WTP_CUDA_CHECK(cudaMemsetAsync(base, 0, 16 * sizeof(uint32_t), ctx->stream));
     return TileFails{base, base + 16};
 }

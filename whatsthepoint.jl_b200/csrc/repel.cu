@@ -75,6 +75,7 @@ __device__ __forceinline__ T force_at_zero(const ForceP<T>& f, T u0sq) {
 }
 
 // ------------------------------------------------------------------- sweep
+template <class T> inline T t_inf_host() { return std::numeric_limits<T>::infinity(); }
 template <class T> __host__ __device__ inline T t_max();
 template <> __host__ __device__ inline float t_max<float>() { return 3.402823466e+38f; }
 template <> __host__ __device__ inline double t_max<double>() { return 1.7976931348623157e+308; }
@@ -130,6 +131,9 @@ struct SweepArgs {
     P4<T>* Cp[WTP_MAX_PEERS];
     T a_lo, a_max;
     ForceP<T> force;
+    // density classes (graded clouds, variable spacing): this pass answers the points whose spacing at their current
+    // position lies in [cls_lo, cls_hi) on an index whose cell size suits that spacing; cls_hi <= 0: everything
+    T cls_lo, cls_hi;
     uint64_t rng_key;      // sweep_key(kick_seed, iteration): the random directions of coincident pairs (common.cuh)
     RepelPartial<T>* partials;
 };
@@ -301,6 +305,10 @@ repel_tile_kernel(const SweepArgs<T> a, const TileFails fails) {
     TileSearch<T, D> ts(a.g, a.sorted, a.cell_start, smem_raw, sh);
     const uint32_t j = a.s_begin + blockIdx.x * TK_Q + threadIdx.x;
     ts.init(j, j < a.s_end, a.n_fixed + a.id_lo, a.n_fixed + a.id_hi);   // fixed wall / other rank's points are not swept
+    if (a.cls_hi > (T)0 && ts.query) {                                    // another density class answers this point on its own index
+        const T sc = a.s_cur[idx_of(ts.q) - a.n_fixed];
+        ts.query = sc >= a.cls_lo && sc < a.cls_hi;
+    }
     if (a.n_peers > 0 && ts.active && !ts.query)                          // a fixed point of this rank's run: the record as it is
         for (int r = 0; r < a.n_peers; ++r) a.Cp[r][j - a.s_begin] = ts.q;
     RepelPartial<T> acc;
@@ -393,6 +401,25 @@ __global__ void __launch_bounds__(256) repel_finalize_kernel(const RepelPartial<
         __syncthreads();
     }
     if (threadIdx.x == 0) *out = s[0];
+}
+
+// smallest and largest value of an array (the spacing range that decides the density classes): out[0] = min, out[1] = max
+template <class T>
+__global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ v, int64_t n, T* __restrict__ out) {
+    __shared__ T s_lo[8], s_hi[8];
+    T lo = t_inf<T>(), hi = -t_inf<T>();
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const T x = v[i]; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const T a = __shfl_xor_sync(FULL, lo, o), b = __shfl_xor_sync(FULL, hi, o);
+        lo = a < lo ? a : lo; hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lo = s_lo[w] < lo ? s_lo[w] : lo; hi = s_hi[w] > hi ? s_hi[w] : hi; }
+        out[0] = lo; out[1] = hi;
+    }
 }
 
 template <class T>
@@ -650,9 +677,38 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     const bool p2p = by_runs && comm_peer_buffers(ctx, ctx->peers, run_bytes);
     P4<T>* C_local = by_runs && !p2p ? ctx->d_misc2.as<P4<T>>((size_t)run_slot * world) : nullptr;
     uint64_t n_sweeps = 0;
-    // per-CTA partials of the sweep launches of an iteration (general sweep | tiled sweep), folded together
-    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>((size_t)nblocks + (size_t)n_tiled_blocks + 256 + 1 + world);
-    RepelPartial<T>* d_fold = partials + (size_t)nblocks + (size_t)n_tiled_blocks;   // first stage of a two-stage fold
+    // Density classes (graded clouds). One cell size serves a range of about 3 in the local spacing h: with fewer than
+    // ~1.2 points per cell the 3^D block holds too few candidates, with more than ~35 the slab of a CTA no longer fits
+    // its tile. A variable spacing that spans more than that (BoundaryLayerSpacing with bulk / at_wall = 4: a density
+    // ratio of 64) leaves a quarter to a third of the points to the general kernel on any single grid. So the spacing
+    // range [s_min, s_max] of the snapshot is cut into up to three geometric classes; every class gets its own index of
+    // ALL points with a cell size of twice its typical spacing (about 8 points per cell where the class lives), and the
+    // tiled sweep runs once per class with the points of the class switched on (by their spacing at their current
+    // position). Where a class does not live its CTAs hold no query and skip the staging, so the passes add up to
+    // little more than one pass; what is added is an index build per extra class. One GPU, rebuild_every = 1.
+    int n_cls = 1;
+    T cls_bound[4] = {(T)0, (T)0, (T)0, (T)0};
+    double cls_cell[3] = {0, 0, 0};
+    if (variable && world == 1 && tiled_ok && prm->rebuild_every == 1 && std::getenv("WTP_NO_CLASSES") == nullptr) {
+        T* d_mm = ctx->d_reduce.as<T>(2);
+        minmax_kernel<T><<<1, 256, 0, st>>>(spacings, n_all, d_mm);
+        LAUNCH_CHECK(ctx);
+        T h_mm[2];
+        WTP_CUDA_CHECK(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+        const double s_lo = (double)h_mm[0], s_hi = (double)h_mm[1];
+        if (s_lo > 0 && std::isfinite(s_hi) && s_hi / s_lo >= 1.8) {
+            n_cls = std::min(3, (int)std::ceil(std::log(s_hi / s_lo) / std::log(1.7)));
+            for (int c = 0; c <= n_cls; ++c) cls_bound[c] = (T)(s_lo * std::pow(s_hi / s_lo, (double)c / n_cls));
+            for (int c = 0; c < n_cls; ++c) cls_cell[c] = 2.0 * std::sqrt((double)cls_bound[c] * (double)cls_bound[c + 1]);
+            cls_bound[0] = (T)0;                       // the end classes are open: spacings move with the points
+            cls_bound[n_cls] = t_inf_host<T>();
+        }
+    }
+    // per-CTA partials of the sweep launches of an iteration (per class: general sweep | tiled sweep), folded together
+    const size_t partials_per_cls = (size_t)nblocks + (size_t)n_tiled_blocks;
+    RepelPartial<T>* partials = ctx->d_reduce.as<RepelPartial<T>>(partials_per_cls * (size_t)n_cls + 256 + 1 + world);
+    RepelPartial<T>* d_fold = partials + partials_per_cls * (size_t)n_cls;   // first stage of a two-stage fold
     RepelPartial<T>* d_tot = d_fold + 256;
     RepelPartial<T>* d_all = d_tot + 1;
     RepelPartial<T>* h_tot = static_cast<RepelPartial<T>*>(ctx->h_pinned);
@@ -667,6 +723,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     std::normal_distribution<double> kick_normal(0.0, 1.0);
 
     Grid<T> g{};
+    Grid<T> g_cls[3] = {};
     int passes = 0;
     IndexWindow win;
     bool windowed = false;
@@ -707,7 +764,11 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
                 lo[d] = n_fixed > 0 ? std::min(flo[d], mlo[d]) : mlo[d];
                 hi[d] = n_fixed > 0 ? std::max(fhi[d], mhi[d]) : mhi[d];
             }
-            g = make_grid<T>(n_all, D, lo, hi, ctx->cell_occupancy, 0.0, kk);
+            g = n_cls > 1 ? make_grid<T>(n_all, D, lo, hi, 1.0e-6, cls_cell[0], kk) : make_grid<T>(n_all, D, lo, hi, ctx->cell_occupancy, 0.0, kk);
+            for (int c = 1; c < n_cls; ++c) {                                                        // the coarser classes' indices
+                g_cls[c] = make_grid<T>(n_all, D, lo, hi, 1.0e-6, cls_cell[c], kk);
+                build_index<T>(ctx, ctx->index[c], d_snap, n_all, D, g_cls[c]);
+            }
             // by runs, constant spacing: only the window of the grid around this rank's run is indexed (grid.cu); the
             // variable spacings visit the points in the order of the whole sorted set, so they keep the whole index
             windowed = by_runs && !variable && !window_off && std::getenv("WTP_NO_WINDOW") == nullptr &&
@@ -741,21 +802,44 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         a.a_lo = (T)prm->alpha_lo; a.a_max = (T)prm->alpha_max; a.force = force; a.partials = partials;
         a.rng_key = sweep_key(prm->kick_seed, (uint64_t)it);
         a.nq_dev = nullptr;
+        a.cls_lo = (T)0; a.cls_hi = (T)0;
         int n_partials = nblocks;
         const bool tiled_now = rebuild && tiled_ok;
         TileFails fails{};
+        TileFails fails_cls[3] = {};
         {
             ScopedPhase ph(ctx->timer, PH_QUERY);
-            if (tiled_now) {
-                // tiled sweep over every sorted position, then the general sweep over what it handed back
-                fails = tile_fails(ctx, se - sb);
-                SweepArgs<T> at = a;
-                at.qlist = nullptr; at.nq = (uint32_t)(se - sb); at.partials = partials + nblocks;
-                if (n_tiled_blocks > 0) { if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, fails); else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, fails); }
-                a.qlist = fails.list; a.nq = (uint32_t)(se - sb); a.nq_dev = fails.counters;
-                n_partials = nblocks + n_tiled_blocks;
+            if (tiled_now && n_cls > 1) {
+                // one tiled sweep per density class on the class's own index, each followed by the general sweep over what it
+                // handed back (sorted positions of that index)
+                n_partials = 0;
+                for (int c = 0; c < n_cls; ++c) {
+                    const IndexBuffers& ibc = ctx->index[c];
+                    SweepArgs<T> ac = a;
+                    ac.g = c == 0 ? g : g_cls[c]; ac.sorted = ibc.sorted.get<P4<T>>(); ac.cell_start = ibc.cells();
+                    ac.cls_lo = cls_bound[c]; ac.cls_hi = cls_bound[c + 1];
+                    fails_cls[c] = tile_fails(ctx, n_all, c, n_cls);
+                    SweepArgs<T> at = ac;
+                    at.qlist = nullptr; at.nq = (uint32_t)n_all; at.partials = partials + partials_per_cls * (size_t)c + nblocks;
+                    if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, fails_cls[c]); else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, fails_cls[c]);
+                    ac.qlist = fails_cls[c].list; ac.nq = (uint32_t)n_all; ac.nq_dev = fails_cls[c].counters;
+                    ac.partials = partials + partials_per_cls * (size_t)c;
+                    ac.cls_hi = (T)0;                                    // the list holds this class's points only
+                    if (D == 2) launch_sweep<T, 2>(ctx, ac, nblocks); else launch_sweep<T, 3>(ctx, ac, nblocks);
+                }
+                n_partials = (int)(partials_per_cls * (size_t)n_cls);
+            } else {
+                if (tiled_now) {
+                    // tiled sweep over every sorted position, then the general sweep over what it handed back
+                    fails = tile_fails(ctx, se - sb);
+                    SweepArgs<T> at = a;
+                    at.qlist = nullptr; at.nq = (uint32_t)(se - sb); at.partials = partials + nblocks;
+                    if (n_tiled_blocks > 0) { if (D == 2) launch_sweep_tiled<T, 2>(ctx, at, n_tiled_blocks, fails); else launch_sweep_tiled<T, 3>(ctx, at, n_tiled_blocks, fails); }
+                    a.qlist = fails.list; a.nq = (uint32_t)(se - sb); a.nq_dev = fails.counters;
+                    n_partials = nblocks + n_tiled_blocks;
+                }
+                if (D == 2) launch_sweep<T, 2>(ctx, a, nblocks); else launch_sweep<T, 3>(ctx, a, nblocks);
             }
-            if (D == 2) launch_sweep<T, 2>(ctx, a, nblocks); else launch_sweep<T, 3>(ctx, a, nblocks);
         }
         if (mesh) {                                                                                  // constrain(id, xi, xi + disp), :291, 448-469
             ScopedPhase ph(ctx->timer, PH_SCAN);
@@ -801,10 +885,19 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
             }
         } else {
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_tot, sizeof(RepelPartial<T>), cudaMemcpyDeviceToHost, st));
-            if (tiled_now) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, fails.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            if (tiled_now && n_cls > 1) {
+                for (int c = 0; c < n_cls; ++c) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt + 4 * c, fails_cls[c].counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            } else if (tiled_now) {
+                WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, fails.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            }
             WTP_CUDA_CHECK(cudaStreamSynchronize(st));
             tot = h_tot[0];
-            if (tiled_now) { ctx->last_tile_sparse = h_cnt[1]; ctx->last_tile_dense = h_cnt[2]; ctx->last_tile_other = h_cnt[3]; }
+            if (tiled_now) {
+                ctx->last_tile_sparse = ctx->last_tile_dense = ctx->last_tile_other = 0;
+                for (int c = 0; c < (n_cls > 1 ? n_cls : 1); ++c) {
+                    ctx->last_tile_sparse += h_cnt[4 * c + 1]; ctx->last_tile_dense += h_cnt[4 * c + 2]; ctx->last_tile_other += h_cnt[4 * c + 3];
+                }
+            }
         }
         for (int d = 0; d < 3; ++d) { mlo[d] = d < D ? (double)tot.lo[d] : 0.0; mhi[d] = d < D ? (double)tot.hi[d] : 0.0; }
         conv[n_conv++] = tot.max_force;                                                              // :293
