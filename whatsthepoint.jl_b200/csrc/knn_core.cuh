@@ -259,28 +259,6 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatil
 __device__ __forceinline__ int row_dy(int t) { return (int)((0x22161u >> (2 * t)) & 3u) - 1; }   // 0,-1,+1,0,0,-1,+1,-1,+1
 __device__ __forceinline__ int row_dz(int t) { return (int)((0x28215u >> (2 * t)) & 3u) - 1; }   // 0,0,0,-1,+1,-1,-1,+1,+1
 
-// The density-guided radius assumes a ball full of points; next to a face of the grid's box part of the ball is outside
-// the cloud and holds none. Returns the squared radius enlarged so that the part of the ball inside the box has the
-// volume (area) the full ball was meant to have: per face the inside fraction of a ball whose centre is x radii from
-// the plane is 1 - (1 - x)^2 (2 + x) / 4 in 3-D (exact), about 0.5 + 0.6366 x - 0.1366 x^3 in 2-D; faces multiply
-// (exact for one face, a fair guess at edges and corners). Only a guess, like the radius itself: exactness never
-// depends on it.
-template <class T, int D>
-__device__ __forceinline__ float ball_radius2_in_box(const Grid<T>& g, float r2, T qx, T qy, T qz) {
-    const float inv_r = rsqrtf(r2), c = (float)g.c;
-    float f = 1.0f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-        const float q = (float)(d == 0 ? qx : (d == 1 ? qy : qz)), lo = (float)g.lo[d], hi = lo + (float)g.n[d] * c;
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const float x = fminf(fmaxf((side == 0 ? q - lo : hi - q) * inv_r, 0.0f), 1.0f);
-            f *= D == 3 ? 1.0f - 0.25f * (1.0f - x) * (1.0f - x) * (2.0f + x) : 0.5f + x * (0.6366f - 0.1366f * x * x);
-        }
-    }
-    return D == 3 ? r2 * rcbrtf(f * f) : r2 / f;
-}
-
 // ------------------------------------------------------------- the search
 // TILE_CAP: points per warp tile (0 disables staging: general path only).
 template <class T, int D, int KPL, int TILE_CAP>
@@ -298,7 +276,6 @@ struct WarpKnn {
     int scx, scy, scz;  // staged cell (-1: none)
     uint32_t tile_n;    // staged candidates; 0xffffffff: block does not fit the tile
     uint32_t block_n;   // points in the 3^D block of the staged cell
-    int block_cells;    // cells of that block inside the grid
     uint32_t row_begin, row_len;   // lane t < NROWS: its row of the block in the sorted array
     T qx, qy, qz;
     int cx, cy, cz;
@@ -308,7 +285,7 @@ struct WarpKnn {
 
     static constexpr int PF_CAP = 64;
     __device__ __forceinline__ WarpKnn(const Grid<T>& g_, const P4<T>* s, const uint32_t* cs, P4<T>* tile_, Key<T>* buf_, uint64_t* bar_, int lane_)
-        : g(g_), sorted(s), cell_start(cs), tile(tile_), buf(buf_), r0sq((T)0), bar(bar_), phase(0), lane(lane_), scx(-1), scy(-1), scz(-1), tile_n(0), block_n(0), block_cells(D == 3 ? 27 : 9), row_begin(0), row_len(0) {
+        : g(g_), sorted(s), cell_start(cs), tile(tile_), buf(buf_), r0sq((T)0), bar(bar_), phase(0), lane(lane_), scx(-1), scy(-1), scz(-1), tile_n(0), block_n(0), row_begin(0), row_len(0) {
         if (TILE_CAP > 0) {
             if (lane == 0) { mbar_init(bar, 1); fence_mbar_init(); }
             __syncwarp();
@@ -359,12 +336,6 @@ struct WarpKnn {
         const uint32_t total = __shfl_sync(FULL, incl, NROWS - 1);
         scx = cx; scy = cy; scz = cz;
         block_n = total; row_begin = begin; row_len = len;
-        {   // the cells of the block that exist (fewer than 3^D at the border of the grid)
-            const int ry = cy + row_dy(lane < NROWS ? lane : 0), rz = D == 3 ? cz + row_dz(lane < NROWS ? lane : 0) : 0;
-            const bool here = lane < NROWS && ry >= 0 && ry < g.n[1] && rz >= 0 && rz < g.n[2];
-            const int x0 = cx > 0 ? cx - 1 : 0, x1 = cx < g.n[0] - 1 ? cx + 1 : g.n[0] - 1;
-            block_cells = __popc(__ballot_sync(FULL, here)) * (x1 - x0 + 1);
-        }
         if (total > (uint32_t)TILE_CAP) { tile_n = 0xffffffffu; return; }
         tile_n = total;
         if (total == 0) return;
@@ -382,9 +353,9 @@ struct WarpKnn {
         const float target = (float)K + 2.5f * sqrtf((float)K) + 1.0f;
         const float c = (float)g.c;
         float r2;
-        if (D == 3) { const float r3 = target * (float)block_cells / (4.18879f * (float)block_n); r2 = c * c * cbrtf(r3 * r3); }
-        else r2 = c * c * target * (float)block_cells / (3.14159265f * (float)block_n);
-        r0sq = (T)ball_radius2_in_box<T, D>(g, r2, qx, qy, qz);
+        if (D == 3) { const float r3 = target * 27.0f / (4.18879f * (float)block_n); r2 = c * c * cbrtf(r3 * r3); }
+        else r2 = c * c * target * 9.0f / (3.14159265f * (float)block_n);
+        r0sq = (T)r2;
     }
     // Pre-filter: every candidate with d2 <= r0sq goes to the warp's buffer. If between K and
     // PF_CAP candidates qualify, the K best of the block are among them: one bitonic sort

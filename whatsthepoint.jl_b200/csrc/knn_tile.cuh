@@ -64,15 +64,13 @@ __device__ __forceinline__ T block_shell2(const Grid<T>& g, T qx, T qy, T qz, in
     return mul_rn(shell, shell);
 }
 
-// block_cells: the cells of the 3^D block that exist (fewer than 3^D at the border of the grid, where the missing ones
-// would otherwise count as empty space and make the ball too large: half again as many hits as wanted at a face)
 template <class T, int D>
-__device__ __forceinline__ T prefilter_radius2(const Grid<T>& g, uint32_t block_n, int K, int block_cells) {   // WarpKnn::set_prefilter_radius
+__device__ __forceinline__ T prefilter_radius2(const Grid<T>& g, uint32_t block_n, int K) {   // WarpKnn::set_prefilter_radius
     const float target = (float)K + TK_RADIUS_SIGMAS * sqrtf((float)K) + 1.0f;
     const float c = (float)g.c;
     float r2;
-    if (D == 3) { const float r3 = target * (float)block_cells / (4.18879f * (float)block_n); r2 = c * c * cbrtf(r3 * r3); }
-    else r2 = c * c * target * (float)block_cells / (3.14159265f * (float)block_n);
+    if (D == 3) { const float r3 = target * 27.0f / (4.18879f * (float)block_n); r2 = c * c * cbrtf(r3 * r3); }
+    else r2 = c * c * target * 9.0f / (3.14159265f * (float)block_n);
     return (T)r2;
 }
 
@@ -207,14 +205,12 @@ struct TileSearch {
         // list holds at least every block point with canonical d2 <= r0sq.
         uint32_t b[NROWS], e[NROWS];
         block_n = 0;
-        int rows_here = 0;
         const int xa = cx > 0 ? cx - 1 : 0, xb = cx < g.n[0] - 1 ? cx + 1 : g.n[0] - 1;
 #pragma unroll
         for (int r = 0; r < NROWS; ++r) {
             const uint32_t base = sh.run_base[r];
             b[r] = e[r] = 0;
             if (base != 0xffffffffu) {
-                ++rows_here;
                 const uint32_t shift = sh.run_off[r] - sh.run_begin[r];
                 b[r] = __ldg(cell_start + base + xa) + shift;
                 e[r] = __ldg(cell_start + base + xb + 1) + shift;
@@ -223,7 +219,7 @@ struct TileSearch {
         }
         if (!fits) return TK_DENSE;
         if (block_n < (uint32_t)K) return TK_SPARSE;
-        r0sq = (T)ball_radius2_in_box<T, D>(g, (float)prefilter_radius2<T, D>(g, block_n, K, rows_here * (xb - xa + 1)), q.x, q.y, q.z);
+        r0sq = prefilter_radius2<T, D>(g, block_n, K);
         const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));
         const uint32_t my_s = smem_u32(my), lim = my_s + (uint32_t)(TK_LCAP + 1) * 2u;
         uint32_t addr = my_s;
