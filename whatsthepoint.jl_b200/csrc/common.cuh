@@ -257,9 +257,9 @@ struct RowMap {
     // offset of the row's first element in the output table
     __host__ __device__ int64_t elem(uint32_t sorted_pos, uint32_t caller_idx, int k_out) const {
         if (n_owners > 0) {
-            int r = 0;
-            for (int t = 1; t < n_owners; ++t) r += caller_idx >= owner_begin[t] ? 1 : 0;
-            return (int64_t)owner_delta[r] + (int64_t)caller_idx * k_out;
+            long long delta = owner_delta[0];          // constant indices only (the loop unrolls): the arrays stay in the parameter bank
+            for (int t = 1; t < WTP_MAX_PEERS; ++t) delta = (t < n_owners && caller_idx >= owner_begin[t]) ? owner_delta[t] : delta;
+            return (int64_t)delta + (int64_t)caller_idx * k_out;
         }
         return row(sorted_pos, caller_idx) * k_out;
     }
