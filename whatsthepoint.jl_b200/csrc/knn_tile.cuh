@@ -40,9 +40,6 @@ constexpr int TK_LSTRIDE = TK_FILTER_WIDE > 1 ? 54 : 50;
 #ifndef TK_RADIUS_SIGMAS
 #define TK_RADIUS_SIGMAS 2.1f
 #endif
-#ifndef TK_RETRY_LANES
-#define TK_RETRY_LANES 6           // lanes of a warp whose lists overflowed before they sweep again with a smaller radius (33: never)
-#endif
 constexpr int kSweepUnroll = TK_SWEEP_UNROLL;
 template <class T> __host__ __device__ constexpr int tk_cap() { return sizeof(T) == 4 ? TK_CAP_F32 : 1664; }   // records per CTA tile
 template <class T> __host__ __device__ constexpr size_t tk_smem() { return (size_t)tk_cap<T>() * sizeof(P4<T>) + (size_t)TK_LSTRIDE * TK_Q * sizeof(uint16_t); }
@@ -223,17 +220,9 @@ struct TileSearch {
         if (!fits) return TK_DENSE;
         if (block_n < (uint32_t)K) return TK_SPARSE;
         r0sq = prefilter_radius2<T, D>(g, block_n, K);
-        const T pad = (T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16);
-        T r0pad = r0sq * pad;
+        const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));
         const uint32_t my_s = smem_u32(my), lim = my_s + (uint32_t)(TK_LCAP + 1) * 2u;
         uint32_t addr = my_s;
-        // Where the density changes across the block (graded clouds, the faces of the domain) the guess is too large on the
-        // dense side and the list overflows. If that happens to several queries of the warp at once, those queries sweep
-        // their block a second time with the radius shrunk to ~0.59 of the ball's volume instead of going to the general
-        // kernel (one retry: a warp whose other lanes are done pays one more sweep for them, so it has to be worth it).
-#pragma unroll 1
-        for (int attempt = 0;; ++attempt) {
-        addr = my_s;
 #if TK_FILTER_WIDE > 1
         // TK_FILTER_WIDE candidates per trip: their tile reads are independent and issued back to back, so the latency of
         // one shared-memory read is paid once per trip instead of once per candidate. Reads past the end of the run stay
@@ -274,11 +263,6 @@ struct TileSearch {
         }
 #endif
         asm volatile("" ::: "memory");                     // the appends are done before the lists are read
-        const bool over = ((addr - my_s) >> 1) > (uint32_t)TK_LCAP;
-        if (attempt == 1 || __popc(__ballot_sync(__activemask(), over)) < TK_RETRY_LANES || !over) break;
-        r0sq = r0sq * (T)0.70;
-        r0pad = r0sq * pad;
-        }
         const uint32_t cnt = (addr - my_s) >> 1;
         if (cnt < (uint32_t)K) return TK_SPARSE;
         if (cnt > (uint32_t)TK_LCAP) return TK_DENSE;
