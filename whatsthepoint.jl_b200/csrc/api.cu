@@ -340,7 +340,7 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
     bool counters_read = false;
     auto read_counters = [&] {
         WTP_CUDA_CHECK(cudaMemcpyAsync(h_exp, d_exp, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        if (tiled) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, ctx->d_fail.get<uint32_t>(), 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (tiled) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, ctx->d_fail.get<uint32_t>(), 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
         WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     };
     auto compute = [&](void* d_idx, T* d_dist, bool out32) {
@@ -481,7 +481,7 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         if (!counters_read) read_counters();
         else WTP_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
-    ctx->last_tile_sparse = tiled ? h_cnt[1] : 0; ctx->last_tile_dense = tiled ? h_cnt[2] : 0; ctx->last_tile_other = tiled ? h_cnt[3] : 0;
+    ctx->last_tile_sparse = tiled ? h_cnt[1] : 0; ctx->last_tile_dense = tiled ? h_cnt[2] + h_cnt[4] : 0; ctx->last_tile_other = tiled ? h_cnt[3] : 0;
     finish_timing(ctx, passes, n_chunks, g.ncells, (int64_t)*h_exp);
     ctx->last_timing.n_peer_ranks = exchange ? ctx->world : 0;
     ctx->last_timing.bytes_d2h = !h_out_idx ? 0

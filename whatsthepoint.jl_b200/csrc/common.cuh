@@ -270,7 +270,7 @@ struct RowMap {
 // tile, or more than TK_LCAP hits (too coarse there). TK_OTHER: look-alike key images or exact ties. Anything but
 // TK_OK is appended to one list of sorted positions and answered by the general kernel; the per-kind counters are
 // statistics.
-enum { TK_OK = 0, TK_SPARSE = 1, TK_DENSE = 2, TK_OTHER = 3 };
+enum { TK_OK = 0, TK_SPARSE = 1, TK_DENSE = 2, TK_OTHER = 3, TK_NOFIT = 4 };   // TK_NOFIT: the slab does not fit the tile (counted apart, reported with the dense ones)
 struct TileFails {
     uint32_t* counters;    // [0] length of the list, [1] sparse, [2] dense, [3] other
     uint32_t* list;        // sorted positions

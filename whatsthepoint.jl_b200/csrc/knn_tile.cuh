@@ -217,7 +217,7 @@ struct TileSearch {
                 block_n += e[r] - b[r];
             }
         }
-        if (!fits) return TK_DENSE;
+        if (!fits) return TK_NOFIT;
         if (block_n < (uint32_t)K) return TK_SPARSE;
         r0sq = prefilter_radius2<T, D>(g, block_n, K);
         const T r0pad = r0sq * ((T)1 + (T)8 * (sizeof(T) == 4 ? (T)1.1920929e-7 : (T)2.220446049250313e-16));

@@ -404,11 +404,17 @@ __global__ void __launch_bounds__(256) repel_finalize_kernel(const RepelPartial<
 }
 
 // smallest and largest value of an array (the spacing range that decides the density classes): out[0] = min, out[1] = max
+// (stage 1: CTA b writes its pair to out[2b], out[2b + 1]; stage 2: one CTA over those pairs, `pairs` = 1)
 template <class T>
-__global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ v, int64_t n, T* __restrict__ out) {
+__global__ void __launch_bounds__(256) minmax_kernel(const T* __restrict__ v, int64_t n, T* __restrict__ out, int pairs) {
     __shared__ T s_lo[8], s_hi[8];
     T lo = t_inf<T>(), hi = -t_inf<T>();
-    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const T x = v[i]; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+    out += 2 * blockIdx.x;
+    if (pairs) {
+        for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const T a = v[2 * i], b = v[2 * i + 1]; lo = a < lo ? a : lo; hi = b > hi ? b : hi; }
+    } else {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) { const T x = v[i]; lo = x < lo ? x : lo; hi = x > hi ? x : hi; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const T a = __shfl_xor_sync(FULL, lo, o), b = __shfl_xor_sync(FULL, hi, o);
@@ -644,8 +650,8 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
 
     T* spacings = ctx->d_spacings.as<T>((size_t)n_all);
     T* s_cur = variable ? ctx->d_nn.as<T>((size_t)n_move) : nullptr;
-    uint32_t* nn_cache = variable ? ctx->d_counts.as<uint32_t>((size_t)n_move) : nullptr;   // per-point BVH start hint
-    spacing_eval<T>(ctx, sp, ctx->bvh, d_snap, n_all, D, spacings);                                 // :209
+    uint32_t* hint_all = variable ? ctx->d_counts.as<uint32_t>((size_t)n_all) : nullptr;   // per-point BVH start hint (snapshot-global)
+    uint32_t* nn_cache = variable ? hint_all + n_fixed : nullptr;
     T* Pa = ctx->d_p_new.as<T>((size_t)2 * n_move * D);
     T* Pb = Pa + (size_t)n_move * D;
     T* S_tail = d_snap + (size_t)n_fixed * D;
@@ -655,6 +661,27 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     double flo[3] = {0, 0, 0}, fhi[3] = {0, 0, 0}, mlo[3], mhi[3];
     if (n_fixed > 0) compute_bbox<T>(ctx, ib, d_snap, n_fixed, D, flo, fhi);
     compute_bbox<T>(ctx, ib, S_tail, n_move, D, mlo, mhi);
+
+    // spacings = ustrip.(spacing.(snap)) (:209). A variable spacing costs a BVH walk per point: the points are visited
+    // in the order of a preliminary index of the snapshot (neighbours in space walk the tree together: 8.4 -> ~3 ms at
+    // 2 M points against the caller's order), the walk leaves every point's nearest boundary point behind as the next
+    // walk's starting bound, and the first sweep's spacing(xi) (:260) is this same evaluation (same positions): a copy.
+    bool s_cur_ready = false;
+    if (variable) {
+        ScopedPhase ph(ctx->timer, PH_SCAN);
+        double lo0[3], hi0[3];
+        for (int d = 0; d < 3; ++d) {
+            lo0[d] = n_fixed > 0 ? std::min(flo[d], mlo[d]) : mlo[d];
+            hi0[d] = n_fixed > 0 ? std::max(fhi[d], mhi[d]) : mhi[d];
+        }
+        const Grid<T> g0 = make_grid<T>(n_all, D, lo0, hi0, ctx->cell_occupancy, 0.0, kk);
+        build_index<T>(ctx, ib, d_snap, n_all, D, g0);
+        spacing_eval_ordered<T>(ctx, sp, ctx->bvh, d_snap, n_all, D, spacings, hint_all, false, ib.sorted.get<P4<T>>(), n_all, 0);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(s_cur, spacings + n_fixed, (size_t)n_move * sizeof(T), cudaMemcpyDeviceToDevice, st));
+        s_cur_ready = true;
+    } else {
+        spacing_eval<T>(ctx, sp, ctx->bvh, d_snap, n_all, D, spacings);
+    }
 
     const int32_t rank = ctx->rank, world = ctx->world;
     // Sharding. By runs (the default whenever the tiled sweep applies): rank r sweeps the run [gsb, gse) of the
@@ -690,8 +717,11 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     T cls_bound[4] = {(T)0, (T)0, (T)0, (T)0};
     double cls_cell[3] = {0, 0, 0};
     if (variable && world == 1 && tiled_ok && prm->rebuild_every == 1 && std::getenv("WTP_NO_CLASSES") == nullptr) {
-        T* d_mm = ctx->d_reduce.as<T>(2);
-        minmax_kernel<T><<<1, 256, 0, st>>>(spacings, n_all, d_mm);
+        const int mm_blocks = (int)std::min<int64_t>((n_all + 255) / 256, (int64_t)kNumSMs * 4);
+        T* d_mm = ctx->d_reduce.as<T>(2 + 2 * (size_t)mm_blocks);
+        minmax_kernel<T><<<mm_blocks, 256, 0, st>>>(spacings, n_all, d_mm + 2, 0);
+        LAUNCH_CHECK(ctx);
+        minmax_kernel<T><<<1, 256, 0, st>>>(d_mm + 2, mm_blocks, d_mm, 1);
         LAUNCH_CHECK(ctx);
         T h_mm[2];
         WTP_CUDA_CHECK(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
@@ -750,11 +780,10 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     uint32_t nq = (uint32_t)n_all;
     while (it <= prm->max_iters) {                                                                   // :243
         const bool rebuild = (it - 1) % prm->rebuild_every == 0;                                     // :245
-        if (variable) {                                                                              // spacing(xi), :260 (and :251)
+        if (variable && !(it == 1 && s_cur_ready)) {                                                 // spacing(xi), :260 (and :251)
             ScopedPhase ph(ctx->timer, PH_SCAN);
-            // after the first build the previous iteration's sorted records give a spatially coherent visiting order
-            if (it > 1) spacing_eval_ordered<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, true, ib.sorted.get<P4<T>>(), n_all, n_fixed);
-            else spacing_eval<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, false);
+            // the previous iteration's sorted records give a spatially coherent visiting order, its nearest boundary points the bounds
+            spacing_eval_ordered<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, true, ib.sorted.get<P4<T>>(), n_all, n_fixed);
         }
         if (rebuild) {
             WTP_CUDA_CHECK(cudaMemcpyAsync(S_tail, Pa, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));   // :246
@@ -886,16 +915,19 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         } else {
             WTP_CUDA_CHECK(cudaMemcpyAsync(h_tot, d_tot, sizeof(RepelPartial<T>), cudaMemcpyDeviceToHost, st));
             if (tiled_now && n_cls > 1) {
-                for (int c = 0; c < n_cls; ++c) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt + 4 * c, fails_cls[c].counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                for (int c = 0; c < n_cls; ++c) WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt + 8 * c, fails_cls[c].counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             } else if (tiled_now) {
-                WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, fails.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                WTP_CUDA_CHECK(cudaMemcpyAsync(h_cnt, fails.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             }
             WTP_CUDA_CHECK(cudaStreamSynchronize(st));
             tot = h_tot[0];
             if (tiled_now) {
                 ctx->last_tile_sparse = ctx->last_tile_dense = ctx->last_tile_other = 0;
                 for (int c = 0; c < (n_cls > 1 ? n_cls : 1); ++c) {
-                    ctx->last_tile_sparse += h_cnt[4 * c + 1]; ctx->last_tile_dense += h_cnt[4 * c + 2]; ctx->last_tile_other += h_cnt[4 * c + 3];
+                    ctx->last_tile_sparse += h_cnt[8 * c + 1]; ctx->last_tile_dense += h_cnt[8 * c + 2] + h_cnt[8 * c + 4]; ctx->last_tile_other += h_cnt[8 * c + 3];
+                    if (std::getenv("WTP_REPEL_DEBUG") && it <= 2)
+                        fprintf(stderr, "[wtp repel] it %d class %d/%d [%g, %g) cell %g: leftovers %u = sparse %u, list overflow %u, ties %u, slab too large %u\n", it, c, n_cls,
+                                (double)cls_bound[c], (double)cls_bound[c + 1], n_cls > 1 ? cls_cell[c] : (double)g.c, h_cnt[8 * c], h_cnt[8 * c + 1], h_cnt[8 * c + 2], h_cnt[8 * c + 3], h_cnt[8 * c + 4]);
                 }
             }
         }
