@@ -105,7 +105,8 @@ struct TileSearch {
     struct Shared {
         uint64_t bar;
         uint32_t rowid[TK_Q];
-        uint32_t next[2], total;       // next[p]: first thread of the group formed in pass p (double-buffered)
+        int cx[TK_Q];                  // the x cell of every thread's record: where a group is cut when its slab does not fit
+        uint32_t next[2], total, tail; // next[p]: first thread of the group formed in pass p (double-buffered); tail: last thread of the current group
         int x0, x1;
         uint32_t run_begin[NROWS], run_off[NROWS], run_base[NROWS];   // base: first cell id of the row (0xffffffff: outside)
     };
@@ -145,6 +146,7 @@ struct TileSearch {
         }
         rowid = active ? (uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy : 0xffffffffu;
         sh.rowid[tid] = rowid;
+        sh.cx[tid] = cx;
         if (tid == 0) { sh.next[0] = 0; mbar_init(&sh.bar, 1); fence_mbar_init(); }
         shell2 = block_shell2<T, D>(g, q.x, q.y, q.z, cx, cy, cz);
     }
@@ -159,37 +161,68 @@ struct TileSearch {
             in_group = active && (uint32_t)tid >= first && rowid == grp_row;
             const bool tail = in_group && (tid == TK_Q - 1 || sh.rowid[tid + 1] != grp_row);
             if ((uint32_t)tid == first) sh.x0 = cx;
-            if (tail) { sh.x1 = cx; sh.next[(pass + 1u) & 1u] = (uint32_t)tid + 1; }   // the other slot: nobody reads it in this pass
+            if (tail) { sh.x1 = cx; sh.tail = (uint32_t)tid; sh.next[(pass + 1u) & 1u] = (uint32_t)tid + 1; }   // the other slot: nobody reads it in this pass
             const bool any_query = __syncthreads_or(in_group && query) != 0;
             ++pass;
-            const uint32_t nxt = sh.next[pass & 1u];
-            last = nxt >= TK_Q || sh.rowid[nxt] == 0xffffffffu;
-            if (!any_query) { in_group = false; continue; }          // nothing to answer in this row: no staging
+            if (!any_query) {                                            // nothing to answer in this row: no staging
+                const uint32_t nxt = sh.next[pass & 1u];
+                last = nxt >= TK_Q || sh.rowid[nxt] == 0xffffffffu;
+                in_group = false;
+                continue;
+            }
             if (warp == 0) {
-                uint32_t begin = 0, len = 0, base = 0xffffffffu;
-                if (lane < NROWS) {
-                    const int gy = (int)(grp_row % (uint32_t)g.n[1]), gz = (int)(grp_row / (uint32_t)g.n[1]);
-                    const int ry = gy + row_dy(lane), rz = D == 3 ? gz + row_dz(lane) : 0;
-                    if (ry >= 0 && ry < g.n[1] && rz >= 0 && rz < g.n[2]) {
-                        const int x0 = sh.x0 > 0 ? sh.x0 - 1 : 0, x1 = sh.x1 < g.n[0] - 1 ? sh.x1 + 1 : g.n[0] - 1;
-                        base = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
-                        begin = cell_start[base + x0];
-                        len = cell_start[base + x1 + 1] - begin;
+                // The slab: the rows of the group's 3^(D-1) neighbourhood over the x-range of its cells widened by one. Where
+                // the density rises steeply across the rows (graded clouds: a neighbouring row nearer the wall holds several
+                // times the points) the slab of a whole group does not fit the tile although the group's own row is sparse:
+                // the group is then cut at half its x-range (again and again, down to one column of cells) and the rest of
+                // its threads form the next group.
+                const int gx0 = sh.x0;
+                int gx1 = sh.x1;
+                uint32_t begin = 0, len = 0, base = 0xffffffffu, incl = 0, total = 0;
+                for (;;) {
+                    begin = 0; len = 0; base = 0xffffffffu;
+                    if (lane < NROWS) {
+                        const int gy = (int)(grp_row % (uint32_t)g.n[1]), gz = (int)(grp_row / (uint32_t)g.n[1]);
+                        const int ry = gy + row_dy(lane), rz = D == 3 ? gz + row_dz(lane) : 0;
+                        if (ry >= 0 && ry < g.n[1] && rz >= 0 && rz < g.n[2]) {
+                            const int x0 = gx0 > 0 ? gx0 - 1 : 0, x1 = gx1 < g.n[0] - 1 ? gx1 + 1 : g.n[0] - 1;
+                            base = ((uint32_t)rz * (uint32_t)g.n[1] + (uint32_t)ry) * (uint32_t)g.n[0];
+                            begin = cell_start[base + x0];
+                            len = cell_start[base + x1 + 1] - begin;
+                        }
                     }
-                }
-                uint32_t incl = len;
+                    incl = len;
 #pragma unroll
-                for (int o = 1; o < 16; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
+                    for (int o = 1; o < 16; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    total = __shfl_sync(FULL, incl, NROWS - 1);
+                    if (total <= (uint32_t)CAP || gx1 == gx0) break;
+                    gx1 = gx0 + (gx1 - gx0) / 2;
                 }
-                const uint32_t total = __shfl_sync(FULL, incl, NROWS - 1);
+                if (gx1 != sh.x1) {                                      // cut: the last thread of the group whose cell is still inside
+                    const uint32_t old_tail = sh.tail;
+                    uint32_t best = first;
+#pragma unroll
+                    for (int jj = 0; jj < TK_Q / 32; ++jj) {
+                        const uint32_t t = (uint32_t)lane * (TK_Q / 32) + (uint32_t)jj;
+                        if (t >= first && t <= old_tail && sh.cx[t] <= gx1) best = max(best, t);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+                    __syncwarp();
+                    if (lane == 0) { sh.x1 = gx1; sh.tail = best; sh.next[pass & 1u] = best + 1; }
+                }
                 if (lane < NROWS) { sh.run_begin[lane] = begin; sh.run_off[lane] = incl - len; sh.run_base[lane] = base; }
                 if (lane == 0) { sh.total = total; if (total > 0 && total <= (uint32_t)CAP) mbar_expect_tx(&sh.bar, total * (uint32_t)sizeof(P4<T>)); }
                 __syncwarp();
                 if (total > 0 && total <= (uint32_t)CAP && len > 0) tma_bulk_g2s(tile + (incl - len), sorted + begin, len * (uint32_t)sizeof(P4<T>), &sh.bar);
             }
             __syncthreads();
+            in_group = in_group && (uint32_t)tid <= sh.tail;
+            const uint32_t nxt = sh.next[pass & 1u];
+            last = nxt >= TK_Q || sh.rowid[nxt] == 0xffffffffu;
             const uint32_t total = sh.total;
             fits = total <= (uint32_t)CAP;
             if (fits && total > 0) { mbar_wait(&sh.bar, phase); phase ^= 1u; }
