@@ -9,7 +9,7 @@ bounding box -> cell keys -> radix sort -> gather -> tiled k-NN, N x 21 int64 ou
             events on the launching stream, max over ranks.
   e2e     : the same metric through the host C-ABI call a Julia user makes (wtp_knn_f32):
             pinned host points in, N x 21 int64 table in host memory out, copies inside the timed region
-            (the rows cross PCIe as 4-byte indices and are widened on the host by the library).
+            (the rows cross PCIe as 3- or 4-byte indices and are widened on the host by the library).
   roofline: the k-NN query kernels, 96 algorithmic bytes per query, timed by
             CUDA events inside the library on the same stream, against MEASURED_PEAKS.json.
             `traffic` is the ncu dram__bytes of the same launch at the same N when a capture of
@@ -562,7 +562,11 @@ def main():
                     "api": "wtp_knn_f32: pinned host points in, N x 21 int64 table in host memory out. " +
                            ("Sharded: the kernels hand every row to the rank owning its caller range over NVLink (peer stores); each rank's contiguous "
                             "part of the table goes back as int64 written by the DMA engine (the table is pinned)" if e2e_direct else
-                            "The rows cross PCIe as 4-byte indices and are widened to int64 by the library's host threads")},
+                            (("The rows cross PCIe packed to 3 bytes per index (every index is below 2^24)" if e2e_bytes[1] is not None and e2e_bytes[1] < nq_e2e * K * 4
+                              else "The rows cross PCIe as 4-byte indices") + " through a ring of pinned staging slots and are widened to int64 by the "
+                             "library's host threads while later chunks are on the wire" +
+                             ("; sharded: the kernels hand every row to the rank owning its caller range over NVLink (peer stores), every rank uploads its "
+                              "slice of the points (all-gathered over NVLink) and brings back one contiguous part of the table" if world > 1 else "")))},
             "gpu_launches": int(launches),
             "roofline": roofline("knn_tile_kernel<float,3> (+ knn_kernel<float,3,1> for its leftovers)", ALGO_BYTES_PER_QUERY["f32"] * nq, q_ms,
                                  traffic=measured_traffic("knn", world),
