@@ -54,8 +54,10 @@ typedef enum {
     WTP_ERR_STATE = 7          /* e.g. wtp_radius_fill without a preceding count        */
 } wtp_status;
 
-/* Largest list length the warp-resident top-k holds (k+1 for topology, k for repel). */
-#define WTP_MAX_K 128
+/* Largest list length the warp-resident top-k holds: k+1 for topology and search (up to 8 list rows per lane), k for
+ * repel (up to 4). Beyond that the call fails with WTP_ERR_K_TOO_LARGE (no fallback). */
+#define WTP_MAX_K 256
+#define WTP_MAX_K_REPEL 128
 
 /* ------------------------------------------------------------------ context */
 

@@ -53,6 +53,23 @@ for dt in (np.float32, np.float64):
         sp, _ = ctx.make_spacing("constant", h); osp, _ = oracle.make_spacing("constant", h)
         out, conv, res, _ = ctx.repel(pts, nf, sp, ctx.make_force("clipped", 0.2), max_iters=50, tol=1e-12, cv_target=10.0, stall_after=0, alpha_lo=h / 2000, alpha_max=h / 20)
         check(f"repel cv_target stop {dt.__name__} D={D}", res["iters"] == 1 and res["stop_reason"] == "cv_target" and np.array_equal(out, pts))
+# the opt-in path of the row exchange: a pinned table, int64 written by the copy engines (WTP_D2H_DIRECT=1)
+pts = rng.random((200003, 3)).astype(np.float32)
+ref = oracle.knn(pts, 21)
+pinned = torch.zeros((len(pts), 21), dtype=torch.int64).pin_memory()
+os.environ["WTP_D2H_DIRECT"] = "1"
+ctx.knn(pts, 21, out_idx=pinned.numpy())
+os.environ.pop("WTP_D2H_DIRECT")
+own = ctx.owned() - 1
+b, e = ctx.shard(len(pts))
+tm = ctx.timing()
+check(f"knn row exchange, direct int64 DMA (bytes_d2h={tm['bytes_d2h']})", np.array_equal(own, np.arange(b, e)) and np.array_equal(pinned.numpy()[own], ref[own])
+      and tm["n_peer_ranks"] == world and tm["bytes_d2h"] == (e - b) * 21 * 8)
+staged = np.zeros((len(pts), 21), dtype=np.int64)
+ctx.knn(pts, 21, out_idx=staged)
+tm = ctx.timing()
+check(f"knn row exchange, staged 3-byte indices (bytes_d2h={tm['bytes_d2h']}, bytes_h2d={tm['bytes_h2d']})", np.array_equal(staged[own], ref[own]) and (staged[:b] == 0).all() and (staged[e:] == 0).all()
+      and tm["bytes_d2h"] < (e - b) * 21 * 4 and tm["bytes_h2d"] == (e - b) * 3 * 4)
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -52,7 +52,7 @@ def test_struct_layouts_match_header(pkg, tmp_path):
 
 def test_header_is_plain_c(tmp_path):
     csrc = tmp_path / "plain.c"
-    csrc.write_text('#include "wtp_cuda.h"\nint main(void){return WTP_MAX_K == 128 ? 0 : 1;}\n')
+    csrc.write_text('#include "wtp_cuda.h"\nint main(void){return WTP_MAX_K == 256 && WTP_MAX_K_REPEL == 128 ? 0 : 1;}\n')
     subprocess.run(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(csrc), "-o",
                     str(tmp_path / "plain")], check=True)
 

@@ -18,7 +18,7 @@ def rows_of(off, ind):
 # ------------------------------------------------------------------ k-NN
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("D", [2, 3])
-@pytest.mark.parametrize("N,k", [(50, 5), (1000, 21), (30000, 21), (5000, 40), (3000, 100), (22, 21), (2, 1)])
+@pytest.mark.parametrize("N,k", [(50, 5), (1000, 21), (30000, 21), (5000, 40), (3000, 100), (2500, 200), (22, 21), (2, 1)])
 def test_knn_bit_exact(ctx, oracle, dt, D, N, k):
     pts = np.random.default_rng(N + k + D).random((N, D)).astype(dt)
     a, ad = ctx.knn(pts, k, dists=True)
@@ -66,9 +66,27 @@ def test_knn_errors(ctx, pkg):
     with pytest.raises(pkg.WtpArgumentError):                        # k + 1 > N
         ctx.knn(pts, 5)
     with pytest.raises(pkg.WtpArgumentError):
-        ctx.knn(np.random.rand(500, 3), 200)                         # above WTP_MAX_K
+        ctx.knn(np.random.rand(500, 3), 300)                         # above WTP_MAX_K
     with pytest.raises(pkg.WtpArgumentError):
         ctx.knn(np.random.rand(10, 4), 2)
+
+
+def test_knn_host_pipeline_variants(ctx, oracle, monkeypatch):
+    """The host entry point's ways back to the caller's int64 table: 3-byte packed indices (every index below 2^24, the
+    default here), plain 4-byte indices (WTP_NO_PACK24: what larger point sets use), other staging geometries."""
+    pts = np.random.default_rng(77).random((300_000, 3)).astype(np.float32)      # 6.3 M entries: the chunked pipeline, not the small-result copy
+    ref = oracle.knn(pts, 21)
+    assert np.array_equal(ctx.knn(pts, 21), ref)
+    monkeypatch.setenv("WTP_NO_PACK24", "1")
+    assert np.array_equal(ctx.knn(pts, 21), ref)
+    monkeypatch.delenv("WTP_NO_PACK24")
+    for mb, slots in (("1", "3"), ("16", "2")):
+        monkeypatch.setenv("WTP_STAGE_MB", mb); monkeypatch.setenv("WTP_STAGE_SLOTS", slots)
+        assert np.array_equal(ctx.knn(pts, 21), ref)
+    monkeypatch.delenv("WTP_STAGE_MB"); monkeypatch.delenv("WTP_STAGE_SLOTS")
+    off, ind = ctx.radius(pts[:200_000], 0.03)                                   # > 4 M entries: the CSR indices take the same path
+    roff, rind = oracle.radius(pts[:200_000], 0.03)
+    assert len(ind) > (4 << 20) and np.array_equal(off, roff) and np.array_equal(ind, rind)
 
 
 def test_knn_cell_occupancy_invariance(ctx, oracle):

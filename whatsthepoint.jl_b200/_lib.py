@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwtp_cuda.so")
 
-WTP_MAX_K = 128
+WTP_MAX_K = 256
 
 STATUS = {0: "ok", 1: "bad_arg", 2: "k_too_large", 3: "unsupported", 4: "cuda", 5: "nccl", 6: "oom", 7: "state"}
 FORCE_KINDS = {"inverse": 0, "equilibrium": 1, "clipped": 2, "strong": 3}

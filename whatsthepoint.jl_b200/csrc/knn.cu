@@ -94,7 +94,8 @@ static void launch_knn(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, i
     const uint32_t* cs = ib.cells();
     if (K1 <= 32) launch_knn_kpl<T, D, 1>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
     else if (K1 <= 64) launch_knn_kpl<T, D, 2>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
-    else launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
+    else if (K1 <= 128) launch_knn_kpl<T, D, 4>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
+    else launch_knn_kpl<T, D, 8>(ctx, nblocks, g, sorted, cs, d_qlist, nq, d_nq, rows, K1, drop, d_out_idx, out32, d_out_dist, d_exp, d_ext_q);
     LAUNCH_CHECK(ctx);
 }
 
@@ -103,7 +104,7 @@ void knn_query(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int64_t N
                const uint32_t* d_qlist, int64_t n_queries, const RowMap& rows, void* d_out_idx, T* d_out_dist,
                unsigned long long* d_expanded_counter, bool out32) {
     (void)N;
-    WTP_REQUIRE(K1 >= 1 && K1 <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K (128 list entries)");
+    WTP_REQUIRE(K1 >= 1 && K1 <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K (256 list entries)");
     if (n_queries <= 0) return;
     ScopedPhase ph(ctx->timer, PH_QUERY);
     if (D == 2) launch_knn<T, 2>(ctx, ib, g, K1, drop_first, d_qlist, n_queries, nullptr, rows, d_out_idx, out32 ? 1 : 0, d_out_dist, d_expanded_counter);
@@ -119,7 +120,7 @@ template void knn_query<double>(wtp_ctx*, const IndexBuffers&, const Grid<double
 // ascending (d2, index). Used by the deposition pass of repel (knn(tree, site, kq), src/repel.jl:502).
 template <class T>
 void knn_points(wtp_ctx* ctx, const IndexBuffers& ib, const Grid<T>& g, int D, int K, const T* d_q, int64_t n_q, uint32_t* d_out_idx32) {
-    WTP_REQUIRE(K >= 1 && K <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K (128 list entries)");
+    WTP_REQUIRE(K >= 1 && K <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K (256 list entries)");
     if (n_q <= 0) return;
     const RowMap rows{0u, 0u, 1};
     if (D == 2) launch_knn<T, 2>(ctx, ib, g, K, 0, nullptr, n_q, nullptr, rows, d_out_idx32, 1, nullptr, nullptr, d_q);

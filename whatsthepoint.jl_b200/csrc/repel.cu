@@ -633,7 +633,7 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
     const int64_t n_all = n_fixed + n_move;
     WTP_REQUIRE(n_all < (int64_t)0xfffffff0u, WTP_ERR_BAD_ARG, "snapshot too large");
     const int kk = (int)std::min<int64_t>(prm->k, n_all);                                           // :208
-    WTP_REQUIRE(kk <= WTP_MAX_K, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K");
+    WTP_REQUIRE(kk <= WTP_MAX_K_REPEL, WTP_ERR_K_TOO_LARGE, "k exceeds WTP_MAX_K_REPEL (128 neighbours per sweep)");
     res->iters = 0; res->stop_reason = WTP_STOP_MAX_ITERS; res->last_cv = std::numeric_limits<double>::quiet_NaN();
     if (n_move == 0 || prm->max_iters == 0) {
         // the reference still runs sweeps over zero points and records conv = 0 each time (:293)
