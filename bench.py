@@ -19,7 +19,7 @@ bounding box -> cell keys -> radix sort -> gather -> tiled k-NN, N x 21 int64 ou
   extras  : the other BASELINE configurations, each with its own roofline object: k-NN on the
             10 M cloud in Float64, config #3 (repel on the 2 M graded cube, Float32 and Float64),
             config #4 (radius CSR on the 10 M quadtree-graded square).
-  parity_check (world > 1): outside the timed regions every rank brute-forces 256 of the rows it
+  parity_check: outside the timed regions every rank brute-forces 256 of the rows it
             answered and 64 positions of one sharded repel sweep in numpy.
 
 `--impl reference` times the CPU port (the reference itself is Julia and cannot run here) on
@@ -368,11 +368,11 @@ def main():
 
     # ---------------------------------------------------------------- parity of the sharded rows (world > 1)
     parity = None
-    if world > 1 and not args.no_parity:
+    if not args.no_parity:
         rng = np.random.default_rng(1000 + rank)
         rows_t = np.sort(rng.choice(nq, size=min(256, nq), replace=False))
         got = d_idx[torch.from_numpy(rows_t).to(dev)].cpu().numpy()
-        want = sample_rows_brute_force(pts_h, own_all[rows_t] - 1, K)
+        want = sample_rows_brute_force(pts_h, (own_all[rows_t] - 1) if world > 1 else rows_t, K)
         parity = {"knn_rows_checked_per_rank": int(len(rows_t)), "knn_ok": all_ranks_ok(bool(np.array_equal(got, want)))}
 
     # ------------------------------------------------------------------ end-to-end arm
@@ -397,8 +397,8 @@ def main():
         e2e_val = n / (e2e_ms * 1e-3) / 1e6
         if world == 1:
             assert np.array_equal(h_idx_np[own - 1], chk), "host and device entry points disagree"
-        else:   # the host call fills the rows wtp_shard_owned reports (a contiguous caller range with the row exchange)
-            own_h = ctx.owned()
+        if True:   # the host call fills the rows wtp_shard_owned reports (a contiguous caller range with the row exchange)
+            own_h = ctx.owned() if world > 1 else np.arange(1, n + 1)
             qs = own_h[:: max(len(own_h) // 64, 1)][:64] - 1
             ok_rows = bool(np.array_equal(h_idx_np[qs], sample_rows_brute_force(pts_h, qs, K)))
             if parity is not None:
@@ -431,8 +431,8 @@ def main():
         sp, _ = ctx.make_spacing("constant", a=h)
         fm = ctx.make_force("clipped", 0.2)
         kw = dict(k=K, tol=0.0, stall_after=0, alpha_lo=h / 2000, alpha_max=h / 20)
-        if world > 1 and not args.no_parity:
-            # one sharded sweep from the known snapshot, every rank checks 64 points anywhere in the cloud (so also
+        if not args.no_parity:
+            # one (sharded) sweep from the known snapshot, every rank checks 64 points anywhere in the cloud (so also
             # points another rank swept and sent over NVLink) against the numpy restatement of the sweep
             one = snap.clone()
             ctx.repel_dev(one.data_ptr(), 0, nr, 3, np.float32, sp, fm, max_iters=1, **kw)
