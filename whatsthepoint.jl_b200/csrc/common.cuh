@@ -200,6 +200,7 @@ struct IndexBuffers {
     DevBuf block_hist;                      // 256 x numBlocks digit histogram
     DevBuf scan_tmp;                        // block sums of the scans
     DevBuf sorted;                          // P4<T>[N]
+    DevBuf staging;                         // counting build: caller indices grouped by cell, arrival order inside a cell
     DevBuf cell_start;                      // u32[ncells + 1]
     DevBuf bbox_partial;                    // per-block min/max
     DevBuf bbox;                            // 6 x T

@@ -6,6 +6,7 @@
 // BallSearch at src/topology.jl:80,93 and KDTree(coords) at src/repel.jl:218,252).
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -24,18 +25,60 @@ template <> struct Lim<double> { static __host__ __device__ double inf() { retur
 
 constexpr int BBOX_THREADS = 256;
 
+template <class T> struct Vec16;
+template <> struct Vec16<float> { using type = float4; static constexpr int n = 4; };
+template <> struct Vec16<double> { using type = double2; static constexpr int n = 2; };
+__device__ inline void unpack16(const float4& v, float* e) { e[0] = v.x; e[1] = v.y; e[2] = v.z; e[3] = v.w; }
+__device__ inline void unpack16(const double2& v, double* e) { e[0] = v.x; e[1] = v.y; }
+
+// The coordinates are read as one flat stream of 16-byte vectors. The grid stride is a multiple of D elements
+// (gridDim.x is a multiple of 3), so component c of a thread's vector belongs to the same axis in every iteration.
 template <class T, int D>
 __global__ void __launch_bounds__(BBOX_THREADS) bbox_partial_kernel(const T* __restrict__ pts, int64_t N, T* __restrict__ partial) {
+    using V = typename Vec16<T>::type;
+    constexpr int VN = Vec16<T>::n;
+    const int64_t F = N * D;
+    int64_t head = (int64_t)(((16u - (unsigned)(reinterpret_cast<uintptr_t>(pts) & 15u)) & 15u) / sizeof(T));
+    head = head < F ? head : F;
+    const int64_t nv = (F - head) / VN;
+    const V* __restrict__ vp = reinterpret_cast<const V*>(pts + head);
+    T vlo[VN], vhi[VN];
+#pragma unroll
+    for (int c = 0; c < VN; ++c) { vlo[c] = Lim<T>::inf(); vhi[c] = -Lim<T>::inf(); }
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = gtid; v < nv; v += stride) {
+        T e[VN];
+        unpack16(vp[v], e);
+#pragma unroll
+        for (int c = 0; c < VN; ++c) {
+            vlo[c] = e[c] < vlo[c] ? e[c] : vlo[c];
+            vhi[c] = e[c] > vhi[c] ? e[c] : vhi[c];
+        }
+    }
     T lo[3], hi[3];
 #pragma unroll
     for (int d = 0; d < 3; ++d) { lo[d] = Lim<T>::inf(); hi[d] = -Lim<T>::inf(); }
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < VN; ++c) {
+        const int ax = (int)((head + (int64_t)VN * gtid + c) % D);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            T v = pts[i * D + d];
-            lo[d] = v < lo[d] ? v : lo[d];
-            hi[d] = v > hi[d] ? v : hi[d];
+            lo[d] = (ax == d && vlo[c] < lo[d]) ? vlo[c] : lo[d];
+            hi[d] = (ax == d && vhi[c] > hi[d]) ? vhi[c] : hi[d];
         }
+    }
+    if (gtid == 0) {   // the unaligned head and the tail shorter than one vector
+        auto fold = [&](int64_t f) {
+            const T v = pts[f];
+            const int ax = (int)(f % D);
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                lo[d] = (ax == d && v < lo[d]) ? v : lo[d];
+                hi[d] = (ax == d && v > hi[d]) ? v : hi[d];
+            }
+        };
+        for (int64_t f = 0; f < head; ++f) fold(f);
+        for (int64_t f = head + nv * VN; f < F; ++f) fold(f);
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -83,8 +126,9 @@ __global__ void bbox_final_kernel(const T* __restrict__ partial, int nblocks, T*
 template <class T>
 void compute_bbox(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, double lo[3], double hi[3]) {
     ScopedPhase ph(ctx->timer, PH_BBOX);
-    int nblocks = (int)std::min<int64_t>((N + BBOX_THREADS - 1) / BBOX_THREADS, (int64_t)kNumSMs * 8);
-    if (nblocks < 1) nblocks = 1;
+    // a multiple of 3 CTAs: the kernel's grid stride must be a multiple of D elements
+    int nblocks = (int)std::min<int64_t>((N * D / 4 + BBOX_THREADS - 1) / BBOX_THREADS, (int64_t)kNumSMs * 8);
+    nblocks = std::max((nblocks + 2) / 3 * 3, 3);
     T* partial = ib.bbox_partial.as<T>((size_t)nblocks * 6);
     T* bbox = ib.bbox.as<T>(6);
     if (D == 2) bbox_partial_kernel<T, 2><<<nblocks, BBOX_THREADS, 0, ctx->stream>>>(d_pts, N, partial);
@@ -436,6 +480,166 @@ __global__ void __launch_bounds__(256) reorder_kernel(const T* __restrict__ pts,
         for (uint32_t c = key + 1; c <= ncells; ++c) cell_start[c] = N;
 }
 
+
+// ====================================================== counting-sort build
+// The cell keys are small integers and the index needs them grouped, not globally merged: count the points of every
+// cell while computing the keys (the atomic's return value is the point's arrival number in its cell), scan the counts
+// into cell_start, store every point's caller index at cell_start[key] + arrival number (a 4 N-byte array that stays in
+// L2), then put the (at most a few dozen) entries of every cell in ascending caller index — the order the stable radix
+// sort gives, so both builds produce the same records — while gathering the records. No digit passes.
+//   cell_count_kernel        keys, arrival numbers, per-cell counts (fused with the key computation)
+//   count_keys_kernel        the same from existing keys (windowed build)
+//   max_u32_kernel           heaviest cell (decides the placement kernels; > CS_BIG_MAX: radix build instead)
+//   cell_scatter_kernel      caller index -> order[cell_start[key] + arrival number]
+//   cell_place_kernel        one thread per entry: rank among the entries of its cell by caller index, gather, store
+//   cell_place_big_kernel    cells above CS_RANK_LIMIT points: one CTA per cell, bitonic sort in shared memory
+constexpr uint32_t CS_RANK_LIMIT = 64;      // cells up to this many points are ranked by counting (O(n) per point)
+constexpr uint32_t CS_BIG_MAX = 8192;       // heaviest cell the shared-memory sort takes
+
+template <class T, int D>
+__device__ inline uint32_t cell_key_of(const Grid<T>& g, T x, T y, T z) {
+    const int cx = cell_coord(g, x, 0);
+    const int cy = cell_coord(g, y, 1);
+    const int cz = D == 3 ? cell_coord(g, z, 2) : 0;
+    return ((uint32_t)cz * (uint32_t)g.n[1] + (uint32_t)cy) * (uint32_t)g.n[0] + (uint32_t)cx;
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(256) cell_count_kernel(const T* __restrict__ pts, int64_t N, Grid<T> g, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ arrival, uint32_t* __restrict__ cell_count) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint32_t key = cell_key_of<T, D>(g, pts[i * D + 0], pts[i * D + 1], pts[i * D + (D - 1)]);
+    keys[i] = key;
+    arrival[i] = atomicAdd(cell_count + key, 1u);
+}
+
+__global__ void __launch_bounds__(256) count_keys_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t* __restrict__ arrival,
+                                                         uint32_t* __restrict__ cell_count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) arrival[i] = atomicAdd(cell_count + keys[i], 1u);
+}
+
+__global__ void __launch_bounds__(256) max_u32_kernel(const uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ out) {
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+template <class T, int D>
+__device__ inline P4<T> point_record(const T* __restrict__ pts, uint32_t i) {
+    P4<T> p;
+    p.x = pts[(size_t)i * D + 0];
+    p.y = pts[(size_t)i * D + 1];
+    p.z = D == 3 ? pts[(size_t)i * D + (D - 1)] : (T)0;
+    p.w = idx_bits((T)0, i);
+    return p;
+}
+
+__global__ void __launch_bounds__(256) cell_scatter_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ arrival,
+                                                           const uint32_t* __restrict__ ids, uint32_t n, const uint32_t* __restrict__ cell_start,
+                                                           uint32_t* __restrict__ order) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) order[cell_start[keys[i]] + arrival[i]] = ids ? ids[i] : i;
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(256) cell_place_kernel(const T* __restrict__ pts, const uint32_t* __restrict__ order, uint32_t n, Grid<T> g,
+                                                         uint32_t key_lo, const uint32_t* __restrict__ cell_start, P4<T>* __restrict__ sorted,
+                                                         uint32_t* __restrict__ big_list) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t mine = order[j];
+    const P4<T> me = point_record<T, D>(pts, mine);
+    const uint32_t key = cell_key_of<T, D>(g, me.x, me.y, me.z) - key_lo;
+    const uint32_t s = cell_start[key], e = cell_start[key + 1];
+    if (e - s > CS_RANK_LIMIT) {
+        if (j == s) big_list[1 + atomicAdd(big_list, 1u)] = key;
+        return;
+    }
+    uint32_t rank = 0;
+    for (uint32_t m = s; m < e; ++m) rank += order[m] < mine ? 1u : 0u;
+    sorted[s + rank] = me;
+}
+
+template <class T, int D>
+__global__ void __launch_bounds__(256) cell_place_big_kernel(const T* __restrict__ pts, const uint32_t* __restrict__ order,
+                                                             const uint32_t* __restrict__ cell_start, P4<T>* __restrict__ sorted,
+                                                             const uint32_t* __restrict__ big_list) {
+    __shared__ uint32_t s_idx[CS_BIG_MAX];
+    const uint32_t n_big = big_list[0];
+    for (uint32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
+        const uint32_t cell = big_list[1 + b];
+        const uint32_t s = cell_start[cell], n = cell_start[cell + 1] - s;
+        uint32_t np2 = 1;
+        while (np2 < n) np2 <<= 1;
+        for (uint32_t t = threadIdx.x; t < np2; t += blockDim.x) s_idx[t] = t < n ? order[s + t] : 0xffffffffu;
+        __syncthreads();
+        for (uint32_t k = 2; k <= np2; k <<= 1) {
+            for (uint32_t h = k >> 1; h > 0; h >>= 1) {
+                for (uint32_t t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+                    const uint32_t lo = 2 * t - (t & (h - 1)), hi = lo + h;       // pair (lo, lo + h) of the h-block
+                    const uint32_t a = s_idx[lo], c = s_idx[hi];
+                    const bool up = (lo & k) == 0;
+                    if ((a > c) == up) { s_idx[lo] = c; s_idx[hi] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) sorted[s + t] = point_record<T, D>(pts, s_idx[t]);
+        __syncthreads();
+    }
+}
+
+// Groups the `n` points (keys[i], arrival[i], ids ? ids[i] : i) by key into `sorted`, ascending caller index within
+// a cell, and fills cell_start[0 .. ncells]. cell_count[0 .. ncells) holds the points per cell (keys are cell ids
+// minus key_lo), cell_count[ncells + 1] is zero. Returns false (nothing placed) when a cell is heavier than
+// CS_BIG_MAX: the caller runs the radix build.
+template <class T>
+static bool place_counted(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int D, const Grid<T>& g, uint32_t key_lo, const uint32_t* keys,
+                          const uint32_t* arrival, const uint32_t* ids, uint32_t n, uint32_t ncells, uint32_t* cell_count, P4<T>* sorted,
+                          uint32_t* cell_start) {
+    cudaStream_t st = ctx->stream;
+    uint32_t heaviest = 0;
+    const unsigned nb = (n + 255u) / 256u;
+    uint32_t* order = ib.staging.as<uint32_t>((size_t)n);
+    uint32_t* big_list = ib.keys_b.as<uint32_t>((size_t)n / CS_RANK_LIMIT + 2);
+    {
+        ScopedPhase ph(ctx->timer, PH_SORT);
+        uint32_t* d_max = cell_count + ncells + 1;
+        max_u32_kernel<<<(unsigned)std::min<uint32_t>((ncells + 255u) / 256u, (uint32_t)kNumSMs * 4u), 256, 0, st>>>(cell_count, ncells, d_max);
+        LAUNCH_CHECK(ctx);
+        uint32_t* h = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 3584);
+        WTP_CUDA_CHECK(cudaMemcpyAsync(h, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        exclusive_scan_u32(ctx, ib.scan_tmp, cell_count, cell_start, (int64_t)ncells);
+        WTP_CUDA_CHECK(cudaMemsetAsync(big_list, 0, sizeof(uint32_t), st));
+        WTP_CUDA_CHECK(cudaStreamSynchronize(st));
+        heaviest = *h;
+        if (heaviest > CS_BIG_MAX) return false;
+        cell_scatter_kernel<<<nb, 256, 0, st>>>(keys, arrival, ids, n, cell_start, order);
+        LAUNCH_CHECK(ctx);
+    }
+    {
+        ScopedPhase ph(ctx->timer, PH_REORDER);
+        if (D == 2) cell_place_kernel<T, 2><<<nb, 256, 0, st>>>(d_pts, order, n, g, key_lo, cell_start, sorted, big_list);
+        else cell_place_kernel<T, 3><<<nb, 256, 0, st>>>(d_pts, order, n, g, key_lo, cell_start, sorted, big_list);
+        LAUNCH_CHECK(ctx);
+        if (heaviest > CS_RANK_LIMIT) {
+            if (D == 2) cell_place_big_kernel<T, 2><<<kNumSMs * 6, 256, 0, st>>>(d_pts, order, cell_start, sorted, big_list);
+            else cell_place_big_kernel<T, 3><<<kNumSMs * 6, 256, 0, st>>>(d_pts, order, cell_start, sorted, big_list);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    return true;
+}
+
+static bool counting_build_enabled() {
+    const char* e = std::getenv("WTP_RADIX_BUILD");     // read per build: the tests switch it inside one process
+    return !(e && e[0] == '1');
+}
+
 template <class T>
 int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D, const Grid<T>& g) {
     WTP_REQUIRE(N > 0 && N < (int64_t)0xfffffff0u, WTP_ERR_BAD_ARG, "point count must be in [1, 2^32)");
@@ -446,6 +650,20 @@ int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D
     uint32_t* cell_start = ib.cell_start.as<uint32_t>((size_t)g.ncells + 1);
     ib.cs_rebase = 0;
     const unsigned nb256 = (unsigned)((N + 255) / 256);
+    if (counting_build_enabled()) {
+        uint32_t* cell_count = ib.block_hist.as<uint32_t>((size_t)g.ncells + 2);
+        {
+            ScopedPhase ph(ctx->timer, PH_CELLKEY);
+            WTP_CUDA_CHECK(cudaMemsetAsync(cell_count, 0, ((size_t)g.ncells + 2) * sizeof(uint32_t), st));
+            uint32_t* arrival = ib.vals_b.as<uint32_t>((size_t)N);
+            if (D == 2) cell_count_kernel<T, 2><<<nb256, 256, 0, st>>>(d_pts, N, g, keys_a, arrival, cell_count);
+            else cell_count_kernel<T, 3><<<nb256, 256, 0, st>>>(d_pts, N, g, keys_a, arrival, cell_count);
+            LAUNCH_CHECK(ctx);
+        }
+        if (place_counted<T>(ctx, ib, d_pts, D, g, 0u, keys_a, ib.vals_b.get<uint32_t>(), nullptr, (uint32_t)N, g.ncells, cell_count, sorted,
+                             cell_start))
+            return 0;
+    }
     {
         ScopedPhase ph(ctx->timer, PH_CELLKEY);
         if (D == 2) cellkey_kernel<T, 2><<<nb256, 256, 0, st>>>(d_pts, N, g, keys_a, vals_a);
@@ -642,14 +860,30 @@ bool build_index_window(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t 
         LAUNCH_CHECK(ctx);
     }
     const uint32_t ncells_w = win->key_hi - win->key_lo;
+    P4<T>* sorted = ib.sorted.as<P4<T>>((size_t)M);
+    uint32_t* cell_start = ib.cell_start.as<uint32_t>((size_t)ncells_w + 1);
+    ib.cs_rebase = (int64_t)win->key_lo;
+    g.w_lo = win->w_lo;
+    g.w_hi = win->w_hi;
+    if (counting_build_enabled()) {
+        uint32_t* cell_count = ib.block_hist.as<uint32_t>((size_t)ncells_w + 2);     // the compaction's block counts are consumed
+        {
+            ScopedPhase ph(ctx->timer, PH_SORT);
+            WTP_CUDA_CHECK(cudaMemsetAsync(cell_count, 0, ((size_t)ncells_w + 2) * sizeof(uint32_t), st));
+            count_keys_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(keys_a, (uint32_t)M, ib.vals_b.as<uint32_t>((size_t)M), cell_count);
+            LAUNCH_CHECK(ctx);
+        }
+        if (place_counted<T>(ctx, ib, d_pts, D, g, win->key_lo, keys_a, ib.vals_b.get<uint32_t>(), vals_a, (uint32_t)M, ncells_w, cell_count,
+                             sorted, cell_start)) {
+            if (passes_out) *passes_out = 0;
+            return true;
+        }
+    }
     int bits = 0;
     while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)ncells_w) ++bits;
     const int passes = radix_sort_pairs(ctx, ib, M, bits);
     keys_a = ib.keys_a.get<uint32_t>();
     vals_a = ib.vals_a.get<uint32_t>();
-    P4<T>* sorted = ib.sorted.as<P4<T>>((size_t)M);
-    uint32_t* cell_start = ib.cell_start.as<uint32_t>((size_t)ncells_w + 1);
-    ib.cs_rebase = (int64_t)win->key_lo;
     {
         ScopedPhase ph(ctx->timer, PH_REORDER);
         const unsigned nbm = (unsigned)((M + 255) / 256);
@@ -657,8 +891,6 @@ bool build_index_window(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t 
         else reorder_kernel<T, 3><<<nbm, 256, 0, st>>>(d_pts, keys_a, vals_a, (uint32_t)M, ncells_w, sorted, cell_start);
         LAUNCH_CHECK(ctx);
     }
-    g.w_lo = win->w_lo;
-    g.w_hi = win->w_hi;
     if (passes_out) *passes_out = passes;
     return true;
 }
