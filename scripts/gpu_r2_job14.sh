@@ -2,7 +2,7 @@
 # Round 2, GPU job 14 (1 GPU): counting build (caller indices scattered, records gathered by the placement kernel) — equality test,
 # bench, per-kernel times of one step from an ncu launch list.
 out=gpurun_out; mkdir -p $out; tag=${1:-r2j14}
-( timeout 900 python -m pytest tests/test_gpu_index_build.py tests/test_gpu_parity.py -m gpu -q -x > $out/pytest_$tag.log 2>&1; echo "pytest_rc=$?" ); tail -5 $out/pytest_$tag.log
+( timeout 900 python -m pytest tests/test_gpu_index_build.py tests/test_gpu_parity.py tests/test_gpu_baseline_configs.py -m gpu -q -x > $out/pytest_$tag.log 2>&1; echo "pytest_rc=$?" ); tail -5 $out/pytest_$tag.log
 timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu > $out/bench_$tag.json 2> $out/bench_$tag.err; echo "bench_rc=$?"
 python - $tag <<'PY'
 import json, sys
