@@ -183,6 +183,72 @@ __device__ __forceinline__ T bvh_nearest_d2(const BvhView<T>& bv, T qx, T qy, T 
     return best;
 }
 
+// The same search for the 32 queries of a warp at once (spacing_eval_ordered_kernel: the lanes are neighbours in space).
+// One traversal per warp with warp-uniform control flow: a node is visited when ANY lane's bound reaches into its
+// box, every lane keeps its own best; box and point loads are the same address on all lanes (one broadcast request
+// instead of 32 diverging ones) and the stack is one per warp. Per lane the result is exact for the same reason as
+// above: a subtree is skipped only when its box is no nearer than the lane's best at that moment, and bests only shrink.
+// Idle lanes (live = false) never ask for a node. `wstack`: this warp's stack in shared memory (BVH_STACK entries).
+constexpr int BVH_STACK = 64;
+template <class T, int D>
+__device__ __forceinline__ T bvh_nearest_d2_packet(const BvhView<T>& bv, T qx, T qy, T qz, bool live, uint32_t& hint, int* wstack) {
+    const int lane = threadIdx.x & 31;
+    auto box_lb = [&](int64_t i) -> T {
+        const Box<T> b = bv.boxes[i];
+        T gx = qx < b.lo[0] ? sub_rn(b.lo[0], qx) : (qx > b.hi[0] ? sub_rn(qx, b.hi[0]) : (T)0);
+        T gy = qy < b.lo[1] ? sub_rn(b.lo[1], qy) : (qy > b.hi[1] ? sub_rn(qy, b.hi[1]) : (T)0);
+        T s = add_rn(mul_rn(gx, gx), mul_rn(gy, gy));
+        if (D == 3) {
+            T gz = qz < b.lo[2] ? sub_rn(b.lo[2], qz) : (qz > b.hi[2] ? sub_rn(qz, b.hi[2]) : (T)0);
+            s = add_rn(s, mul_rn(gz, gz));
+        }
+        return s;  // +inf for empty nodes (lo = +inf)
+    };
+    T best = live ? t_inf<T>() : (T)-1;                 // no box is nearer than -1: an idle lane wants nothing
+    if (live && hint != 0xffffffffu) {
+        const P4<T> p = load_p4<T>(bv.pts + hint);
+        best = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
+    }
+    int sp = 0;
+    int64_t node = 1;
+    bool fresh = true;                                   // node comes straight from its parent's test (not from the stack)
+    for (;;) {
+        bool descend = true;
+        if (!fresh) descend = __any_sync(0xffffffffu, box_lb(node) < best);   // the bests have shrunk since the push
+        if (descend) {
+            if (node >= bv.leaf_pow2) {
+                const int64_t j0 = (node - bv.leaf_pow2) * BVH_LEAF, j1 = j0 + BVH_LEAF < bv.n ? j0 + BVH_LEAF : bv.n;
+                for (int64_t j = j0; j < j1; ++j) {
+                    const P4<T> p = load_p4<T>(bv.pts + j);
+                    const T d = dist2_rn<T, D>(qx, qy, qz, p.x, p.y, p.z);
+                    if (d < best) { best = d; hint = (uint32_t)j; }
+                }
+            } else {
+                const T ll = box_lb(2 * node), lr = box_lb(2 * node + 1);
+                const bool wl = ll < best, wr = lr < best;
+                const unsigned ml = __ballot_sync(0xffffffffu, wl), mr = __ballot_sync(0xffffffffu, wr);
+                if (ml != 0u && mr != 0u) {
+                    // both children: first the one that is the nearer for most of the interested lanes
+                    const unsigned left_nearer = __ballot_sync(0xffffffffu, wl && (!wr || ll <= lr));
+                    const bool left_first = 2 * __popc(left_nearer) >= __popc(ml | mr);
+                    if (lane == 0) wstack[sp] = (int)(2 * node + (left_first ? 1 : 0));
+                    ++sp;
+                    __syncwarp();
+                    node = 2 * node + (left_first ? 0 : 1);
+                    fresh = true;
+                    continue;
+                }
+                if (ml != 0u || mr != 0u) { node = 2 * node + (ml != 0u ? 0 : 1); fresh = true; continue; }
+            }
+        }
+        if (sp == 0) break;
+        __syncwarp();
+        node = wstack[--sp];
+        fresh = false;
+    }
+    return best;
+}
+
 template <class T>
 __device__ __forceinline__ T spacing_from_dmin(const SpacingP<T>& sp, T dmin) {
     if (sp.kind == WTP_SPACING_LOGLIKE) {                 // spacings.jl:67-72
@@ -216,15 +282,23 @@ template <class T, int D>
 __global__ void __launch_bounds__(128) spacing_eval_ordered_kernel(const SpacingP<T> sp, const BvhView<T> bv, const T* __restrict__ pts,
                                                                    const P4<T>* __restrict__ order, int64_t n_order, uint32_t n_fixed, int64_t n,
                                                                    T* __restrict__ out, uint32_t* __restrict__ cache, int use_cache) {
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_order) return;
-    const uint32_t g = idx_of(order[t]);
-    if (g < n_fixed) return;
-    const int64_t i = (int64_t)g - n_fixed;
-    if (i >= n) return;
-    const T qx = pts[i * D + 0], qy = pts[i * D + 1], qz = D == 3 ? pts[i * D + (D - 1)] : (T)0;
-    uint32_t hint = (cache && use_cache) ? cache[i] : 0xffffffffu;
-    const T dmin = sqrt(bvh_nearest_d2<T, D>(bv, qx, qy, qz, hint));
+    __shared__ int s_stack[128 / 32][BVH_STACK];
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // every lane stays for the warp's traversal; lanes without a movable point are idle
+    int64_t i = -1;
+    if (t < n_order) {
+        const uint32_t g = idx_of(order[t]);
+        if (g >= n_fixed && (int64_t)g - n_fixed < n) i = (int64_t)g - n_fixed;
+    }
+    const bool live = i >= 0;
+    T qx = (T)0, qy = (T)0, qz = (T)0;
+    uint32_t hint = 0xffffffffu;
+    if (live) {
+        qx = pts[i * D + 0]; qy = pts[i * D + 1]; qz = D == 3 ? pts[i * D + (D - 1)] : (T)0;
+        if (cache && use_cache) hint = cache[i];
+    }
+    const T dmin = sqrt(bvh_nearest_d2_packet<T, D>(bv, qx, qy, qz, live, hint, s_stack[threadIdx.x >> 5]));
+    if (!live) return;
     if (cache) cache[i] = hint;
     out[i] = spacing_from_dmin<T>(sp, dmin);
 }
