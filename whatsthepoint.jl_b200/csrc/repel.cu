@@ -782,8 +782,12 @@ void relax_device(wtp_ctx* ctx, T* d_snap, int64_t n_fixed, int64_t n_move, int 
         const bool rebuild = (it - 1) % prm->rebuild_every == 0;                                     // :245
         if (variable && !(it == 1 && s_cur_ready)) {                                                 // spacing(xi), :260 (and :251)
             ScopedPhase ph(ctx->timer, PH_SCAN);
-            // the previous iteration's sorted records give a spatially coherent visiting order, its nearest boundary points the bounds
-            spacing_eval_ordered<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, true, ib.sorted.get<P4<T>>(), n_all, n_fixed);
+            // the previous iteration's sorted records give a spatially coherent visiting order, its nearest boundary points the
+            // bounds. With density classes the order of the COARSEST class's index: 32 consecutive records of the finest grid
+            // are a stick of 30 cells where the cloud is coarse, of the coarsest grid a cell or a few neighbouring ones
+            // everywhere, and the warp walks the tree for the union of its lanes (bvh.cu)
+            const IndexBuffers& ib_order = ctx->index[n_cls > 1 && it > 1 ? n_cls - 1 : 0];
+            spacing_eval_ordered<T>(ctx, sp, ctx->bvh, Pa, n_move, D, s_cur, nn_cache, true, ib_order.sorted.get<P4<T>>(), n_all, n_fixed);
         }
         if (rebuild) {
             WTP_CUDA_CHECK(cudaMemcpyAsync(S_tail, Pa, (size_t)n_move * D * sizeof(T), cudaMemcpyDeviceToDevice, st));   // :246
