@@ -1,10 +1,10 @@
-"""GPU (-m gpu): the two index builds of grid.cu — counting sort (default) and the stable radix sort (WTP_RADIX_BUILD=1,
-also the fallback when a cell holds more than 8192 points) — must produce the SAME sorted order: cells ascending,
+"""GPU (-m gpu): the two index builds of grid.cu — counting sort (default) and the stable radix sort (WTP_RADIX_BUILD=1)
+— must produce the SAME sorted order: cells ascending,
 ascending caller index inside a cell. wtp_shard_owned on an unsharded context returns that order (row t of the
 compact table = sorted position t), so the test reads it back after a k-NN call under either build.
 
 Covers the three placement paths: cells of a few points (ranked by counting), heavy cells (one CTA sorts the cell in
-shared memory), and a cell above the limit (radix fallback)."""
+shared memory), and cells above the shared-memory size (the CTA sorts them in global memory)."""
 import os
 
 import numpy as np
@@ -24,14 +24,17 @@ def _clouds():
     same = np.repeat(np.array([[0.25, 0.75, 0.5]], dtype=np.float32), 100, axis=0)
     heavy = np.concatenate([base, ball, same])
     out["heavy_cells_f32"] = heavy[rng.permutation(len(heavy))]
-    # one cell heavier than the shared-memory sort takes: the counting build hands over to the radix build
+    # cells heavier than the shared-memory sort takes (8192): sorted in global memory, 9000 and 20000 points (not powers of two)
     blob = (0.5 + rng.random((9000, 3)) * 1e-7)
     over = np.concatenate([rng.random((20_000, 3)), blob])
     out["over_limit_f64"] = over[rng.permutation(len(over))]
+    blob2 = (np.float32(0.3) + rng.random((20_000, 3), dtype=np.float32) * np.float32(1e-6))
+    over2 = np.concatenate([rng.random((30_000, 3), dtype=np.float32), blob2, ball])
+    out["far_over_limit_f32"] = over2[rng.permutation(len(over2))]
     return out
 
 
-@pytest.mark.parametrize("name", ["uniform3d_f32", "uniform2d_f64", "heavy_cells_f32", "over_limit_f64"])
+@pytest.mark.parametrize("name", ["uniform3d_f32", "uniform2d_f64", "heavy_cells_f32", "over_limit_f64", "far_over_limit_f32"])
 def test_counting_build_equals_radix_build(ctx, name):
     pts = _clouds()[name]
     k = 5

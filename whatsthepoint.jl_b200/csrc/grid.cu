@@ -489,12 +489,12 @@ __global__ void __launch_bounds__(256) reorder_kernel(const T* __restrict__ pts,
 // sort gives, so both builds produce the same records — while gathering the records. No digit passes.
 //   cell_count_kernel        keys, arrival numbers, per-cell counts (fused with the key computation)
 //   count_keys_kernel        the same from existing keys (windowed build)
-//   max_u32_kernel           heaviest cell (decides the placement kernels; > CS_BIG_MAX: radix build instead)
 //   cell_scatter_kernel      caller index -> order[cell_start[key] + arrival number]
 //   cell_place_kernel        one thread per entry: rank among the entries of its cell by caller index, gather, store
-//   cell_place_big_kernel    cells above CS_RANK_LIMIT points: one CTA per cell, bitonic sort in shared memory
+//   cell_place_big_kernel    cells above CS_RANK_LIMIT points: one CTA per cell, bitonic sort in shared memory (in global
+//                            memory above CS_BIG_MAX points: degenerate clouds only)
 constexpr uint32_t CS_RANK_LIMIT = 64;      // cells up to this many points are ranked by counting (O(n) per point)
-constexpr uint32_t CS_BIG_MAX = 8192;       // heaviest cell the shared-memory sort takes
+constexpr uint32_t CS_BIG_MAX = 8192;       // heaviest cell sorted in shared memory
 
 template <class T, int D>
 __device__ inline uint32_t cell_key_of(const Grid<T>& g, T x, T y, T z) {
@@ -518,14 +518,6 @@ __global__ void __launch_bounds__(256) count_keys_kernel(const uint32_t* __restr
                                                          uint32_t* __restrict__ cell_count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) arrival[i] = atomicAdd(cell_count + keys[i], 1u);
-}
-
-__global__ void __launch_bounds__(256) max_u32_kernel(const uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ out) {
-    uint32_t m = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, v[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 template <class T, int D>
@@ -564,8 +556,31 @@ __global__ void __launch_bounds__(256) cell_place_kernel(const T* __restrict__ p
     sorted[s + rank] = me;
 }
 
+// Ascending sort of a[0 .. n) by the threads of one CTA: the bitonic network in its all-ascending form (the first stage
+// of every merge compares i with its mirror image in the run, the later ones i with i + j), so that the positions
+// n .. 2^ceil(log2 n) behave as +inf without existing: a comparison that would touch them changes nothing.
+__device__ inline void cta_sort_u32(uint32_t* a, uint32_t n) {
+    uint32_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (uint32_t k = 2; k <= np2; k <<= 1) {
+        const uint32_t hk = k >> 1;
+        for (uint32_t t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+            const uint32_t r = t & (hk - 1), i = ((t - r) << 1) + r, l = i + k - 1 - 2 * r;      // mirror image of i in its run of k
+            if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+        }
+        __syncthreads();
+        for (uint32_t j = hk >> 1; j > 0; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
+                const uint32_t i = 2 * t - (t & (j - 1)), l = i + j;
+                if (l < n) { const uint32_t x = a[i], y = a[l]; if (x > y) { a[i] = y; a[l] = x; } }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 template <class T, int D>
-__global__ void __launch_bounds__(256) cell_place_big_kernel(const T* __restrict__ pts, const uint32_t* __restrict__ order,
+__global__ void __launch_bounds__(256) cell_place_big_kernel(const T* __restrict__ pts, uint32_t* __restrict__ order,
                                                              const uint32_t* __restrict__ cell_start, P4<T>* __restrict__ sorted,
                                                              const uint32_t* __restrict__ big_list) {
     __shared__ uint32_t s_idx[CS_BIG_MAX];
@@ -573,51 +588,34 @@ __global__ void __launch_bounds__(256) cell_place_big_kernel(const T* __restrict
     for (uint32_t b = blockIdx.x; b < n_big; b += gridDim.x) {
         const uint32_t cell = big_list[1 + b];
         const uint32_t s = cell_start[cell], n = cell_start[cell + 1] - s;
-        uint32_t np2 = 1;
-        while (np2 < n) np2 <<= 1;
-        for (uint32_t t = threadIdx.x; t < np2; t += blockDim.x) s_idx[t] = t < n ? order[s + t] : 0xffffffffu;
-        __syncthreads();
-        for (uint32_t k = 2; k <= np2; k <<= 1) {
-            for (uint32_t h = k >> 1; h > 0; h >>= 1) {
-                for (uint32_t t = threadIdx.x; t < (np2 >> 1); t += blockDim.x) {
-                    const uint32_t lo = 2 * t - (t & (h - 1)), hi = lo + h;       // pair (lo, lo + h) of the h-block
-                    const uint32_t a = s_idx[lo], c = s_idx[hi];
-                    const bool up = (lo & k) == 0;
-                    if ((a > c) == up) { s_idx[lo] = c; s_idx[hi] = a; }
-                }
-                __syncthreads();
-            }
+        uint32_t* a = order + s;                              // cells above the shared-memory size are sorted where they are
+        if (n <= CS_BIG_MAX) {
+            for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) s_idx[t] = order[s + t];
+            a = s_idx;
         }
-        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) sorted[s + t] = point_record<T, D>(pts, s_idx[t]);
+        __syncthreads();
+        cta_sort_u32(a, n);
+        for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) sorted[s + t] = point_record<T, D>(pts, a[t]);
         __syncthreads();
     }
 }
 
 // Groups the `n` points (keys[i], arrival[i], ids ? ids[i] : i) by key into `sorted`, ascending caller index within
 // a cell, and fills cell_start[0 .. ncells]. cell_count[0 .. ncells) holds the points per cell (keys are cell ids
-// minus key_lo), cell_count[ncells + 1] is zero. Returns false (nothing placed) when a cell is heavier than
-// CS_BIG_MAX: the caller runs the radix build.
+// minus key_lo). No host round trip: the placement kernel lists the cells too heavy for it and the kernel behind it
+// takes whatever is on the list.
 template <class T>
-static bool place_counted(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int D, const Grid<T>& g, uint32_t key_lo, const uint32_t* keys,
+static void place_counted(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int D, const Grid<T>& g, uint32_t key_lo, const uint32_t* keys,
                           const uint32_t* arrival, const uint32_t* ids, uint32_t n, uint32_t ncells, uint32_t* cell_count, P4<T>* sorted,
                           uint32_t* cell_start) {
     cudaStream_t st = ctx->stream;
-    uint32_t heaviest = 0;
     const unsigned nb = (n + 255u) / 256u;
     uint32_t* order = ib.staging.as<uint32_t>((size_t)n);
     uint32_t* big_list = ib.keys_b.as<uint32_t>((size_t)n / CS_RANK_LIMIT + 2);
     {
         ScopedPhase ph(ctx->timer, PH_SORT);
-        uint32_t* d_max = cell_count + ncells + 1;
-        max_u32_kernel<<<(unsigned)std::min<uint32_t>((ncells + 255u) / 256u, (uint32_t)kNumSMs * 4u), 256, 0, st>>>(cell_count, ncells, d_max);
-        LAUNCH_CHECK(ctx);
-        uint32_t* h = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->h_pinned) + 3584);
-        WTP_CUDA_CHECK(cudaMemcpyAsync(h, d_max, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         exclusive_scan_u32(ctx, ib.scan_tmp, cell_count, cell_start, (int64_t)ncells);
         WTP_CUDA_CHECK(cudaMemsetAsync(big_list, 0, sizeof(uint32_t), st));
-        WTP_CUDA_CHECK(cudaStreamSynchronize(st));
-        heaviest = *h;
-        if (heaviest > CS_BIG_MAX) return false;
         cell_scatter_kernel<<<nb, 256, 0, st>>>(keys, arrival, ids, n, cell_start, order);
         LAUNCH_CHECK(ctx);
     }
@@ -626,13 +624,10 @@ static bool place_counted(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int D,
         if (D == 2) cell_place_kernel<T, 2><<<nb, 256, 0, st>>>(d_pts, order, n, g, key_lo, cell_start, sorted, big_list);
         else cell_place_kernel<T, 3><<<nb, 256, 0, st>>>(d_pts, order, n, g, key_lo, cell_start, sorted, big_list);
         LAUNCH_CHECK(ctx);
-        if (heaviest > CS_RANK_LIMIT) {
-            if (D == 2) cell_place_big_kernel<T, 2><<<kNumSMs * 6, 256, 0, st>>>(d_pts, order, cell_start, sorted, big_list);
-            else cell_place_big_kernel<T, 3><<<kNumSMs * 6, 256, 0, st>>>(d_pts, order, cell_start, sorted, big_list);
-            LAUNCH_CHECK(ctx);
-        }
+        if (D == 2) cell_place_big_kernel<T, 2><<<kNumSMs * 4, 256, 0, st>>>(d_pts, order, cell_start, sorted, big_list);
+        else cell_place_big_kernel<T, 3><<<kNumSMs * 4, 256, 0, st>>>(d_pts, order, cell_start, sorted, big_list);
+        LAUNCH_CHECK(ctx);
     }
-    return true;
 }
 
 static bool counting_build_enabled() {
@@ -660,9 +655,8 @@ int build_index(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t N, int D
             else cell_count_kernel<T, 3><<<nb256, 256, 0, st>>>(d_pts, N, g, keys_a, arrival, cell_count);
             LAUNCH_CHECK(ctx);
         }
-        if (place_counted<T>(ctx, ib, d_pts, D, g, 0u, keys_a, ib.vals_b.get<uint32_t>(), nullptr, (uint32_t)N, g.ncells, cell_count, sorted,
-                             cell_start))
-            return 0;
+        place_counted<T>(ctx, ib, d_pts, D, g, 0u, keys_a, ib.vals_b.get<uint32_t>(), nullptr, (uint32_t)N, g.ncells, cell_count, sorted, cell_start);
+        return 0;
     }
     {
         ScopedPhase ph(ctx->timer, PH_CELLKEY);
@@ -873,11 +867,10 @@ bool build_index_window(wtp_ctx* ctx, IndexBuffers& ib, const T* d_pts, int64_t 
             count_keys_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(keys_a, (uint32_t)M, ib.vals_b.as<uint32_t>((size_t)M), cell_count);
             LAUNCH_CHECK(ctx);
         }
-        if (place_counted<T>(ctx, ib, d_pts, D, g, win->key_lo, keys_a, ib.vals_b.get<uint32_t>(), vals_a, (uint32_t)M, ncells_w, cell_count,
-                             sorted, cell_start)) {
-            if (passes_out) *passes_out = 0;
-            return true;
-        }
+        place_counted<T>(ctx, ib, d_pts, D, g, win->key_lo, keys_a, ib.vals_b.get<uint32_t>(), vals_a, (uint32_t)M, ncells_w, cell_count, sorted,
+                         cell_start);
+        if (passes_out) *passes_out = 0;
+        return true;
     }
     int bits = 0;
     while (bits < 32 && ((uint64_t)1 << bits) < (uint64_t)ncells_w) ++bits;
