@@ -304,29 +304,19 @@ radius_tile_fill_kernel(const Grid<T> g, const P4<T>* __restrict__ sorted, const
                     }
                 }
                 // the smallest head is the next entry of the row; its run advances (selects, no branches: the runs'
-                // list positions are distinct, so exactly one matches). The key behind every head is held too, so that an
-                // advance is a register move and the two dependent shared-memory reads of the key behind the NEW head
-                // (list slot, then the record's index) have a whole iteration to arrive: `pend` is committed one trip later.
-                uint32_t h[R::NRUNS], nx[R::NRUNS];
+                // list positions are distinct, so exactly one matches)
+                uint32_t h[R::NRUNS];
 #pragma unroll
-                for (int i = 0; i < R::NRUNS; ++i) { h[i] = key_at(ptr[i]); nx[i] = key_at(min(ptr[i] + 2u, lim)); }
-                uint32_t pend_ptr = 0u, pend_val = 0u;
+                for (int i = 0; i < R::NRUNS; ++i) h[i] = key_at(ptr[i]);
 #pragma unroll 1
                 for (uint32_t o = 0; o < cnt; ++o) {
                     uint32_t m = h[0], ma = ptr[0];
 #pragma unroll
                     for (int i = 1; i < R::NRUNS; ++i) { const bool lt = h[i] < m; m = lt ? h[i] : m; ma = lt ? ptr[i] : ma; }
                     out[o] = (int64_t)m + 1;
-                    const uint32_t na = ma + 2u;
+                    const uint32_t na = ma + 2u, nv = key_at(na);
 #pragma unroll
-                    for (int i = 0; i < R::NRUNS; ++i) {
-                        nx[i] = ptr[i] == pend_ptr ? pend_val : nx[i];
-                        const bool w = ptr[i] == ma;
-                        h[i] = w ? nx[i] : h[i];
-                        ptr[i] = w ? na : ptr[i];
-                    }
-                    pend_ptr = na;
-                    pend_val = key_at(min(na + 2u, lim));
+                    for (int i = 0; i < R::NRUNS; ++i) { const bool w = ptr[i] == ma; ptr[i] = w ? na : ptr[i]; h[i] = w ? nv : h[i]; }
                 }
             }
         }
