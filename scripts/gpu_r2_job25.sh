@@ -3,13 +3,13 @@
 # with parity_check on every rank.
 out=gpurun_out; mkdir -p $out; tag=r2j25
 nvidia-smi -L > $out/host_$tag.txt; nproc >> $out/host_$tag.txt
-for n in 8 4; do
+for n in ${NLIST:-8}; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2955$n bench.py --gpus $n --steps 10 --warmup 3 > $out/bench${n}_$tag.json 2> $out/bench${n}_$tag.err
   echo "bench${n}_rc=$?"; tail -2 $out/bench${n}_$tag.err
 done
 python - <<'PY'
 import json
-for n in (8, 4):
+for n in (8, 4)[:1]:
     try: d=json.loads([l for l in open('gpurun_out/bench%d_r2j25.json' % n) if l.startswith('{')][0])
     except Exception as e: print(n, 'unreadable', e); continue
     print(n, 'value',round(d['value'],1),'ms',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value'],1),round(d['e2e']['ms_per_step'],2),d['e2e']['phases_ms'])
