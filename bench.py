@@ -378,6 +378,7 @@ def main():
     # ------------------------------------------------------------------ end-to-end arm
     ctx.set_timing(False)
     e2e_ms, e2e_val, e2e_phases, e2e_direct, e2e_bytes, nq_e2e = None, None, None, False, (int(pts_h.nbytes), None), nq
+    e2e_per_rank = None
     if not args.no_e2e:
         h_pts = torch.from_numpy(pts_h).pin_memory()
         h_idx = torch.empty((n, K), dtype=torch.int64).pin_memory()
@@ -393,8 +394,15 @@ def main():
         for _ in range(args.steps):
             step_e2e()
         barrier()
-        e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        mine_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        e2e_ms = max_over_ranks(mine_ms)
         e2e_val = n / (e2e_ms * 1e-3) / 1e6
+        e2e_per_rank = [mine_ms]
+        if world > 1:
+            tm = torch.tensor([mine_ms], dtype=torch.float64, device=dev)
+            allm = [torch.zeros_like(tm) for _ in range(world)]
+            dist.all_gather(allm, tm)
+            e2e_per_rank = [float(x.item()) for x in allm]
         if world == 1:
             assert np.array_equal(h_idx_np[own - 1], chk), "host and device entry points disagree"
         if True:   # the host call fills the rows wtp_shard_owned reports (a contiguous caller range with the row exchange)
@@ -418,6 +426,11 @@ def main():
         e2e_bytes = (int(te["bytes_h2d"]), int(te["bytes_d2h"]))
         e2e_phases = {"ms_h2d": float(te["ms_h2d"]), "ms_device_compute": float(dev_ms), "ms_exchange_barrier": float(te["ms_comm"]),
                       "ms_d2h_and_widen": float(max(wall - te["ms_h2d"] - dev_ms, 0.0)), "ms_wall_this_call": float(wall)}
+        if world > 1:   # every rank's wall time of that one call (the ranks leave the call together only as far as its barrier goes)
+            tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+            allw = [torch.zeros_like(tw) for _ in range(world)]
+            dist.all_gather(allw, tw)
+            e2e_phases["ms_wall_this_call_per_rank"] = [round(float(x.item()), 3) for x in allw]
         del h_pts, h_idx
 
     # --------------------------------------------------------------------- repel extra
@@ -557,7 +570,7 @@ def main():
             "run": {"sharding": f"queries split in {world} contiguous runs of the spatially sorted order; every GPU holds the point set and indexes "
                                 f"the window of the grid around its run (the whole grid at 1 GPU); no collective",
                     "l2": "working set (120 MB points + 160 MB sorted tiles + 1.68 GB output per step) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1],   # per rank, as counted by the library
+            "e2e": {"value": e2e_val, "unit": "Mqueries/s", "ms_per_step": e2e_ms, "ms_per_step_per_rank": e2e_per_rank, "h2d_bytes_per_step": e2e_bytes[0], "d2h_bytes_per_step": e2e_bytes[1],   # per rank, as counted by the library
                     "phases_ms": e2e_phases,
                     "api": "wtp_knn_f32: pinned host points in, N x 21 int64 table in host memory out. " +
                            ("Sharded: the kernels hand every row to the rank owning its caller range over NVLink (peer stores); each rank's contiguous "
