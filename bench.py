@@ -483,6 +483,7 @@ def main():
         ctx.set_timing(True)
         steps_x, warm_x = max(3, min(args.steps, 5)), 3
         # k-NN on the same cloud in Float64 (Julia's default coordinate type)
+        d_idx_chk = d_idx[:4096].clone()           # rows of the timed int64 table, for the int32-table extra below
         d64 = d_pts.double()
         d_idx.zero_()
         ms = timed_dev(lambda: ctx.knn_dev(d64.data_ptr(), n, 3, K, np.float64, d_idx.data_ptr()), steps_x, warm_x)
@@ -492,6 +493,17 @@ def main():
                                  "roofline": roofline("knn_tile_kernel<double,3> (+ leftovers)", ALGO_BYTES_PER_QUERY["f64"] * nq, float(tq["ms_query"]),
                                                       traffic=measured_traffic("knn_f64", world))}
         del d64
+        # the same k-NN step with the int32 device table (wtp_knn_dev_i32_f32): what the int64 rows cost the kernels
+        d_idx32 = torch.empty((nq, K), dtype=torch.int32, device=dev)
+        ms32 = timed_dev(lambda: ctx.knn_dev(d_pts.data_ptr(), n, 3, K, np.float32, d_idx32.data_ptr(), idx32=True), steps_x, warm_x)
+        t32 = ctx.timing()
+        same32 = bool(torch.equal(d_idx32[:4096].to(torch.int64), d_idx_chk)) if d_idx_chk is not None else None
+        extras["knn_f32_10M_int32_table"] = {"metric": "knn_k21_Mqueries_per_s", "value": n / (ms32 * 1e-3) / 1e6, "unit": "Mqueries/s", "dtype": "f32", "ms_per_step": ms32,
+                                            "rows_equal_int64_table": same32,
+                                            "config": {"workload": f"U3({n}) uniform 3-D, KNNTopology k=21, float32, N x 21 int32 device table", "points": n},
+                                            "roofline": roofline("knn_tile_kernel<float,3> (+ leftovers), int32 rows", ALGO_BYTES_PER_QUERY["f32"] * nq, float(t32["ms_query"]),
+                                                                 traffic=None)}
+        del d_idx32
         # config #3: repel on the 2 M graded cube, BoundaryLayerSpacing, Float32 and Float64
         for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
             gp, nw, hw = synth.graded_cube(2_000_000, dt)

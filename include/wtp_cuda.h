@@ -175,6 +175,13 @@ int32_t wtp_knn_dev_f32(wtp_ctx*, const float* d_pts, int64_t N, int32_t D, int3
                         int64_t* d_out_idx, float* d_out_dist);
 int32_t wtp_knn_dev_f64(wtp_ctx*, const double* d_pts, int64_t N, int32_t D, int32_t k,
                         int64_t* d_out_idx, double* d_out_dist);
+/* The same table as 4-byte indices (N < 2^31): for a caller that keeps the adjacency on the device or backs its row type
+ * with Int32 storage (an AbstractVector{Int} row converting on getindex satisfies KNNTopology, src/topology.jl:25). The
+ * kernels write half the bytes; contents and order are those of the int64 table. Device pointers only. */
+int32_t wtp_knn_dev_i32_f32(wtp_ctx*, const float* d_pts, int64_t N, int32_t D, int32_t k,
+                            int32_t* d_out_idx, float* d_out_dist);
+int32_t wtp_knn_dev_i32_f64(wtp_ctx*, const double* d_pts, int64_t N, int32_t D, int32_t k,
+                            int32_t* d_out_idx, double* d_out_dist);
 
 /* search / searchdists (src/neighbors.jl:9-21): the k nearest points INCLUDING the
  * query's own entry (position 1 whenever the point is not duplicated). */

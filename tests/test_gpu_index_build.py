@@ -62,3 +62,31 @@ def test_counting_build_radius_rows(ctx, oracle):
     off, ind = ctx.radius(pts, 0.03)
     ro, ri = oracle.radius(pts, 0.03)
     assert np.array_equal(off, ro) and np.array_equal(ind, ri)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_int32_device_table_equals_int64_table(ctx, dt):
+    """wtp_knn_dev_i32_*: the same rows as 4-byte indices (device pointers in and out), distances included, tiled pass
+    and general kernel (k = 40) alike; a sharded context writes the same compact table."""
+    import torch
+    rng = np.random.default_rng(9)
+    pts = rng.random((120_000, 3)).astype(dt)
+    dev = torch.device("cuda", 0)
+    d = torch.from_numpy(pts).to(dev)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        for k in (21, 40):
+            i64 = torch.empty((len(pts), k), dtype=torch.int64, device=dev)
+            i32 = torch.full((len(pts), k), -1, dtype=torch.int32, device=dev)
+            dist = torch.empty((len(pts), k), dtype=torch.float32 if dt == np.float32 else torch.float64, device=dev)
+            dist32 = torch.empty_like(dist)
+            ctx.knn_dev(d.data_ptr(), len(pts), 3, k, dt, i64.data_ptr(), dist.data_ptr())
+            ctx.knn_dev(d.data_ptr(), len(pts), 3, k, dt, i32.data_ptr(), dist32.data_ptr(), idx32=True)
+            torch.cuda.synchronize()
+            assert torch.equal(i64, i32.to(torch.int64)) and torch.equal(dist, dist32)
+            i32n = torch.full((len(pts), k), -1, dtype=torch.int32, device=dev)
+            ctx.knn_dev(d.data_ptr(), len(pts), 3, k, dt, i32n.data_ptr(), 0, idx32=True)     # indices only (the row-per-store path)
+            torch.cuda.synchronize()
+            assert torch.equal(i32, i32n)
+    finally:
+        ctx.set_stream(None)

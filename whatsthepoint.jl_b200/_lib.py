@@ -239,8 +239,9 @@ class Context:
         self._check(fn(self._h, _vp(pts), C.c_int64(n), C.c_int32(d), C.c_int32(k), _vp(idx), _vp(dist)))
         return (idx, dist) if (dists or out_dist is not None) else idx
 
-    def knn_dev(self, d_pts_ptr: int, n: int, d: int, k: int, dtype, d_out_idx_ptr: int, d_out_dist_ptr: int = 0):
-        fn = getattr(self._lib, "wtp_knn_dev_" + _sfx(dtype))
+    def knn_dev(self, d_pts_ptr: int, n: int, d: int, k: int, dtype, d_out_idx_ptr: int, d_out_dist_ptr: int = 0, *, idx32: bool = False):
+        """Device pointers in and out. idx32: the table is int32 (wtp_knn_dev_i32_*), int64 otherwise."""
+        fn = getattr(self._lib, ("wtp_knn_dev_i32_" if idx32 else "wtp_knn_dev_") + _sfx(dtype))
         self._check(fn(self._h, C.c_void_p(d_pts_ptr), C.c_int64(n), C.c_int32(d), C.c_int32(k),
                        C.c_void_p(d_out_idx_ptr), C.c_void_p(d_out_dist_ptr or 0)))
 

@@ -300,7 +300,7 @@ static void widen_on_device(wtp_ctx* ctx, const uint32_t* d_in, size_t n, int64_
 //   caller's int64 table on the host pool while the next chunk is on the wire: 4 B per neighbour cross PCIe, not 8.
 template <class T>
 static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bool drop_first, int64_t* d_out_idx, T* d_out_dist,
-                       int64_t* h_out_idx = nullptr, T* h_out_dist = nullptr) {
+                       int64_t* h_out_idx = nullptr, T* h_out_dist = nullptr, bool dev_out32 = false) {
     WTP_REQUIRE(D == 2 || D == 3, WTP_ERR_BAD_ARG, "D must be 2 or 3");
     WTP_REQUIRE(k >= 1, WTP_ERR_BAD_ARG, "k must be >= 1");
     const int K1 = k + (drop_first ? 1 : 0);
@@ -410,7 +410,7 @@ static void knn_device(wtp_ctx* ctx, const T* d_pts, int64_t N, int D, int k, bo
         ctx->owned_begin = cb; ctx->owned_end = ce;
         ctx->last_d2h_direct = direct;
     } else if (!h_out_idx) {
-        compute(d_out_idx, d_out_dist, false);
+        compute(d_out_idx, d_out_dist, dev_out32);    // dev_out32: d_out_idx is an int32 table (wtp_knn_dev_i32_*)
     } else if (!sharded && nq * (int64_t)k < ((int64_t)4 << 20)) {
         // small result: int64 rows straight from the device table
         int64_t* d_idx = ctx->d_out_idx.as<int64_t>((size_t)nq * k);
@@ -533,12 +533,12 @@ static int32_t knn_host(wtp_ctx* ctx, const T* pts, int64_t N, int32_t D, int32_
 }
 
 template <class T>
-static int32_t knn_dev(wtp_ctx* ctx, const T* d_pts, int64_t N, int32_t D, int32_t k, int64_t* d_out_idx, T* d_out_dist) {
+static int32_t knn_dev(wtp_ctx* ctx, const T* d_pts, int64_t N, int32_t D, int32_t k, void* d_out_idx, T* d_out_dist, bool out32 = false) {
     API_BEGIN(ctx)
     WTP_REQUIRE(d_pts && d_out_idx && N > 0, WTP_ERR_BAD_ARG, "null pointer or empty point set");
     ctx->timer.reset(ctx->stream);
     ctx->timer.begin_total();
-    knn_device<T>(ctx, d_pts, N, D, k, true, d_out_idx, d_out_dist);
+    knn_device<T>(ctx, d_pts, N, D, k, true, static_cast<int64_t*>(d_out_idx), d_out_dist, nullptr, nullptr, out32);
     ctx->timer.end_total();
     API_END(ctx)
 }
@@ -568,6 +568,8 @@ int32_t wtp_knn_self_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32
 int32_t wtp_knn_self_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return knn_entry<double>(c, p, N, D, k, false, oi, od); }
 int32_t wtp_knn_dev_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int64_t* oi, float* od) { return is_multi(c) ? no_device_pointers(c) : knn_dev<float>(c, p, N, D, k, oi, od); }
 int32_t wtp_knn_dev_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int64_t* oi, double* od) { return is_multi(c) ? no_device_pointers(c) : knn_dev<double>(c, p, N, D, k, oi, od); }
+int32_t wtp_knn_dev_i32_f32(wtp_ctx* c, const float* p, int64_t N, int32_t D, int32_t k, int32_t* oi, float* od) { return is_multi(c) ? no_device_pointers(c) : knn_dev<float>(c, p, N, D, k, oi, od, true); }
+int32_t wtp_knn_dev_i32_f64(wtp_ctx* c, const double* p, int64_t N, int32_t D, int32_t k, int32_t* oi, double* od) { return is_multi(c) ? no_device_pointers(c) : knn_dev<double>(c, p, N, D, k, oi, od, true); }
 
 int64_t wtp_shard_owned_count(const wtp_ctx* ctx) { return ctx ? ctx->owned_end - ctx->owned_begin : -1; }
 int32_t wtp_shard_owned_dev(wtp_ctx* ctx, int64_t* d_ids) {
