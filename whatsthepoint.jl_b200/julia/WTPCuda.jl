@@ -32,7 +32,7 @@
 
 module WTPCuda
 
-using Meshes, Unitful, StaticArrays, Random, LinearAlgebra
+using Meshes, CoordRefSystems, Unitful, StaticArrays, Random, LinearAlgebra   # CRS comes from CoordRefSystems, as in src/WhatsThePoint.jl:4
 import Meshes: search, searchdists
 import ..WhatsThePoint
 import ..WhatsThePoint: _build_knn_neighbors, _build_radius_neighbors, _relax!, _get_radius, _edge_key,
@@ -212,12 +212,14 @@ end
 
 # search / searchdists over cloud types (src/neighbors.jl:9-21): the KNearestSearch object only contributes its k
 # (its KD-tree was built by the caller and is not used); per-point results keep the reference's shapes.
-const CloudLike = Union{PointCloud, PointBoundary, PointSurface}
-function search(cloud::CloudLike, method::KNearestSearch)
+# (Euclidean clouds only: strictly more specific than the reference's Union{PointCloud, PointBoundary, PointSurface}
+# methods — the same signature would be a method overwrite, which precompilation refuses)
+const CloudLike{N} = Union{PointCloud{𝔼{N}}, PointBoundary{𝔼{N}}, PointSurface{𝔼{N}}}
+function search(cloud::CloudLike{N}, method::KNearestSearch) where {N}
     out, _ = knn_table(points(cloud), method.k; include_self = true)
     return [Vector{Int}(view(out, :, i)) for i in axes(out, 2)]
 end
-function searchdists(cloud::CloudLike, method::KNearestSearch)
+function searchdists(cloud::CloudLike{N}, method::KNearestSearch) where {N}
     pts = points(cloud)
     out, dist = knn_table(pts, method.k; include_self = true, dists = true)
     u = Unitful.unit(Meshes.to(first(pts))[1])
