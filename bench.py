@@ -18,7 +18,8 @@ bounding box -> cell keys -> radix sort -> gather -> tiled k-NN, N x 21 int64 ou
   repel   : extra object — iterations/s of the fused repel sweep on the same cloud size.
   extras  : the other BASELINE configurations, each with its own roofline object: k-NN on the
             10 M cloud in Float64, config #3 (repel on the 2 M graded cube, Float32 and Float64),
-            config #4 (radius CSR on the 10 M quadtree-graded square).
+            config #4 (radius CSR on the 10 M quadtree-graded square), the int32 device table, and config #5's size
+            (k-NN + 3 repel iterations on 100 M points generated on the device; --points5 0 skips it).
   parity_check: outside the timed regions every rank brute-forces 256 of the rows it
             answered and 64 positions of one sharded repel sweep in numpy.
 
@@ -264,6 +265,7 @@ def main():
     ap.add_argument("--points", type=int, default=10_000_000)
     ap.add_argument("--repel-points", type=int, default=10_000_000)
     ap.add_argument("--repel-iters", type=int, default=20)
+    ap.add_argument("--points5", type=int, default=100_000_000, help="size of the config-#5 extra (k-NN + a few repel iterations, points generated on the device); 0 skips it")
     ap.add_argument("--no-repel", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configurations (f64 k-NN, config #3, config #4)")
@@ -557,6 +559,62 @@ def main():
                                  (40.0 * (e4 - b4) + 4.0 * nnz), msr, traffic=measured_traffic("radius_config4", world),
                                  note="algorithmic bytes = 2*D*T read + 4 count + 4 offset per point + 4 per entry (SURVEY.md §8d; the device writes int64 entries)")}
         del d_q, d_off, d_ind
+        # config #5's size: U3(100 M) float32 generated on the device (same stream of torch's Philox on every rank), k-NN into
+        # the int32 device table, then a few repel iterations; 8 rows per rank against brute force on the device. Last of the
+        # extras and fenced: whatever happens here, the line above it is printed.
+        # (one GPU by default: the sharded run of it is opt-in, WTP_BENCH_CONFIG5_SHARDED=1 — a rank failing inside this block
+        # would leave its peers waiting in a collective)
+        if args.points5 > 0 and (world == 1 or os.environ.get("WTP_BENCH_CONFIG5_SHARDED") == "1"):
+            try:
+                n5 = args.points5
+                gen5 = torch.Generator(device=dev)
+                gen5.manual_seed(0x57545035)
+                p5 = torch.rand((n5, 3), generator=gen5, device=dev, dtype=torch.float32)
+                b5, e5 = ctx.shard(n5)
+                t5 = torch.empty((e5 - b5, K), dtype=torch.int32, device=dev)
+                ms5 = timed_dev(lambda: ctx.knn_dev(p5.data_ptr(), n5, 3, K, np.float32, t5.data_ptr(), idx32=True), 3, 1)
+                tq5 = ctx.timing()
+                own5 = ctx.owned() if world > 1 else None
+                ok5 = True
+                for tt in np.random.default_rng(5000 + rank).choice(e5 - b5, size=8, replace=False):
+                    i5 = int(own5[tt] - 1) if own5 is not None else int(tt)
+                    q5 = p5[i5]
+                    dx5 = p5[:, 0] - q5[0]
+                    d25 = dx5 * dx5
+                    dx5 = p5[:, 1] - q5[1]
+                    d25 = d25 + dx5 * dx5
+                    dx5 = p5[:, 2] - q5[2]
+                    d25 = d25 + dx5 * dx5                                    # the operation order of the library's d2 (eager mode: no FMA)
+                    d25[i5] = float("inf")
+                    want5 = torch.topk(d25, K, largest=False, sorted=True).values
+                    ok5 = ok5 and bool(torch.equal(d25[t5[int(tt)].to(torch.int64) - 1], want5))
+                    del d25, dx5
+                extras["knn_config5_100M_f32"] = {
+                    "metric": "knn_k21_Mqueries_per_s", "value": n5 / (ms5 * 1e-3) / 1e6, "unit": "Mqueries/s", "dtype": "f32", "ms_per_step": ms5,
+                    "rows_checked_per_rank": 8, "rows_ok": all_ranks_ok(ok5),
+                    "phases_ms": {k2: float(tq5[k2]) for k2 in ("ms_bbox", "ms_cellkey", "ms_sort", "ms_reorder", "ms_query")},
+                    "config": {"workload": f"U3({n5}) uniform 3-D generated on the device, KNNTopology k=21, float32, int32 device table", "points": n5},
+                    "roofline": roofline("knn_tile_kernel<float,3> (+ leftovers)", ALGO_BYTES_PER_QUERY["f32"] * (e5 - b5), float(tq5["ms_query"]), traffic=None)}
+                del t5
+                h5 = n5 ** (-1.0 / 3.0)
+                sp5, _ = ctx.make_spacing("constant", a=h5)
+                kw5 = dict(k=K, tol=0.0, stall_after=0, alpha_lo=h5 / 2000, alpha_max=h5 / 20)
+                ctx.repel_dev(p5.data_ptr(), 0, n5, 3, np.float32, sp5, ctx.make_force("clipped", 0.2), max_iters=1, **kw5)
+                barrier()
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                v0.record(stream)
+                _, res5 = ctx.repel_dev(p5.data_ptr(), 0, n5, 3, np.float32, sp5, ctx.make_force("clipped", 0.2), max_iters=3, **kw5)
+                v1.record(stream)
+                barrier()
+                it5 = max(res5["iters"], 1)
+                msr5 = max_over_ranks(v0.elapsed_time(v1)) / it5
+                extras["repel_config5_100M_f32"] = {
+                    "metric": "repel_iters_per_s", "value": 1e3 / msr5, "unit": "iters/s", "dtype": "f32", "ms_per_iter": msr5, "iters": res5["iters"],
+                    "config": {"workload": f"U3({n5}) uniform 3-D, repel beta=0.2 k=21 constant spacing, float32", "points": n5, "seconds_per_100_iters": msr5 / 10.0},
+                    "roofline": roofline("repel_tile_kernel<float,3,clipped> + index rebuild (whole iteration)", ALGO_BYTES_REPEL["f32"] * n5 / world, msr5, traffic=None)}
+                del p5
+            except Exception as ex:                                          # noqa: BLE001 — reported in the line, never fatal to it
+                extras["config5_100M_error"] = str(ex)[:400]
 
     if rank == 0:
         cpu = None
