@@ -3,7 +3,7 @@
 # methods reached through `invoke`.
 #
 #   WTP_CUDA_LIB=/path/to/libwtp_cuda.so julia --project=/path/to/WhatsThePoint.jl scripts/julia_smoke.jl
-using WhatsThePoint, Meshes, Unitful, Random, Test
+using WhatsThePoint, Meshes, Unitful, Random, Statistics, Test
 import WhatsThePoint: _build_knn_neighbors, _build_radius_neighbors
 @assert isdefined(WhatsThePoint, :WTPCuda) "include(\"WTPCuda.jl\") is missing from src/WhatsThePoint.jl"
 

@@ -6,7 +6,7 @@
 #
 # Written against the reference sources (src/topology.jl:79-100, src/repel.jl:202-206, src/repel_forces.jl:88-100,
 # src/discretization/spacings.jl:35-39, 93-133); not executed in the build image (no Julia there).
-using WhatsThePoint, Meshes, Unitful, JSON
+using WhatsThePoint, Meshes, Unitful, JSON        # JSON is not a dependency of the reference: `] add JSON` in the environment used to run this
 import WhatsThePoint: _build_knn_neighbors, _build_radius_neighbors, _relax!
 
 root = length(ARGS) >= 1 ? ARGS[1] : joinpath(@__DIR__, "..", "tests", "golden", "reference")
